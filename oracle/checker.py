@@ -1,0 +1,498 @@
+"""oracle/checker.py — TEST INFRASTRUCTURE: ctypes faces over the two CPU checkers.
+
+* ``Oracle()``  -> oracle/libgcn_oracle.so, the plain-C restatement (gcn_oracle.c, prefix ``gcno_``).
+* ``Ref()``     -> oracle/_ref/libgcnref.so, the UNMODIFIED reference compiled by oracle/Makefile
+                   (ref_shim.cpp, prefix ``gcnref_``).  Exists only where `make -C oracle ref` ran
+                   (this container) or where the prebuilt file travelled (the GPU box).
+
+Both expose the same numpy-level methods so a test can run one against the other.  Only tests/,
+tools/make_golden.py, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
+import this module; the product package never does.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+HERE = Path(__file__).resolve().parent
+ORACLE_SO = HERE / "libgcn_oracle.so"
+REF_SO = HERE / "_ref" / "libgcnref.so"
+REF_SEQ = HERE / "_ref" / "gcn-seq"
+REF_TIMESHIM = HERE / "_ref" / "libtimeshim.so"
+
+_f32p = np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS")
+_i32p = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
+_u8p = np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS")
+
+
+def build_oracle(force: bool = False) -> Path:
+    """Compile the C restatement with gcc (seconds).  Building the checker is not using it."""
+    src = HERE / "gcn_oracle.c"
+    if force or not ORACLE_SO.exists() or ORACLE_SO.stat().st_mtime < src.stat().st_mtime:
+        subprocess.run(["make", "-C", str(HERE), "oracle"], check=True, capture_output=True)
+    return ORACLE_SO
+
+
+def build_ref() -> Path | None:
+    """Compile the unmodified reference into oracle/_ref when /root/reference is present."""
+    subprocess.run(["make", "-C", str(HERE), "ref"], check=True, capture_output=True)
+    return REF_SO if REF_SO.exists() else None
+
+
+def ref_available() -> bool:
+    return REF_SO.exists()
+
+
+def f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+class _Data(C.Structure):
+    _fields_ = [("num_nodes", C.c_int), ("input_dim", C.c_int), ("output_dim", C.c_int),
+                ("graph_nnz", C.c_long), ("feature_nnz", C.c_long), ("n_label", C.c_long), ("n_split", C.c_long),
+                ("graph_indptr", C.POINTER(C.c_int)), ("graph_indices", C.POINTER(C.c_int)),
+                ("feature_indptr", C.POINTER(C.c_int)), ("feature_indices", C.POINTER(C.c_int)),
+                ("feature_value", C.POINTER(C.c_float)), ("label", C.POINTER(C.c_int)), ("split", C.POINTER(C.c_int))]
+
+
+class _HParams(C.Structure):
+    _fields_ = [("hidden_dim", C.c_int), ("dropout", C.c_float), ("learning_rate", C.c_float),
+                ("weight_decay", C.c_float), ("epochs", C.c_int), ("early_stopping", C.c_int)]
+
+
+class GraphData:
+    """Host-side GCNData (gcn.h:16-22) as numpy arrays."""
+
+    def __init__(self, graph_indptr, graph_indices, feature_indptr, feature_indices, feature_value, label, split,
+                 input_dim=None, output_dim=None):
+        self.graph_indptr = i32(graph_indptr)
+        self.graph_indices = i32(graph_indices)
+        self.feature_indptr = i32(feature_indptr)
+        self.feature_indices = i32(feature_indices)
+        self.feature_value = f32(feature_value)
+        self.label = i32(label)
+        self.split = i32(split)
+        self.num_nodes = len(self.graph_indptr) - 1
+        # parser.cpp:90-91
+        self.input_dim = int(input_dim if input_dim is not None else
+                             (self.feature_indices.max() + 1 if len(self.feature_indices) else 1))
+        self.output_dim = int(output_dim if output_dim is not None else max(int(self.label.max()), 0) + 1)
+
+
+class _Base:
+    """Shared numpy-level API; subclasses bind the symbols."""
+
+    def graphsum(self, indptr, indices, x, dim, backward=False):
+        raise NotImplementedError
+
+
+class Oracle(_Base):
+    name = "port"
+
+    def __init__(self):
+        build_oracle()
+        L = self.L = C.CDLL(str(ORACLE_SO))
+        L.gcno_rand.restype = C.c_uint32
+        L.gcno_set_rand_state.argtypes = [C.c_uint64, C.c_uint64]
+        L.gcno_init_rand_state.argtypes = [C.c_long]
+        L.gcno_get_rand_state.argtypes = [C.POINTER(C.c_uint64)]
+        L.gcno_glorot.argtypes = [_f32p, C.c_int, C.c_int]
+        L.gcno_matmul_fw.argtypes = [_f32p, _f32p, _f32p, C.c_int, C.c_int, C.c_int]
+        L.gcno_matmul_bw.argtypes = [_f32p, _f32p, _f32p, _f32p, _f32p, C.c_int, C.c_int, C.c_int]
+        L.gcno_spmm_fw.argtypes = [_i32p, _i32p, _f32p, _f32p, _f32p, C.c_int, C.c_int, C.c_int]
+        L.gcno_spmm_bw.argtypes = [_i32p, _i32p, _f32p, _f32p, _f32p, C.c_int, C.c_int, C.c_int]
+        L.gcno_graphsum.argtypes = [_i32p, _i32p, C.c_int, C.c_int, _f32p, _f32p]
+        L.gcno_cross_entropy.argtypes = [_f32p, _i32p, _f32p, C.c_int, C.c_int, C.c_int]
+        L.gcno_cross_entropy.restype = C.c_float
+        L.gcno_relu_fw.argtypes = [_f32p, _u8p, C.c_int, C.c_int]
+        L.gcno_relu_bw.argtypes = [_f32p, _u8p, C.c_int]
+        L.gcno_dropout_fw.argtypes = [_f32p, C.c_void_p, C.c_int, C.c_float, C.c_int]
+        L.gcno_dropout_bw.argtypes = [_f32p, _i32p, C.c_int, C.c_float]
+        L.gcno_adam_create.restype = C.c_void_p
+        L.gcno_adam_create.argtypes = [C.c_int, _i32p, _i32p, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float]
+        L.gcno_adam_step.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
+        L.gcno_adam_destroy.argtypes = [C.c_void_p]
+        L.gcno_set_truth.argtypes = [_i32p, _i32p, _i32p, C.c_int, C.c_int]
+        L.gcno_accuracy.argtypes = [_f32p, _i32p, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.gcno_accuracy.restype = C.c_float
+        L.gcno_l2_penalty.argtypes = [_f32p, C.c_int, C.c_float]
+        L.gcno_l2_penalty.restype = C.c_float
+        L.gcno_parse.argtypes = [C.POINTER(_Data), C.c_char_p, C.c_char_p]
+        L.gcno_data_free.argtypes = [C.POINTER(_Data)]
+        L.gcno_default_hparams.restype = _HParams
+        L.gcno_gcn_create.restype = C.c_void_p
+        L.gcno_gcn_create.argtypes = [C.POINTER(_Data), _HParams, C.c_long]
+        L.gcno_gcn_destroy.argtypes = [C.c_void_p]
+        L.gcno_gcn_train_epoch.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+        L.gcno_gcn_eval.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+        L.gcno_gcn_var_size.argtypes = [C.c_void_p, C.c_int]
+        L.gcno_gcn_var_size.restype = C.c_long
+        L.gcno_gcn_get_var.argtypes = [C.c_void_p, C.c_int, C.c_int, _f32p]
+        L.gcno_gcn_run.argtypes = [C.c_void_p]
+
+    # --- rng
+    def init_rand_state(self, seed): self.L.gcno_init_rand_state(seed)
+    def set_rand_state(self, a, b): self.L.gcno_set_rand_state(a, b)
+
+    def get_rand_state(self):
+        out = (C.c_uint64 * 2)()
+        self.L.gcno_get_rand_state(out)
+        return int(out[0]), int(out[1])
+
+    def rand(self, n):
+        return np.array([self.L.gcno_rand() for _ in range(n)], dtype=np.uint32)
+
+    def glorot(self, in_size, out_size):
+        w = np.empty(in_size * out_size, np.float32)
+        self.L.gcno_glorot(w, in_size, out_size)
+        return w
+
+    # --- modules
+    def matmul_fw(self, a, b, m, n, p):
+        c = np.empty(m * p, np.float32)
+        self.L.gcno_matmul_fw(f32(a), f32(b), c, m, n, p)
+        return c
+
+    def matmul_bw(self, a, b, c_grad, m, n, p):
+        ag, bg = np.empty(m * n, np.float32), np.empty(n * p, np.float32)
+        self.L.gcno_matmul_bw(f32(a), f32(b), f32(c_grad), ag, bg, m, n, p)
+        return ag, bg
+
+    def spmm_fw(self, indptr, indices, values, b, m, n, p):
+        c = np.empty(m * p, np.float32)
+        self.L.gcno_spmm_fw(i32(indptr), i32(indices), f32(values), f32(b), c, m, n, p)
+        return c
+
+    def spmm_bw(self, indptr, indices, values, c_grad, m, n, p):
+        bg = np.empty(n * p, np.float32)
+        self.L.gcno_spmm_bw(i32(indptr), i32(indices), f32(values), f32(c_grad), bg, m, n, p)
+        return bg
+
+    def graphsum(self, indptr, indices, x, dim, backward=False):
+        n = len(indptr) - 1
+        out = np.empty(n * dim, np.float32)
+        self.L.gcno_graphsum(i32(indptr), i32(indices), n, dim, f32(x).ravel(), out)
+        return out
+
+    def cross_entropy(self, logits, truth, num_classes, training=True):
+        lg = f32(logits).ravel().copy()
+        n = len(lg) // num_classes
+        grad = np.zeros(len(lg), np.float32)
+        loss = self.L.gcno_cross_entropy(lg, i32(truth), grad, n, num_classes, int(training))
+        return float(np.float32(loss)), lg, (grad if training else None)
+
+    def relu(self, x, grad=None, training=True):
+        x = f32(x).ravel().copy()
+        mask = np.zeros(len(x), np.uint8)
+        self.L.gcno_relu_fw(x, mask, len(x), int(training))
+        g = None
+        if grad is not None:
+            g = f32(grad).ravel().copy()
+            self.L.gcno_relu_bw(g, mask, len(x))
+        return x, mask, g
+
+    def dropout(self, x, p, grad=None, training=True, with_grad=True):
+        x = f32(x).ravel().copy()
+        mask = np.zeros(len(x), np.int32)
+        self.L.gcno_dropout_fw(x, mask.ctypes.data if with_grad else None, len(x), p, int(training))
+        g = None
+        if grad is not None and with_grad:
+            g = f32(grad).ravel().copy()
+            self.L.gcno_dropout_bw(g, mask, len(x), p)
+        return x, mask, g
+
+    def adam(self, datas, grads_per_step, decay, lr, weight_decay, beta1=0.9, beta2=0.999, eps=1e-8):
+        """Run len(grads_per_step) steps; returns final data arrays."""
+        datas = [f32(d).copy() for d in datas]
+        sizes = i32([len(d) for d in datas])
+        h = self.L.gcno_adam_create(len(datas), sizes, i32(decay), lr, beta1, beta2, eps, weight_decay)
+        for grads in grads_per_step:
+            grads = [f32(g) for g in grads]
+            dp = (C.c_void_p * len(datas))(*[d.ctypes.data for d in datas])
+            gp = (C.c_void_p * len(datas))(*[g.ctypes.data for g in grads])
+            self.L.gcno_adam_step(h, dp, gp)
+        self.L.gcno_adam_destroy(h)
+        return datas
+
+    def set_truth(self, split, label, current):
+        t = np.empty(len(split), np.int32)
+        self.L.gcno_set_truth(t, i32(split), i32(label), len(split), current)
+        return t
+
+    def accuracy(self, logits, truth, num_classes):
+        w, t = C.c_int(), C.c_int()
+        acc = self.L.gcno_accuracy(f32(logits).ravel(), i32(truth), len(truth), num_classes, C.byref(w), C.byref(t))
+        return float(np.float32(acc)), w.value, t.value
+
+    def l2_penalty(self, w, weight_decay):
+        return float(np.float32(self.L.gcno_l2_penalty(f32(w).ravel(), len(w), weight_decay)))
+
+    # --- parser
+    def parse(self, directory, name):
+        d = _Data()
+        ok = self.L.gcno_parse(C.byref(d), str(directory).encode(), name.encode())
+        if not ok:
+            return None
+        n = d.num_nodes
+
+        def arr(ptr, cnt, dt):
+            return np.ctypeslib.as_array(ptr, shape=(cnt,)).astype(dt).copy() if cnt else np.zeros(0, dt)
+        out = dict(num_nodes=n, input_dim=d.input_dim, output_dim=d.output_dim,
+                   graph_indptr=arr(d.graph_indptr, n + 1, np.int32), graph_indices=arr(d.graph_indices, d.graph_nnz, np.int32),
+                   feature_indptr=arr(d.feature_indptr, d.n_label + 1, np.int32),
+                   feature_indices=arr(d.feature_indices, d.feature_nnz, np.int32),
+                   feature_value=arr(d.feature_value, d.feature_nnz, np.float32),
+                   label=arr(d.label, d.n_label, np.int32), split=arr(d.split, d.n_split, np.int32))
+        self.L.gcno_data_free(C.byref(d))
+        return out
+
+    # --- whole model
+    def gcn(self, data: GraphData, hidden_dim=16, dropout=0.5, lr=0.01, weight_decay=5e-4, epochs=100,
+            early_stopping=0, seed=1):
+        return _OracleGCN(self, data, _HParams(hidden_dim, dropout, lr, weight_decay, epochs, early_stopping), seed)
+
+
+class _OracleGCN:
+    def __init__(self, o: Oracle, data: GraphData, hp, seed):
+        self.o, self.data = o, data          # keep the arrays alive: the model borrows them
+        d = self.d = _Data()
+        d.num_nodes, d.input_dim, d.output_dim = data.num_nodes, data.input_dim, data.output_dim
+        d.graph_nnz, d.feature_nnz = len(data.graph_indices), len(data.feature_indices)
+        d.n_label, d.n_split = len(data.label), len(data.split)
+        as_i = lambda a: a.ctypes.data_as(C.POINTER(C.c_int))
+        d.graph_indptr, d.graph_indices = as_i(data.graph_indptr), as_i(data.graph_indices)
+        d.feature_indptr, d.feature_indices = as_i(data.feature_indptr), as_i(data.feature_indices)
+        d.feature_value = data.feature_value.ctypes.data_as(C.POINTER(C.c_float))
+        d.label, d.split = as_i(data.label), as_i(data.split)
+        self.h = o.L.gcno_gcn_create(C.byref(d), hp, seed)
+
+    def train_epoch(self):
+        a, b = C.c_float(), C.c_float()
+        self.o.L.gcno_gcn_train_epoch(self.h, C.byref(a), C.byref(b))
+        return a.value, b.value
+
+    def eval(self, split):
+        a, b = C.c_float(), C.c_float()
+        self.o.L.gcno_gcn_eval(self.h, split, C.byref(a), C.byref(b))
+        return a.value, b.value
+
+    def var(self, idx, grad=False):
+        out = np.empty(self.o.L.gcno_gcn_var_size(self.h, idx), np.float32)
+        self.o.L.gcno_gcn_get_var(self.h, idx, int(grad), out)
+        return out
+
+    def run(self):
+        return self.o.L.gcno_gcn_run(self.h)
+
+    def close(self):
+        if self.h:
+            self.o.L.gcno_gcn_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+
+class Ref(_Base):
+    """The unmodified reference (oracle/_ref/libgcnref.so)."""
+    name = "reference"
+
+    def __init__(self):
+        if not REF_SO.exists():
+            raise FileNotFoundError(f"{REF_SO} missing: run `make -C oracle ref` where /root/reference exists")
+        L = self.L = C.CDLL(str(REF_SO))
+        L.gcnref_rand.restype = C.c_uint32
+        L.gcnref_set_rand_state.argtypes = [C.c_uint64, C.c_uint64]
+        L.gcnref_init_rand_state.argtypes = [C.c_long]
+        L.gcnref_get_rand_state.argtypes = [C.POINTER(C.c_uint64)]
+        L.gcnref_glorot.argtypes = [_f32p, C.c_int, C.c_int]
+        L.gcnref_matmul_fw.argtypes = [_f32p, _f32p, _f32p, C.c_int, C.c_int, C.c_int]
+        L.gcnref_matmul_bw.argtypes = [_f32p, _f32p, _f32p, _f32p, _f32p, C.c_int, C.c_int, C.c_int]
+        L.gcnref_spmm_fw.argtypes = [_i32p, _i32p, _f32p, _f32p, _f32p, C.c_int, C.c_int, C.c_int]
+        L.gcnref_spmm_bw.argtypes = [_i32p, _i32p, _f32p, _f32p, _f32p, C.c_int, C.c_int, C.c_int]
+        L.gcnref_graphsum.argtypes = [_i32p, _i32p, C.c_int, C.c_int, _f32p, _f32p, C.c_int]
+        L.gcnref_cross_entropy.argtypes = [_f32p, _i32p, _f32p, C.c_int, C.c_int, C.c_int]
+        L.gcnref_cross_entropy.restype = C.c_float
+        L.gcnref_relu.argtypes = [_f32p, _u8p, C.c_void_p, C.c_int, C.c_int]
+        L.gcnref_dropout.argtypes = [_f32p, _i32p, C.c_void_p, C.c_int, C.c_float, C.c_int, C.c_int]
+        L.gcnref_adam_create.restype = C.c_void_p
+        L.gcnref_adam_create.argtypes = [C.c_int, _i32p, _i32p, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float]
+        L.gcnref_adam_set.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.gcnref_adam_step.argtypes = [C.c_void_p]
+        L.gcnref_adam_get.argtypes = [C.c_void_p, C.c_int, _f32p]
+        L.gcnref_adam_destroy.argtypes = [C.c_void_p]
+        L.gcnref_data_new.restype = C.c_void_p
+        L.gcnref_data_free.argtypes = [C.c_void_p]
+        L.gcnref_parse.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p]
+        L.gcnref_data_fill.argtypes = [C.c_void_p, C.c_int, _i32p, _i32p, _i32p, _i32p, _f32p, _i32p, _i32p, C.c_int, C.c_int]
+        L.gcnref_data_sizes.argtypes = [C.c_void_p, C.POINTER(C.c_long)]
+        L.gcnref_data_get.argtypes = [C.c_void_p] + [C.c_void_p] * 7
+        L.gcnref_data_set_hparams.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_float, C.c_int, C.c_int]
+        L.gcnref_gcn_create.restype = C.c_void_p
+        L.gcnref_gcn_create.argtypes = [C.c_void_p, C.c_long]
+        L.gcnref_gcn_destroy.argtypes = [C.c_void_p]
+        L.gcnref_gcn_train_epoch.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+        L.gcnref_gcn_eval.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+        L.gcnref_gcn_var_size.argtypes = [C.c_void_p, C.c_int]
+        L.gcnref_gcn_var_size.restype = C.c_long
+        L.gcnref_gcn_get_var.argtypes = [C.c_void_p, C.c_int, C.c_int, _f32p]
+        L.gcnref_gcn_run.argtypes = [C.c_void_p]
+
+    def init_rand_state(self, seed): self.L.gcnref_init_rand_state(seed)
+    def set_rand_state(self, a, b): self.L.gcnref_set_rand_state(a, b)
+
+    def get_rand_state(self):
+        out = (C.c_uint64 * 2)()
+        self.L.gcnref_get_rand_state(out)
+        return int(out[0]), int(out[1])
+
+    def rand(self, n):
+        return np.array([self.L.gcnref_rand() for _ in range(n)], dtype=np.uint32)
+
+    def glorot(self, in_size, out_size):
+        w = np.empty(in_size * out_size, np.float32)
+        self.L.gcnref_glorot(w, in_size, out_size)
+        return w
+
+    def matmul_fw(self, a, b, m, n, p):
+        c = np.empty(m * p, np.float32)
+        self.L.gcnref_matmul_fw(f32(a), f32(b), c, m, n, p)
+        return c
+
+    def matmul_bw(self, a, b, c_grad, m, n, p):
+        ag, bg = np.empty(m * n, np.float32), np.empty(n * p, np.float32)
+        self.L.gcnref_matmul_bw(f32(a), f32(b), f32(c_grad), ag, bg, m, n, p)
+        return ag, bg
+
+    def spmm_fw(self, indptr, indices, values, b, m, n, p):
+        c = np.empty(m * p, np.float32)
+        self.L.gcnref_spmm_fw(i32(indptr), i32(indices), f32(values), f32(b), c, m, n, p)
+        return c
+
+    def spmm_bw(self, indptr, indices, values, c_grad, m, n, p):
+        bg = np.empty(n * p, np.float32)
+        self.L.gcnref_spmm_bw(i32(indptr), i32(indices), f32(values), f32(c_grad), bg, m, n, p)
+        return bg
+
+    def graphsum(self, indptr, indices, x, dim, backward=False):
+        n = len(indptr) - 1
+        out = np.empty(n * dim, np.float32)
+        self.L.gcnref_graphsum(i32(indptr), i32(indices), n, dim, f32(x).ravel(), out, int(backward))
+        return out
+
+    def cross_entropy(self, logits, truth, num_classes, training=True):
+        lg = f32(logits).ravel().copy()
+        n = len(lg) // num_classes
+        grad = np.zeros(len(lg), np.float32)
+        loss = self.L.gcnref_cross_entropy(lg, i32(truth), grad, n, num_classes, int(training))
+        return float(np.float32(loss)), lg, (grad if training else None)
+
+    def relu(self, x, grad=None, training=True):
+        x = f32(x).ravel().copy()
+        mask = np.zeros(len(x), np.uint8)
+        g = f32(grad).ravel().copy() if grad is not None else None
+        self.L.gcnref_relu(x, mask, g.ctypes.data if g is not None else None, len(x), int(training))
+        return x, mask, g
+
+    def dropout(self, x, p, grad=None, training=True, with_grad=True):
+        x = f32(x).ravel().copy()
+        mask = np.zeros(len(x), np.int32)
+        g = f32(grad).ravel().copy() if (grad is not None and with_grad) else None
+        self.L.gcnref_dropout(x, mask, g.ctypes.data if g is not None else None, len(x), p, int(training), int(with_grad))
+        return x, mask, g
+
+    def adam(self, datas, grads_per_step, decay, lr, weight_decay, beta1=0.9, beta2=0.999, eps=1e-8):
+        datas = [f32(d).copy() for d in datas]
+        sizes = i32([len(d) for d in datas])
+        h = self.L.gcnref_adam_create(len(datas), sizes, i32(decay), lr, beta1, beta2, eps, weight_decay)
+        for i, d in enumerate(datas):
+            self.L.gcnref_adam_set(h, i, d.ctypes.data, None)
+        for grads in grads_per_step:
+            for i, g in enumerate(grads):
+                g = f32(g)
+                self.L.gcnref_adam_set(h, i, None, g.ctypes.data)
+            self.L.gcnref_adam_step(h)
+        out = []
+        for i, d in enumerate(datas):
+            r = np.empty_like(d)
+            self.L.gcnref_adam_get(h, i, r)
+            out.append(r)
+        self.L.gcnref_adam_destroy(h)
+        return out
+
+    def parse(self, directory, name):
+        h = self.L.gcnref_data_new()
+        ok = self.L.gcnref_parse(h, str(directory).encode(), name.encode())
+        if not ok:
+            self.L.gcnref_data_free(h)
+            return None
+        out = self._data_out(h)
+        self.L.gcnref_data_free(h)
+        return out
+
+    def _data_out(self, h):
+        s = (C.c_long * 7)()
+        self.L.gcnref_data_sizes(h, s)
+        n, fin, cout, gnnz, fnnz, nl, ns = [int(v) for v in s]
+        gp, gi = np.zeros(n + 1, np.int32), np.zeros(gnnz, np.int32)
+        fp, fi, fv = np.zeros(nl + 1, np.int32), np.zeros(fnnz, np.int32), np.zeros(fnnz, np.float32)
+        lab, spl = np.zeros(nl, np.int32), np.zeros(ns, np.int32)
+        self.L.gcnref_data_get(h, *[a.ctypes.data for a in (gp, gi, fp, fi, fv, lab, spl)])
+        return dict(num_nodes=n, input_dim=fin, output_dim=cout, graph_indptr=gp, graph_indices=gi,
+                    feature_indptr=fp, feature_indices=fi, feature_value=fv, label=lab, split=spl)
+
+    def gcn(self, data: GraphData, hidden_dim=16, dropout=0.5, lr=0.01, weight_decay=5e-4, epochs=100,
+            early_stopping=0, seed=1):
+        return _RefGCN(self, data, (hidden_dim, dropout, lr, weight_decay, epochs, early_stopping), seed)
+
+
+class _RefGCN:
+    def __init__(self, r: Ref, data: GraphData, hp, seed):
+        self.r = r
+        L = r.L
+        self.dh = L.gcnref_data_new()
+        L.gcnref_data_fill(self.dh, data.num_nodes, data.graph_indptr, data.graph_indices, data.feature_indptr,
+                           data.feature_indices, data.feature_value, data.label, data.split, data.input_dim,
+                           data.output_dim)
+        L.gcnref_data_set_hparams(self.dh, *hp)
+        self.h = L.gcnref_gcn_create(self.dh, seed)
+
+    def train_epoch(self):
+        a, b = C.c_float(), C.c_float()
+        self.r.L.gcnref_gcn_train_epoch(self.h, C.byref(a), C.byref(b))
+        return a.value, b.value
+
+    def eval(self, split):
+        a, b = C.c_float(), C.c_float()
+        self.r.L.gcnref_gcn_eval(self.h, split, C.byref(a), C.byref(b))
+        return a.value, b.value
+
+    def var(self, idx, grad=False):
+        out = np.empty(self.r.L.gcnref_gcn_var_size(self.h, idx), np.float32)
+        self.r.L.gcnref_gcn_get_var(self.h, idx, int(grad), out)
+        return out
+
+    def run(self):
+        self.r.L.gcnref_gcn_run(self.h)
+
+    def close(self):
+        if self.h:
+            self.r.L.gcnref_gcn_destroy(self.h)
+            self.r.L.gcnref_data_free(self.dh)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+
+def best_checker():
+    """The real reference when its prebuilt library is present, else the C restatement."""
+    return Ref() if ref_available() else Oracle()
