@@ -1,0 +1,304 @@
+// elementwise.cu — ReLU, Dropout application, masked labels, softmax cross-entropy (+accuracy), Adam,
+// L2 penalty.  Replaces reference kernels K8-K13, K15, K16 and the thrust reductions T1/T2
+// (src/cuda/cuda_kernel.cu:166-240,270-288; cuda_module.cu:121-146; cuda_gcn.cu:100-134).
+// CPU semantics: src/seq/module.cpp:124-233, src/seq/optim.cpp:24-37, src/seq/gcn.cpp:78-105.
+//
+// All reductions are two-level with a fixed order (per-CTA tree, then CTA order), so loss, counts and
+// the L2 penalty are reproducible run to run.  Adam keeps the reference's mixed fp32/fp64 arithmetic
+// with explicitly rounded operations (no FMA contraction), so given bit-identical gradients its
+// update is bit-identical to the CPU reference.
+#include <algorithm>
+
+#include "common.cuh"
+
+using namespace gcnk;
+
+namespace {
+
+// ------------------------------------------------------------------------------------ ReLU ----
+__global__ void relu_fw_kernel(float *__restrict__ x, uint32_t *__restrict__ mask, int64_t n, int training) {
+    // one mask word (32 elements) per thread: no two threads ever share a word
+    const int64_t words = (n + 31) / 32;
+    int64_t w = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; w < words; w += stride) {
+        uint32_t bits = 0;
+        const int64_t base = w * 32;
+        const int cnt = (int)min((int64_t)32, n - base);
+        for (int i = 0; i < cnt; i++) {
+            const float v = x[base + i];
+            const bool keep = v > 0.f;                        // NaN and -0 go to 0 (module.cpp:179-181)
+            bits |= (uint32_t)keep << i;
+            if (!keep) x[base + i] = 0.f;
+        }
+        if (training && mask) mask[w] = bits;
+    }
+}
+
+__global__ void relu_bw_kernel(float *__restrict__ grad, const uint32_t *__restrict__ mask, int64_t n) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride)
+        if (!((mask[i >> 5] >> (i & 31)) & 1u)) grad[i] = 0.f;
+}
+
+// --------------------------------------------------------------------------------- Dropout ----
+__global__ void dropout_apply_kernel(float *__restrict__ x, const uint32_t *__restrict__ keep, int64_t n, float scale) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) x[i] *= ((keep[i >> 5] >> (i & 31)) & 1u) ? scale : 0.f;
+}
+
+__global__ void set_truth_kernel(int *__restrict__ truth, const int *__restrict__ split, const int *__restrict__ label,
+                                 int cur, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) truth[i] = split[i] == cur ? label[i] : -1;
+}
+
+// ------------------------------------------------------------------- softmax cross-entropy ----
+struct CePartial { float loss; int count; int wrong; int pad; };
+
+__device__ __forceinline__ void block_reduce_ce(float loss, int count, int wrong, CePartial *out) {
+    __shared__ float s_loss[32];
+    __shared__ int s_count[32], s_wrong[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = (blockDim.x + 31) >> 5;
+    loss = warp_sum(loss); count = warp_sum_int(count); wrong = warp_sum_int(wrong);
+    if (lane == 0) { s_loss[warp] = loss; s_count[warp] = count; s_wrong[warp] = wrong; }
+    __syncthreads();
+    if (warp == 0) {
+        loss = lane < nwarps ? s_loss[lane] : 0.f;
+        count = lane < nwarps ? s_count[lane] : 0;
+        wrong = lane < nwarps ? s_wrong[lane] : 0;
+        loss = warp_sum(loss); count = warp_sum_int(count); wrong = warp_sum_int(wrong);
+        if (lane == 0) { out->loss = loss; out->count = count; out->wrong = wrong; out->pad = 0; }
+    }
+}
+
+// thread per row: max, in-place shift, sum of exp, loss term, un-normalised gradient, accuracy flag
+__global__ void __launch_bounds__(256) ce_rows_kernel(float *__restrict__ logits, const int *__restrict__ truth,
+                                                       float *__restrict__ grad, int n, int c, int training,
+                                                       CePartial *__restrict__ partials) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    float loss = 0.f;
+    int count = 0, wrong = 0;
+    if (i < n) {
+        float *row = logits + (size_t)i * c;
+        float *g = grad ? grad + (size_t)i * c : nullptr;
+        const int t = truth[i];
+        if (t < 0) {
+            if (training && g) for (int j = 0; j < c; j++) g[j] = 0.f;   // zero_grad (module.cpp:129)
+        } else {
+            count = 1;
+            float mx = -1e30f;
+            for (int j = 0; j < c; j++) mx = fmaxf(mx, row[j]);
+            float sum = 0.f;
+            for (int j = 0; j < c; j++) {
+                const float v = row[j] - mx;
+                row[j] = v;                                               // in place (module.cpp:140)
+                sum += expf(v);
+            }
+            const float tv = row[t];
+            loss = logf(sum) - tv;
+            bool w = false;
+            for (int j = 0; j < c; j++) w |= row[j] > tv;                  // strict: ties are correct (gcn.cpp:88-93)
+            wrong = w;
+            if (training && g) {
+                for (int j = 0; j < c; j++) g[j] = expf(row[j]) / sum;
+                g[t] -= 1.0f;
+            }
+        }
+    }
+    block_reduce_ce(loss, count, wrong, partials + blockIdx.x);
+}
+
+// single CTA: sums the per-CTA partials in CTA order per thread, then a fixed tree
+__global__ void __launch_bounds__(256) ce_finish_kernel(const CePartial *__restrict__ partials, int parts,
+                                                         gcnk_ce_result *__restrict__ result) {
+    float loss = 0.f;
+    int count = 0, wrong = 0;
+    for (int b = threadIdx.x; b < parts; b += blockDim.x) { loss += partials[b].loss; count += partials[b].count; wrong += partials[b].wrong; }
+    __shared__ CePartial total;
+    block_reduce_ce(loss, count, wrong, &total);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        result->loss = total.loss / (float)total.count;                   // count == 0 -> NaN, as the reference
+        result->count = total.count; result->wrong = total.wrong; result->pad = 0;
+    }
+}
+
+__global__ void ce_scale_grad_kernel(float *__restrict__ grad, int64_t n, const gcnk_ce_result *__restrict__ result) {
+    const float cnt = (float)result->count;
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) grad[i] = grad[i] / cnt;                   // a true division, as module.cpp:156-158
+}
+
+__global__ void __launch_bounds__(256) accuracy_kernel(const float *__restrict__ logits, const int *__restrict__ truth,
+                                                        int n, int c, CePartial *__restrict__ partials) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int count = 0, wrong = 0;
+    if (i < n && truth[i] >= 0) {
+        const float *row = logits + (size_t)i * c;
+        const float tv = row[truth[i]];
+        bool w = false;
+        for (int j = 0; j < c; j++) w |= row[j] > tv;
+        count = 1; wrong = w;
+    }
+    block_reduce_ce(0.f, count, wrong, partials + blockIdx.x);
+}
+
+__global__ void __launch_bounds__(256) accuracy_finish_kernel(const CePartial *__restrict__ partials, int parts, int *out2) {
+    int count = 0, wrong = 0;
+    for (int b = threadIdx.x; b < parts; b += blockDim.x) { count += partials[b].count; wrong += partials[b].wrong; }
+    __shared__ CePartial total;
+    block_reduce_ce(0.f, count, wrong, &total);
+    __syncthreads();
+    if (threadIdx.x == 0) { out2[0] = total.wrong; out2[1] = total.count; }
+}
+
+// ------------------------------------------------------------------------------------ Adam ----
+constexpr int ADAM_MAX = 8;
+struct AdamPack { gcnk_adam_tensor t[ADAM_MAX]; };
+
+__global__ void __launch_bounds__(256) adam_kernel(const AdamPack pack, float step_size, float beta1, float beta2,
+                                                    float eps, float weight_decay) {
+    const gcnk_adam_tensor T = pack.t[blockIdx.y];
+    const double ob1 = 1.0 - (double)beta1, ob2 = 1.0 - (double)beta2;     // (1.0 - beta) promotes to double (optim.cpp:32-33)
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < T.size; i += gridDim.x * blockDim.x) {
+        float g = T.grad[i];
+        const float w = T.data[i];
+        if (T.decay) g = __fadd_rn(g, __fmul_rn(weight_decay, w));
+        const float m = (float)__dadd_rn((double)__fmul_rn(beta1, T.m[i]), __dmul_rn(ob1, (double)g));
+        const float v = (float)__dadd_rn((double)__fmul_rn(beta2, T.v[i]), __dmul_rn(__dmul_rn(ob2, (double)g), (double)g));
+        T.m[i] = m;
+        T.v[i] = v;
+        T.data[i] = __fsub_rn(w, __fdiv_rn(__fmul_rn(step_size, m), __fadd_rn(__fsqrt_rn(v), eps)));
+    }
+}
+
+// single CTA, fixed order: per-thread strided partial, then a tree
+__global__ void __launch_bounds__(1024) sum_squares_kernel(const float *__restrict__ w, int64_t n, float *__restrict__ out) {
+    float s = 0.f;
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) s = fmaf(w[i], w[i], s);
+    __shared__ float sh[32];
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        s = threadIdx.x < (blockDim.x >> 5) ? sh[threadIdx.x] : 0.f;
+        s = warp_sum(s);
+        if (threadIdx.x == 0) *out = s;
+    }
+}
+
+int ew_grid(int64_t n) { return (int)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, (int64_t)sm_count() * 16)); }
+
+}  // namespace
+
+extern "C" {
+
+int gcnk_relu_fw(float *x, uint32_t *mask_bits, int64_t n, int training, gcnk_stream_t stream) {
+    GCNK_REQUIRE(x && n >= 0 && (!training || mask_bits), "bad arguments");
+    if (!n) return GCNK_OK;
+    relu_fw_kernel<<<ew_grid((n + 31) / 32), 256, 0, S(stream)>>>(x, mask_bits, n, training);
+    GCNK_LAUNCHED();
+    return GCNK_OK;
+}
+
+int gcnk_relu_bw(float *grad, const uint32_t *mask_bits, int64_t n, gcnk_stream_t stream) {
+    GCNK_REQUIRE(grad && mask_bits && n >= 0, "bad arguments");
+    if (!n) return GCNK_OK;
+    relu_bw_kernel<<<ew_grid(n), 256, 0, S(stream)>>>(grad, mask_bits, n);
+    GCNK_LAUNCHED();
+    return GCNK_OK;
+}
+
+int gcnk_dropout_apply(float *x, const uint32_t *keep_bits, int64_t n, float p, gcnk_stream_t stream) {
+    GCNK_REQUIRE(x && keep_bits && n >= 0, "bad arguments");
+    if (!n) return GCNK_OK;
+    const float scale = 1 / (1 - p);                                       // module.cpp:212
+    dropout_apply_kernel<<<ew_grid(n), 256, 0, S(stream)>>>(x, keep_bits, n, scale);
+    GCNK_LAUNCHED();
+    return GCNK_OK;
+}
+
+int gcnk_set_truth(int *truth, const int *split, const int *label, int current_split, int n, gcnk_stream_t stream) {
+    GCNK_REQUIRE(truth && split && label && n >= 0, "bad arguments");
+    if (!n) return GCNK_OK;
+    set_truth_kernel<<<(n + 255) / 256, 256, 0, S(stream)>>>(truth, split, label, current_split, n);
+    GCNK_LAUNCHED();
+    return GCNK_OK;
+}
+
+size_t gcnk_softmax_ce_workspace(int n, int c) {
+    (void)c;
+    return sizeof(CePartial) * (size_t)std::max(1, (n + 255) / 256);
+}
+
+int gcnk_softmax_ce(float *logits, const int *truth, float *grad, int n, int c, int training, gcnk_ce_result *d_result,
+                    float *workspace, size_t workspace_bytes, gcnk_stream_t stream) {
+    GCNK_REQUIRE(logits && truth && d_result && n >= 0 && c > 0 && (!training || grad), "bad arguments");
+    GCNK_REQUIRE(workspace && workspace_bytes >= gcnk_softmax_ce_workspace(n, c), "workspace too small");
+    cudaStream_t st = S(stream);
+    const int parts = std::max(1, (n + 255) / 256);
+    CePartial *partials = reinterpret_cast<CePartial *>(workspace);
+    ce_rows_kernel<<<parts, 256, 0, st>>>(logits, truth, training ? grad : nullptr, n, c, training, partials);
+    GCNK_LAUNCHED();
+    ce_finish_kernel<<<1, 256, 0, st>>>(partials, parts, d_result);
+    GCNK_LAUNCHED();
+    if (training && n) {
+        const int64_t total = (int64_t)n * c;
+        ce_scale_grad_kernel<<<ew_grid(total), 256, 0, st>>>(grad, total, d_result);
+        GCNK_LAUNCHED();
+    }
+    return GCNK_OK;
+}
+
+int gcnk_accuracy(const float *logits, const int *truth, int n, int c, int *d_wrong_total2, gcnk_stream_t stream) {
+    GCNK_REQUIRE(logits && truth && d_wrong_total2 && n >= 0 && c > 0, "bad arguments");
+    cudaStream_t st = S(stream);
+    const int parts = std::max(1, (n + 255) / 256);
+    static CePartial *scratch[64] = {nullptr};
+    static int scratch_parts[64] = {0};
+    int dev = 0;
+    GCNK_CUDA(cudaGetDevice(&dev));
+    if (scratch_parts[dev] < parts) {
+        GCNK_CUDA(cudaStreamSynchronize(st));
+        if (scratch[dev]) GCNK_CUDA(cudaFree(scratch[dev]));
+        GCNK_CUDA(cudaMalloc(&scratch[dev], sizeof(CePartial) * parts));
+        scratch_parts[dev] = parts;
+    }
+    accuracy_kernel<<<parts, 256, 0, st>>>(logits, truth, n, c, scratch[dev]);
+    GCNK_LAUNCHED();
+    accuracy_finish_kernel<<<1, 256, 0, st>>>(scratch[dev], parts, d_wrong_total2);
+    GCNK_LAUNCHED();
+    return GCNK_OK;
+}
+
+int gcnk_sum_squares(const float *w, int64_t n, float *d_out, gcnk_stream_t stream) {
+    GCNK_REQUIRE(w && d_out && n >= 0, "bad arguments");
+    sum_squares_kernel<<<1, 1024, 0, S(stream)>>>(w, n, d_out);
+    GCNK_LAUNCHED();
+    return GCNK_OK;
+}
+
+int gcnk_adam_step(const gcnk_adam_tensor *h_tensors, int count, float step_size, float beta1, float beta2, float eps,
+                   float weight_decay, float *d_sumsq, gcnk_stream_t stream) {
+    GCNK_REQUIRE(h_tensors && count > 0 && count <= ADAM_MAX, "1..8 tensors per call");
+    AdamPack pack = {};
+    int max_size = 0;
+    for (int i = 0; i < count; i++) {
+        GCNK_REQUIRE(h_tensors[i].data && h_tensors[i].grad && h_tensors[i].m && h_tensors[i].v && h_tensors[i].size >= 0, "bad tensor");
+        pack.t[i] = h_tensors[i];
+        max_size = std::max(max_size, h_tensors[i].size);
+    }
+    if (max_size) {
+        dim3 grid(std::max(1, std::min((max_size + 255) / 256, sm_count() * 4)), count, 1);
+        adam_kernel<<<grid, 256, 0, S(stream)>>>(pack, step_size, beta1, beta2, eps, weight_decay);
+        GCNK_LAUNCHED();
+    }
+    if (d_sumsq) return gcnk_sum_squares(h_tensors[0].data, h_tensors[0].size, d_sumsq, stream);
+    return GCNK_OK;
+}
+
+}  // extern "C"

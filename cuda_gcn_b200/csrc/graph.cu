@@ -1,0 +1,496 @@
+// graph.cu — GraphSum, the hot path.  Replaces cuda_GraphSum_forward/backward_kernel
+// (reference src/cuda/cuda_kernel.cu:126-162; CPU semantics src/seq/module.cpp:83-119).
+//
+// Design (B200-first, not a translation):
+//   * gcnk_graph_create() does once per graph what the reference redoes per edge per launch: the
+//     degree vector d^-1/2, and a STATIC degree-balanced schedule (longest-processing-time bins of
+//     rows per warp, rows above a degree threshold get a whole CTA).  Static => every sum has a fixed
+//     order => results are reproducible run to run and identical for 1 and N ranks.
+//   * the gather source is pre-scaled by d^-1/2 of its own row (by the producing kernel's epilogue),
+//     so an edge costs one index (streamed, coalesced, L1-bypassing) and one vectorised row gather;
+//     no sqrtf, no division, no second random indptr read per edge.
+//   * each warp keeps the row sum in registers and WRITES the row once (no global +=, no memset).
+//   * the epilogue fuses the degree normalisation with ReLU + Dropout (+ mask) forward, or with the
+//     Dropout/ReLU backward mask, and with the pre-scale for the next gather.
+//
+// Roofline: HBM traffic is 4*nnz (indices) + 8*n*dim; the edge gathers (dim*4 bytes each) are served
+// by L2, where the [n x dim] source is resident (14.9 MB at Reddit shape, dim 16).
+#include <algorithm>
+#include <queue>
+#include <vector>
+
+#include "common.cuh"
+
+using namespace gcnk;
+
+struct gcnk_graph {
+    const int *indptr = nullptr, *indices = nullptr;
+    int n = 0, n_cols = 0;
+    int64_t nnz = 0;
+    float *dinv = nullptr;            // [n] d^-1/2 of the local rows
+    const float *dinv_cols = nullptr; // [n_cols] d^-1/2 of the gather-source rows (== dinv when n_cols == n)
+    int *heavy_rows = nullptr; int n_heavy = 0;
+    int *bin_ptr = nullptr, *bin_rows = nullptr; int n_bins = 0;   // n_bins is a multiple of WARPS
+    int max_degree = 0, symmetric = 0;
+    float *scratch = nullptr; size_t scratch_elems = 0;            // pre-scaled copy for gcnk_graphsum
+};
+
+namespace {
+
+constexpr int THREADS = 256, WARPS = THREADS / 32;
+constexpr int HEAVY_DEGREE = 2048;     // rows above this get a whole CTA
+constexpr int ROW_OVERHEAD = 24;       // per-row cost in edge-equivalents for the bin balance
+
+enum Mode { MODE_PLAIN = 0, MODE_RELU_DROP = 1, MODE_MASK = 2 };
+
+struct GatherArgs {
+    const int *indptr, *indices;
+    const float *in;
+    float *out;
+    const float *dinv;
+    const int *heavy_rows, *bin_ptr, *bin_rows;
+    int n_heavy, dim, mode, mask_stride;   // mask_stride: bits per row of the written/read mask
+    const uint32_t *drop_bits;             // flat: bit s*dim+j (may be NULL)
+    uint32_t *mask_out;                    // MODE_RELU_DROP (may be NULL)
+    const uint32_t *mask_in;               // MODE_MASK
+    float scale;
+};
+
+__host__ __device__ inline int mask_stride_bits(int dim) { return dim <= 8 ? 8 : dim <= 16 ? 16 : (dim + 31) / 32 * 32; }
+
+template <int VEC> struct Acc;
+template <> struct Acc<4> {
+    float4 v;
+    __device__ void zero() { v = make_float4(0.f, 0.f, 0.f, 0.f); }
+    __device__ void load_add(const float *p) {
+        const float4 x = __ldg(reinterpret_cast<const float4 *>(p));
+        v.x += x.x; v.y += x.y; v.z += x.z; v.w += x.w;
+    }
+    __device__ void add(const Acc &o) { v.x += o.v.x; v.y += o.v.y; v.z += o.v.z; v.w += o.v.w; }
+    __device__ void shfl_xor_add(int off) {
+        v.x += __shfl_xor_sync(FULL, v.x, off); v.y += __shfl_xor_sync(FULL, v.y, off);
+        v.z += __shfl_xor_sync(FULL, v.z, off); v.w += __shfl_xor_sync(FULL, v.w, off);
+    }
+    __device__ float get(int i) const { return i == 0 ? v.x : i == 1 ? v.y : i == 2 ? v.z : v.w; }
+    __device__ void set(int i, float f) { if (i == 0) v.x = f; else if (i == 1) v.y = f; else if (i == 2) v.z = f; else v.w = f; }
+};
+template <> struct Acc<1> {
+    float v;
+    __device__ void zero() { v = 0.f; }
+    __device__ void load_add(const float *p) { v += __ldg(p); }
+    __device__ void add(const Acc &o) { v += o.v; }
+    __device__ void shfl_xor_add(int off) { v += __shfl_xor_sync(FULL, v, off); }
+    __device__ float get(int) const { return v; }
+    __device__ void set(int, float f) { v = f; }
+};
+
+// One warp sums the gather-source rows of edges [beg,end), taking 32-edge chunks beg+32*(first+k*step).
+// Lane layout: LPR lanes per source row (q = lane % LPR covers elements (q + LPR*a)*VEC..+VEC),
+// G = 32/LPR edges in flight per gather instruction (g = lane / LPR).
+template <int VEC, int LPR, int NACC, bool EXACT>
+__device__ __forceinline__ void accumulate(Acc<VEC> (&acc)[NACC], const GatherArgs &a, int beg, int end, int first,
+                                           int step, int lane) {
+    constexpr int G = 32 / LPR;
+    const int g = lane / LPR, q = lane % LPR;
+    const int dim = a.dim;
+    int e = beg + 32 * first;
+    int idx = (e + lane < end) ? ld_stream_i32(a.indices + e + lane) : -1;
+    while (e < end) {
+        const int e_next = e + 32 * step;
+        // software pipeline: the next chunk's indices are in flight while this chunk's rows are gathered
+        const int idx_next = (e_next + lane < end) ? ld_stream_i32(a.indices + e_next + lane) : -1;
+#pragma unroll
+        for (int j = 0; j < LPR; j++) {
+            const int d = __shfl_sync(FULL, idx, j * G + g);
+            if (d >= 0) {
+                const float *row = a.in + (size_t)d * dim;
+#pragma unroll
+                for (int t = 0; t < NACC; t++) {
+                    const int u = (q + LPR * t) * VEC;
+                    if (EXACT || u < dim) acc[t].load_add(row + u);   // EXACT: dim == VEC*LPR*NACC
+                }
+            }
+        }
+        idx = idx_next;
+        e = e_next;
+    }
+}
+
+template <int VEC, int LPR, int NACC>
+__device__ __forceinline__ void reduce_groups(Acc<VEC> (&acc)[NACC]) {
+#pragma unroll
+    for (int off = LPR; off < 32; off <<= 1)
+#pragma unroll
+        for (int t = 0; t < NACC; t++) acc[t].shfl_xor_add(off);
+}
+
+// Row epilogue.  Called by the whole warp (uses warp-wide reductions for the mask words); the row sum
+// is valid in lanes < LPR.
+template <int VEC, int LPR, int NACC>
+__device__ __forceinline__ void epilogue(Acc<VEC> (&acc)[NACC], const GatherArgs &a, int s, int lane) {
+    const int q = lane % LPR, dim = a.dim;
+    const bool owner = lane < LPR;
+    const float di = a.dinv[s];
+    float *orow = a.out + (size_t)s * dim;
+    if (a.mode == MODE_PLAIN) {
+        if (owner) {
+#pragma unroll
+            for (int t = 0; t < NACC; t++) {
+                const int u = (q + LPR * t) * VEC;
+                if (u < dim) {
+                    if constexpr (VEC == 4) {
+                        const float4 o = make_float4(di * acc[t].v.x, di * acc[t].v.y, di * acc[t].v.z, di * acc[t].v.w);
+                        *reinterpret_cast<float4 *>(orow + u) = o;
+                    } else {
+                        orow[u] = di * acc[t].v;
+                    }
+                }
+            }
+        }
+        return;
+    }
+    const int words = (dim + 31) / 32;
+    const size_t mbase = (size_t)s * a.mask_stride;   // bit offset of this row in the padded mask
+    for (int w = 0; w < words; w++) {
+        uint32_t bits = 0;
+        // which of this lane's elements fall into mask word w
+#pragma unroll
+        for (int t = 0; t < NACC; t++) {
+            const int u = (q + LPR * t) * VEC;
+            if (owner && u < dim && (u >> 5) == w) {
+                Acc<VEC> o;
+#pragma unroll
+                for (int v = 0; v < VEC; v++) {
+                    const int j = u + v;
+                    const float x = di * acc[t].get(v);
+                    bool pass;
+                    if (a.mode == MODE_RELU_DROP) {
+                        bool keep = true;
+                        if (a.drop_bits) {
+                            const size_t b = (size_t)s * dim + j;
+                            keep = (a.drop_bits[b >> 5] >> (b & 31)) & 1u;
+                        }
+                        pass = (x > 0.f) && keep;
+                    } else {
+                        const size_t b = mbase + j;
+                        pass = (a.mask_in[b >> 5] >> (b & 31)) & 1u;
+                    }
+                    o.set(v, pass ? di * (x * a.scale) : 0.f);
+                    bits |= (uint32_t)pass << (j & 31);
+                }
+                if constexpr (VEC == 4) *reinterpret_cast<float4 *>(orow + u) = o.v;
+                else orow[u] = o.v;
+            }
+        }
+        if (a.mode == MODE_RELU_DROP && a.mask_out) {
+            bits = __reduce_or_sync(FULL, bits);
+            if (lane == 0) {
+                if (a.mask_stride == 8) reinterpret_cast<uint8_t *>(a.mask_out)[s] = (uint8_t)bits;
+                else if (a.mask_stride == 16) reinterpret_cast<uint16_t *>(a.mask_out)[s] = (uint16_t)bits;
+                else a.mask_out[(mbase >> 5) + w] = bits;
+            }
+        }
+    }
+}
+
+template <int VEC, int LPR, int NACC, bool EXACT>
+__global__ void __launch_bounds__(THREADS) gather_kernel(const GatherArgs a) {
+    extern __shared__ float smem[];   // heavy rows only: [WARPS][dim]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    Acc<VEC> acc[NACC];
+
+    if ((int)blockIdx.x < a.n_heavy) {
+        // a whole CTA on one high-degree row: warps take interleaved 32-edge chunks, partials are
+        // combined through shared memory in warp order (fixed => deterministic)
+        const int s = a.heavy_rows[blockIdx.x];
+        const int beg = a.indptr[s], end = a.indptr[s + 1];
+#pragma unroll
+        for (int t = 0; t < NACC; t++) acc[t].zero();
+        accumulate<VEC, LPR, NACC, EXACT>(acc, a, beg, end, warp, WARPS, lane);
+        reduce_groups<VEC, LPR, NACC>(acc);
+        const int q = lane % LPR;
+        if (lane < LPR) {
+#pragma unroll
+            for (int t = 0; t < NACC; t++) {
+                const int u = (q + LPR * t) * VEC;
+#pragma unroll
+                for (int v = 0; v < VEC; v++)
+                    if (u + v < a.dim) smem[warp * a.dim + u + v] = acc[t].get(v);
+            }
+        }
+        __syncthreads();
+        if (warp == 0) {
+#pragma unroll
+            for (int t = 0; t < NACC; t++) {
+                const int u = (q + LPR * t) * VEC;
+#pragma unroll
+                for (int v = 0; v < VEC; v++) {
+                    float sum = 0.f;
+                    if (lane < LPR && u + v < a.dim)
+                        for (int w = 0; w < WARPS; w++) sum += smem[w * a.dim + u + v];
+                    acc[t].set(v, sum);
+                }
+            }
+            epilogue<VEC, LPR, NACC>(acc, a, s, lane);
+        }
+        return;
+    }
+
+    const int bin = ((int)blockIdx.x - a.n_heavy) * WARPS + warp;
+    const int r_end = a.bin_ptr[bin + 1];
+    for (int r = a.bin_ptr[bin]; r < r_end; r++) {
+        const int s = a.bin_rows[r];
+        const int beg = a.indptr[s], end = a.indptr[s + 1];
+#pragma unroll
+        for (int t = 0; t < NACC; t++) acc[t].zero();
+        accumulate<VEC, LPR, NACC, EXACT>(acc, a, beg, end, 0, 1, lane);
+        reduce_groups<VEC, LPR, NACC>(acc);
+        epilogue<VEC, LPR, NACC>(acc, a, s, lane);
+    }
+}
+
+template <int VEC, int LPR, int NACC>
+int launch_variant(const gcnk_graph *g, const GatherArgs &a, cudaStream_t st) {
+    const int grid = g->n_heavy + g->n_bins / WARPS;
+    if (grid == 0) return GCNK_OK;
+    const size_t smem = g->n_heavy ? sizeof(float) * WARPS * (size_t)a.dim : 0;
+    if (a.dim == VEC * LPR * NACC) gather_kernel<VEC, LPR, NACC, true><<<grid, THREADS, smem, st>>>(a);
+    else gather_kernel<VEC, LPR, NACC, false><<<grid, THREADS, smem, st>>>(a);
+    GCNK_LAUNCHED();
+    return GCNK_OK;
+}
+
+int launch_gather(const gcnk_graph *g, GatherArgs a, cudaStream_t st) {
+    const int dim = a.dim;
+    a.indptr = g->indptr; a.indices = g->indices; a.dinv = g->dinv;
+    a.heavy_rows = g->heavy_rows; a.n_heavy = g->n_heavy; a.bin_ptr = g->bin_ptr; a.bin_rows = g->bin_rows;
+    a.mask_stride = mask_stride_bits(dim);
+    const bool vec4 = dim % 4 == 0 && (reinterpret_cast<uintptr_t>(a.in) % 16 == 0) &&
+                      (reinterpret_cast<uintptr_t>(a.out) % 16 == 0);
+    if (vec4) {
+        const int units = dim / 4;
+        if (units <= 1) return launch_variant<4, 1, 1>(g, a, st);
+        if (units <= 2) return launch_variant<4, 2, 1>(g, a, st);
+        if (units <= 4) return launch_variant<4, 4, 1>(g, a, st);
+        if (units <= 8) return launch_variant<4, 8, 1>(g, a, st);
+        if (units <= 16) return launch_variant<4, 16, 1>(g, a, st);
+        if (units <= 32) return launch_variant<4, 32, 1>(g, a, st);
+        if (units <= 64) return launch_variant<4, 32, 2>(g, a, st);
+        if (units <= 128) return launch_variant<4, 32, 4>(g, a, st);
+        if (units <= 256) return launch_variant<4, 32, 8>(g, a, st);
+    } else {
+        if (dim <= 1) return launch_variant<1, 1, 1>(g, a, st);
+        if (dim <= 2) return launch_variant<1, 2, 1>(g, a, st);
+        if (dim <= 4) return launch_variant<1, 4, 1>(g, a, st);
+        if (dim <= 8) return launch_variant<1, 8, 1>(g, a, st);
+        if (dim <= 16) return launch_variant<1, 16, 1>(g, a, st);
+        if (dim <= 32) return launch_variant<1, 32, 1>(g, a, st);
+        if (dim <= 64) return launch_variant<1, 32, 2>(g, a, st);
+        if (dim <= 128) return launch_variant<1, 32, 4>(g, a, st);
+        if (dim <= 256) return launch_variant<1, 32, 8>(g, a, st);
+        if (dim <= 512) return launch_variant<1, 32, 16>(g, a, st);
+        if (dim <= 1024) return launch_variant<1, 32, 32>(g, a, st);
+    }
+    set_error("gather: dim %d unsupported (max 1024, as the reference's GPU path, cuda_module.cu:79)", dim);
+    return GCNK_EUNSUPPORTED;
+}
+
+__global__ void dinv_kernel(const int *indptr, float *dinv, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const int deg = indptr[i + 1] - indptr[i];
+        // 1/sqrt(deg) in IEEE fp32; a zero-degree row (impossible after the parser's self loop) yields 0
+        dinv[i] = deg > 0 ? 1.0f / sqrtf((float)deg) : 0.f;
+    }
+}
+
+// symmetric iff every stored (s,d) has a stored (d,s); rows must be sorted after the leading self
+// loop for the binary search to succeed — an unsorted input simply reports "not verified".
+__global__ void symmetry_kernel(const int *indptr, const int *indices, int n, int n_cols, int *asym) {
+    const int s = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32, lane = threadIdx.x & 31;
+    if (s >= n) return;
+    for (int e = indptr[s] + lane; e < indptr[s + 1]; e += 32) {
+        const int d = indices[e];
+        if (d == s) continue;
+        if (d < 0 || d >= n_cols || d >= n) { atomicOr(asym, 1); continue; }
+        int lo = indptr[d], hi = indptr[d + 1];
+        if (lo < hi && indices[lo] == d) lo++;             // skip the leading self loop
+        bool found = false;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1, v = indices[mid];
+            if (v == s) { found = true; break; }
+            if (v < s) lo = mid + 1; else hi = mid;
+        }
+        if (!found) atomicOr(asym, 1);
+    }
+}
+
+__global__ void scale_rows_kernel(const float *__restrict__ dinv, const float *__restrict__ in, float *__restrict__ out,
+                                  int64_t total, int dim) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < total; i += stride) out[i] = dinv[i / dim] * in[i];
+}
+
+}  // namespace
+
+extern "C" {
+
+int gcnk_graph_create(gcnk_graph **out, const int *d_indptr, const int *d_indices, int n, int64_t nnz, int n_cols,
+                      const float *d_dinv_global, gcnk_stream_t stream) {
+    GCNK_REQUIRE(out && d_indptr && (d_indices || nnz == 0) && n >= 0 && n_cols >= n, "bad arguments");
+    GCNK_REQUIRE(n_cols == n || d_dinv_global, "a row partition (n_cols > n) needs the global d^-1/2 vector");
+    cudaStream_t st = S(stream);
+    gcnk_graph *g = new gcnk_graph;
+    g->indptr = d_indptr; g->indices = d_indices; g->n = n; g->n_cols = n_cols; g->nnz = nnz;
+
+    std::vector<int> indptr((size_t)n + 1, 0);
+    GCNK_CUDA(cudaMemcpyAsync(indptr.data(), d_indptr, sizeof(int) * ((size_t)n + 1), cudaMemcpyDeviceToHost, st));
+    GCNK_CUDA(cudaMalloc(&g->dinv, sizeof(float) * std::max(n, 1)));
+    if (n) { dinv_kernel<<<(n + 255) / 256, 256, 0, st>>>(d_indptr, g->dinv, n); GCNK_LAUNCHED(); }
+    g->dinv_cols = d_dinv_global ? d_dinv_global : g->dinv;
+    int *d_asym = nullptr, asym = 0;
+    GCNK_CUDA(cudaMalloc(&d_asym, sizeof(int)));
+    GCNK_CUDA(cudaMemsetAsync(d_asym, 0, sizeof(int), st));
+    if (n && n_cols == n) { symmetry_kernel<<<(n + 7) / 8, 256, 0, st>>>(d_indptr, d_indices, n, n_cols, d_asym); GCNK_LAUNCHED(); }
+    GCNK_CUDA(cudaMemcpyAsync(&asym, d_asym, sizeof(int), cudaMemcpyDeviceToHost, st));
+    GCNK_CUDA(cudaStreamSynchronize(st));
+    GCNK_CUDA(cudaFree(d_asym));
+    g->symmetric = (n_cols == n) && !asym;
+    if (n && indptr[n] != nnz) { delete g; set_error("gcnk_graph_create: indptr[n]=%d != nnz=%lld", indptr[n], (long long)nnz); return GCNK_EINVAL; }
+
+    // ---- static schedule: heavy rows -> one CTA each; the rest -> LPT bins, one warp per bin ----
+    std::vector<int> heavy, light;
+    int max_deg = 0;
+    for (int i = 0; i < n; i++) {
+        const int deg = indptr[i + 1] - indptr[i];
+        max_deg = std::max(max_deg, deg);
+        (deg > HEAVY_DEGREE ? heavy : light).push_back(i);
+    }
+    g->max_degree = max_deg;
+    auto deg_of = [&](int r) { return indptr[r + 1] - indptr[r]; };
+    std::stable_sort(heavy.begin(), heavy.end(), [&](int x, int y) { return deg_of(x) > deg_of(y); });
+    std::stable_sort(light.begin(), light.end(), [&](int x, int y) { return deg_of(x) > deg_of(y); });
+    // 4 bins per resident warp slot keeps the tail short without shrinking bins below a few rows
+    int n_bins = sm_count() * 64 * 4;
+    n_bins = std::min<int64_t>(n_bins, std::max<int64_t>((int64_t)light.size(), 1));
+    n_bins = (n_bins + WARPS - 1) / WARPS * WARPS;
+    if (light.empty()) n_bins = 0;
+    std::vector<std::vector<int>> bins(n_bins);
+    {
+        typedef std::pair<int64_t, int> Item;   // (load, bin) — min-heap on load, ties by bin id => deterministic
+        std::priority_queue<Item, std::vector<Item>, std::greater<Item>> heap;
+        for (int b = 0; b < n_bins; b++) heap.push({0, b});
+        for (int r : light) {
+            Item it = heap.top(); heap.pop();
+            bins[it.second].push_back(r);
+            it.first += deg_of(r) + ROW_OVERHEAD;
+            heap.push(it);
+        }
+    }
+    // bin b was filled in decreasing-load order for increasing b at the start, so low block ids
+    // (launched first) carry the heaviest rows
+    std::vector<int> bin_ptr(n_bins + 1, 0), bin_rows;
+    bin_rows.reserve(light.size());
+    for (int b = 0; b < n_bins; b++) {
+        bin_rows.insert(bin_rows.end(), bins[b].begin(), bins[b].end());
+        bin_ptr[b + 1] = (int)bin_rows.size();
+    }
+    g->n_heavy = (int)heavy.size(); g->n_bins = n_bins;
+    GCNK_CUDA(cudaMalloc(&g->heavy_rows, sizeof(int) * std::max<size_t>(heavy.size(), 1)));
+    GCNK_CUDA(cudaMalloc(&g->bin_ptr, sizeof(int) * (n_bins + 1)));
+    GCNK_CUDA(cudaMalloc(&g->bin_rows, sizeof(int) * std::max<size_t>(bin_rows.size(), 1)));
+    if (!heavy.empty()) GCNK_CUDA(cudaMemcpyAsync(g->heavy_rows, heavy.data(), sizeof(int) * heavy.size(), cudaMemcpyHostToDevice, st));
+    GCNK_CUDA(cudaMemcpyAsync(g->bin_ptr, bin_ptr.data(), sizeof(int) * bin_ptr.size(), cudaMemcpyHostToDevice, st));
+    if (!bin_rows.empty()) GCNK_CUDA(cudaMemcpyAsync(g->bin_rows, bin_rows.data(), sizeof(int) * bin_rows.size(), cudaMemcpyHostToDevice, st));
+    GCNK_CUDA(cudaStreamSynchronize(st));
+    *out = g;
+    return GCNK_OK;
+}
+
+int gcnk_graph_destroy(gcnk_graph *g) {
+    if (!g) return GCNK_OK;
+    cudaFree(g->dinv); cudaFree(g->heavy_rows); cudaFree(g->bin_ptr); cudaFree(g->bin_rows); cudaFree(g->scratch);
+    delete g;
+    return GCNK_OK;
+}
+
+int gcnk_graph_dinv(const gcnk_graph *g, const float **d) { GCNK_REQUIRE(g && d, "null"); *d = g->dinv; return GCNK_OK; }
+
+int gcnk_graph_stats(const gcnk_graph *g, int *n, int64_t *nnz, int *max_degree, int *is_symmetric, int *n_bins) {
+    GCNK_REQUIRE(g, "null graph");
+    if (n) *n = g->n;
+    if (nnz) *nnz = g->nnz;
+    if (max_degree) *max_degree = g->max_degree;
+    if (is_symmetric) *is_symmetric = g->symmetric;
+    if (n_bins) *n_bins = g->n_bins;
+    return GCNK_OK;
+}
+
+int gcnk_scale_rows(const float *dinv, const float *in, float *out, int rows, int dim, gcnk_stream_t stream) {
+    GCNK_REQUIRE(dinv && in && out && rows >= 0 && dim > 0, "bad arguments");
+    const int64_t total = (int64_t)rows * dim;
+    if (!total) return GCNK_OK;
+    const int grid = (int)std::min<int64_t>((total + 255) / 256, (int64_t)sm_count() * 16);
+    scale_rows_kernel<<<grid, 256, 0, S(stream)>>>(dinv, in, out, total, dim);
+    GCNK_LAUNCHED();
+    return GCNK_OK;
+}
+
+int gcnk_gather_plain(const gcnk_graph *g, const float *in_scaled, float *out, int dim, gcnk_stream_t stream) {
+    GCNK_REQUIRE(g && in_scaled && out && dim > 0, "bad arguments");
+    GatherArgs a = {};
+    a.in = in_scaled; a.out = out; a.dim = dim; a.mode = MODE_PLAIN; a.scale = 1.f;
+    return launch_gather(g, a, S(stream));
+}
+
+int gcnk_gather_relu_drop(const gcnk_graph *g, const float *in_scaled, float *out_scaled, const uint32_t *drop_bits,
+                          uint32_t *mask_bits, float scale, int dim, gcnk_stream_t stream) {
+    GCNK_REQUIRE(g && in_scaled && out_scaled && dim > 0, "bad arguments");
+    GatherArgs a = {};
+    a.in = in_scaled; a.out = out_scaled; a.dim = dim; a.mode = MODE_RELU_DROP;
+    a.drop_bits = drop_bits; a.mask_out = mask_bits; a.scale = scale;
+    return launch_gather(g, a, S(stream));
+}
+
+int gcnk_gather_mask(const gcnk_graph *g, const float *in_scaled, float *out_scaled, const uint32_t *mask_bits,
+                     float scale, int dim, gcnk_stream_t stream) {
+    GCNK_REQUIRE(g && in_scaled && out_scaled && mask_bits && dim > 0, "bad arguments");
+    GatherArgs a = {};
+    a.in = in_scaled; a.out = out_scaled; a.dim = dim; a.mode = MODE_MASK; a.mask_in = mask_bits; a.scale = scale;
+    return launch_gather(g, a, S(stream));
+}
+
+int gcnk_mask_row_stride_bits(int dim) { return mask_stride_bits(dim); }
+
+int gcnk_graphsum(const gcnk_graph *gc, const float *in, float *out, int dim, gcnk_stream_t stream) {
+    GCNK_REQUIRE(gc && in && out && dim > 0, "bad arguments");
+    gcnk_graph *g = const_cast<gcnk_graph *>(gc);
+    const size_t need = (size_t)g->n_cols * dim;
+    if (g->scratch_elems < need) {
+        GCNK_CUDA(cudaStreamSynchronize(S(stream)));
+        if (g->scratch) GCNK_CUDA(cudaFree(g->scratch));
+        g->scratch = nullptr; g->scratch_elems = 0;
+        GCNK_CUDA(cudaMalloc(&g->scratch, sizeof(float) * std::max<size_t>(need, 4)));
+        g->scratch_elems = need;
+    }
+    int rc = gcnk_scale_rows(g->dinv_cols, in, g->scratch, g->n_cols, dim, stream);
+    if (rc) return rc;
+    return gcnk_gather_plain(g, g->scratch, out, dim, stream);
+}
+
+int gcnk_partition_rows(const int *h_indptr, int n, int parts, int *h_row_begin) {
+    GCNK_REQUIRE(h_indptr && h_row_begin && n >= 0 && parts > 0, "bad arguments");
+    const int64_t nnz = h_indptr[n];
+    h_row_begin[0] = 0;
+    for (int k = 1; k < parts; k++) {
+        // first row whose prefix nnz reaches k/parts of the total (keeps every cut monotone)
+        const int64_t target = (nnz * k + parts - 1) / parts;
+        const int *p = std::lower_bound(h_indptr + h_row_begin[k - 1], h_indptr + n, (int)std::min<int64_t>(target, INT32_MAX));
+        h_row_begin[k] = (int)(p - h_indptr);
+    }
+    h_row_begin[parts] = n;
+    return GCNK_OK;
+}
+
+}  // extern "C"

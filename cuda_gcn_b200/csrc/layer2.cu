@@ -1,0 +1,201 @@
+// layer2.cu — the row-local half of GCN layer 2, fused: Matmul forward (K1), softmax cross-entropy
+// (K8/K9 + thrust reductions), accuracy (CUDAGCN::get_accuracy, a D2H copy + host loop in the
+// reference, cuda_gcn.cu:100-120), Matmul backward-A (K2) and backward-B (K3) in ONE pass over the
+// aggregated hidden rows.  Reference semantics: src/seq/module.cpp:11-42,124-161, src/seq/gcn.cpp:83-96.
+//
+// It relies on the re-ordering  A_hat*(H1*W2) = (A_hat*H1)*W2  (hard part 3): the gather that
+// precedes this kernel runs at the hidden width h (16) instead of the class count c (41), and the
+// logits [n x c] (38 MB at Reddit shape) never have to exist in HBM.  For the backward,
+//     dH1 = A_hat * (dlogits * W2^T)          -> this kernel emits G = dinv (.) (dlogits * W2^T), pre-scaled
+//     dW2 = H1^T * (A_hat * dlogits) = P^T * dlogits   for a symmetric A_hat, P = A_hat*H1 (already here)
+// so the class-width backward gather of the reference disappears as well.
+//
+// One warp per row (static row -> warp map => fixed summation order): lane l owns classes l, l+32, ...
+#include <algorithm>
+
+#include "common.cuh"
+
+using namespace gcnk;
+
+namespace {
+
+constexpr int L2_THREADS = 256, L2_WARPS = L2_THREADS / 32, CPL_MAX = 4;   // c <= 128
+
+struct L2Partial { float loss; int count; int wrong; int pad; };
+
+__global__ void __launch_bounds__(L2_THREADS) layer2_kernel(const float *__restrict__ P, const float *__restrict__ W2,
+                                                             const int *__restrict__ split, const int *__restrict__ label,
+                                                             int current_split, int n, int h, int c, int training, float count_f,
+                                                             const float *__restrict__ dinv, float *__restrict__ G,
+                                                             float *__restrict__ logits_out, L2Partial *__restrict__ ce_partials,
+                                                             float *__restrict__ dw_partials) {
+    extern __shared__ __align__(16) float smem[];
+    float *sW = smem;                               // [h][c]
+    float *sDl = sW + h * c;                        // [warps][c]   dlogits of the warp's current row
+    float *sP = sDl + L2_WARPS * c;                 // [warps][h]   P row
+    float *sAcc = sP + L2_WARPS * h;                // [warps][h*c] per-warp dW2 accumulators (training only)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < h * c; i += L2_THREADS) sW[i] = W2[i];
+    if (training)
+        for (int i = threadIdx.x; i < L2_WARPS * h * c; i += L2_THREADS) sAcc[i] = 0.f;
+    __syncthreads();
+    float *dl = sDl + warp * c, *pr = sP + warp * h, *acc = sAcc + warp * h * c;
+
+    float loss = 0.f;
+    int count = 0, wrong = 0;
+    const int total_warps = gridDim.x * L2_WARPS;
+    for (int s = blockIdx.x * L2_WARPS + warp; s < n; s += total_warps) {
+        for (int k = lane; k < h; k += 32) pr[k] = P[(size_t)s * h + k];
+        __syncwarp();
+        float lg[CPL_MAX];
+#pragma unroll
+        for (int t = 0; t < CPL_MAX; t++) {
+            const int cls = lane + 32 * t;
+            float v = 0.f;
+            if (cls < c)
+                for (int k = 0; k < h; k++) v = fmaf(pr[k], sW[k * c + cls], v);
+            lg[t] = v;
+            if (logits_out && cls < c) logits_out[(size_t)s * c + cls] = v;
+        }
+        const int truth = split[s] == current_split ? label[s] : -1;        // set_truth (gcn.cpp:78-81)
+        if (truth >= 0) {                                                    // warp-uniform
+            float mx = -1e30f;
+#pragma unroll
+            for (int t = 0; t < CPL_MAX; t++) if (lane + 32 * t < c) mx = fmaxf(mx, lg[t]);
+            mx = warp_max(mx);
+            float ex[CPL_MAX], sum = 0.f;
+#pragma unroll
+            for (int t = 0; t < CPL_MAX; t++) {
+                ex[t] = (lane + 32 * t < c) ? expf(lg[t] - mx) : 0.f;
+                sum += ex[t];
+            }
+            sum = warp_sum(sum);
+            float tl = 0.f;                                                  // the truth logit, broadcast from its owner
+#pragma unroll
+            for (int t = 0; t < CPL_MAX; t++) if (t == truth / 32) tl = lg[t];
+            tl = __shfl_sync(FULL, tl, truth % 32);
+            bool w = false;
+#pragma unroll
+            for (int t = 0; t < CPL_MAX; t++) w |= (lane + 32 * t < c) && lg[t] > tl;   // strict (gcn.cpp:88-93)
+            w = __any_sync(FULL, w);
+            count++;
+            wrong += w;
+            loss += logf(sum) - (tl - mx);
+            if (training) {
+#pragma unroll
+                for (int t = 0; t < CPL_MAX; t++) {
+                    const int cls = lane + 32 * t;
+                    if (cls < c) {
+                        float g = ex[t] / sum;
+                        if (cls == truth) g -= 1.0f;
+                        g = g / count_f;                                     // grad /= count (module.cpp:156-158)
+                        dl[cls] = g;
+                        for (int k = 0; k < h; k++) acc[k * c + cls] = fmaf(pr[k], g, acc[k * c + cls]);   // dW2 += P^T dlogits
+                    }
+                }
+                __syncwarp();
+                const float di = dinv[s];
+                for (int k = lane; k < h; k += 32) {
+                    float v = 0.f;
+                    for (int cls = 0; cls < c; cls++) v = fmaf(dl[cls], sW[k * c + cls], v);   // dlogits * W2^T
+                    G[(size_t)s * h + k] = di * v;
+                }
+            }
+        } else if (training) {
+            for (int k = lane; k < h; k += 32) G[(size_t)s * h + k] = 0.f;   // unlabelled rows carry no gradient
+        }
+        __syncwarp();
+    }
+
+    // per-CTA partials, combined in warp order
+    __shared__ float s_loss[L2_WARPS];
+    __shared__ int s_count[L2_WARPS], s_wrong[L2_WARPS];
+    if (lane == 0) { s_loss[warp] = loss; s_count[warp] = count; s_wrong[warp] = wrong; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float l = 0.f; int cn = 0, wr = 0;
+        for (int w = 0; w < L2_WARPS; w++) { l += s_loss[w]; cn += s_count[w]; wr += s_wrong[w]; }
+        ce_partials[blockIdx.x] = L2Partial{l, cn, wr, 0};
+    }
+    if (training) {
+        float *out = dw_partials + (size_t)blockIdx.x * h * c;
+        for (int i = threadIdx.x; i < h * c; i += L2_THREADS) {
+            float v = 0.f;
+            for (int w = 0; w < L2_WARPS; w++) v += sAcc[w * h * c + i];
+            out[i] = v;
+        }
+    }
+}
+
+// block 0 also produces the scalar result; every block reduces a slice of dW2 over the CTA partials
+__global__ void __launch_bounds__(256) layer2_finish_kernel(const L2Partial *__restrict__ ce_partials, const float *__restrict__ dw_partials,
+                                                             int parts, int hc, int training, float *__restrict__ W2_grad,
+                                                             gcnk_ce_result *__restrict__ result) {
+    if (training) {
+        const int i = blockIdx.x * blockDim.x + threadIdx.x;
+        if (i < hc) {
+            float v = 0.f;
+            for (int b = 0; b < parts; b++) v += dw_partials[(size_t)b * hc + i];
+            W2_grad[i] = v;
+        }
+    }
+    if (blockIdx.x == 0) {
+        __shared__ float s_loss[256];
+        __shared__ int s_count[256], s_wrong[256];
+        float l = 0.f; int cn = 0, wr = 0;
+        for (int b = threadIdx.x; b < parts; b += 256) { l += ce_partials[b].loss; cn += ce_partials[b].count; wr += ce_partials[b].wrong; }
+        s_loss[threadIdx.x] = l; s_count[threadIdx.x] = cn; s_wrong[threadIdx.x] = wr;
+        __syncthreads();
+        for (int o = 128; o > 0; o >>= 1) {
+            if (threadIdx.x < o) {
+                s_loss[threadIdx.x] += s_loss[threadIdx.x + o];
+                s_count[threadIdx.x] += s_count[threadIdx.x + o];
+                s_wrong[threadIdx.x] += s_wrong[threadIdx.x + o];
+            }
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) {
+            result->loss = s_loss[0] / (float)s_count[0];
+            result->count = s_count[0]; result->wrong = s_wrong[0]; result->pad = 0;
+        }
+    }
+}
+
+int l2_grid(int n) { return std::max(1, std::min(sm_count() * 2, (n + L2_WARPS - 1) / L2_WARPS)); }
+
+}  // namespace
+
+extern "C" {
+
+size_t gcnk_layer2_workspace(int n, int h, int c) {
+    const size_t g = (size_t)l2_grid(n);
+    return g * sizeof(L2Partial) + g * (size_t)h * c * sizeof(float);
+}
+
+int gcnk_layer2_fused(const float *P, const float *W2, const int *split, const int *label, int current_split, int n, int h,
+                      int c, int training, int count, const float *d_dinv, float *G_scaled, float *W2_grad, float *logits_out,
+                      gcnk_ce_result *d_result, float *workspace, size_t workspace_bytes, gcnk_stream_t stream) {
+    GCNK_REQUIRE(P && W2 && split && label && d_result && n >= 0 && h > 0 && c > 0, "bad arguments");
+    GCNK_REQUIRE(c <= 32 * CPL_MAX && (size_t)h * c <= 4096, "needs c <= 128 and h*c <= 4096");
+    GCNK_REQUIRE(!training || (G_scaled && W2_grad && d_dinv), "training needs G, W2_grad and dinv");
+    GCNK_REQUIRE(workspace && workspace_bytes >= gcnk_layer2_workspace(n, h, c), "workspace too small");
+    cudaStream_t st = S(stream);
+    const int grid = l2_grid(n);
+    L2Partial *ce_partials = reinterpret_cast<L2Partial *>(workspace);
+    float *dw_partials = reinterpret_cast<float *>(ce_partials + grid);
+    const size_t smem = sizeof(float) * ((size_t)h * c + L2_WARPS * (size_t)c + L2_WARPS * (size_t)h +
+                                         (training ? L2_WARPS * (size_t)h * c : 0));
+    if (smem > 48 * 1024) {
+        GCNK_REQUIRE(smem <= 200 * 1024, "h*c too large for shared memory");
+        GCNK_CUDA(cudaFuncSetAttribute(layer2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
+    layer2_kernel<<<grid, L2_THREADS, smem, st>>>(P, W2, split, label, current_split, n, h, c, training, (float)count, d_dinv,
+                                                  G_scaled, logits_out, ce_partials, dw_partials);
+    GCNK_LAUNCHED();
+    const int hc = h * c;
+    layer2_finish_kernel<<<training ? (hc + 255) / 256 : 1, 256, 0, st>>>(ce_partials, dw_partials, grid, hc, training, W2_grad, d_result);
+    GCNK_LAUNCHED();
+    return GCNK_OK;
+}
+
+}  // extern "C"

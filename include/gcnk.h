@@ -1,0 +1,193 @@
+/* include/gcnk.h — the C ABI of libgcnk.so: hand-written sm_100a kernels for the full-batch GCN
+ * training path of hengdashi/cuda_gcn, one entry point per kernel row of the reference
+ * (src/cuda/cuda_kernel.cuh:20-90) plus the fused variants the B200 plan uses.
+ *
+ * Conventions
+ *   - plain C: raw DEVICE pointers unless a parameter is named h_* (host), sizes as int / int64_t,
+ *     a stream as `gcnk_stream_t` (a cudaStream_t passed as void*; NULL = the legacy default stream).
+ *   - every function returns 0 on success, a positive cudaError_t on a CUDA failure, or a negative
+ *     GCNK_E* code on a bad argument.  gcnk_last_error() returns a message for the calling thread.
+ *     (The reference's convention is CUDA_CHECK -> print + exit, cuda_kernel.cuh:11-18; the C++ host
+ *     layer in cuda_gcn_b200/host keeps that convention on top of these return codes.)
+ *   - all launches are asynchronous on `stream`; nothing here synchronises unless it says so.
+ *   - outputs are WRITTEN, never accumulated into: callers need no zero()/zero_grad() memsets
+ *     (the reference needs them because its kernels `+=` into global memory, cuda_module.cu:11,27,45).
+ *   - floating point is fp32 (as the reference), indices int32, mask storage is bit-packed uint32.
+ *   - there is no CPU fallback anywhere behind this interface.
+ */
+#ifndef GCNK_H
+#define GCNK_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void *gcnk_stream_t;
+
+enum { GCNK_OK = 0, GCNK_EINVAL = -1, GCNK_ENOMEM = -2, GCNK_EUNSUPPORTED = -3, GCNK_ENODEVICE = -4 };
+
+/* ---- library / device ------------------------------------------------------------------------ */
+int         gcnk_version(void);                        /* 10000*major + 100*minor + patch */
+const char *gcnk_last_error(void);
+int         gcnk_device_count(int *count);             /* GCNK_ENODEVICE (and *count = 0) without a GPU */
+int         gcnk_set_device(int device);
+int         gcnk_device_info(int device, int *sm_count, int *cc_major, int *cc_minor, size_t *total_mem, int *l2_bytes);
+int64_t     gcnk_launch_count(void);                   /* kernels launched by this library so far (process-wide) */
+
+/* ---- memory, streams, events (thin, so a C/C++/ctypes host needs no other CUDA binding) -------- */
+int gcnk_malloc(void **ptr, size_t bytes);
+int gcnk_free(void *ptr);
+int gcnk_malloc_host(void **ptr, size_t bytes);        /* pinned */
+int gcnk_free_host(void *ptr);
+int gcnk_memcpy_h2d(void *dst, const void *h_src, size_t bytes, gcnk_stream_t stream);
+int gcnk_memcpy_d2h(void *h_dst, const void *src, size_t bytes, gcnk_stream_t stream);
+int gcnk_memcpy_d2d(void *dst, const void *src, size_t bytes, gcnk_stream_t stream);
+int gcnk_memset(void *dst, int value, size_t bytes, gcnk_stream_t stream);
+int gcnk_stream_create(gcnk_stream_t *stream);
+int gcnk_stream_destroy(gcnk_stream_t stream);
+int gcnk_stream_sync(gcnk_stream_t stream);
+int gcnk_device_sync(void);
+int gcnk_event_create(void **event);
+int gcnk_event_destroy(void *event);
+int gcnk_event_record(void *event, gcnk_stream_t stream);
+int gcnk_event_sync(void *event);
+int gcnk_event_elapsed_ms(void *start, void *stop, float *ms);
+int gcnk_flush_l2(gcnk_stream_t stream);               /* writes a >L2 scratch buffer (bench hygiene) */
+
+/* ---- graph preparation ------------------------------------------------------------------------
+ * Replaces the per-edge work the reference redoes in every launch (cuda_kernel.cu:133-136: two
+ * indptr loads, an int product, sqrtf and a division per edge per thread): the degree vector
+ * d^-1/2 and a static, degree-balanced row->warp schedule are computed once per graph.
+ * `d_indptr`/`d_indices` are borrowed and must outlive the handle.  n_cols >= n is the number of
+ * rows the gather source has (n_cols > n for a row partition whose column ids are global);
+ * d_dinv_global (may be NULL when n_cols == n) supplies d^-1/2 for all n_cols columns. */
+typedef struct gcnk_graph gcnk_graph;
+int gcnk_graph_create(gcnk_graph **g, const int *d_indptr, const int *d_indices, int n, int64_t nnz,
+                      int n_cols, const float *d_dinv_global, gcnk_stream_t stream);
+int gcnk_graph_destroy(gcnk_graph *g);
+int gcnk_graph_dinv(const gcnk_graph *g, const float **d_dinv);   /* [n] d^-1/2 of the local rows */
+int gcnk_graph_stats(const gcnk_graph *g, int *n, int64_t *nnz, int *max_degree, int *is_symmetric, int *n_bins);
+
+/* ---- GraphSum: K6/K7, cuda_kernel.cu:126-162 (CPU: module.cpp:83-119) ---------------------------
+ * out[s,:] = sum_{d in row s} in[d,:] / sqrt(deg(s)*deg(d)).  Forward and backward are the same
+ * operation on (data) resp. (grad) buffers, exactly as in the reference.  `in` has n_cols rows. */
+int gcnk_graphsum(const gcnk_graph *g, const float *in, float *out, int dim, gcnk_stream_t stream);
+
+/* Building blocks of the fused plan (all row-major [rows x dim], `scaled` = already multiplied by
+ * d^-1/2 of its own row so the gather needs no per-edge coefficient):
+ *   gcnk_scale_rows:       out[r,:] = dinv[r] * in[r,:]
+ *   gcnk_gather_plain:     out[s,:] = dinv[s] * sum_d in_scaled[d,:]
+ *   gcnk_gather_relu_drop: a = dinv[s]*sum_d in_scaled[d,:]; h = relu(a); keep = drop bit (NULL: keep all);
+ *                          out_scaled[s,:] = dinv[s] * (keep ? h*scale : 0); mask bit = (a>0) & keep
+ *                          [fuses K6 + K10 + K12 + the pre-scale for the next gather]
+ *   gcnk_gather_mask:      a = dinv[s]*sum_d in_scaled[d,:]; out_scaled[s,:] = dinv[s] * (mask bit ? a*scale : 0)
+ *                          [fuses K7 + K13 + K11 + the pre-scale for the next gather]
+ * drop_bits is the flat keep stream of gcnk_dropout_mask: bit i*dim+j belongs to element (i,j).
+ * mask_bits (written by gather_relu_drop, read by gather_mask) is row-padded so that concurrent rows
+ * never share a word: row i starts at bit i*gcnk_mask_row_stride_bits(dim) (8, 16, or dim rounded up
+ * to 32), i.e. it holds n*stride/32 words (rounded up). */
+int gcnk_mask_row_stride_bits(int dim);
+int gcnk_scale_rows(const float *d_dinv, const float *in, float *out, int rows, int dim, gcnk_stream_t stream);
+int gcnk_gather_plain(const gcnk_graph *g, const float *in_scaled, float *out, int dim, gcnk_stream_t stream);
+int gcnk_gather_relu_drop(const gcnk_graph *g, const float *in_scaled, float *out_scaled, const uint32_t *drop_bits,
+                          uint32_t *mask_bits, float scale, int dim, gcnk_stream_t stream);
+int gcnk_gather_mask(const gcnk_graph *g, const float *in_scaled, float *out_scaled, const uint32_t *mask_bits,
+                     float scale, int dim, gcnk_stream_t stream);
+
+/* ---- SparseMatmul: K4/K5, cuda_kernel.cu:100-122 (CPU: module.cpp:47-77) -------------------------
+ * gcnk_spmat wraps the CSR index of the feature matrix X[m x n] (borrowed device arrays) and adds,
+ * once, what the kernels need: a transposed (CSC) view so the backward is a deterministic gather
+ * (the reference's backward kernel races on b_grad), and detection of the "dense
+ * features" layout (every row stores exactly n entries with column ids 0..n-1, e.g. Reddit as
+ * written by reddit_preprocess.py:161-167), for which the index array is never read.
+ * fw: c[m x p] = X * b[n x p];   bw: b_grad[n x p] = X^T * c_grad.   values[nnz] are X's entries.
+ * Optional fusions (pass NULL / 1.0f to disable):
+ *   drop_bits: bit jj set = keep value jj; kept values are multiplied by drop_scale on read (K12
+ *              fused; the pristine values are never modified, so no per-pass H2D restore is needed);
+ *   row_scale: c[i,:] *= row_scale[i] on write (the d^-1/2 pre-scale for the following gather). */
+typedef struct gcnk_spmat gcnk_spmat;
+int gcnk_spmat_create(gcnk_spmat **sp, const int *d_indptr, const int *d_indices, int m, int n, int64_t nnz,
+                      gcnk_stream_t stream);
+int gcnk_spmat_destroy(gcnk_spmat *sp);
+int gcnk_spmat_is_dense(const gcnk_spmat *sp, int *is_dense);
+int gcnk_spmm_fw(const gcnk_spmat *sp, const float *values, const float *b, float *c, int p,
+                 const uint32_t *drop_bits, float drop_scale, const float *row_scale, gcnk_stream_t stream);
+int gcnk_spmm_bw(gcnk_spmat *sp, const float *values, const float *c_grad, float *b_grad, int p,
+                 const uint32_t *drop_bits, float drop_scale, gcnk_stream_t stream);
+
+/* ---- Matmul: K1/K2/K3, cuda_kernel.cu:6-96 (CPU: module.cpp:11-42) -------------------------------- */
+int gcnk_matmul_fw(const float *a, const float *b, float *c, int m, int n, int p, gcnk_stream_t stream);   /* c = a*b       */
+int gcnk_matmul_bw_a(const float *c_grad, const float *b, float *a_grad, int m, int n, int p, gcnk_stream_t stream); /* a_grad = c_grad * b^T */
+int gcnk_matmul_bw_b(const float *a, const float *c_grad, float *b_grad, int m, int n, int p,
+                     float *workspace, size_t workspace_bytes, gcnk_stream_t stream);                      /* b_grad = a^T * c_grad */
+size_t gcnk_matmul_bw_b_workspace(int m, int n, int p);
+
+/* ---- ReLU: K10/K11, cuda_kernel.cu:204-219 (CPU: module.cpp:175-194) ------------------------------- */
+int gcnk_relu_fw(float *x, uint32_t *mask_bits, int64_t n, int training, gcnk_stream_t stream);  /* mask untouched when !training */
+int gcnk_relu_bw(float *grad, const uint32_t *mask_bits, int64_t n, gcnk_stream_t stream);
+
+/* ---- Dropout: K12/K13, cuda_kernel.cu:223-240 (CPU: module.cpp:207-233) -----------------------------
+ * The reference CPU engine draws one xorshift128+ value per element from a single global stream
+ * (rand.cpp:17-28) and keeps element i iff (int)draw >= int(p*0x7fffffff).  gcnk_rng reproduces THAT
+ * stream bit-for-bit in parallel: xorshift128+ is linear over GF(2), so every thread jumps to its own
+ * offset with precomputed powers of the transition matrix.  (This replaces the reference GPU path's
+ * racy shared cuRAND states, cuda_kernel.cu:229.)  State lives on the host, like rand_state[2]. */
+typedef struct gcnk_rng gcnk_rng;
+int gcnk_rng_create(gcnk_rng **rng, uint64_t s0, uint64_t s1);
+int gcnk_rng_destroy(gcnk_rng *rng);
+int gcnk_rng_seed(gcnk_rng *rng, long seed);                 /* srand(seed); rand(); rand() exactly as rand.cpp:6-15 */
+int gcnk_rng_get_state(const gcnk_rng *rng, uint64_t *h_state2);
+int gcnk_rng_set_state(gcnk_rng *rng, uint64_t s0, uint64_t s1);
+int gcnk_rng_skip(gcnk_rng *rng, uint64_t n_draws);          /* advance the host state by n draws, O(log n) */
+int gcnk_rng_next_host(gcnk_rng *rng, uint32_t *h_out, int64_t n);   /* host-side draws (Glorot init), advances */
+/* keep bits for the next n draws (bit i set = keep), advances the stream by n.  p is the dropout rate. */
+int gcnk_dropout_mask(gcnk_rng *rng, uint32_t *keep_bits, int64_t n, float p, gcnk_stream_t stream);
+int gcnk_dropout_apply(float *x, const uint32_t *keep_bits, int64_t n, float p, gcnk_stream_t stream);  /* fw and bw: x *= keep ? 1/(1-p) : 0 */
+
+/* ---- CrossEntropyLoss: K8/K9 + thrust reductions, cuda_kernel.cu:166-200, cuda_module.cu:121-146
+ * (CPU: module.cpp:124-161) and GCN::get_accuracy (gcn.cpp:83-96) in the same pass.
+ * logits[n x c] are shifted in place by the row max for labelled rows (as the reference does);
+ * grad (NULL when !training) receives (softmax - onehot)/count, zeros for unlabelled rows.
+ * d_result[4] (device floats/ints, written): {loss (mean over labelled rows), count, wrong, 0}. */
+typedef struct { float loss; int count; int wrong; int pad; } gcnk_ce_result;
+int gcnk_softmax_ce(float *logits, const int *truth, float *grad, int n, int c, int training,
+                    gcnk_ce_result *d_result, float *workspace, size_t workspace_bytes, gcnk_stream_t stream);
+size_t gcnk_softmax_ce_workspace(int n, int c);
+int gcnk_accuracy(const float *logits, const int *truth, int n, int c, int *d_wrong_total2, gcnk_stream_t stream);
+int gcnk_set_truth(int *truth, const int *split, const int *label, int current_split, int n, gcnk_stream_t stream);  /* K16 */
+
+/* ---- Adam: K15, cuda_kernel.cu:270-281 (CPU: optim.cpp:24-37) + L2 penalty (gcn.cpp:98-105) ---------
+ * One launch for all tensors.  step_size = lr*sqrtf(1-beta2^t)/(1-beta1^t) is computed by the caller
+ * in fp32 as the reference does.  m,v must start zeroed (the reference GPU path forgets).
+ * d_sumsq (may be NULL): receives sum(w^2) of tensor 0 AFTER the update (the next pass's L2 penalty). */
+typedef struct { float *data; const float *grad; float *m; float *v; int size; int decay; } gcnk_adam_tensor;
+int gcnk_adam_step(const gcnk_adam_tensor *h_tensors, int count, float step_size, float beta1, float beta2,
+                   float eps, float weight_decay, float *d_sumsq, gcnk_stream_t stream);
+int gcnk_sum_squares(const float *w, int64_t n, float *d_out, gcnk_stream_t stream);
+
+/* ---- fused layer 2 (row-local): Matmul (K1-K3) + CE (K8/K9) + accuracy in one pass ------------------
+ * For each row s with P[s,:] = (A_hat * H1)[s,:] already aggregated (hidden dim h):
+ *   logits = P[s,:] * W2  (h x c);  labelled rows (split[s]==current_split): loss, wrong;
+ *   training: dlogits = (softmax-onehot)/count;  G_scaled[s,:] = dinv[s] * (dlogits * W2^T);
+ *             W2_grad = P^T * dlogits  (= H1^T * A_hat * dlogits for a symmetric A_hat)
+ * This is the algebraic re-ordering A_hat*(H1*W2) -> (A_hat*H1)*W2 (hard part 3): the
+ * gather runs at width h instead of c.  logits_out may be NULL.  count = #labelled rows (static).
+ * d_result as gcnk_softmax_ce.  Requires h*c <= 4096. */
+int gcnk_layer2_fused(const float *P, const float *W2, const int *split, const int *label, int current_split,
+                      int n, int h, int c, int training, int count, const float *d_dinv,
+                      float *G_scaled, float *W2_grad, float *logits_out, gcnk_ce_result *d_result,
+                      float *workspace, size_t workspace_bytes, gcnk_stream_t stream);
+size_t gcnk_layer2_workspace(int n, int h, int c);
+
+/* ---- host-side, bit-exact integer work --------------------------------------------------------------
+ * Contiguous nnz-balanced row partition of a CSR: h_row_begin[parts+1] receives the cuts;
+ * slice k is rows [h_row_begin[k], h_row_begin[k+1]) with column ids left global. */
+int gcnk_partition_rows(const int *h_indptr, int n, int parts, int *h_row_begin);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GCNK_H */
