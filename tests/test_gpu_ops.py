@@ -1,0 +1,405 @@
+"""Per-op parity: every C-ABI kernel (include/gcnk.h, called through ctypes exactly as a host binds it)
+against the CPU checker on the same seeded inputs.  Integer/bit outputs (masks, counts, wrong flags,
+RNG draws, keep bits) must be bit-exact; fp32 outputs within the tolerance written beside each check
+(GPU uses FMA and a different — but fixed — summation order)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from tests.util import make_dataset, make_features, make_graph
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 2e-5     # relative to the largest magnitude of the tensor (fp32 sums of up to a few thousand terms)
+
+
+def close(got, want, rtol=RTOL, what=""):
+    got, want = np.asarray(got, np.float64).ravel(), np.asarray(want, np.float64).ravel()
+    assert got.shape == want.shape, (what, got.shape, want.shape)
+    scale = max(np.abs(want).max() if want.size else 0.0, 1e-30)
+    err = np.abs(got - want).max() if want.size else 0.0
+    assert err <= rtol * scale, f"{what}: max abs err {err:.3e} vs scale {scale:.3e} (rtol {rtol})"
+
+
+@pytest.fixture(scope="module")
+def abi():
+    from cuda_gcn_b200 import abi
+    abi.require_device(0)
+    return abi
+
+
+@pytest.fixture(scope="module")
+def chk():
+    from oracle.checker import best_checker
+    return best_checker()
+
+
+def unpack_bits(words, n):
+    return np.unpackbits(np.ascontiguousarray(words).view(np.uint8), bitorder="little")[:n].astype(bool)
+
+
+def pack_bits(bits):
+    bits = np.asarray(bits, bool)
+    pad = (-len(bits)) % 32
+    return np.packbits(np.concatenate([bits, np.zeros(pad, bool)]), bitorder="little").view(np.uint32)
+
+
+def unpack_row_mask(abi, words, n, dim):
+    stride = abi.k.gcnk_mask_row_stride_bits(dim)
+    allbits = np.unpackbits(np.ascontiguousarray(words).view(np.uint8), bitorder="little")
+    return allbits[: n * stride].reshape(n, stride)[:, :dim].astype(bool)
+
+
+GRAPHS = {
+    "small": dict(n=300, n_undirected=900, seed=1),
+    "isolated": dict(n=257, n_undirected=400, seed=2, isolated=40),
+    "hub": dict(n=6000, n_undirected=20000, seed=3, hub=(17, 5000), alpha=1.6),
+    "directed": dict(n=500, n_undirected=3000, seed=4, symmetric=False),
+    "tiny": dict(n=1, n_undirected=0, seed=5),
+}
+
+
+@pytest.mark.parametrize("gname", list(GRAPHS))
+@pytest.mark.parametrize("dim", [1, 3, 7, 16, 41, 47, 64, 100, 256])
+def test_graphsum(abi, chk, gname, dim):
+    if gname == "tiny":
+        indptr, indices = np.array([0, 1], np.int32), np.array([0], np.int32)
+    else:
+        indptr, indices = make_graph(**GRAPHS[gname])
+    n = len(indptr) - 1
+    x = np.random.default_rng(dim).standard_normal((n, dim)).astype(np.float32)
+    want = chk.graphsum(indptr, indices, x, dim)
+    g = abi.Graph(indptr, indices)
+    st = g.stats()
+    assert st["n"] == n and st["nnz"] == len(indices)
+    assert st["max_degree"] == int(np.diff(indptr).max())
+    assert st["symmetric"] == (gname != "directed")
+    din, dout = abi.dev(x), abi.DeviceArray((n, dim), np.float32)
+    abi.k.gcnk_graphsum(g.h, din.ptr, dout.ptr, dim, None)
+    close(dout.numpy(), want, what=f"graphsum {gname} dim {dim}")
+    # d^-1/2 is correctly rounded: bit-equal to numpy's IEEE 1/sqrt
+    deg = np.diff(indptr).astype(np.float32)
+    assert (g.dinv().view(np.uint32) == (np.float32(1) / np.sqrt(deg)).view(np.uint32)).all()
+
+
+def test_graphsum_empty(abi):
+    g = abi.Graph(np.zeros(1, np.int32), np.zeros(0, np.int32))
+    d = abi.DeviceArray((4,), np.float32)
+    abi.k.gcnk_graphsum(g.h, d.ptr, d.ptr, 4, None)      # n == 0: no launch, no error
+    abi.k.gcnk_device_sync()
+
+
+@pytest.mark.parametrize("dim", [6, 16, 41, 64])
+@pytest.mark.parametrize("p", [0.0, 0.5])
+def test_fused_gather_chain(abi, chk, dim, p):
+    """gather_relu_drop / gather_mask == GraphSum + ReLU + Dropout forward and their backward, with the
+    d^-1/2 pre-scale carried between kernels.  Masks are bit-exact; floats within RTOL."""
+    indptr, indices = make_graph(n=2000, n_undirected=9000, seed=7, hub=(3, 2500), alpha=1.4)
+    n = len(indptr) - 1
+    rng = np.random.default_rng(11)
+    x = rng.standard_normal((n, dim)).astype(np.float32)
+    gout = rng.standard_normal((n, dim)).astype(np.float32)     # upstream gradient wrt the layer output
+    keep = rng.random(n * dim) >= p
+    scale = np.float32(1 / (1 - np.float32(p)))
+    # ---- checker: the unfused module chain
+    agg = chk.graphsum(indptr, indices, x, dim).reshape(n, dim)
+    relu_mask = agg > 0
+    h = np.where(relu_mask, agg, 0).astype(np.float32)
+    h = np.where(keep.reshape(n, dim), h * scale, 0).astype(np.float32)
+    gb = np.where(keep.reshape(n, dim), gout * scale, 0).astype(np.float32)     # Dropout.bw
+    gb = np.where(relu_mask, gb, 0).astype(np.float32)                            # ReLU.bw
+    gin = chk.graphsum(indptr, indices, gb, dim)                                  # GraphSum.bw
+    # ---- device: x_scaled -> gather_relu_drop -> (h scaled by dinv)
+    g = abi.Graph(indptr, indices)
+    dinv = g.dinv()
+    xs = abi.DeviceArray((n, dim), np.float32)
+    abi.k.gcnk_scale_rows(g.dinv_ptr(), abi.dev(x).ptr, xs.ptr, n, dim, None)
+    stride = abi.k.gcnk_mask_row_stride_bits(dim)
+    mask = abi.DeviceArray.zeros(((n * stride + 31) // 32 + 4,), np.uint32)
+    hs = abi.DeviceArray((n, dim), np.float32)
+    drop = abi.dev(pack_bits(keep))
+    abi.k.gcnk_gather_relu_drop(g.h, xs.ptr, hs.ptr, drop.ptr, mask.ptr, float(scale), dim, None)
+    close(hs.numpy() / dinv[:, None], h, what="relu_drop forward")
+    got_mask = unpack_row_mask(abi, mask.numpy(), n, dim)
+    want_mask = relu_mask & keep.reshape(n, dim)
+    # a row sum within rounding of 0 may legitimately flip the x>0 test; everything else is exact
+    flips = got_mask != want_mask
+    assert (np.abs(agg[flips]) < 1e-5).all() and flips.mean() < 1e-3
+    # ---- backward: gout -> gather_mask(prev mask) needs gout aggregated first in the real plan; here
+    # check the kernel's own contract: out = dinv * (mask ? (dinv * sum in_scaled) * scale : 0)
+    gs = abi.DeviceArray((n, dim), np.float32)
+    abi.k.gcnk_scale_rows(g.dinv_ptr(), abi.dev(gout).ptr, gs.ptr, n, dim, None)
+    outm = abi.DeviceArray((n, dim), np.float32)
+    abi.k.gcnk_gather_mask(g.h, gs.ptr, outm.ptr, mask.ptr, float(scale), dim, None)
+    agg_g = chk.graphsum(indptr, indices, gout, dim).reshape(n, dim)
+    want = np.where(got_mask, agg_g * scale, 0) * dinv[:, None]
+    close(outm.numpy(), want, what="gather_mask")
+    # and the full backward chain through gather_plain: gin = A_hat * gb
+    gbs = abi.DeviceArray((n, dim), np.float32)
+    abi.k.gcnk_scale_rows(g.dinv_ptr(), abi.dev(gb).ptr, gbs.ptr, n, dim, None)
+    gin_d = abi.DeviceArray((n, dim), np.float32)
+    abi.k.gcnk_gather_plain(g.h, gbs.ptr, gin_d.ptr, dim, None)
+    close(gin_d.numpy(), gin, what="gather_plain backward")
+
+
+def test_graph_row_partition(abi, chk):
+    """A row slice with global column ids (n_cols > n) reproduces the same rows of the full product."""
+    indptr, indices = make_graph(n=3000, n_undirected=12000, seed=9, alpha=1.3)
+    n, dim = len(indptr) - 1, 16
+    x = np.random.default_rng(1).standard_normal((n, dim)).astype(np.float32)
+    want = chk.graphsum(indptr, indices, x, dim).reshape(n, dim)
+    cuts = np.zeros(4, np.int32)
+    abi.k.gcnk_partition_rows(indptr.ctypes.data, n, 3, cuts.ctypes.data)
+    assert cuts[0] == 0 and cuts[-1] == n and (np.diff(cuts) > 0).all()
+    dinv = (np.float32(1) / np.sqrt(np.diff(indptr).astype(np.float32))).astype(np.float32)
+    pieces_ptr, pieces_idx = [], []
+    for kpart in range(3):
+        lo, hi = cuts[kpart], cuts[kpart + 1]
+        ip = (indptr[lo:hi + 1] - indptr[lo]).astype(np.int32)
+        ix = indices[indptr[lo]:indptr[hi]]
+        pieces_ptr.append(ip); pieces_idx.append(ix)
+        g = abi.Graph(ip, ix, n_cols=n, dinv_global=dinv)
+        out = abi.DeviceArray((hi - lo, dim), np.float32)
+        abi.k.gcnk_graphsum(g.h, abi.dev(x).ptr, out.ptr, dim, None)
+        close(out.numpy(), want[lo:hi], what=f"partition {kpart}")
+    # bit-exact: concatenating the slices reproduces the CSR
+    assert (np.concatenate(pieces_idx) == indices).all()
+    re = np.concatenate([[0]] + [p[1:] + indptr[cuts[i]] for i, p in enumerate(pieces_ptr)])
+    assert (re == indptr).all()
+
+
+@pytest.mark.parametrize("p_out", [1, 5, 16, 33, 64])
+@pytest.mark.parametrize("dense", [False, True])
+def test_spmm(abi, chk, p_out, dense):
+    m, f = (700, 96) if dense else (1500, 300)
+    fp, fi, fv = make_features(m, f, 12, seed=p_out, dense=dense, empty_rows=0 if dense else 20)
+    rng = np.random.default_rng(5)
+    w = rng.standard_normal((f, p_out)).astype(np.float32)
+    cg = rng.standard_normal((m, p_out)).astype(np.float32)
+    want_fw = chk.spmm_fw(fp, fi, fv, w, m, f, p_out)
+    want_bw = chk.spmm_bw(fp, fi, fv, cg, m, f, p_out)
+    sp = abi.SpMat(fp, fi, m, f)
+    assert sp.is_dense() == dense
+    dv, dw, dc = abi.dev(fv), abi.dev(w), abi.DeviceArray((m, p_out), np.float32)
+    abi.k.gcnk_spmm_fw(sp.h, dv.ptr, dw.ptr, dc.ptr, p_out, None, 1.0, None, None)
+    close(dc.numpy(), want_fw, what="spmm fw")
+    dg = abi.DeviceArray((f, p_out), np.float32)
+    abi.k.gcnk_spmm_bw(sp.h, dv.ptr, abi.dev(cg).ptr, dg.ptr, p_out, None, 1.0, None)
+    close(dg.numpy(), want_bw, rtol=5e-5, what="spmm bw")
+    # fused dropout-on-read + row scale == dropout applied to the values first
+    keep = rng.random(len(fv)) >= 0.5
+    rs = rng.random(m).astype(np.float32) + 0.5
+    fv2 = np.where(keep, fv * np.float32(2), 0).astype(np.float32)
+    want2 = chk.spmm_fw(fp, fi, fv2, w, m, f, p_out).reshape(m, p_out) * rs[:, None]
+    drop = abi.dev(pack_bits(keep))
+    abi.k.gcnk_spmm_fw(sp.h, dv.ptr, dw.ptr, dc.ptr, p_out, drop.ptr, 2.0, abi.dev(rs).ptr, None)
+    close(dc.numpy(), want2, what="spmm fw + dropout + row scale")
+    abi.k.gcnk_spmm_bw(sp.h, dv.ptr, abi.dev(cg).ptr, dg.ptr, p_out, drop.ptr, 2.0, None)
+    close(dg.numpy(), chk.spmm_bw(fp, fi, fv2, cg, m, f, p_out), rtol=5e-5, what="spmm bw + dropout")
+
+
+def test_spmm_dense_reddit_width(abi, chk):
+    """The dense fast path at Reddit's width (602 features -> hidden 16), ragged row count."""
+    m, f, h = 1237, 602, 16
+    fp, fi, fv = make_features(m, f, 0, seed=3, dense=True)
+    rng = np.random.default_rng(8)
+    w = (rng.standard_normal((f, h)) * 0.1).astype(np.float32)
+    cg = rng.standard_normal((m, h)).astype(np.float32)
+    sp = abi.SpMat(fp, fi, m, f)
+    assert sp.is_dense()
+    dc = abi.DeviceArray((m, h), np.float32)
+    abi.k.gcnk_spmm_fw(sp.h, abi.dev(fv).ptr, abi.dev(w).ptr, dc.ptr, h, None, 1.0, None, None)
+    close(dc.numpy(), chk.spmm_fw(fp, fi, fv, w, m, f, h), what="dense fw16")
+    dg = abi.DeviceArray((f, h), np.float32)
+    abi.k.gcnk_spmm_bw(sp.h, abi.dev(fv).ptr, abi.dev(cg).ptr, dg.ptr, h, None, 1.0, None)
+    close(dg.numpy(), chk.spmm_bw(fp, fi, fv, cg, m, f, h), rtol=5e-5, what="dense bw16")
+
+
+@pytest.mark.parametrize("m,n,p", [(1, 1, 1), (300, 16, 7), (1000, 16, 41), (777, 256, 47), (5000, 100, 256), (64, 64, 64)])
+def test_matmul(abi, chk, m, n, p):
+    rng = np.random.default_rng(m + n + p)
+    a = rng.standard_normal((m, n)).astype(np.float32)
+    b = rng.standard_normal((n, p)).astype(np.float32)
+    cg = rng.standard_normal((m, p)).astype(np.float32)
+    want_c = chk.matmul_fw(a, b, m, n, p)
+    want_ag, want_bg = chk.matmul_bw(a, b, cg, m, n, p)
+    da, db, dcg = abi.dev(a), abi.dev(b), abi.dev(cg)
+    dc, dag, dbg = (abi.DeviceArray(s, np.float32) for s in ((m, p), (m, n), (n, p)))
+    abi.k.gcnk_matmul_fw(da.ptr, db.ptr, dc.ptr, m, n, p, None)
+    close(dc.numpy(), want_c, what="matmul fw")
+    abi.k.gcnk_matmul_bw_a(dcg.ptr, db.ptr, dag.ptr, m, n, p, None)
+    close(dag.numpy(), want_ag, what="matmul bw a")
+    wsb = abi.k.gcnk_matmul_bw_b_workspace(m, n, p)
+    ws = abi.DeviceArray((max(wsb, 16) // 4,), np.float32)
+    abi.k.gcnk_matmul_bw_b(da.ptr, dcg.ptr, dbg.ptr, m, n, p, ws.ptr, wsb, None)
+    close(dbg.numpy(), want_bg, rtol=5e-5, what="matmul bw b")
+
+
+def test_relu(abi, chk):
+    n = 10007
+    rng = np.random.default_rng(2)
+    x = rng.standard_normal(n).astype(np.float32)
+    x[:5] = [0.0, -0.0, np.nan, 1e-30, -1e-30]
+    g = rng.standard_normal(n).astype(np.float32)
+    want_x, want_mask, want_g = chk.relu(x, g, True)
+    dx, dmask, dg = abi.dev(x), abi.DeviceArray.zeros(((n + 31) // 32,), np.uint32), abi.dev(g)
+    abi.k.gcnk_relu_fw(dx.ptr, dmask.ptr, n, 1, None)
+    abi.k.gcnk_relu_bw(dg.ptr, dmask.ptr, n, None)
+    assert (dx.numpy().view(np.uint32) == want_x.view(np.uint32)).all()
+    assert (unpack_bits(dmask.numpy(), n) == want_mask.astype(bool)).all()
+    assert (dg.numpy().view(np.uint32) == want_g.view(np.uint32)).all()
+    # eval: mask untouched
+    before = dmask.numpy().copy()
+    abi.k.gcnk_relu_fw(abi.dev(-x).ptr, dmask.ptr, n, 0, None)
+    assert (dmask.numpy() == before).all()
+
+
+@pytest.mark.parametrize("n", [1, 31, 512, 65536, 65537, 300001])
+@pytest.mark.parametrize("p", [0.0, 0.5, 0.9])
+def test_dropout_stream_bit_exact(abi, chk, n, p):
+    """The device keep bits are the reference's xorshift128+ stream, bit for bit (rand.cpp:17-28,
+    module.cpp:211-216), and the host state afterwards equals the reference's after n draws."""
+    seed = 4242 + n
+    chk.init_rand_state(seed)
+    x = np.ones(n, np.float32)
+    want_x, want_mask, _ = chk.dropout(x, p, grad=np.ones(n, np.float32), training=True, with_grad=True)
+    want_state = chk.get_rand_state()
+    r = abi.Rng()
+    r.seed(seed)
+    bits = abi.DeviceArray.zeros(((n + 31) // 32,), np.uint32)
+    abi.k.gcnk_dropout_mask(r.h, bits.ptr, n, p, None)
+    got = unpack_bits(bits.numpy(), n)
+    assert (got == want_mask.astype(bool)).all()
+    assert r.state() == want_state
+    dx = abi.dev(x)
+    abi.k.gcnk_dropout_apply(dx.ptr, bits.ptr, n, p, None)
+    assert (dx.numpy().view(np.uint32) == want_x.view(np.uint32)).all()
+    # bits beyond n in the last word stay 0
+    if n % 32:
+        assert bits.numpy()[-1] >> (n % 32) == 0
+
+
+def test_rng_host_draws_and_skip(abi, chk):
+    chk.init_rand_state(99)
+    want = chk.rand(1000)
+    r = abi.Rng()
+    r.seed(99)
+    assert (r.next_host(1000) == want).all()
+    r.seed(99)
+    r.skip(600)
+    assert (r.next_host(400) == want[600:]).all()
+
+
+@pytest.mark.parametrize("n,c", [(1, 2), (1000, 7), (3001, 41), (513, 47), (200, 130)])
+@pytest.mark.parametrize("training", [1, 0])
+def test_softmax_ce(abi, chk, n, c, training):
+    rng = np.random.default_rng(n * c)
+    logits = (rng.standard_normal((n, c)) * 3).astype(np.float32)
+    truth = rng.integers(-1, c, n).astype(np.int32)
+    truth[0] = 0
+    logits[0, :] = logits[0, 0]                     # a full tie counts as correct (gcn.cpp:88-93)
+    want_loss, want_shift, want_grad = chk.cross_entropy(logits, truth, c, bool(training))
+    want_acc, want_wrong, want_total = chk.accuracy(want_shift, truth, c)
+    dl, dt = abi.dev(logits), abi.dev(truth)
+    dg = abi.DeviceArray((n, c), np.float32)
+    res = abi.DeviceArray((4,), np.int32)
+    wsb = abi.k.gcnk_softmax_ce_workspace(n, c)
+    ws = abi.DeviceArray((wsb // 4 + 4,), np.float32)
+    abi.k.gcnk_softmax_ce(dl.ptr, dt.ptr, dg.ptr if training else None, n, c, training, res.ptr, ws.ptr, wsb, None)
+    r = res.numpy()
+    loss = r[:1].view(np.float32)[0]
+    assert r[1] == want_total == int((truth >= 0).sum())
+    assert r[2] == want_wrong                                                  # bit-exact integer work
+    assert abs(loss - want_loss) <= 1e-5 * max(abs(want_loss), 1e-6)           # 1e-5 rel: fixed-order fp32 sum
+    close(dl.numpy(), want_shift, rtol=1e-6, what="shifted logits")
+    if training:
+        close(dg.numpy(), want_grad, rtol=1e-5, what="ce grad")
+    acc2 = abi.DeviceArray((2,), np.int32)
+    abi.k.gcnk_accuracy(dl.ptr, dt.ptr, n, c, acc2.ptr, None)
+    assert tuple(acc2.numpy()) == (want_wrong, want_total)
+
+
+def test_set_truth(abi, chk):
+    rng = np.random.default_rng(0)
+    split = rng.integers(0, 4, 5000).astype(np.int32)
+    label = rng.integers(0, 41, 5000).astype(np.int32)
+    out = abi.DeviceArray((5000,), np.int32)
+    for cur in (1, 2, 3):
+        abi.k.gcnk_set_truth(out.ptr, abi.dev(split).ptr, abi.dev(label).ptr, cur, 5000, None)
+        assert (out.numpy() == chk.set_truth(split, label, cur)).all()
+
+
+def test_adam_bit_exact(abi, chk):
+    """Given identical gradients the update is bit-identical to optim.cpp:24-37 over 5 steps."""
+    rng = np.random.default_rng(6)
+    sizes, decay = [9632, 656], [1, 0]
+    datas = [rng.standard_normal(s).astype(np.float32) * 0.3 for s in sizes]
+    steps = [[rng.standard_normal(s).astype(np.float32) * 0.01 for s in sizes] for _ in range(5)]
+    lr, wd, b1, b2, eps = 0.01, 5e-4, 0.9, 0.999, 1e-8
+    want = chk.adam(datas, steps, decay, lr, wd, b1, b2, eps)
+    dd = [abi.dev(d) for d in datas]
+    dm = [abi.DeviceArray.zeros((s,), np.float32) for s in sizes]
+    dv = [abi.DeviceArray.zeros((s,), np.float32) for s in sizes]
+    dg = [abi.DeviceArray((s,), np.float32) for s in sizes]
+    sumsq = abi.DeviceArray((1,), np.float32)
+    for t, grads in enumerate(steps, 1):
+        for g, h in zip(dg, grads):
+            g.upload(h)
+        # optim.cpp:26 in fp32: lr * sqrtf(1 - powf(beta2,t)) / (1 - powf(beta1,t))
+        f = np.float32
+        step_size = f(lr) * np.sqrt(f(1) - f(np.power(f(b2), f(t), dtype=f)), dtype=f) / (f(1) - np.power(f(b1), f(t), dtype=f))
+        arr = (abi.AdamTensor * 2)(*[abi.AdamTensor(dd[i].ptr, dg[i].ptr, dm[i].ptr, dv[i].ptr, sizes[i], decay[i]) for i in range(2)])
+        abi.k.gcnk_adam_step(arr, 2, float(step_size), b1, b2, eps, wd, sumsq.ptr, None)
+    for i in range(2):
+        got = dd[i].numpy()
+        same = got.view(np.uint32) == want[i].view(np.uint32)
+        # powf/sqrtf on the host side of this test may differ from glibc's by an ulp in step_size;
+        # allow that, but nothing larger
+        assert same.mean() > 0.99 or np.abs(got - want[i]).max() <= 2e-7 * np.abs(want[i]).max(), same.mean()
+        close(got, want[i], rtol=1e-6, what=f"adam tensor {i}")
+    close(sumsq.numpy()[0], np.sum(dd[0].numpy().astype(np.float64) ** 2), rtol=1e-5, what="sum of squares")
+
+
+@pytest.mark.parametrize("n,h,c", [(3000, 16, 7), (5000, 16, 41), (1000, 32, 47), (100, 8, 3)])
+@pytest.mark.parametrize("training", [1, 0])
+def test_layer2_fused(abi, chk, n, h, c, training):
+    """Matmul + CE + accuracy + Matmul backward in one pass == the reference's module chain on P."""
+    rng = np.random.default_rng(n + c)
+    P = rng.standard_normal((n, h)).astype(np.float32)
+    W2 = (rng.standard_normal((h, c)) * 0.5).astype(np.float32)
+    split = rng.integers(0, 4, n).astype(np.int32)
+    label = rng.integers(0, c, n).astype(np.int32)
+    dinv = (rng.random(n).astype(np.float32) + 0.1)
+    truth = chk.set_truth(split, label, 1)
+    count = int((truth >= 0).sum())
+    logits = chk.matmul_fw(P, W2, n, h, c)
+    want_loss, shifted, grad = chk.cross_entropy(logits, truth, c, bool(training))
+    _, want_wrong, want_total = chk.accuracy(shifted, truth, c)
+    dP, dW = abi.dev(P), abi.dev(W2)
+    G, Wg = abi.DeviceArray((n, h), np.float32), abi.DeviceArray((h, c), np.float32)
+    lo = abi.DeviceArray((n, c), np.float32)
+    res = abi.DeviceArray((4,), np.int32)
+    wsb = abi.k.gcnk_layer2_workspace(n, h, c)
+    ws = abi.DeviceArray((wsb // 4 + 4,), np.float32)
+    abi.k.gcnk_layer2_fused(dP.ptr, dW.ptr, abi.dev(split).ptr, abi.dev(label).ptr, 1, n, h, c, training, count,
+                            abi.dev(dinv).ptr, G.ptr if training else None, Wg.ptr if training else None, lo.ptr,
+                            res.ptr, ws.ptr, wsb, None)
+    r = res.numpy()
+    assert r[1] == want_total and r[2] == want_wrong
+    loss = r[:1].view(np.float32)[0]
+    assert abs(loss - want_loss) <= 2e-5 * abs(want_loss)
+    close(lo.numpy(), logits, what="logits")
+    if training:
+        ag, bg = chk.matmul_bw(P, W2, grad, n, h, c)
+        close(G.numpy(), ag.reshape(n, h) * dinv[:, None], rtol=5e-5, what="G = dinv * dlogits W2^T")
+        close(Wg.numpy(), bg, rtol=5e-5, what="W2 grad")
+
+
+def test_error_convention(abi):
+    """Bad arguments return GCNK_EINVAL with a message; nothing falls back."""
+    L = abi.load()
+    assert L.gcnk_graphsum(None, None, None, 16, None) == -1
+    assert b"bad arguments" in L.gcnk_last_error()
+    with pytest.raises(abi.GcnkError):
+        abi.k.gcnk_matmul_fw(None, None, None, 1, 1, 1, None)
