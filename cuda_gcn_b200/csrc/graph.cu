@@ -466,6 +466,7 @@ int gcnk_mask_row_stride_bits(int dim) { return mask_stride_bits(dim); }
 int gcnk_graphsum(const gcnk_graph *gc, const float *in, float *out, int dim, gcnk_stream_t stream) {
     GCNK_REQUIRE(gc && in && out && dim > 0, "bad arguments");
     gcnk_graph *g = const_cast<gcnk_graph *>(gc);
+    if (g->n == 0) return GCNK_OK;
     const size_t need = (size_t)g->n_cols * dim;
     if (g->scratch_elems < need) {
         GCNK_CUDA(cudaStreamSynchronize(S(stream)));

@@ -346,6 +346,15 @@ class Ref(_Base):
         L.gcnref_gcn_get_var.argtypes = [C.c_void_p, C.c_int, C.c_int, _f32p]
         L.gcnref_gcn_run.argtypes = [C.c_void_p]
 
+    def __getattr__(self, name):
+        # the few helpers ref_shim.cpp has no face for (set_truth, accuracy, l2_penalty: private members of
+        # the reference's GCN class) come from the C restatement, itself pinned to the reference's GCN loop
+        if name in ("set_truth", "accuracy", "l2_penalty"):
+            if "_oracle" not in self.__dict__:
+                self.__dict__["_oracle"] = Oracle()
+            return getattr(self.__dict__["_oracle"], name)
+        raise AttributeError(name)
+
     def init_rand_state(self, seed): self.L.gcnref_init_rand_state(seed)
     def set_rand_state(self, a, b): self.L.gcnref_set_rand_state(a, b)
 

@@ -35,6 +35,21 @@ def chk():
     return best_checker()
 
 
+@pytest.fixture
+def D(abi):
+    """numpy -> device pointer; the allocation stays alive until the test ends (a temporary
+    DeviceArray would be freed before the asynchronous kernel reads it)."""
+    live = []
+
+    def up(a, dtype=None):
+        d = abi.dev(a, dtype)
+        live.append(d)
+        return d.ptr
+    yield up
+    abi.k.gcnk_device_sync()
+    live.clear()
+
+
 def unpack_bits(words, n):
     return np.unpackbits(np.ascontiguousarray(words).view(np.uint8), bitorder="little")[:n].astype(bool)
 
@@ -92,7 +107,7 @@ def test_graphsum_empty(abi):
 
 @pytest.mark.parametrize("dim", [6, 16, 41, 64])
 @pytest.mark.parametrize("p", [0.0, 0.5])
-def test_fused_gather_chain(abi, chk, dim, p):
+def test_fused_gather_chain(abi, chk, D, dim, p):
     """gather_relu_drop / gather_mask == GraphSum + ReLU + Dropout forward and their backward, with the
     d^-1/2 pre-scale carried between kernels.  Masks are bit-exact; floats within RTOL."""
     indptr, indices = make_graph(n=2000, n_undirected=9000, seed=7, hub=(3, 2500), alpha=1.4)
@@ -114,7 +129,7 @@ def test_fused_gather_chain(abi, chk, dim, p):
     g = abi.Graph(indptr, indices)
     dinv = g.dinv()
     xs = abi.DeviceArray((n, dim), np.float32)
-    abi.k.gcnk_scale_rows(g.dinv_ptr(), abi.dev(x).ptr, xs.ptr, n, dim, None)
+    abi.k.gcnk_scale_rows(g.dinv_ptr(), D(x), xs.ptr, n, dim, None)
     stride = abi.k.gcnk_mask_row_stride_bits(dim)
     mask = abi.DeviceArray.zeros(((n * stride + 31) // 32 + 4,), np.uint32)
     hs = abi.DeviceArray((n, dim), np.float32)
@@ -129,7 +144,7 @@ def test_fused_gather_chain(abi, chk, dim, p):
     # ---- backward: gout -> gather_mask(prev mask) needs gout aggregated first in the real plan; here
     # check the kernel's own contract: out = dinv * (mask ? (dinv * sum in_scaled) * scale : 0)
     gs = abi.DeviceArray((n, dim), np.float32)
-    abi.k.gcnk_scale_rows(g.dinv_ptr(), abi.dev(gout).ptr, gs.ptr, n, dim, None)
+    abi.k.gcnk_scale_rows(g.dinv_ptr(), D(gout), gs.ptr, n, dim, None)
     outm = abi.DeviceArray((n, dim), np.float32)
     abi.k.gcnk_gather_mask(g.h, gs.ptr, outm.ptr, mask.ptr, float(scale), dim, None)
     agg_g = chk.graphsum(indptr, indices, gout, dim).reshape(n, dim)
@@ -137,13 +152,13 @@ def test_fused_gather_chain(abi, chk, dim, p):
     close(outm.numpy(), want, what="gather_mask")
     # and the full backward chain through gather_plain: gin = A_hat * gb
     gbs = abi.DeviceArray((n, dim), np.float32)
-    abi.k.gcnk_scale_rows(g.dinv_ptr(), abi.dev(gb).ptr, gbs.ptr, n, dim, None)
+    abi.k.gcnk_scale_rows(g.dinv_ptr(), D(gb), gbs.ptr, n, dim, None)
     gin_d = abi.DeviceArray((n, dim), np.float32)
     abi.k.gcnk_gather_plain(g.h, gbs.ptr, gin_d.ptr, dim, None)
     close(gin_d.numpy(), gin, what="gather_plain backward")
 
 
-def test_graph_row_partition(abi, chk):
+def test_graph_row_partition(abi, chk, D):
     """A row slice with global column ids (n_cols > n) reproduces the same rows of the full product."""
     indptr, indices = make_graph(n=3000, n_undirected=12000, seed=9, alpha=1.3)
     n, dim = len(indptr) - 1, 16
@@ -161,7 +176,7 @@ def test_graph_row_partition(abi, chk):
         pieces_ptr.append(ip); pieces_idx.append(ix)
         g = abi.Graph(ip, ix, n_cols=n, dinv_global=dinv)
         out = abi.DeviceArray((hi - lo, dim), np.float32)
-        abi.k.gcnk_graphsum(g.h, abi.dev(x).ptr, out.ptr, dim, None)
+        abi.k.gcnk_graphsum(g.h, D(x), out.ptr, dim, None)
         close(out.numpy(), want[lo:hi], what=f"partition {kpart}")
     # bit-exact: concatenating the slices reproduces the CSR
     assert (np.concatenate(pieces_idx) == indices).all()
@@ -171,7 +186,7 @@ def test_graph_row_partition(abi, chk):
 
 @pytest.mark.parametrize("p_out", [1, 5, 16, 33, 64])
 @pytest.mark.parametrize("dense", [False, True])
-def test_spmm(abi, chk, p_out, dense):
+def test_spmm(abi, chk, D, p_out, dense):
     m, f = (700, 96) if dense else (1500, 300)
     fp, fi, fv = make_features(m, f, 12, seed=p_out, dense=dense, empty_rows=0 if dense else 20)
     rng = np.random.default_rng(5)
@@ -185,7 +200,7 @@ def test_spmm(abi, chk, p_out, dense):
     abi.k.gcnk_spmm_fw(sp.h, dv.ptr, dw.ptr, dc.ptr, p_out, None, 1.0, None, None)
     close(dc.numpy(), want_fw, what="spmm fw")
     dg = abi.DeviceArray((f, p_out), np.float32)
-    abi.k.gcnk_spmm_bw(sp.h, dv.ptr, abi.dev(cg).ptr, dg.ptr, p_out, None, 1.0, None)
+    abi.k.gcnk_spmm_bw(sp.h, dv.ptr, D(cg), dg.ptr, p_out, None, 1.0, None)
     close(dg.numpy(), want_bw, rtol=5e-5, what="spmm bw")
     # fused dropout-on-read + row scale == dropout applied to the values first
     keep = rng.random(len(fv)) >= 0.5
@@ -193,13 +208,13 @@ def test_spmm(abi, chk, p_out, dense):
     fv2 = np.where(keep, fv * np.float32(2), 0).astype(np.float32)
     want2 = chk.spmm_fw(fp, fi, fv2, w, m, f, p_out).reshape(m, p_out) * rs[:, None]
     drop = abi.dev(pack_bits(keep))
-    abi.k.gcnk_spmm_fw(sp.h, dv.ptr, dw.ptr, dc.ptr, p_out, drop.ptr, 2.0, abi.dev(rs).ptr, None)
+    abi.k.gcnk_spmm_fw(sp.h, dv.ptr, dw.ptr, dc.ptr, p_out, drop.ptr, 2.0, D(rs), None)
     close(dc.numpy(), want2, what="spmm fw + dropout + row scale")
-    abi.k.gcnk_spmm_bw(sp.h, dv.ptr, abi.dev(cg).ptr, dg.ptr, p_out, drop.ptr, 2.0, None)
+    abi.k.gcnk_spmm_bw(sp.h, dv.ptr, D(cg), dg.ptr, p_out, drop.ptr, 2.0, None)
     close(dg.numpy(), chk.spmm_bw(fp, fi, fv2, cg, m, f, p_out), rtol=5e-5, what="spmm bw + dropout")
 
 
-def test_spmm_dense_reddit_width(abi, chk):
+def test_spmm_dense_reddit_width(abi, chk, D):
     """The dense fast path at Reddit's width (602 features -> hidden 16), ragged row count."""
     m, f, h = 1237, 602, 16
     fp, fi, fv = make_features(m, f, 0, seed=3, dense=True)
@@ -209,10 +224,10 @@ def test_spmm_dense_reddit_width(abi, chk):
     sp = abi.SpMat(fp, fi, m, f)
     assert sp.is_dense()
     dc = abi.DeviceArray((m, h), np.float32)
-    abi.k.gcnk_spmm_fw(sp.h, abi.dev(fv).ptr, abi.dev(w).ptr, dc.ptr, h, None, 1.0, None, None)
+    abi.k.gcnk_spmm_fw(sp.h, D(fv), D(w), dc.ptr, h, None, 1.0, None, None)
     close(dc.numpy(), chk.spmm_fw(fp, fi, fv, w, m, f, h), what="dense fw16")
     dg = abi.DeviceArray((f, h), np.float32)
-    abi.k.gcnk_spmm_bw(sp.h, abi.dev(fv).ptr, abi.dev(cg).ptr, dg.ptr, h, None, 1.0, None)
+    abi.k.gcnk_spmm_bw(sp.h, D(fv), D(cg), dg.ptr, h, None, 1.0, None)
     close(dg.numpy(), chk.spmm_bw(fp, fi, fv, cg, m, f, h), rtol=5e-5, what="dense bw16")
 
 
@@ -236,7 +251,7 @@ def test_matmul(abi, chk, m, n, p):
     close(dbg.numpy(), want_bg, rtol=5e-5, what="matmul bw b")
 
 
-def test_relu(abi, chk):
+def test_relu(abi, chk, D):
     n = 10007
     rng = np.random.default_rng(2)
     x = rng.standard_normal(n).astype(np.float32)
@@ -251,7 +266,7 @@ def test_relu(abi, chk):
     assert (dg.numpy().view(np.uint32) == want_g.view(np.uint32)).all()
     # eval: mask untouched
     before = dmask.numpy().copy()
-    abi.k.gcnk_relu_fw(abi.dev(-x).ptr, dmask.ptr, n, 0, None)
+    abi.k.gcnk_relu_fw(D(-x), dmask.ptr, n, 0, None)
     assert (dmask.numpy() == before).all()
 
 
@@ -320,13 +335,13 @@ def test_softmax_ce(abi, chk, n, c, training):
     assert tuple(acc2.numpy()) == (want_wrong, want_total)
 
 
-def test_set_truth(abi, chk):
+def test_set_truth(abi, chk, D):
     rng = np.random.default_rng(0)
     split = rng.integers(0, 4, 5000).astype(np.int32)
     label = rng.integers(0, 41, 5000).astype(np.int32)
     out = abi.DeviceArray((5000,), np.int32)
     for cur in (1, 2, 3):
-        abi.k.gcnk_set_truth(out.ptr, abi.dev(split).ptr, abi.dev(label).ptr, cur, 5000, None)
+        abi.k.gcnk_set_truth(out.ptr, D(split), D(label), cur, 5000, None)
         assert (out.numpy() == chk.set_truth(split, label, cur)).all()
 
 
@@ -363,7 +378,7 @@ def test_adam_bit_exact(abi, chk):
 
 @pytest.mark.parametrize("n,h,c", [(3000, 16, 7), (5000, 16, 41), (1000, 32, 47), (100, 8, 3)])
 @pytest.mark.parametrize("training", [1, 0])
-def test_layer2_fused(abi, chk, n, h, c, training):
+def test_layer2_fused(abi, chk, D, n, h, c, training):
     """Matmul + CE + accuracy + Matmul backward in one pass == the reference's module chain on P."""
     rng = np.random.default_rng(n + c)
     P = rng.standard_normal((n, h)).astype(np.float32)
@@ -382,8 +397,8 @@ def test_layer2_fused(abi, chk, n, h, c, training):
     res = abi.DeviceArray((4,), np.int32)
     wsb = abi.k.gcnk_layer2_workspace(n, h, c)
     ws = abi.DeviceArray((wsb // 4 + 4,), np.float32)
-    abi.k.gcnk_layer2_fused(dP.ptr, dW.ptr, abi.dev(split).ptr, abi.dev(label).ptr, 1, n, h, c, training, count,
-                            abi.dev(dinv).ptr, G.ptr if training else None, Wg.ptr if training else None, lo.ptr,
+    abi.k.gcnk_layer2_fused(dP.ptr, dW.ptr, D(split), D(label), 1, n, h, c, training, count,
+                            D(dinv), G.ptr if training else None, Wg.ptr if training else None, lo.ptr,
                             res.ptr, ws.ptr, wsb, None)
     r = res.numpy()
     assert r[1] == want_total and r[2] == want_wrong
