@@ -1,0 +1,147 @@
+// capi.cpp — extern "C" face of the host layer (include/gcn_host.h).
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+
+#include "check.h"
+#include "gcn.h"
+#include "gcn_host.h"
+#include "parser.h"
+#include "rand.h"
+#include "synth.h"
+#include "timer.h"
+
+struct gcnh_data { GCNData d; };
+struct gcnh_engine { GCN *g; };
+
+static GCNParams to_cpp(const gcnh_params &p) {
+    return GCNParams{p.num_nodes, p.input_dim, p.hidden_dim, p.output_dim, p.dropout, p.learning_rate, p.weight_decay, p.epochs, p.early_stopping};
+}
+static gcnh_params to_c(const GCNParams &p) {
+    return gcnh_params{p.num_nodes, p.input_dim, p.hidden_dim, p.output_dim, p.dropout, p.learning_rate, p.weight_decay, p.epochs, p.early_stopping};
+}
+
+extern "C" {
+
+gcnh_params gcnh_default_params(void) { return to_c(GCNParams::get_default()); }
+
+gcnh_data *gcnh_data_new(void) { return new gcnh_data; }
+void gcnh_data_free(gcnh_data *d) { delete d; }
+
+int gcnh_data_parse(gcnh_data *d, const char *root, const char *name, gcnh_params *params, int quiet) {
+    GCNParams p = to_cpp(*params);
+    d->d = GCNData();
+    Parser parser(&p, &d->d, name, root ? root : "");
+    parser.set_quiet(quiet != 0);
+    if (!parser.parse()) return 0;
+    *params = to_c(p);
+    return 1;
+}
+
+int gcnh_data_fill(gcnh_data *d, int n, const int *gp, const int *gi, const int *fp, const int *fi, const float *fv,
+                   const int *label, const int *split) {
+    GCNData &x = d->d;
+    x.graph.release_device();
+    x.feature_index.release_device();
+    x.graph.indptr.assign(gp, gp + n + 1);
+    x.graph.indices.assign(gi, gi + gp[n]);
+    x.feature_index.indptr.assign(fp, fp + n + 1);
+    x.feature_index.indices.assign(fi, fi + fp[n]);
+    x.feature_value.assign(fv, fv + fp[n]);
+    x.label.assign(label, label + n);
+    x.split.assign(split, split + n);
+    return 1;
+}
+
+int gcnh_data_synth(gcnh_data *d, const char *preset, double scale, uint64_t seed, gcnh_params *params) {
+    SynthSpec spec;
+    if (!synth_preset(preset, scale, &spec)) { fprintf(stderr, "unknown synthetic preset '%s'\n", preset); return 0; }
+    if (seed) spec.seed = seed;
+    GCNParams p = to_cpp(*params);
+    d->d.graph.release_device();
+    d->d.feature_index.release_device();
+    if (!synth_generate(spec, &p, &d->d)) return 0;
+    *params = to_c(p);
+    return 1;
+}
+
+void gcnh_data_sizes(const gcnh_data *d, int64_t *s) {
+    const GCNData &x = d->d;
+    s[0] = x.graph.rows();
+    s[1] = x.graph.nnz();
+    s[2] = x.feature_index.nnz();
+    s[3] = (int64_t)x.label.size();
+    s[4] = (int64_t)x.split.size();
+    int md = 0;
+    for (int i = 0; i < x.graph.rows(); i++) md = std::max(md, x.graph.indptr[i + 1] - x.graph.indptr[i]);
+    s[5] = md;
+    s[6] = x.feature_index.rows();
+}
+
+const int *gcnh_data_graph_indptr(const gcnh_data *d) { return d->d.graph.indptr.data(); }
+const int *gcnh_data_graph_indices(const gcnh_data *d) { return d->d.graph.indices.data(); }
+const int *gcnh_data_feature_indptr(const gcnh_data *d) { return d->d.feature_index.indptr.data(); }
+const int *gcnh_data_feature_indices(const gcnh_data *d) { return d->d.feature_index.indices.data(); }
+const float *gcnh_data_feature_value(const gcnh_data *d) { return d->d.feature_value.data(); }
+const int *gcnh_data_label(const gcnh_data *d) { return d->d.label.data(); }
+const int *gcnh_data_split(const gcnh_data *d) { return d->d.split.data(); }
+
+gcnh_engine *gcnh_engine_create(const gcnh_params *params, gcnh_data *data, long seed, int plan, int device) {
+    GCNK_CHECK(gcnk_set_device(device));
+    if (seed >= 0) {
+        // GCN's constructor seeds from $GCN_SEED or time(NULL) (rand.cpp:6-15); pin it for this construction
+        char buf[32];
+        snprintf(buf, sizeof buf, "%ld", seed);
+        setenv("GCN_SEED", buf, 1);
+    }
+    gcnh_engine *e = new gcnh_engine;
+    e->g = new GCN(to_cpp(*params), &data->d, (GCNPlan)plan, true);
+    return e;
+}
+
+void gcnh_engine_destroy(gcnh_engine *e) { if (e) { delete e->g; delete e; } }
+int gcnh_engine_plan(const gcnh_engine *e) { return (int)e->g->plan(); }
+
+void gcnh_engine_train_epoch(gcnh_engine *e, float *loss, float *acc) {
+    auto r = e->g->train_epoch();
+    if (loss) *loss = r.first;
+    if (acc) *acc = r.second;
+}
+
+void gcnh_engine_eval(gcnh_engine *e, int split, float *loss, float *acc) {
+    auto r = e->g->eval(split);
+    if (loss) *loss = r.first;
+    if (acc) *acc = r.second;
+}
+
+void gcnh_engine_last_counts(const gcnh_engine *e, int *count, int *wrong) {
+    if (count) *count = e->g->last_count;
+    if (wrong) *wrong = e->g->last_wrong;
+}
+
+int gcnh_engine_run(gcnh_engine *e, int quiet) {
+    GCN *g = e->g;
+    (void)quiet;
+    g->run();
+    return g->epochs_run;
+}
+
+void gcnh_engine_set_input_host(gcnh_engine *e, const float *h) { e->g->set_input_from_host(h); }
+int64_t gcnh_engine_var_size(const gcnh_engine *e, int idx) { return e->g->var_size(idx); }
+void gcnh_engine_get_var(gcnh_engine *e, int idx, int grad, float *out) { e->g->get_var(idx, grad != 0, out); }
+
+void gcnh_timer_enable_gpu(int on) { gpu_timer_enable(on != 0); }
+void gcnh_timer_reset(void) { timer_reset_all(); }
+float gcnh_timer_total(int slot) { return slot >= 0 && slot < __NUM_TMR ? timer_total((timer_instance)slot) : 0.f; }
+int gcnh_timer_calls(int slot) { return slot >= 0 && slot < __NUM_TMR ? timer_calls((timer_instance)slot) : 0; }
+const char *gcnh_timer_name(int slot) { return timer_name((timer_instance)slot); }
+int gcnh_timer_count(void) { return __NUM_TMR; }
+
+float *gcnh_alloc_pinned(int64_t n) {
+    void *p = nullptr;
+    GCNK_CHECK(gcnk_malloc_host(&p, sizeof(float) * (size_t)n));
+    return (float *)p;
+}
+void gcnh_free_pinned(float *p) { gcnk_free_host(p); }
+
+}  // extern "C"

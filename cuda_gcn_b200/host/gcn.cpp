@@ -1,0 +1,376 @@
+#include "gcn.h"
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <tuple>
+
+#include "check.h"
+#include "rand.h"
+#include "timer.h"
+
+GCNParams GCNParams::get_default() { return {2708, 1433, 16, 7, 0.5f, 0.01f, 5e-4f, 100, 0}; }   // gcn.cpp:9-11
+
+// Buffers of the fused plan.  "_s" = already multiplied by d^-1/2 of its own row (the gather kernels
+// take pre-scaled sources, so an edge costs one index and one row read; see csrc/graph.cu).
+struct GCN::Fused {
+    float *xw_s = nullptr;     // [N x H]  dinv (.) (dropout(X) * W1)
+    float *h1_s = nullptr;     // [N x H]  dinv (.) dropout(relu(A_hat * X W1))
+    float *P = nullptr;        // [N x H]  A_hat * H1
+    float *G = nullptr;        // [N x H]  dinv (.) (dlogits * W2^T)
+    float *Gm = nullptr;       // [N x H]  dinv (.) dropout'/relu'(A_hat * dlogits W2^T)
+    float *dxw = nullptr;      // [N x H]  gradient wrt X W1
+    uint32_t *keep0 = nullptr, *keep1 = nullptr, *mask = nullptr;
+    float *ws = nullptr; size_t ws_bytes = 0;
+    gcnk_ce_result *d_result = nullptr, *h_result = nullptr;   // device / pinned host
+    float *d_sumsq = nullptr, *h_sumsq = nullptr;
+    float sumsq = 0;           // sum(W1^2) of the current weights
+    ~Fused() {
+        for (void *p : {(void *)xw_s, (void *)h1_s, (void *)P, (void *)G, (void *)Gm, (void *)dxw, (void *)keep0, (void *)keep1,
+                        (void *)mask, (void *)ws, (void *)d_result, (void *)d_sumsq})
+            if (p) gcnk_free(p);
+        if (h_result) gcnk_free_host(h_result);
+        if (h_sumsq) gcnk_free_host(h_sumsq);
+    }
+};
+
+static GCNPlan plan_from_env() {
+    const char *s = getenv("GCN_PLAN");
+    if (!s || !*s || !strcmp(s, "auto")) return PLAN_AUTO;
+    if (!strcmp(s, "modules")) return PLAN_MODULES;
+    if (!strcmp(s, "fused")) return PLAN_FUSED;
+    fprintf(stderr, "GCN_PLAN must be auto, modules or fused (got '%s')\n", s);
+    exit(EXIT_FAILURE);
+}
+
+GCN::GCN(GCNParams params_, GCNData *input_data) : params(params_), data(input_data) { build(plan_from_env()); }
+
+GCN::GCN(GCNParams params_, GCNData *input_data, GCNPlan plan, bool quiet) : params(params_), data(input_data), quiet_(quiet) {
+    build(plan);
+}
+
+template <typename T>
+static T *upload(const std::vector<T> &h) {
+    T *d = nullptr;
+    GCNK_CHECK(gcnk_malloc((void **)&d, sizeof(T) * h.size()));
+    GCNK_CHECK(gcnk_memcpy_h2d(d, h.data(), sizeof(T) * h.size(), nullptr));
+    GCNK_CHECK(gcnk_stream_sync(nullptr));
+    return d;
+}
+
+void GCN::build(GCNPlan plan) {
+    int n_dev = 0;
+    GCNK_CHECK(gcnk_device_count(&n_dev));                // no GPU -> fatal: there is no CPU engine behind this class
+    init_rand_state();                                    // gcn.cpp:14
+
+    const int N = params.num_nodes, F = params.input_dim, H = params.hidden_dim, C = params.output_dim;
+    const size_t nnzX = data->feature_index.indices.size();
+    if ((int)data->graph.indptr.size() != N + 1 || (int)data->feature_index.indptr.size() != N + 1 ||
+        (int)data->label.size() != N || (int)data->split.size() != N || data->feature_value.size() != nnzX) {
+        fprintf(stderr, "GCN: inconsistent input: num_nodes=%d graph rows=%zu feature rows=%zu labels=%zu splits=%zu\n", N,
+                data->graph.indptr.size() - 1, data->feature_index.indptr.size() - 1, data->label.size(), data->split.size());
+        exit(EXIT_FAILURE);
+    }
+    for (int i = 0; i < N; i++)
+        if (data->split[i] >= 1 && data->split[i] <= 3 && data->label[i] >= 0) split_count[data->split[i]]++;   // truth >= 0 rows
+
+    d_feature_value = upload(data->feature_value);
+    d_split = upload(data->split);
+    d_label = upload(data->label);
+    GCNK_CHECK(gcnk_malloc((void **)&d_truth, sizeof(int) * (size_t)N));
+
+    int symmetric = 0;
+    GCNK_CHECK(gcnk_graph_stats(data->graph.graph(), nullptr, nullptr, nullptr, &symmetric, nullptr));
+    const bool fusable = symmetric && C <= 128 && (size_t)H * C <= 4096;
+    if (plan == PLAN_AUTO) plan = fusable ? PLAN_FUSED : PLAN_MODULES;
+    if (plan == PLAN_FUSED && !fusable) {
+        // the layer-2 re-ordering needs A_hat = A_hat^T for the W2 gradient (csrc/layer2.cu)
+        fprintf(stderr, "GCN: fused plan needs a symmetric adjacency, output_dim <= 128 and hidden*output <= 4096\n");
+        exit(EXIT_FAILURE);
+    }
+    plan_ = plan;
+
+    modules.reserve(8);
+    variables.reserve(8);
+    AdamParams adam_params = AdamParams::get_default();
+    adam_params.lr = params.learning_rate;
+    adam_params.weight_decay = params.weight_decay;
+
+    if (plan_ == PLAN_MODULES) {
+        // the reference's network, Variable for Variable and Module for Module (gcn.cpp:20-65)
+        variables.emplace_back((int)nnzX, false);
+        input = &variables.back();
+        modules.push_back(new Dropout(input, params.dropout));
+        variables.emplace_back(N * H);
+        Variable *layer1_var1 = &variables.back();
+        variables.emplace_back(F * H, true);
+        Variable *layer1_weight = &variables.back();
+        layer1_weight->glorot(F, H);
+        modules.push_back(new SparseMatmul(input, layer1_weight, layer1_var1, &data->feature_index, N, F, H));
+        variables.emplace_back(N * H);
+        Variable *layer1_var2 = &variables.back();
+        modules.push_back(new GraphSum(layer1_var1, layer1_var2, &data->graph, H));
+        modules.push_back(new ReLU(layer1_var2));
+        modules.push_back(new Dropout(layer1_var2, params.dropout));
+        variables.emplace_back(N * C);
+        Variable *layer2_var1 = &variables.back();
+        variables.emplace_back(H * C, true);
+        Variable *layer2_weight = &variables.back();
+        layer2_weight->glorot(H, C);
+        modules.push_back(new Matmul(layer1_var2, layer2_weight, layer2_var1, N, H, C));
+        variables.emplace_back(N * C);
+        output = &variables.back();
+        modules.push_back(new GraphSum(layer2_var1, output, &data->graph, C));
+        ce_module = new CrossEntropyLoss(output, d_truth, &loss, C);
+        modules.push_back(ce_module);
+        optimizer = Adam({{layer1_weight, true}, {layer2_weight, false}}, adam_params);
+        return;
+    }
+
+    // fused plan: only the weights are Variables; slots 0,1,3,4,6 stay empty so indices match gcn.cpp:21-53
+    for (int idx = 0; idx < 7; idx++) {
+        if (idx == 2) { variables.emplace_back(F * H, true); variables.back().glorot(F, H); }
+        else if (idx == 5) { variables.emplace_back(H * C, true); variables.back().glorot(H, C); }
+        else variables.emplace_back(0, false);
+    }
+    optimizer = Adam({{&variables[2], true}, {&variables[5], false}}, adam_params);
+
+    fz.reset(new Fused);
+    const size_t nh = sizeof(float) * (size_t)N * H;
+    for (float **p : {&fz->xw_s, &fz->h1_s, &fz->P, &fz->G, &fz->Gm, &fz->dxw}) GCNK_CHECK(gcnk_malloc((void **)p, nh));
+    GCNK_CHECK(gcnk_malloc((void **)&fz->keep0, sizeof(uint32_t) * (nnzX / 32 + 4)));
+    GCNK_CHECK(gcnk_malloc((void **)&fz->keep1, sizeof(uint32_t) * ((size_t)N * H / 32 + 4)));
+    GCNK_CHECK(gcnk_malloc((void **)&fz->mask, sizeof(uint32_t) * ((size_t)N * gcnk_mask_row_stride_bits(H) / 32 + 4)));
+    fz->ws_bytes = gcnk_layer2_workspace(N, H, C);
+    GCNK_CHECK(gcnk_malloc((void **)&fz->ws, fz->ws_bytes));
+    GCNK_CHECK(gcnk_malloc((void **)&fz->d_result, sizeof(gcnk_ce_result)));
+    GCNK_CHECK(gcnk_malloc((void **)&fz->d_sumsq, sizeof(float)));
+    GCNK_CHECK(gcnk_malloc_host((void **)&fz->h_result, sizeof(gcnk_ce_result)));
+    GCNK_CHECK(gcnk_malloc_host((void **)&fz->h_sumsq, sizeof(float)));
+    GCNK_CHECK(gcnk_sum_squares(variables[2].data, variables[2].size, fz->d_sumsq, nullptr));
+    GCNK_CHECK(gcnk_memcpy_d2h(fz->h_sumsq, fz->d_sumsq, sizeof(float), nullptr));
+    GCNK_CHECK(gcnk_stream_sync(nullptr));
+    fz->sumsq = *fz->h_sumsq;
+    (void)data->feature_index.spmat(N, F);                // build the handle (dense detection) up front
+}
+
+GCN::~GCN() {
+    for (auto m : modules) delete m;
+    for (void *p : {(void *)d_truth, (void *)d_split, (void *)d_label, (void *)d_feature_value})
+        if (p) gcnk_free(p);
+}
+
+void GCN::set_input_from_host(const float *h_values) {
+    GCNK_CHECK(gcnk_memcpy_h2d(d_feature_value, h_values, sizeof(float) * data->feature_index.indices.size(), nullptr));
+}
+
+// ---------------------------------------------------------------------------- modules plan ----
+void GCN::set_input() {
+    // restores the feature values the in-place Dropout of the previous pass destroyed (gcn.cpp:73-76);
+    // device-to-device here, where the reference GPU path re-uploads them from the host (cuda_gcn.cu:81-83)
+    GCNK_CHECK(gcnk_memcpy_d2d(input->data, d_feature_value, sizeof(float) * (size_t)input->size, nullptr));
+}
+
+void GCN::set_truth(int current_split) {
+    GCNK_CHECK(gcnk_set_truth(d_truth, d_split, d_label, current_split, params.num_nodes, nullptr));
+}
+
+float GCN::get_accuracy() {
+    // counted on the device inside the CrossEntropyLoss forward with the reference's rule (gcn.cpp:83-96)
+    last_count = ce_module->last_count;
+    last_wrong = ce_module->last_wrong;
+    return float(last_count - last_wrong) / last_count;
+}
+
+float GCN::get_l2_penalty() {
+    static thread_local float *d_out = nullptr;
+    if (!d_out) GCNK_CHECK(gcnk_malloc((void **)&d_out, sizeof(float)));
+    float l2 = 0;
+    GCNK_CHECK(gcnk_sum_squares(variables[2].data, variables[2].size, d_out, nullptr));
+    GCNK_CHECK(gcnk_memcpy_d2h(&l2, d_out, sizeof(float), nullptr));
+    GCNK_CHECK(gcnk_stream_sync(nullptr));
+    return params.weight_decay * l2 / 2;
+}
+
+// ------------------------------------------------------------------------------ fused plan ----
+std::pair<float, float> GCN::fused_pass(int current_split, bool training) {
+    Fused &z = *fz;
+    const int N = params.num_nodes, F = params.input_dim, H = params.hidden_dim, C = params.output_dim;
+    const int64_t nnzX = (int64_t)data->feature_index.indices.size();
+    const float p = params.dropout;
+    const float scale = 1 / (1 - p);                                      // module.cpp:212
+    const bool drop = training && (int)(p * (float)MY_RAND_MAX) > 0;      // threshold 0 keeps everything
+    gcnk_graph *g = data->graph.graph();
+    gcnk_spmat *sp = data->feature_index.spmat(N, F);
+    const float *dinv = nullptr;
+    GCNK_CHECK(gcnk_graph_dinv(g, &dinv));
+    Variable &W1 = variables[2], &W2 = variables[5];
+
+    // M0 Dropout + M1 SparseMatmul: the keep bits are drawn from the shared stream in element order and
+    // applied on read; the stored feature values are never modified, so no set_input() copy is needed
+    if (training) {
+        gpu_timer_begin(TMR_DROPOUT_FW);
+        if (drop) GCNK_CHECK(gcnk_dropout_mask(global_rng(), z.keep0, nnzX, p, nullptr));
+        else GCNK_CHECK(gcnk_rng_skip(global_rng(), (uint64_t)nnzX));     // the reference still consumes the draws
+        gpu_timer_end(TMR_DROPOUT_FW);
+    }
+    gpu_timer_begin(TMR_SPMATMUL_FW);
+    GCNK_CHECK(gcnk_spmm_fw(sp, d_feature_value, W1.data, z.xw_s, H, drop ? z.keep0 : nullptr, scale, dinv, nullptr));
+    gpu_timer_end(TMR_SPMATMUL_FW);
+
+    // M2 GraphSum + M3 ReLU + M4 Dropout in the gather's epilogue, then the layer-2 aggregation at width H
+    if (training) {
+        gpu_timer_begin(TMR_DROPOUT_FW);
+        if (drop) GCNK_CHECK(gcnk_dropout_mask(global_rng(), z.keep1, (int64_t)N * H, p, nullptr));
+        else GCNK_CHECK(gcnk_rng_skip(global_rng(), (uint64_t)N * H));
+        gpu_timer_end(TMR_DROPOUT_FW);
+    }
+    gpu_timer_begin(TMR_GRAPHSUM_FW);
+    GCNK_CHECK(gcnk_gather_relu_drop(g, z.xw_s, z.h1_s, drop ? z.keep1 : nullptr, training ? z.mask : nullptr,
+                                     training ? scale : 1.0f, H, nullptr));
+    GCNK_CHECK(gcnk_gather_plain(g, z.h1_s, z.P, H, nullptr));
+    gpu_timer_end(TMR_GRAPHSUM_FW);
+
+    // M5 Matmul + M7 CrossEntropyLoss + get_accuracy (+ Matmul backward when training), row-local
+    gpu_timer_begin(TMR_LOSS_FW);
+    GCNK_CHECK(gcnk_layer2_fused(z.P, W2.data, d_split, d_label, current_split, N, H, C, training, split_count[current_split & 3],
+                                 dinv, training ? z.G : nullptr, training ? W2.grad : nullptr, nullptr, z.d_result, z.ws,
+                                 z.ws_bytes, nullptr));
+    gpu_timer_end(TMR_LOSS_FW);
+    GCNK_CHECK(gcnk_memcpy_d2h(z.h_result, z.d_result, sizeof(gcnk_ce_result), nullptr));
+
+    const float sumsq_before = z.sumsq;
+    if (training) {
+        // backward of M6/M5 is inside layer2; M4/M3/M2 backward = one masked gather + one plain gather
+        gpu_timer_begin(TMR_GRAPHSUM_BW);
+        GCNK_CHECK(gcnk_gather_mask(g, z.G, z.Gm, z.mask, scale, H, nullptr));
+        GCNK_CHECK(gcnk_gather_plain(g, z.Gm, z.dxw, H, nullptr));
+        gpu_timer_end(TMR_GRAPHSUM_BW);
+        gpu_timer_begin(TMR_SPMATMUL_BW);
+        GCNK_CHECK(gcnk_spmm_bw(sp, d_feature_value, z.dxw, W1.grad, H, drop ? z.keep0 : nullptr, scale, nullptr));
+        gpu_timer_end(TMR_SPMATMUL_BW);
+        optimizer.step(z.d_sumsq);
+        GCNK_CHECK(gcnk_memcpy_d2h(z.h_sumsq, z.d_sumsq, sizeof(float), nullptr));
+    }
+    GCNK_CHECK(gcnk_stream_sync(nullptr));                                // the one host sync of the pass
+    gpu_timer_resolve();
+    if (training) z.sumsq = *z.h_sumsq;
+    last_count = z.h_result->count;
+    last_wrong = z.h_result->wrong;
+    const float l2 = params.weight_decay * sumsq_before / 2;              // gcn.cpp:98-105, W1 as it was in this forward
+    return {z.h_result->loss + l2, float(last_count - last_wrong) / last_count};
+}
+
+// -------------------------------------------------------------------------------- the loop ----
+std::pair<float, float> GCN::train_epoch() {
+    if (plan_ == PLAN_FUSED) return fused_pass(1, true);
+    set_input();
+    set_truth(1);
+    for (auto m : modules) m->forward(true);
+    const float train_loss = loss + get_l2_penalty();
+    const float train_acc = get_accuracy();
+    for (int i = (int)modules.size() - 1; i >= 0; i--) modules[i]->backward();
+    optimizer.step();
+    gpu_timer_resolve();
+    return {train_loss, train_acc};
+}
+
+std::pair<float, float> GCN::eval(int current_split) {
+    if (plan_ == PLAN_FUSED) return fused_pass(current_split, false);
+    set_input();
+    set_truth(current_split);
+    for (auto m : modules) m->forward(false);
+    const float test_loss = loss + get_l2_penalty();
+    const float test_acc = get_accuracy();
+    gpu_timer_resolve();
+    return {test_loss, test_acc};
+}
+
+void GCN::run() {
+    // line formats: gcn.cpp:139,147,152,157
+    int epoch = 1;
+    std::vector<float> loss_history;
+    for (; epoch <= params.epochs; epoch++) {
+        float train_loss, train_acc, val_loss, val_acc;
+        timer_start(TMR_TRAIN);
+        std::tie(train_loss, train_acc) = train_epoch();
+        std::tie(val_loss, val_acc) = eval(2);
+        const float dt = timer_stop(TMR_TRAIN);
+        epochs_run = epoch;
+        if (!quiet_)
+            printf("epoch=%d train_loss=%.5f train_acc=%.5f val_loss=%.5f val_acc=%.5f time=%.5f\n", epoch, train_loss, train_acc,
+                   val_loss, val_acc, dt);
+        loss_history.push_back(val_loss);
+        if (params.early_stopping > 0 && epoch >= params.early_stopping) {
+            float recent_loss = 0.0;
+            for (int i = epoch - params.early_stopping; i < epoch; i++) recent_loss += loss_history[i];
+            if (val_loss > recent_loss / params.early_stopping) {
+                if (!quiet_) printf("Early stopping...\n");
+                break;
+            }
+        }
+    }
+    if (!quiet_) printf("total training time=%.5f\n", timer_total(TMR_TRAIN));
+    float test_loss, test_acc;
+    timer_start(TMR_TEST);
+    std::tie(test_loss, test_acc) = eval(3);
+    const float dt = timer_stop(TMR_TEST);
+    if (!quiet_) printf("test_loss=%.5f test_acc=%.5f time=%.5f\n", test_loss, test_acc, dt);
+}
+
+// ------------------------------------------------------------------------------ inspection ----
+long GCN::var_size(int idx) const {
+    const long N = params.num_nodes, F = params.input_dim, H = params.hidden_dim, C = params.output_dim;
+    switch (idx) {
+    case 0: return (long)data->feature_index.indices.size();
+    case 1: case 3: return N * H;
+    case 2: return F * H;
+    case 4: return plan_ == PLAN_MODULES ? N * C : 0;
+    case 5: return H * C;
+    case 6: return N * C;
+    }
+    return 0;
+}
+
+void GCN::get_var(int idx, bool grad, float *h_out) {
+    const long size = var_size(idx);
+    if (size == 0) return;
+    auto d2h = [&](const float *d, long count) {
+        GCNK_CHECK(gcnk_memcpy_d2h(h_out, d, sizeof(float) * (size_t)count, nullptr));
+        GCNK_CHECK(gcnk_stream_sync(nullptr));
+    };
+    if (plan_ == PLAN_MODULES) {
+        const Variable &v = variables[idx];
+        if (grad && !v.grad) { memset(h_out, 0, sizeof(float) * (size_t)size); return; }
+        d2h(grad ? v.grad : v.data, size);
+        return;
+    }
+    Fused &z = *fz;
+    const int N = params.num_nodes, H = params.hidden_dim, C = params.output_dim;
+    if (idx == 2 || idx == 5) { d2h(grad ? variables[idx].grad : variables[idx].data, size); return; }
+    if (idx == 0) { if (grad) memset(h_out, 0, sizeof(float) * (size_t)size); else d2h(d_feature_value, size); return; }
+    if (idx == 6) {
+        // the logits are never stored by the fused plan: recompute them from the last pass's P with the CURRENT W2
+        if (grad) { memset(h_out, 0, sizeof(float) * (size_t)size); return; }
+        float *d_logits = nullptr;
+        GCNK_CHECK(gcnk_malloc((void **)&d_logits, sizeof(float) * (size_t)size));
+        GCNK_CHECK(gcnk_layer2_fused(z.P, variables[5].data, d_split, d_label, 0, N, H, C, 0, 0, nullptr, nullptr, nullptr, d_logits,
+                                     z.d_result, z.ws, z.ws_bytes, nullptr));
+        d2h(d_logits, size);
+        GCNK_CHECK(gcnk_free(d_logits));
+        return;
+    }
+    // 1 and 3: stored pre-scaled by d^-1/2; undo it on the host (inspection only)
+    const float *src = idx == 1 ? (grad ? z.dxw : z.xw_s) : (grad ? z.Gm : z.h1_s);
+    d2h(src, size);
+    if (!(idx == 1 && grad)) {
+        const float *d_dinv = nullptr;
+        GCNK_CHECK(gcnk_graph_dinv(data->graph.graph(), &d_dinv));
+        std::vector<float> dinv((size_t)N);
+        GCNK_CHECK(gcnk_memcpy_d2h(dinv.data(), d_dinv, sizeof(float) * (size_t)N, nullptr));
+        GCNK_CHECK(gcnk_stream_sync(nullptr));
+        for (int i = 0; i < N; i++)
+            for (int j = 0; j < H; j++) h_out[(size_t)i * H + j] /= dinv[i];
+    }
+}

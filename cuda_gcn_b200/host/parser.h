@@ -1,0 +1,29 @@
+// parser.h — the data parser with the reference's public shape (src/common/parser.h:14-28):
+// Parser(GCNParams*, GCNData*, graph_name) + bool parse(), reading data/<name>.{graph,split,svmlight}.
+// The accepted-input behaviour of src/common/parser.cpp:20-119 is reproduced bit-exactly (implicit
+// self loop first in every row, neighbours in file order with duplicates kept, a last line without
+// '\n' dropped, 0-based feature keys, input_dim = max key + 1, output_dim = max label + 1); the
+// istringstream-per-line tokenisers are replaced by one pass over the file bytes.  Malformed
+// feature tokens, which the reference turns into uninitialised garbage, are an
+// error here: parse() prints what is wrong and returns false.
+#pragma once
+#include <string>
+
+#include "gcn.h"
+
+class Parser {
+public:
+    // root defaults to the reference's hard-coded "data/" (parser.cpp:12); $GCN_DATA_DIR overrides it
+    Parser(GCNParams *gcnParams, GCNData *gcnData, std::string graph_name, std::string root = "");
+    bool parse();
+private:
+    std::string graph_path, split_path, svmlight_path;
+    GCNParams *gcnParams;
+    GCNData *gcnData;
+    bool quiet = false;
+    bool parseGraph(const std::string &bytes);
+    bool parseNode(const std::string &bytes);
+    bool parseSplit(const std::string &bytes);
+public:
+    void set_quiet(bool q) { quiet = q; }
+};

@@ -1,0 +1,204 @@
+"""cuda_gcn_b200/host_api.py — ctypes binding of libgcnhost.so (include/gcn_host.h): the C face of the
+C++ host layer (Parser, GCNData, GCN training loop, timers).  Used by the tests and bench.py only;
+it computes nothing itself and has no fallback (a missing library or GPU is an error)."""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+import numpy as np
+
+HERE = Path(__file__).resolve().parent
+LIB_PATH = HERE / "libgcnhost.so"
+
+
+class Params(C.Structure):
+    _fields_ = [("num_nodes", C.c_int), ("input_dim", C.c_int), ("hidden_dim", C.c_int), ("output_dim", C.c_int),
+                ("dropout", C.c_float), ("learning_rate", C.c_float), ("weight_decay", C.c_float),
+                ("epochs", C.c_int), ("early_stopping", C.c_int)]
+
+
+vp, ip, fp = C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_float)
+_i32 = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
+_f32 = np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS")
+
+SIGNATURES = {
+    "gcnh_default_params": (Params, []),
+    "gcnh_data_new": (vp, []),
+    "gcnh_data_free": (None, [vp]),
+    "gcnh_data_parse": (C.c_int, [vp, C.c_char_p, C.c_char_p, C.POINTER(Params), C.c_int]),
+    "gcnh_data_fill": (C.c_int, [vp, C.c_int, _i32, _i32, _i32, _i32, _f32, _i32, _i32]),
+    "gcnh_data_synth": (C.c_int, [vp, C.c_char_p, C.c_double, C.c_uint64, C.POINTER(Params)]),
+    "gcnh_data_sizes": (None, [vp, C.POINTER(C.c_int64)]),
+    "gcnh_data_graph_indptr": (ip, [vp]),
+    "gcnh_data_graph_indices": (ip, [vp]),
+    "gcnh_data_feature_indptr": (ip, [vp]),
+    "gcnh_data_feature_indices": (ip, [vp]),
+    "gcnh_data_feature_value": (fp, [vp]),
+    "gcnh_data_label": (ip, [vp]),
+    "gcnh_data_split": (ip, [vp]),
+    "gcnh_engine_create": (vp, [C.POINTER(Params), vp, C.c_long, C.c_int, C.c_int]),
+    "gcnh_engine_destroy": (None, [vp]),
+    "gcnh_engine_plan": (C.c_int, [vp]),
+    "gcnh_engine_train_epoch": (None, [vp, fp, fp]),
+    "gcnh_engine_eval": (None, [vp, C.c_int, fp, fp]),
+    "gcnh_engine_last_counts": (None, [vp, ip, ip]),
+    "gcnh_engine_run": (C.c_int, [vp, C.c_int]),
+    "gcnh_engine_set_input_host": (None, [vp, vp]),
+    "gcnh_engine_var_size": (C.c_int64, [vp, C.c_int]),
+    "gcnh_engine_get_var": (None, [vp, C.c_int, C.c_int, _f32]),
+    "gcnh_timer_enable_gpu": (None, [C.c_int]),
+    "gcnh_timer_reset": (None, []),
+    "gcnh_timer_total": (C.c_float, [C.c_int]),
+    "gcnh_timer_calls": (C.c_int, [C.c_int]),
+    "gcnh_timer_name": (C.c_char_p, [C.c_int]),
+    "gcnh_timer_count": (C.c_int, []),
+    "gcnh_alloc_pinned": (vp, [C.c_int64]),
+    "gcnh_free_pinned": (None, [vp]),
+}
+
+_lib = None
+
+
+def load():
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            raise RuntimeError(f"{LIB_PATH} is not built (make -C cuda_gcn_b200/host); there is no fallback")
+        L = C.CDLL(str(LIB_PATH))
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = L
+    return _lib
+
+
+PLAN_AUTO, PLAN_MODULES, PLAN_FUSED = 0, 1, 2
+
+
+class Data:
+    """GCNData (gcn.h:16-22) living in the C++ host layer; numpy views are zero-copy and read-only by convention."""
+
+    def __init__(self):
+        self.L = load()
+        self.h = self.L.gcnh_data_new()
+        self.params = self.L.gcnh_default_params()
+
+    @classmethod
+    def parse(cls, root, name, quiet=True):
+        d = cls()
+        ok = d.L.gcnh_data_parse(d.h, str(root).encode() if root else None, name.encode(), C.byref(d.params), int(quiet))
+        return d if ok else None
+
+    @classmethod
+    def from_arrays(cls, gd):
+        """gd: oracle.checker.GraphData-like (numpy arrays)."""
+        d = cls()
+        c = lambda a, t: np.ascontiguousarray(a, dtype=t)
+        d.L.gcnh_data_fill(d.h, gd.num_nodes, c(gd.graph_indptr, np.int32), c(gd.graph_indices, np.int32),
+                           c(gd.feature_indptr, np.int32), c(gd.feature_indices, np.int32), c(gd.feature_value, np.float32),
+                           c(gd.label, np.int32), c(gd.split, np.int32))
+        d.params.num_nodes, d.params.input_dim, d.params.output_dim = gd.num_nodes, gd.input_dim, gd.output_dim
+        return d
+
+    @classmethod
+    def synth(cls, preset, scale=1.0, seed=0):
+        d = cls()
+        if not d.L.gcnh_data_synth(d.h, preset.encode(), float(scale), int(seed), C.byref(d.params)):
+            raise RuntimeError(f"synthetic preset {preset!r} failed")
+        return d
+
+    def sizes(self):
+        s = (C.c_int64 * 7)()
+        self.L.gcnh_data_sizes(self.h, s)
+        keys = ("num_nodes", "graph_nnz", "feature_nnz", "n_label", "n_split", "max_degree", "feature_rows")
+        return dict(zip(keys, [int(v) for v in s]))
+
+    def arrays(self):
+        s = self.sizes()
+
+        def view(ptr, n, dt):
+            return np.ctypeslib.as_array(ptr, shape=(n,)).view(dt) if n else np.zeros(0, dt)
+        L, h = self.L, self.h
+        return dict(graph_indptr=view(L.gcnh_data_graph_indptr(h), s["num_nodes"] + 1, np.int32),
+                    graph_indices=view(L.gcnh_data_graph_indices(h), s["graph_nnz"], np.int32),
+                    feature_indptr=view(L.gcnh_data_feature_indptr(h), s["feature_rows"] + 1, np.int32),
+                    feature_indices=view(L.gcnh_data_feature_indices(h), s["feature_nnz"], np.int32),
+                    feature_value=view(L.gcnh_data_feature_value(h), s["feature_nnz"], np.float32),
+                    label=view(L.gcnh_data_label(h), s["n_label"], np.int32),
+                    split=view(L.gcnh_data_split(h), s["n_split"], np.int32))
+
+    def close(self):
+        if self.h:
+            self.L.gcnh_data_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Engine:
+    """GCN (gcn.h:24-44) on one GPU."""
+
+    def __init__(self, data: Data, hidden_dim=16, dropout=0.5, lr=0.01, weight_decay=5e-4, epochs=100, early_stopping=0,
+                 seed=1, plan=PLAN_AUTO, device=0):
+        self.L, self.data = load(), data
+        p = Params(data.params.num_nodes, data.params.input_dim, hidden_dim, data.params.output_dim, dropout, lr,
+                   weight_decay, epochs, early_stopping)
+        self.params = p
+        self.h = self.L.gcnh_engine_create(C.byref(p), data.h, seed, plan, device)
+
+    @property
+    def plan(self):
+        return self.L.gcnh_engine_plan(self.h)
+
+    def train_epoch(self):
+        a, b = C.c_float(), C.c_float()
+        self.L.gcnh_engine_train_epoch(self.h, C.byref(a), C.byref(b))
+        return a.value, b.value
+
+    def eval(self, split):
+        a, b = C.c_float(), C.c_float()
+        self.L.gcnh_engine_eval(self.h, split, C.byref(a), C.byref(b))
+        return a.value, b.value
+
+    def last_counts(self):
+        a, b = C.c_int(), C.c_int()
+        self.L.gcnh_engine_last_counts(self.h, C.byref(a), C.byref(b))
+        return a.value, b.value
+
+    def run(self):
+        return self.L.gcnh_engine_run(self.h, 0)
+
+    def set_input_host(self, ptr):
+        self.L.gcnh_engine_set_input_host(self.h, ptr)
+
+    def var(self, idx, grad=False):
+        out = np.zeros(self.L.gcnh_engine_var_size(self.h, idx), np.float32)
+        if len(out):
+            self.L.gcnh_engine_get_var(self.h, idx, int(grad), out)
+        return out
+
+    def close(self):
+        if self.h:
+            self.L.gcnh_engine_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def timers():
+    L = load()
+    out = {}
+    for t in range(L.gcnh_timer_count()):
+        calls = L.gcnh_timer_calls(t)
+        if calls:
+            out[L.gcnh_timer_name(t).decode()] = (L.gcnh_timer_total(t), calls)
+    return out

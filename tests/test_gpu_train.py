@@ -1,0 +1,181 @@
+"""End-to-end parity of the training loop (GCN::train_epoch / eval, reference src/seq/gcn.cpp:107-128)
+through the C face of the host layer, against the CPU checker on the same arrays and the same seed.
+
+Contract (BASELINE.json north_star): integer work bit-exact; per-epoch loss within 1e-4 relative with
+dropout off or a shared RNG stream; final test accuracy within 0.2 points.  The engine reproduces the
+reference's xorshift128+ stream on the device, so dropout ON is checked too."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+LOSS_RTOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def host():
+    from cuda_gcn_b200 import abi, host_api
+    abi.require_device(0)
+    host_api.load()
+    return host_api
+
+
+@pytest.fixture(scope="module")
+def chk():
+    from oracle.checker import best_checker
+    return best_checker()
+
+
+def graph_data(d):
+    from oracle.checker import GraphData
+    a = d.arrays()
+    return GraphData(a["graph_indptr"], a["graph_indices"], a["feature_indptr"], a["feature_indices"], a["feature_value"],
+                     a["label"], a["split"], input_dim=d.params.input_dim, output_dim=d.params.output_dim)
+
+
+def run_pair(host, chk, d, plan, dropout, epochs, hidden=16, seed=7):
+    gd = graph_data(d)
+    ref = chk.gcn(gd, hidden_dim=hidden, dropout=dropout, epochs=epochs, seed=seed)
+    eng = host.Engine(d, hidden_dim=hidden, dropout=dropout, epochs=epochs, seed=seed, plan=plan)
+    # identical initial weights: same seed -> same glibc rand() -> same xorshift128+ -> same Glorot draws
+    assert (eng.var(2).view(np.uint32) == ref.var(2).view(np.uint32)).all()
+    assert (eng.var(5).view(np.uint32) == ref.var(5).view(np.uint32)).all()
+    n_split = {s: int(((gd.split == s) & (gd.label >= 0)).sum()) for s in (1, 2, 3)}
+    worst = 0.0
+    for e in range(epochs):
+        want = (*ref.train_epoch(), *ref.eval(2))
+        tl, ta = eng.train_epoch()
+        cnt_t, wrong_t = eng.last_counts()
+        vl, va = eng.eval(2)
+        cnt_v, wrong_v = eng.last_counts()
+        assert cnt_t == n_split[1] and cnt_v == n_split[2]                       # integer work: exact
+        for got, w in ((tl, want[0]), (vl, want[2])):
+            rel = abs(got - w) / max(abs(w), 1e-12)
+            worst = max(worst, rel)
+            assert rel <= LOSS_RTOL, f"epoch {e}: loss {got} vs {w} (rel {rel:.2e})"
+        # accuracies are ratios of integer counts: allow a flip only for rows whose logit margin is at rounding level
+        assert abs(round(ta * cnt_t) - round(want[1] * cnt_t)) <= max(1, cnt_t // 2000), (e, ta, want[1])
+        assert abs(round(va * cnt_v) - round(want[3] * cnt_v)) <= max(1, cnt_v // 2000), (e, va, want[3])
+    test_ref, test_eng = ref.eval(3), eng.eval(3)
+    assert abs(test_eng[0] - test_ref[0]) <= LOSS_RTOL * abs(test_ref[0])
+    assert abs(test_eng[1] - test_ref[1]) <= 0.002                               # 0.2 points
+    return ref, eng, worst
+
+
+@pytest.mark.parametrize("preset,scale", [("cora", 1.0), ("citeseer", 1.0), ("pubmed", 1.0)])
+@pytest.mark.parametrize("plan", ["modules", "fused"])
+@pytest.mark.parametrize("dropout", [0.0, 0.5])
+def test_small_shapes(host, chk, preset, scale, plan, dropout):
+    d = host.Data.synth(preset, scale)
+    plan_id = host.PLAN_MODULES if plan == "modules" else host.PLAN_FUSED
+    ref, eng, worst = run_pair(host, chk, d, plan_id, dropout, epochs=12)
+    assert eng.plan == plan_id
+    # weights after 12 Adam steps
+    for idx in (2, 5):
+        w, g = ref.var(idx), eng.var(idx)
+        assert np.abs(w - g).max() <= 2e-4 * np.abs(w).max(), idx
+    # final logits (eval pass): the fused plan recomputes them from (A_hat*H1)*W2
+    lw, lg = ref.var(6), eng.var(6)
+    # the reference shifts labelled rows by their max in place (module.cpp:140); compare shift-invariantly
+    c = d.params.output_dim
+    lw, lg = lw.reshape(-1, c), lg.reshape(-1, c)
+    lw, lg = lw - lw.max(1, keepdims=True), lg - lg.max(1, keepdims=True)
+    assert np.abs(lw - lg).max() <= 2e-4 * max(np.abs(lw).max(), 1.0)
+    ref.close(); eng.close()
+
+
+def test_modules_plan_intermediates(host, chk):
+    """Every Variable of gcn.cpp:21-53 after one training epoch, data and grad, modules plan vs checker
+    (dropout ON: the masks come from the same stream, so even the dropped positions agree)."""
+    d = host.Data.synth("cora", 1.0)
+    gd = graph_data(d)
+    ref = chk.gcn(gd, dropout=0.5, epochs=1, seed=3)
+    eng = host.Engine(d, dropout=0.5, epochs=1, seed=3, plan=host.PLAN_MODULES)
+    ref.train_epoch(); eng.train_epoch()
+    for idx in range(7):
+        for grad in (False, True):
+            if idx == 0 and grad:
+                continue
+            w, g = ref.var(idx, grad), eng.var(idx, grad)
+            assert w.shape == g.shape
+            if idx in (2, 5) and not grad:
+                continue        # weights after the step are compared below
+            scale = max(np.abs(w).max(), 1e-20)
+            assert np.abs(w - g).max() <= 5e-5 * scale, (idx, grad, np.abs(w - g).max(), scale)
+            if idx in (0, 3) and not grad:
+                assert ((w == 0) == (g == 0)).mean() > 0.9999          # same dropout / ReLU pattern
+    for idx in (2, 5):
+        w, g = ref.var(idx), eng.var(idx)
+        assert np.abs(w - g).max() <= 1e-5 * np.abs(w).max()
+    ref.close(); eng.close()
+
+
+def test_fused_equals_modules(host):
+    """The two plans are the same computation: identical counts, losses within fp32 rounding."""
+    d = host.Data.synth("pubmed", 0.5)
+    a = host.Engine(d, dropout=0.5, seed=11, plan=host.PLAN_MODULES)
+    b = host.Engine(d, dropout=0.5, seed=11, plan=host.PLAN_FUSED)
+    for _ in range(8):
+        ra, rb = a.train_epoch(), b.train_epoch()
+        assert abs(ra[0] - rb[0]) <= 2e-5 * abs(ra[0]) and a.last_counts()[0] == b.last_counts()[0]
+        ra, rb = a.eval(2), b.eval(2)
+        assert abs(ra[0] - rb[0]) <= 2e-5 * abs(ra[0])
+        assert abs(a.last_counts()[1] - b.last_counts()[1]) <= 1
+    a.close(); b.close()
+
+
+def test_directed_graph_falls_back_to_modules(host, chk):
+    """A non-symmetric adjacency: the reference still computes A_hat*grad (not the transpose) in backward
+    (module.cpp:103-119); the auto plan must pick the modules chain and match it."""
+    from tests.util import make_dataset
+    gd = make_dataset(n=600, f=80, c=5, n_undirected=3000, nnz_per_row=8, seed=4, symmetric=False)
+    d = host.Data.from_arrays(gd)
+    ref = chk.gcn(gd, dropout=0.0, epochs=5, seed=2)
+    eng = host.Engine(d, dropout=0.0, epochs=5, seed=2, plan=host.PLAN_AUTO)
+    assert eng.plan == host.PLAN_MODULES
+    for _ in range(5):
+        w, g = ref.train_epoch(), eng.train_epoch()
+        assert abs(w[0] - g[0]) <= LOSS_RTOL * abs(w[0])
+    ref.close(); eng.close()
+
+
+def test_reddit_shape_scaled(host, chk):
+    """Reddit-shape features (dense 602 -> hidden 16 -> 41 classes) on a 2% graph: the dense fast paths,
+    power-law rows, dropout on; 3 epochs against the checker."""
+    d = host.Data.synth("reddit", 0.02)
+    assert d.params.input_dim == 602 and d.params.output_dim == 41
+    ref, eng, worst = run_pair(host, chk, d, host.PLAN_FUSED, 0.5, epochs=3)
+    ref.close(); eng.close()
+
+
+def test_cli_matches_gcn_seq_output_format(host, tmp_path):
+    """`./gcn-cuda <dataset>` on text files prints the reference's lines (gcn.cpp:139,152,157; main.cpp:39)."""
+    import os, re, subprocess
+    from pathlib import Path
+    from tests.util import make_dataset, write_text_dataset
+    root = Path(__file__).resolve().parent.parent
+    gd = make_dataset(n=300, f=50, c=4, n_undirected=900, nnz_per_row=6, seed=9)
+    write_text_dataset(tmp_path, "toy", gd)
+    env = dict(os.environ, GCN_SEED="5")
+    out = subprocess.run([str(root / "gcn-cuda"), "toy", "-", "-", "16", "-", "0.5", "0.01", "5e-4", "7"], cwd=tmp_path, env=env,
+                         capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    lines = out.stdout.strip().splitlines()
+    assert lines[:4] == ["Parse Graph Succeeded.", "Parse Node Succeeded.", "Parse Split Succeeded.", "RUNNING ON GPU"]
+    ep = [l for l in lines if l.startswith("epoch=")]
+    assert len(ep) == 7
+    assert all(re.fullmatch(r"epoch=\d+ train_loss=\d+\.\d{5} train_acc=\d\.\d{5} val_loss=\d+\.\d{5} val_acc=\d\.\d{5} time=\d+\.\d{5}", l) for l in ep)
+    assert re.fullmatch(r"total training time=\d+\.\d{5}", lines[-2])
+    assert re.fullmatch(r"test_loss=\d+\.\d{5} test_acc=\d\.\d{5} time=\d+\.\d{5}", lines[-1])
+    # the same run through gcn-seq (the unmodified reference binary), when it travelled with the snapshot
+    seq = root / "oracle" / "_ref" / "gcn-seq"
+    shim = root / "oracle" / "_ref" / "libtimeshim.so"
+    if seq.exists() and shim.exists():
+        ref = subprocess.run([str(seq), "toy"], cwd=tmp_path, env=dict(os.environ, LD_PRELOAD=str(shim), GCN_SEED="5"),
+                             capture_output=True, text=True, timeout=120)
+        assert ref.returncode == 0
+        ref_ep = [l for l in ref.stdout.splitlines() if l.startswith("epoch=")][:7]
+        for a, b in zip(ep, ref_ep):       # default CLI run: dropout 0.5 from the shared stream
+            fa = [float(x) for x in re.findall(r"=(\d+\.\d+)", a)][:4]
+            fb = [float(x) for x in re.findall(r"=(\d+\.\d+)", b)][:4]
+            assert abs(fa[0] - fb[0]) <= 2e-4 * fb[0] + 1e-5 and abs(fa[2] - fb[2]) <= 2e-4 * fb[2] + 1e-5, (a, b)

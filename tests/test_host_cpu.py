@@ -1,0 +1,99 @@
+"""CPU-only tests of the C++ host layer (libgcnhost.so): parser against the reference's golden outputs,
+the synthetic generator's invariants, exported symbols.  No GPU calls."""
+import re
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+GOLD = ROOT / "tests" / "golden"
+
+
+@pytest.fixture(scope="module")
+def host():
+    subprocess.run(["make", "-C", str(ROOT / "cuda_gcn_b200" / "host")], check=True, capture_output=True)
+    from cuda_gcn_b200 import host_api
+    host_api.load()
+    return host_api
+
+
+def test_libgcnhost_exports_header(host):
+    text = (ROOT / "include" / "gcn_host.h").read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    names = sorted(set(re.findall(r"\b(gcnh_[a-z0-9_]+)\s*\(", text)))
+    assert len(names) >= 30
+    L = host.load()
+    for n in names:
+        assert hasattr(L, n), n
+    assert sorted(host.SIGNATURES) == names
+
+
+@pytest.mark.parametrize("name", ["toy", "quirks"])
+def test_parser_matches_reference_golden(host, name):
+    """Bit-exact integer work: CSR, feature index, labels, split and the derived dims equal what the
+    UNMODIFIED reference parser produced for the same files (tools/make_golden.py)."""
+    want = np.load(GOLD / f"parser_{name}.npz")
+    d = host.Data.parse(GOLD / "parser_toy" / "data", name)
+    assert d is not None
+    got = d.arrays()
+    assert (d.params.num_nodes, d.params.input_dim, d.params.output_dim) == tuple(int(want[k]) for k in ("num_nodes", "input_dim", "output_dim"))
+    for k in ("graph_indptr", "graph_indices", "feature_indptr", "feature_indices", "label", "split"):
+        assert got[k].shape == want[k].shape and (got[k] == want[k]).all(), k
+    assert (got["feature_value"].view(np.uint32) == want["feature_value"].view(np.uint32)).all()
+
+
+def test_parser_matches_oracle_on_generated_text(host, oracle, tmp_path):
+    from tests.util import make_dataset, write_text_dataset
+    gd = make_dataset(n=400, f=90, c=6, n_undirected=1500, nnz_per_row=9, seed=5, isolated=7, empty_rows=3)
+    root = write_text_dataset(tmp_path, "gen", gd, float_fmt="%.9g")
+    d = host.Data.parse(root, "gen")
+    got, want = d.arrays(), oracle.parse(tmp_path, "gen")
+    for k in ("graph_indptr", "graph_indices", "feature_indptr", "feature_indices", "label", "split"):
+        assert (got[k] == want[k]).all(), k
+    assert (got["feature_value"].view(np.uint32) == want["feature_value"].view(np.uint32)).all()
+    # and the round trip reproduces the generator's arrays
+    assert (got["graph_indices"] == gd.graph_indices).all() and (got["feature_value"] == gd.feature_value).all()
+
+
+def test_parser_failures(host, tmp_path):
+    assert host.Data.parse(tmp_path, "missing") is None                 # "Cannot read input" path (main.cpp:33-36)
+    data = tmp_path / "data"
+    data.mkdir()
+    (data / "bad.graph").write_text("1\n0\n")
+    (data / "bad.split").write_text("1\n2\n")
+    (data / "bad.svmlight").write_text("0 3:1.0\n1.0 2:1\n")           # label '1.0': the reference reads garbage here
+    assert host.Data.parse(data, "bad") is None
+    (data / "bad.svmlight").write_text("0 3:1.0\n1 2:1\n")
+    (data / "bad.split").write_text("1\n\n")                            # std::stoi throws on a blank line
+    assert host.Data.parse(data, "bad") is None
+
+
+@pytest.mark.parametrize("preset,scale", [("cora", 1.0), ("citeseer", 1.0), ("pubmed", 0.25), ("reddit", 0.002)])
+def test_synth_invariants(host, preset, scale):
+    d = host.Data.synth(preset, scale)
+    a, s = d.arrays(), d.sizes()
+    n = s["num_nodes"]
+    ip, ix = a["graph_indptr"], a["graph_indices"]
+    assert ip[0] == 0 and ip[-1] == len(ix) and (np.diff(ip) >= 1).all()
+    assert (ix[ip[:-1]] == np.arange(n)).all()                          # the parser's implicit self loop first
+    assert ix.min() >= 0 and ix.max() < n
+    rows = np.repeat(np.arange(n), np.diff(ip))
+    nb = np.ones(len(ix), bool); nb[ip[:-1]] = False
+    keys = rows[nb].astype(np.int64) * n + ix[nb]
+    assert (np.diff(keys) > 0).all()                                    # sorted, unique, no explicit self edge
+    assert (rows[nb] != ix[nb]).all()
+    rev = ix[nb].astype(np.int64) * n + rows[nb]
+    assert np.array_equal(np.sort(rev), keys)                           # symmetric
+    assert s["max_degree"] <= 46340
+    assert len(a["label"]) == n and len(a["split"]) == n
+    assert a["label"].min() == 0 and a["label"].max() == d.params.output_dim - 1
+    assert a["feature_indices"].max() == d.params.input_dim - 1
+    fp = a["feature_indptr"]
+    assert fp[-1] == len(a["feature_value"]) and np.isfinite(a["feature_value"]).all()
+    if preset == "reddit":
+        assert (np.diff(fp) == d.params.input_dim).all()                # dense rows
+    # deterministic
+    d2 = host.Data.synth(preset, scale)
+    assert np.array_equal(d2.arrays()["graph_indices"], ix) and np.array_equal(d2.arrays()["feature_value"], a["feature_value"])
