@@ -111,17 +111,24 @@ def test_modules_plan_intermediates(host, chk):
 
 
 def test_fused_equals_modules(host):
-    """The two plans are the same computation: identical counts, losses within fp32 rounding."""
+    """The two plans are the same computation: identical counts, losses within fp32 rounding.  The RNG
+    stream is process-wide (rand.cpp:5), so the engines run one after the other from the same seed."""
     d = host.Data.synth("pubmed", 0.5)
-    a = host.Engine(d, dropout=0.5, seed=11, plan=host.PLAN_MODULES)
-    b = host.Engine(d, dropout=0.5, seed=11, plan=host.PLAN_FUSED)
-    for _ in range(8):
-        ra, rb = a.train_epoch(), b.train_epoch()
-        assert abs(ra[0] - rb[0]) <= 2e-5 * abs(ra[0]) and a.last_counts()[0] == b.last_counts()[0]
-        ra, rb = a.eval(2), b.eval(2)
-        assert abs(ra[0] - rb[0]) <= 2e-5 * abs(ra[0])
-        assert abs(a.last_counts()[1] - b.last_counts()[1]) <= 1
-    a.close(); b.close()
+    rows = {}
+    for plan in (host.PLAN_MODULES, host.PLAN_FUSED):
+        e = host.Engine(d, dropout=0.5, seed=11, plan=plan)
+        out = []
+        for _ in range(8):
+            tl, _ = e.train_epoch()
+            ct = e.last_counts()
+            vl, _ = e.eval(2)
+            out.append((tl, vl, ct, e.last_counts()))
+        rows[plan] = out
+        e.close()
+    for ra, rb in zip(rows[host.PLAN_MODULES], rows[host.PLAN_FUSED]):
+        assert abs(ra[0] - rb[0]) <= 2e-5 * abs(ra[0]) and abs(ra[1] - rb[1]) <= 2e-5 * abs(ra[1])
+        assert ra[2][0] == rb[2][0] and ra[3][0] == rb[3][0]
+        assert abs(ra[2][1] - rb[2][1]) <= 1 and abs(ra[3][1] - rb[3][1]) <= 1
 
 
 def test_directed_graph_falls_back_to_modules(host, chk):
