@@ -1,0 +1,267 @@
+#!/usr/bin/env python
+"""bench.py — full-batch GCN train epochs/s on the Reddit-shape synthetic graph (BASELINE.json metric).
+
+One "step" = one epoch as the reference times it: train_epoch() + eval(2) (gcn.cpp:136-140), dropout on.
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--scale S]
+N > 1 is launched by torchrun, one rank per GPU (RANK/LOCAL_RANK/WORLD_SIZE from the environment).
+
+Prints ONE JSON line: value = epochs/s with everything resident in HBM; e2e = the same step driven
+through the C face with the feature matrix re-uploaded from pinned host memory every step (what
+CUDAGCN::set_input does each pass, cuda_gcn.cu:81-83) and the scalars read back; roofline = the GraphSum
+gather kernel (algorithmic bytes / CUDA-event duration) against the measured HBM copy peak; cpu_baseline
+= the unmodified reference CPU engine (oracle/_ref) on a bounded sample of the same workload.
+
+`--impl reference` times the reference's own CPU implementation (oracle/_ref/libgcnref.so, built from
+/root/reference by oracle/Makefile; the C restatement when that library is absent) on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "full-batch GCN train epochs/s (Reddit-shape)"
+UNIT = "epochs/s"
+
+
+def measured_peak():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.samples, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for s in self.samples:
+            f = [x.strip() for x in s.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def graph_data(d):
+    from oracle.checker import GraphData
+    a = d.arrays()
+    return GraphData(a["graph_indptr"], a["graph_indices"], a["feature_indptr"], a["feature_indices"], a["feature_value"],
+                     a["label"], a["split"], input_dim=d.params.input_dim, output_dim=d.params.output_dim)
+
+
+def cpu_reference_run(scale, steps, warmup, full_nnz, host_api):
+    """The reference CPU engine on a reddit-shape sample (scale of the node and edge counts); returns
+    (epochs/s extrapolated to the full workload by the edge ratio, description)."""
+    from oracle.checker import best_checker
+    chk = best_checker()
+    d = host_api.Data.synth("reddit", scale)
+    s = d.sizes()
+    ref = chk.gcn(graph_data(d), dropout=0.5, epochs=steps + warmup, seed=1)
+    for _ in range(warmup):
+        ref.train_epoch(); ref.eval(2)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        ref.train_epoch(); ref.eval(2)
+    dt = (time.perf_counter() - t0) / max(steps, 1)
+    ref.close()
+    ratio = s["graph_nnz"] / full_nnz
+    value = (1.0 / dt) * ratio
+    sample = (f"{steps} epoch(s) of train_epoch+eval(2) by the {chk.name} CPU engine on reddit-shape at scale {scale:g} "
+              f"({s['num_nodes']} nodes, {s['graph_nnz']} graph nnz, dense 602 features): {dt:.2f} s/epoch, scaled to the full "
+              f"workload by the graph-nnz ratio {ratio:.4f}")
+    return value, dt, chk.name, sample
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from cuda_gcn_b200 import host_api
+    # the full workload's size without generating it: the generator is deterministic, sizes recorded by a full run
+    full_nnz = FULL_REDDIT_NNZ
+    scale = args.ref_scale
+    value, dt, kind, sample = cpu_reference_run(scale, args.steps, args.warmup, full_nnz, host_api)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 / value, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": {"workload": "reddit-shape 2-layer GCN, hidden 16, dropout 0.5", "scale": 1.0},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "reference" if kind == "reference" else "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# graph nnz (incl. self loops) of synth preset "reddit" at scale 1, seed 4 (deterministic generator)
+FULL_REDDIT_NNZ = 114_862_869
+
+
+def run_ours(args):
+    from cuda_gcn_b200 import abi, host_api
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        raise SystemExit("bench.py: the multi-GPU row-partitioned engine is not wired into bench.py yet")
+    abi.require_device(local)
+    K = abi.k
+    t_gen = time.perf_counter()
+    data = host_api.Data.synth("reddit", args.scale)
+    sizes = data.sizes()
+    t_gen = time.perf_counter() - t_gen
+    N, nnzA, nnzX = sizes["num_nodes"], sizes["graph_nnz"], sizes["feature_nnz"]
+    H, C, F = 16, data.params.output_dim, data.params.input_dim
+    eng = host_api.Engine(data, hidden_dim=H, dropout=0.5, seed=1, plan=host_api.PLAN_FUSED, device=local)
+    L = host_api.load()
+
+    def step():
+        eng.train_epoch()
+        return eng.eval(2)
+
+    for _ in range(args.warmup):
+        step()
+    # ---- timed region: K epochs, everything resident
+    L.gcnh_timer_reset()
+    L.gcnh_timer_enable_gpu(1)
+    clocks = ClockSampler(local)
+    clocks.start()
+    ev0, ev1 = abi.Event(), abi.Event()
+    launches0 = abi.load().gcnk_launch_count()
+    K.gcnk_device_sync()
+    ev0.record()
+    for _ in range(args.steps):
+        last = step()
+    ev1.record()
+    ev1.sync()
+    K.gcnk_device_sync()
+    ms = ev0.elapsed_ms(ev1)
+    launches = abi.load().gcnk_launch_count() - launches0
+    clk = clocks.stop()
+    timers = host_api.timers()
+    L.gcnh_timer_enable_gpu(0)
+    value = args.steps / (ms * 1e-3)
+
+    # ---- roofline of the dominant kernel: the GraphSum gather (each timer interval brackets 2 gather launches)
+    peak, peak_src = measured_peak()
+    g_total = timers.get("graphsum_fw", (0, 0))[0] + timers.get("graphsum_bw", (0, 0))[0]
+    g_launches = 2 * (timers.get("graphsum_fw", (0, 0))[1] + timers.get("graphsum_bw", (0, 0))[1])
+    b_min = 4 * nnzA + 4 * (N + 1) + 8 * N * H
+    t_launch = g_total / max(g_launches, 1)
+    achieved = b_min / t_launch / 1e9 if t_launch > 0 else 0.0
+    traffic = None
+    tp = ROOT / "profiles" / "graphsum_traffic.json"
+    if tp.exists():
+        try:
+            traffic = json.loads(tp.read_text()).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "kernel": "gather_kernel (GraphSum, dim 16)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": b_min,
+                "avg_launch_us": t_launch * 1e6, "launches_timed": g_launches,
+                "share_of_step": g_total / (ms * 1e-3) if ms > 0 else None}
+    breakdown = {k: {"ms_per_step": v[0] * 1e3 / args.steps, "calls_per_step": v[1] / args.steps} for k, v in timers.items()
+                 if k not in ("train", "test")}
+
+    # ---- e2e: the same step through the C face with the feature matrix uploaded from pinned host memory each step
+    pinned = L.gcnh_alloc_pinned(nnzX)
+    host_view = np.ctypeslib.as_array((abi.C.c_float * nnzX).from_address(pinned))
+    host_view[:] = data.arrays()["feature_value"]
+    e2e_steps = max(3, min(args.steps, 10))
+    eng.set_input_host(pinned); step()                      # warm the copy path
+    K.gcnk_device_sync()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        eng.set_input_host(pinned)                          # H2D of nnz(X) floats on the engine's stream
+        step()                                              # train_epoch + eval(2); each reads its scalars back (D2H)
+    K.gcnk_device_sync()
+    e2e_dt = (time.perf_counter() - t0) / e2e_steps
+    L.gcnh_free_pinned(pinned)
+    e2e = {"value": 1.0 / e2e_dt, "unit": UNIT, "h2d_bytes_per_step": int(nnzX * 4), "d2h_bytes_per_step": 2 * 16 + 4,
+           "steps": e2e_steps, "api": "gcnh_engine_set_input_host + gcnh_engine_train_epoch + gcnh_engine_eval (include/gcn_host.h)"}
+    eng.close()
+
+    # ---- CPU baseline: the reference engine on a bounded sample (rank 0, N=1)
+    cpu = None
+    if not args.no_cpu_baseline:
+        v, dt, kind, sample = cpu_reference_run(args.cpu_scale, 1, 0, nnzA, host_api)
+        cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": "reference" if kind == "reference" else "port", "sample": sample}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": "reddit-shape 2-layer GCN (train_epoch + eval per step), hidden 16, dropout 0.5, fused plan",
+                       "scale": args.scale, "nodes": N, "graph_nnz": nnzA, "feature_nnz": nnzX, "features": F, "classes": C,
+                       "max_degree": sizes["max_degree"], "l2": "inputs larger than L2 each step (X 561 MB + CSR indices 459 MB streamed per pass); no flush",
+                       "parallelism": "1 GPU", "generate_s": round(t_gen, 1)},
+            "e2e": e2e, "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "cpu_baseline": cpu,
+            "breakdown": breakdown, "final": {"val_loss": last[0], "val_acc": last[1]}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--scale", type=float, default=1.0, help="fraction of the Reddit-shape node/edge counts (1.0 = the BASELINE config)")
+    ap.add_argument("--cpu-scale", type=float, default=0.125, help="sample of the workload the CPU baseline runs")
+    ap.add_argument("--ref-scale", type=float, default=0.03125, help="--impl reference: sample of the workload per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

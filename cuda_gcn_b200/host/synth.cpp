@@ -41,7 +41,7 @@ bool synth_preset(const char *name, double scale, SynthSpec *out) {
     if (!strcmp(name, "cora"))          s = {2708, 5278, 1.2, 1433, 18, 7, 140.0 / 2708, 500.0 / 2708, 1000.0 / 2708, 1, 0};
     else if (!strcmp(name, "citeseer")) s = {3327, 4552, 1.2, 3703, 32, 6, 120.0 / 3327, 500.0 / 3327, 1000.0 / 3327, 2, 48};
     else if (!strcmp(name, "pubmed"))   s = {19717, 44324, 1.3, 500, 50, 3, 60.0 / 19717, 500.0 / 19717, 1000.0 / 19717, 3, 0};
-    else if (!strcmp(name, "reddit"))   s = {232965, 57307946, 1.55, 602, 0, 41, 0.66, 0.10, 0.24, 4, 0};
+    else if (!strcmp(name, "reddit"))   s = {232965, 58450000, 1.55, 602, 0, 41, 0.66, 0.10, 0.24, 4, 0};
     else if (!strcmp(name, "products")) s = {2449029, 61859140, 1.45, 100, 0, 47, 0.08, 0.02, 0.90, 5, 0};
     else return false;
     if (scale > 0 && scale != 1.0) {
