@@ -19,6 +19,15 @@
 
 using namespace gcnk;
 
+namespace gcnk {   // feature_tc.cu: tensor-core (3xTF32) dense path at p == 16
+bool dense_tc_supported(int n, int p);
+int dense_fw16_tc(const float *x, const float *w, float *c, int m, int n, const uint32_t *bits, int64_t nnz, float scale,
+                  const float *row_scale, cudaStream_t st);
+size_t dense_bw16_tc_parts(int m);
+int dense_bw16_tc(const float *x, const float *g, float *b_grad, float *partials, int m, int n, const uint32_t *bits, int64_t nnz,
+                  float scale, cudaStream_t st);
+}
+
 struct gcnk_spmat {
     const int *indptr = nullptr, *indices = nullptr;
     int m = 0, n = 0;
@@ -352,6 +361,11 @@ int gcnk_spmm_fw(const gcnk_spmat *sp, const float *values, const float *b, floa
     GCNK_REQUIRE(sp && values && b && c && p > 0, "bad arguments");
     cudaStream_t st = S(stream);
     if (sp->m == 0) return GCNK_OK;
+    if (sp->dense && dense_tc_supported(sp->n, p) && reinterpret_cast<uintptr_t>(c) % 8 == 0 &&
+        reinterpret_cast<uintptr_t>(values) % 8 == 0) {
+        const int rc = dense_fw16_tc(values, b, c, sp->m, sp->n, drop_bits, sp->nnz, drop_scale, row_scale, st);
+        if (rc != GCNK_EUNSUPPORTED) return rc;
+    }
     const size_t smem = sizeof(float) * (size_t)sp->n * DF_WSTRIDE;
     if (sp->dense && p == DF_P && smem <= 200 * 1024 && reinterpret_cast<uintptr_t>(c) % 8 == 0) {
         static bool attr_set[64] = {false};
@@ -382,6 +396,17 @@ int gcnk_spmm_bw(gcnk_spmat *sp, const float *values, const float *c_grad, float
     GCNK_REQUIRE(sp && values && c_grad && b_grad && p > 0, "bad arguments");
     cudaStream_t st = S(stream);
     const int n = sp->n;
+    if (sp->dense && dense_tc_supported(n, p) && sp->m > 0 && reinterpret_cast<uintptr_t>(values) % 8 == 0) {
+        const size_t need = dense_bw16_tc_parts(sp->m) * (size_t)n * p;
+        if (sp->partial_elems < need) {
+            GCNK_CUDA(cudaStreamSynchronize(st));
+            if (sp->partials) GCNK_CUDA(cudaFree(sp->partials));
+            sp->partials = nullptr; sp->partial_elems = 0;
+            GCNK_CUDA(cudaMalloc(&sp->partials, sizeof(float) * need));
+            sp->partial_elems = need;
+        }
+        return dense_bw16_tc(values, c_grad, b_grad, sp->partials, sp->m, n, drop_bits, sp->nnz, drop_scale, st);
+    }
     if (sp->dense && p == DB_P && n <= 256 * DB_FPT && sp->m > 0) {
         const int ctas = std::max(1, std::min(sm_count() * 2, (sp->m + 63) / 64));
         const int rows_per_cta = (sp->m + ctas - 1) / ctas;

@@ -127,6 +127,142 @@ __global__ void __launch_bounds__(L2_THREADS) layer2_kernel(const float *__restr
     }
 }
 
+
+// ---------------------------------------------------------------------------- h == 16 fast path ----
+// Same contract as layer2_kernel, specialised for hidden width 16 (the reference default, gcn.cpp:10) and
+// c <= 32*CPL classes.  Everything per-row lives in registers: the P row (16 floats, loaded by every lane
+// from the same address = one broadcast transaction), the lane's logits, and the lane's slice of the
+// W2-gradient accumulator dw[CPL][16] (the generic kernel does 16*c shared-memory read-modify-writes per
+// labelled row instead).  Unlabelled rows cost one split[] read (plus zeroing their G row when training).
+template <int CPL>
+__global__ void __launch_bounds__(L2_THREADS) layer2_h16_kernel(const float *__restrict__ P, const float *__restrict__ W2,
+                                                                 const int *__restrict__ split, const int *__restrict__ label,
+                                                                 int current_split, int n, int c, int training, float count_f,
+                                                                 const float *__restrict__ dinv, float *__restrict__ G,
+                                                                 float *__restrict__ logits_out, L2Partial *__restrict__ ce_partials,
+                                                                 float *__restrict__ dw_partials) {
+    constexpr int H = 16;
+    extern __shared__ __align__(16) float smem[];
+    float *sW = smem;                               // [16][c]
+    float *sDl = sW + H * c;                        // [warps][c]
+    float *sAcc = sDl + L2_WARPS * c;               // [warps][16*c]  (training only; used once, at the end)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < H * c; i += L2_THREADS) sW[i] = W2[i];
+    __syncthreads();
+    float *dl = sDl + warp * c;
+    float dw[CPL][H];
+#pragma unroll
+    for (int t = 0; t < CPL; t++)
+#pragma unroll
+        for (int k = 0; k < H; k++) dw[t][k] = 0.f;
+
+    float loss = 0.f;
+    int count = 0, wrong = 0;
+    const int half = lane >> 4, kk = lane & 15, c_half = (c + 1) >> 1;
+    const int total_warps = gridDim.x * L2_WARPS;
+    for (int s = blockIdx.x * L2_WARPS + warp; s < n; s += total_warps) {
+        const int truth = split[s] == current_split ? label[s] : -1;          // set_truth (gcn.cpp:78-81); warp-uniform
+        if (truth < 0 && !logits_out) {
+            if (training && lane < H) G[(size_t)s * H + lane] = 0.f;          // unlabelled rows carry no gradient
+            continue;
+        }
+        float p[H];
+        {
+            const float4 *pr = reinterpret_cast<const float4 *>(P + (size_t)s * H);
+            const float4 a = __ldg(pr), b = __ldg(pr + 1), d = __ldg(pr + 2), e = __ldg(pr + 3);
+            p[0] = a.x; p[1] = a.y; p[2] = a.z; p[3] = a.w; p[4] = b.x; p[5] = b.y; p[6] = b.z; p[7] = b.w;
+            p[8] = d.x; p[9] = d.y; p[10] = d.z; p[11] = d.w; p[12] = e.x; p[13] = e.y; p[14] = e.z; p[15] = e.w;
+        }
+        float lg[CPL];
+#pragma unroll
+        for (int t = 0; t < CPL; t++) {
+            const int cls = lane + 32 * t;
+            float v = 0.f;
+            if (cls < c) {
+#pragma unroll
+                for (int k = 0; k < H; k++) v = fmaf(p[k], sW[k * c + cls], v);
+                if (logits_out) logits_out[(size_t)s * c + cls] = v;
+            }
+            lg[t] = v;
+        }
+        if (truth < 0) {
+            if (training && lane < H) G[(size_t)s * H + lane] = 0.f;
+            continue;
+        }
+        float mx = -1e30f;
+#pragma unroll
+        for (int t = 0; t < CPL; t++) if (lane + 32 * t < c) mx = fmaxf(mx, lg[t]);
+        mx = warp_max(mx);
+        float ex[CPL], sum = 0.f;
+#pragma unroll
+        for (int t = 0; t < CPL; t++) {
+            ex[t] = (lane + 32 * t < c) ? expf(lg[t] - mx) : 0.f;
+            sum += ex[t];
+        }
+        sum = warp_sum(sum);
+        float tl = 0.f;
+#pragma unroll
+        for (int t = 0; t < CPL; t++) if (t == truth / 32) tl = lg[t];
+        tl = __shfl_sync(FULL, tl, truth % 32);
+        bool w = false;
+#pragma unroll
+        for (int t = 0; t < CPL; t++) w |= (lane + 32 * t < c) && lg[t] > tl;        // strict (gcn.cpp:88-93)
+        w = __any_sync(FULL, w);
+        count++;
+        wrong += w;
+        loss += logf(sum) - (tl - mx);
+        if (training) {
+#pragma unroll
+            for (int t = 0; t < CPL; t++) {
+                const int cls = lane + 32 * t;
+                if (cls < c) {
+                    float g = ex[t] / sum;
+                    if (cls == truth) g -= 1.0f;
+                    g = g / count_f;                                                 // grad /= count (module.cpp:156-158)
+                    dl[cls] = g;
+#pragma unroll
+                    for (int k = 0; k < H; k++) dw[t][k] = fmaf(p[k], g, dw[t][k]);  // dW2 += P^T dlogits
+                }
+            }
+            __syncwarp();
+            // dlogits * W2^T: the two half-warps each take half of the classes for hidden unit kk
+            float v = 0.f;
+            const int c_lo = half * c_half, c_hi = min(c, c_lo + c_half);
+            for (int cls = c_lo; cls < c_hi; cls++) v = fmaf(dl[cls], sW[kk * c + cls], v);
+            v += __shfl_xor_sync(FULL, v, 16);
+            if (lane < H) G[(size_t)s * H + lane] = dinv[s] * v;
+            __syncwarp();
+        }
+    }
+
+    __shared__ float s_loss[L2_WARPS];
+    __shared__ int s_count[L2_WARPS], s_wrong[L2_WARPS];
+    if (lane == 0) { s_loss[warp] = loss; s_count[warp] = count; s_wrong[warp] = wrong; }
+    if (training) {
+#pragma unroll
+        for (int t = 0; t < CPL; t++) {
+            const int cls = lane + 32 * t;
+            if (cls < c)
+#pragma unroll
+                for (int k = 0; k < H; k++) sAcc[warp * H * c + k * c + cls] = dw[t][k];
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float l = 0.f; int cn = 0, wr = 0;
+        for (int w = 0; w < L2_WARPS; w++) { l += s_loss[w]; cn += s_count[w]; wr += s_wrong[w]; }
+        ce_partials[blockIdx.x] = L2Partial{l, cn, wr, 0};
+    }
+    if (training) {
+        float *out = dw_partials + (size_t)blockIdx.x * H * c;
+        for (int i = threadIdx.x; i < H * c; i += L2_THREADS) {
+            float v = 0.f;
+            for (int w = 0; w < L2_WARPS; w++) v += sAcc[w * H * c + i];
+            out[i] = v;
+        }
+    }
+}
+
 // block 0 also produces the scalar result; every block reduces a slice of dW2 over the CTA partials
 __global__ void __launch_bounds__(256) layer2_finish_kernel(const L2Partial *__restrict__ ce_partials, const float *__restrict__ dw_partials,
                                                              int parts, int hc, int training, float *__restrict__ W2_grad,
@@ -161,7 +297,7 @@ __global__ void __launch_bounds__(256) layer2_finish_kernel(const L2Partial *__r
     }
 }
 
-int l2_grid(int n) { return std::max(1, std::min(sm_count() * 2, (n + L2_WARPS - 1) / L2_WARPS)); }
+int l2_grid(int n) { return std::max(1, std::min(sm_count() * 4, (n + L2_WARPS - 1) / L2_WARPS)); }
 
 }  // namespace
 
@@ -185,13 +321,24 @@ int gcnk_layer2_fused(const float *P, const float *W2, const int *split, const i
     float *dw_partials = reinterpret_cast<float *>(ce_partials + grid);
     const size_t smem = sizeof(float) * ((size_t)h * c + L2_WARPS * (size_t)c + L2_WARPS * (size_t)h +
                                          (training ? L2_WARPS * (size_t)h * c : 0));
-    if (smem > 48 * 1024) {
-        GCNK_REQUIRE(smem <= 200 * 1024, "h*c too large for shared memory");
-        GCNK_CUDA(cudaFuncSetAttribute(layer2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (h == 16 && c <= 64) {
+        // registers hold the per-lane slice of dW2; the shared accumulator is only the end-of-kernel exchange
+        if (c <= 32)
+            layer2_h16_kernel<1><<<grid, L2_THREADS, smem, st>>>(P, W2, split, label, current_split, n, c, training, (float)count,
+                                                                d_dinv, G_scaled, logits_out, ce_partials, dw_partials);
+        else
+            layer2_h16_kernel<2><<<grid, L2_THREADS, smem, st>>>(P, W2, split, label, current_split, n, c, training, (float)count,
+                                                                d_dinv, G_scaled, logits_out, ce_partials, dw_partials);
+        GCNK_LAUNCHED();
+    } else {
+        if (smem > 48 * 1024) {
+            GCNK_REQUIRE(smem <= 200 * 1024, "h*c too large for shared memory");
+            GCNK_CUDA(cudaFuncSetAttribute(layer2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        }
+        layer2_kernel<<<grid, L2_THREADS, smem, st>>>(P, W2, split, label, current_split, n, h, c, training, (float)count, d_dinv,
+                                                      G_scaled, logits_out, ce_partials, dw_partials);
+        GCNK_LAUNCHED();
     }
-    layer2_kernel<<<grid, L2_THREADS, smem, st>>>(P, W2, split, label, current_split, n, h, c, training, (float)count, d_dinv,
-                                                  G_scaled, logits_out, ce_partials, dw_partials);
-    GCNK_LAUNCHED();
     const int hc = h * c;
     layer2_finish_kernel<<<training ? (hc + 255) / 256 : 1, 256, 0, st>>>(ce_partials, dw_partials, grid, hc, training, W2_grad, d_result);
     GCNK_LAUNCHED();
