@@ -57,6 +57,7 @@ SIGNATURES = {
     "gcnk_event_elapsed_ms": (i32, [vp, vp, C.POINTER(f32)]),
     "gcnk_flush_l2": (i32, [vp]),
     "gcnk_graph_create": (i32, [C.POINTER(vp), vp, vp, i32, i64, i32, vp, vp]),
+    "gcnk_graph_create_view": (i32, [C.POINTER(vp), vp, vp, vp, vp]),
     "gcnk_graph_destroy": (i32, [vp]),
     "gcnk_graph_dinv": (i32, [vp, C.POINTER(vp)]),
     "gcnk_graph_stats": (i32, [vp, C.POINTER(i32), C.POINTER(i64), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]),
@@ -71,6 +72,7 @@ SIGNATURES = {
     "gcnk_spmat_is_dense": (i32, [vp, C.POINTER(i32)]),
     "gcnk_spmm_fw": (i32, [vp, vp, vp, vp, i32, vp, f32, vp, vp]),
     "gcnk_spmm_bw": (i32, [vp, vp, vp, vp, i32, vp, f32, vp]),
+    "gcnk_dense_transform": (i32, [vp, i32, i32, vp, vp, i32, vp, f32, vp, i32, vp]),
     "gcnk_matmul_fw": (i32, [vp, vp, vp, i32, i32, i32, vp]),
     "gcnk_matmul_bw_a": (i32, [vp, vp, vp, i32, i32, i32, vp]),
     "gcnk_matmul_bw_b": (i32, [vp, vp, vp, i32, i32, i32, vp, sz, vp]),

@@ -22,7 +22,7 @@ using namespace gcnk;
 namespace gcnk {   // feature_tc.cu: tensor-core (3xTF32) dense path at p == 16
 bool dense_tc_supported(int n, int p);
 int dense_fw16_tc(const float *x, const float *w, float *c, int m, int n, const uint32_t *bits, int64_t nnz, float scale,
-                  const float *row_scale, cudaStream_t st);
+                  const float *row_scale, int relu, cudaStream_t st);
 size_t dense_bw16_tc_parts(int m);
 int dense_bw16_tc(const float *x, const float *g, float *b_grad, float *partials, int m, int n, const uint32_t *bits, int64_t nnz,
                   float scale, cudaStream_t st);
@@ -363,7 +363,7 @@ int gcnk_spmm_fw(const gcnk_spmat *sp, const float *values, const float *b, floa
     if (sp->m == 0) return GCNK_OK;
     if (sp->dense && dense_tc_supported(sp->n, p) && reinterpret_cast<uintptr_t>(c) % 8 == 0 &&
         reinterpret_cast<uintptr_t>(values) % 8 == 0) {
-        const int rc = dense_fw16_tc(values, b, c, sp->m, sp->n, drop_bits, sp->nnz, drop_scale, row_scale, st);
+        const int rc = dense_fw16_tc(values, b, c, sp->m, sp->n, drop_bits, sp->nnz, drop_scale, row_scale, 0, st);
         if (rc != GCNK_EUNSUPPORTED) return rc;
     }
     const size_t smem = sizeof(float) * (size_t)sp->n * DF_WSTRIDE;
@@ -389,6 +389,17 @@ int gcnk_spmm_fw(const gcnk_spmat *sp, const float *values, const float *b, floa
     if (p <= 8) return launch_fw_generic<8>(sp, values, b, c, p, drop_bits, drop_scale, row_scale, st);
     if (p <= 16) return launch_fw_generic<16>(sp, values, b, c, p, drop_bits, drop_scale, row_scale, st);
     return launch_fw_generic<32>(sp, values, b, c, p, drop_bits, drop_scale, row_scale, st);
+}
+
+int gcnk_dense_transform(const float *x, int m, int n, const float *w, float *c, int p, const uint32_t *drop_bits,
+                         float drop_scale, const float *row_scale, int relu, gcnk_stream_t stream) {
+    GCNK_REQUIRE(x && w && c && m >= 0 && n > 0 && p > 0, "bad arguments");
+    if (m == 0) return GCNK_OK;
+    if (!dense_tc_supported(n, p) || reinterpret_cast<uintptr_t>(c) % 8 || reinterpret_cast<uintptr_t>(x) % 8) {
+        set_error("gcnk_dense_transform: needs p == 16, an even n >= 8 and 8-byte aligned buffers (got n=%d p=%d)", n, p);
+        return GCNK_EUNSUPPORTED;
+    }
+    return dense_fw16_tc(x, w, c, m, n, drop_bits, (int64_t)m * n, drop_scale, row_scale, relu, S(stream));
 }
 
 int gcnk_spmm_bw(gcnk_spmat *sp, const float *values, const float *c_grad, float *b_grad, int p, const uint32_t *drop_bits,

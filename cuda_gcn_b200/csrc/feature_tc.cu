@@ -21,6 +21,8 @@
 // denotes as long as A and B agree, so logical k = t and k = t+4 are mapped to the ADJACENT physical
 // columns 2t and 2t+1.  One 64-bit load then feeds two fragment registers, and a quad of lanes reads
 // 32 contiguous bytes.
+#include <algorithm>
+
 #include "common.cuh"
 
 using namespace gcnk;
@@ -44,12 +46,22 @@ __device__ __forceinline__ void mma(float (&d)[4], uint32_t a0, uint32_t a1, uin
                  : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
                  : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
-// 3xTF32: small cross terms first, the dominant term last
-__device__ __forceinline__ void mma3(float (&d)[4], const uint32_t (&ab)[4], const uint32_t (&as)[4], uint32_t bb0, uint32_t bb1,
+// 3xTF32 with one accumulator per split term: the three MMAs of a k-step are independent, so the tensor
+// pipe is not serialised on one accumulation chain; the terms are added once, in the epilogue
+// (cross terms first, then the dominant one).
+struct Acc3 {
+    float bb[4], bs[4], sb[4];
+    __device__ __forceinline__ void zero() {
+#pragma unroll
+        for (int e = 0; e < 4; e++) bb[e] = bs[e] = sb[e] = 0.f;
+    }
+    __device__ __forceinline__ float total(int e) const { return (sb[e] + bs[e]) + bb[e]; }
+};
+__device__ __forceinline__ void mma3(Acc3 &d, const uint32_t (&ab)[4], const uint32_t (&as)[4], uint32_t bb0, uint32_t bb1,
                                      uint32_t bs0, uint32_t bs1) {
-    mma(d, as[0], as[1], as[2], as[3], bb0, bb1);
-    mma(d, ab[0], ab[1], ab[2], ab[3], bs0, bs1);
-    mma(d, ab[0], ab[1], ab[2], ab[3], bb0, bb1);
+    mma(d.sb, as[0], as[1], as[2], as[3], bb0, bb1);
+    mma(d.bs, ab[0], ab[1], ab[2], ab[3], bs0, bs1);
+    mma(d.bb, ab[0], ab[1], ab[2], ab[3], bb0, bb1);
 }
 __device__ __forceinline__ float2 ld_stream_f2(const float *p) {
     float2 v;
@@ -92,7 +104,7 @@ __device__ __forceinline__ void fw_load(FwBatch &q, const float *xa, const float
 __global__ void __launch_bounds__(THREADS, 2) dense_fw16_tc_kernel(const float *__restrict__ x, const float *__restrict__ w,
                                                                     float *__restrict__ c, int m, int n,
                                                                     const uint32_t *__restrict__ bits, int64_t bit_words,
-                                                                    float scale, const float *__restrict__ row_scale) {
+                                                                    float scale, const float *__restrict__ row_scale, int relu) {
     extern __shared__ float4 sfrag[];       // [KS][32] big, then [KS][32] small
     const int KS = (n + 7) / 8;
     for (int i = threadIdx.x; i < KS * 32; i += THREADS) {
@@ -115,7 +127,8 @@ __global__ void __launch_bounds__(THREADS, 2) dense_fw16_tc_kernel(const float *
         const bool va = ra < m, vb = rb < m;
         const float *xa = x + (size_t)(va ? ra : 0) * n + 2 * t, *xb = x + (size_t)(vb ? rb : 0) * n + 2 * t;
         const int64_t pa = (int64_t)ra * n, pb = (int64_t)rb * n;
-        float acc0[4] = {0.f, 0.f, 0.f, 0.f}, acc1[4] = {0.f, 0.f, 0.f, 0.f};
+        Acc3 acc0, acc1;
+        acc0.zero(); acc1.zero();
         FwBatch cur, nxt;
         fw_load(cur, xa, xb, va, vb, 2 * t, n, bits, bit_words, pa, pb);
 #pragma unroll 1
@@ -148,17 +161,23 @@ __global__ void __launch_bounds__(THREADS, 2) dense_fw16_tc_kernel(const float *
             cur = nxt;
         }
         // D fragment: c0,c1 = (row g, cols 2t,2t+1), c2,c3 = (row g+8, same cols) of each 8-wide n-tile
+        float r0[4] = {acc0.total(0), acc0.total(1), acc0.total(2), acc0.total(3)};
+        float r1[4] = {acc1.total(0), acc1.total(1), acc1.total(2), acc1.total(3)};
+        if (relu) {                                                  // x > 0 ? x : 0 (module.cpp:179-181)
+#pragma unroll
+            for (int e = 0; e < 4; e++) { r0[e] = r0[e] > 0.f ? r0[e] : 0.f; r1[e] = r1[e] > 0.f ? r1[e] : 0.f; }
+        }
         if (va) {
             const float rs = row_scale ? row_scale[ra] : 1.f;
             float *o = c + (size_t)ra * P + 2 * t;
-            *reinterpret_cast<float2 *>(o) = make_float2(rs * acc0[0], rs * acc0[1]);
-            *reinterpret_cast<float2 *>(o + 8) = make_float2(rs * acc1[0], rs * acc1[1]);
+            *reinterpret_cast<float2 *>(o) = make_float2(rs * r0[0], rs * r0[1]);
+            *reinterpret_cast<float2 *>(o + 8) = make_float2(rs * r1[0], rs * r1[1]);
         }
         if (vb) {
             const float rs = row_scale ? row_scale[rb] : 1.f;
             float *o = c + (size_t)rb * P + 2 * t;
-            *reinterpret_cast<float2 *>(o) = make_float2(rs * acc0[2], rs * acc0[3]);
-            *reinterpret_cast<float2 *>(o + 8) = make_float2(rs * acc1[2], rs * acc1[3]);
+            *reinterpret_cast<float2 *>(o) = make_float2(rs * r0[2], rs * r0[3]);
+            *reinterpret_cast<float2 *>(o + 8) = make_float2(rs * r1[2], rs * r1[3]);
         }
     }
 }
@@ -177,13 +196,15 @@ __global__ void __launch_bounds__(THREADS, 2) dense_bw16_tc_kernel(const float *
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, t = lane & 3, g = lane >> 2;
     const int r_lo = blockIdx.x * rows_per_cta, r_hi = min(m, r_lo + rows_per_cta);
     const int f_band = BAND * warp + blockIdx.y * (BAND * WARPS);
-    float acc[BW_PAIRS][2][4];
+    // two accumulators per n-tile: the dominant big*big chain and the two small cross terms (10 tiles x 2 chains
+    // = 20 independent MMA chains per warp; three per tile would not fit the register budget)
+    float acc[BW_PAIRS][2][4], acs[BW_PAIRS][2][4];
 #pragma unroll
     for (int p = 0; p < BW_PAIRS; p++)
 #pragma unroll
         for (int h = 0; h < 2; h++)
 #pragma unroll
-            for (int e = 0; e < 4; e++) acc[p][h][e] = 0.f;
+            for (int e = 0; e < 4; e++) acc[p][h][e] = acs[p][h][e] = 0.f;
 
     if (f_band < n) {
 #pragma unroll 1
@@ -228,8 +249,12 @@ __global__ void __launch_bounds__(THREADS, 2) dense_bw16_tc_kernel(const float *
                 split(f1.x, bb[1], bs[1]);      //              b1 (logical k t+4 = row 2t+1)
                 split(f0.y, bb[2], bs[2]);      // odd n-tile
                 split(f1.y, bb[3], bs[3]);
-                mma3(acc[p][0], ab, as, bb[0], bb[1], bs[0], bs[1]);
-                mma3(acc[p][1], ab, as, bb[2], bb[3], bs[2], bs[3]);
+                mma(acs[p][0], as[0], as[1], as[2], as[3], bb[0], bb[1]);
+                mma(acs[p][1], as[0], as[1], as[2], as[3], bb[2], bb[3]);
+                mma(acc[p][0], ab[0], ab[1], ab[2], ab[3], bb[0], bb[1]);
+                mma(acc[p][1], ab[0], ab[1], ab[2], ab[3], bb[2], bb[3]);
+                mma(acs[p][0], ab[0], ab[1], ab[2], ab[3], bs[0], bs[1]);
+                mma(acs[p][1], ab[0], ab[1], ab[2], ab[3], bs[2], bs[3]);
             }
         }
     }
@@ -241,8 +266,8 @@ __global__ void __launch_bounds__(THREADS, 2) dense_bw16_tc_kernel(const float *
 #pragma unroll
         for (int h = 0; h < 2; h++) {
             const int fa = f_band + 16 * p + 2 * (2 * t) + h, fb = f_band + 16 * p + 2 * (2 * t + 1) + h;
-            if (fa < n) { out[(size_t)fa * P + g] = acc[p][h][0]; out[(size_t)fa * P + g + 8] = acc[p][h][2]; }
-            if (fb < n) { out[(size_t)fb * P + g] = acc[p][h][1]; out[(size_t)fb * P + g + 8] = acc[p][h][3]; }
+            if (fa < n) { out[(size_t)fa * P + g] = acs[p][h][0] + acc[p][h][0]; out[(size_t)fa * P + g + 8] = acs[p][h][2] + acc[p][h][2]; }
+            if (fb < n) { out[(size_t)fb * P + g] = acs[p][h][1] + acc[p][h][1]; out[(size_t)fb * P + g + 8] = acs[p][h][3] + acc[p][h][3]; }
         }
 }
 
@@ -271,7 +296,7 @@ namespace gcnk {
 bool dense_tc_supported(int n, int p) { return p == gcnk_tc::P && n % 2 == 0 && n >= 8; }
 
 int dense_fw16_tc(const float *x, const float *w, float *c, int m, int n, const uint32_t *bits, int64_t nnz, float scale,
-                  const float *row_scale, cudaStream_t st) {
+                  const float *row_scale, int relu, cudaStream_t st) {
     using namespace gcnk_tc;
     const int KS = (n + 7) / 8;
     const size_t smem = sizeof(float4) * 2 * (size_t)KS * 32;
@@ -285,7 +310,7 @@ int dense_fw16_tc(const float *x, const float *w, float *c, int m, int n, const 
     }
     const int n_tiles = (m + 15) / 16;
     const int grid = std::max(1, std::min(sm_count() * 2, (n_tiles + WARPS - 1) / WARPS));
-    dense_fw16_tc_kernel<<<grid, THREADS, smem, st>>>(x, w, c, m, n, bits, (nnz + 31) / 32, scale, row_scale);
+    dense_fw16_tc_kernel<<<grid, THREADS, smem, st>>>(x, w, c, m, n, bits, (nnz + 31) / 32, scale, row_scale, relu);
     GCNK_LAUNCHED();
     return GCNK_OK;
 }

@@ -33,6 +33,10 @@ struct gcnk_graph {
     int *bin_ptr = nullptr, *bin_rows = nullptr; int n_bins = 0;   // n_bins is a multiple of WARPS
     int max_degree = 0, symmetric = 0;
     float *scratch = nullptr; size_t scratch_elems = 0;            // pre-scaled copy for gcnk_graphsum
+    // views (gcnk_graph_create_view): dinv/dinv_cols are borrowed from `base`; a column-filtered view owns its CSR
+    const gcnk_graph *base = nullptr;
+    int *own_indptr = nullptr, *own_indices = nullptr;
+    int n_rows_scheduled = 0;
 };
 
 namespace {
@@ -332,6 +336,54 @@ __global__ void scale_rows_kernel(const float *__restrict__ dinv, const float *_
     for (; i < total; i += stride) out[i] = dinv[i / dim] * in[i];
 }
 
+// Static schedule over the given rows: heavy rows -> one CTA each; the rest -> LPT bins, one warp per bin.
+int build_schedule(gcnk_graph *g, const std::vector<int> &indptr, const std::vector<int> &rows, cudaStream_t st) {
+    std::vector<int> heavy, light;
+    int max_deg = 0;
+    for (int i : rows) {
+        const int deg = indptr[i + 1] - indptr[i];
+        max_deg = std::max(max_deg, deg);
+        (deg > HEAVY_DEGREE ? heavy : light).push_back(i);
+    }
+    g->max_degree = max_deg;
+    g->n_rows_scheduled = (int)rows.size();
+    auto deg_of = [&](int r) { return indptr[r + 1] - indptr[r]; };
+    std::stable_sort(heavy.begin(), heavy.end(), [&](int x, int y) { return deg_of(x) > deg_of(y); });
+    std::stable_sort(light.begin(), light.end(), [&](int x, int y) { return deg_of(x) > deg_of(y); });
+    // 4 bins per resident warp slot keeps the tail short without shrinking bins below a few rows
+    int n_bins = sm_count() * 64 * 4;
+    n_bins = std::min<int64_t>(n_bins, std::max<int64_t>((int64_t)light.size(), 1));
+    n_bins = (n_bins + WARPS - 1) / WARPS * WARPS;
+    if (light.empty()) n_bins = 0;
+    std::vector<std::vector<int>> bins(n_bins);
+    {
+        typedef std::pair<int64_t, int> Item;   // (load, bin) — min-heap on load, ties by bin id => deterministic
+        std::priority_queue<Item, std::vector<Item>, std::greater<Item>> heap;
+        for (int b = 0; b < n_bins; b++) heap.push({0, b});
+        for (int r : light) {
+            Item it = heap.top(); heap.pop();
+            bins[it.second].push_back(r);
+            it.first += deg_of(r) + ROW_OVERHEAD;
+            heap.push(it);
+        }
+    }
+    std::vector<int> bin_ptr(n_bins + 1, 0), bin_rows;
+    bin_rows.reserve(light.size());
+    for (int b = 0; b < n_bins; b++) {
+        bin_rows.insert(bin_rows.end(), bins[b].begin(), bins[b].end());
+        bin_ptr[b + 1] = (int)bin_rows.size();
+    }
+    g->n_heavy = (int)heavy.size(); g->n_bins = n_bins;
+    GCNK_CUDA(cudaMalloc(&g->heavy_rows, sizeof(int) * std::max<size_t>(heavy.size(), 1)));
+    GCNK_CUDA(cudaMalloc(&g->bin_ptr, sizeof(int) * (n_bins + 1)));
+    GCNK_CUDA(cudaMalloc(&g->bin_rows, sizeof(int) * std::max<size_t>(bin_rows.size(), 1)));
+    if (!heavy.empty()) GCNK_CUDA(cudaMemcpyAsync(g->heavy_rows, heavy.data(), sizeof(int) * heavy.size(), cudaMemcpyHostToDevice, st));
+    GCNK_CUDA(cudaMemcpyAsync(g->bin_ptr, bin_ptr.data(), sizeof(int) * bin_ptr.size(), cudaMemcpyHostToDevice, st));
+    if (!bin_rows.empty()) GCNK_CUDA(cudaMemcpyAsync(g->bin_rows, bin_rows.data(), sizeof(int) * bin_rows.size(), cudaMemcpyHostToDevice, st));
+    GCNK_CUDA(cudaStreamSynchronize(st));
+    return GCNK_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -359,58 +411,84 @@ int gcnk_graph_create(gcnk_graph **out, const int *d_indptr, const int *d_indice
     g->symmetric = (n_cols == n) && !asym;
     if (n && indptr[n] != nnz) { delete g; set_error("gcnk_graph_create: indptr[n]=%d != nnz=%lld", indptr[n], (long long)nnz); return GCNK_EINVAL; }
 
-    // ---- static schedule: heavy rows -> one CTA each; the rest -> LPT bins, one warp per bin ----
-    std::vector<int> heavy, light;
-    int max_deg = 0;
-    for (int i = 0; i < n; i++) {
-        const int deg = indptr[i + 1] - indptr[i];
-        max_deg = std::max(max_deg, deg);
-        (deg > HEAVY_DEGREE ? heavy : light).push_back(i);
-    }
-    g->max_degree = max_deg;
-    auto deg_of = [&](int r) { return indptr[r + 1] - indptr[r]; };
-    std::stable_sort(heavy.begin(), heavy.end(), [&](int x, int y) { return deg_of(x) > deg_of(y); });
-    std::stable_sort(light.begin(), light.end(), [&](int x, int y) { return deg_of(x) > deg_of(y); });
-    // 4 bins per resident warp slot keeps the tail short without shrinking bins below a few rows
-    int n_bins = sm_count() * 64 * 4;
-    n_bins = std::min<int64_t>(n_bins, std::max<int64_t>((int64_t)light.size(), 1));
-    n_bins = (n_bins + WARPS - 1) / WARPS * WARPS;
-    if (light.empty()) n_bins = 0;
-    std::vector<std::vector<int>> bins(n_bins);
+    std::vector<int> rows((size_t)n);
+    for (int i = 0; i < n; i++) rows[i] = i;
     {
-        typedef std::pair<int64_t, int> Item;   // (load, bin) — min-heap on load, ties by bin id => deterministic
-        std::priority_queue<Item, std::vector<Item>, std::greater<Item>> heap;
-        for (int b = 0; b < n_bins; b++) heap.push({0, b});
-        for (int r : light) {
-            Item it = heap.top(); heap.pop();
-            bins[it.second].push_back(r);
-            it.first += deg_of(r) + ROW_OVERHEAD;
-            heap.push(it);
-        }
+        const int rc = build_schedule(g, indptr, rows, st);
+        if (rc) { delete g; return rc; }
     }
-    // bin b was filled in decreasing-load order for increasing b at the start, so low block ids
-    // (launched first) carry the heaviest rows
-    std::vector<int> bin_ptr(n_bins + 1, 0), bin_rows;
-    bin_rows.reserve(light.size());
-    for (int b = 0; b < n_bins; b++) {
-        bin_rows.insert(bin_rows.end(), bins[b].begin(), bins[b].end());
-        bin_ptr[b + 1] = (int)bin_rows.size();
+    *out = g;
+    return GCNK_OK;
+}
+
+
+int gcnk_graph_create_view(gcnk_graph **out, const gcnk_graph *base, const int *d_row_keep, const int *d_col_keep,
+                           gcnk_stream_t stream) {
+    GCNK_REQUIRE(out && base && !base->base, "needs a base graph (not itself a view)");
+    cudaStream_t st = S(stream);
+    const int n = base->n;
+    gcnk_graph *g = new gcnk_graph;
+    *g = *base;
+    g->base = base;
+    g->heavy_rows = nullptr; g->bin_ptr = nullptr; g->bin_rows = nullptr; g->scratch = nullptr; g->scratch_elems = 0;
+    g->own_indptr = nullptr; g->own_indices = nullptr;
+
+    std::vector<int> indptr((size_t)n + 1, 0), row_keep, col_keep;
+    GCNK_CUDA(cudaMemcpyAsync(indptr.data(), base->indptr, sizeof(int) * ((size_t)n + 1), cudaMemcpyDeviceToHost, st));
+    if (d_row_keep) {
+        row_keep.resize((size_t)n);
+        GCNK_CUDA(cudaMemcpyAsync(row_keep.data(), d_row_keep, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, st));
     }
-    g->n_heavy = (int)heavy.size(); g->n_bins = n_bins;
-    GCNK_CUDA(cudaMalloc(&g->heavy_rows, sizeof(int) * std::max<size_t>(heavy.size(), 1)));
-    GCNK_CUDA(cudaMalloc(&g->bin_ptr, sizeof(int) * (n_bins + 1)));
-    GCNK_CUDA(cudaMalloc(&g->bin_rows, sizeof(int) * std::max<size_t>(bin_rows.size(), 1)));
-    if (!heavy.empty()) GCNK_CUDA(cudaMemcpyAsync(g->heavy_rows, heavy.data(), sizeof(int) * heavy.size(), cudaMemcpyHostToDevice, st));
-    GCNK_CUDA(cudaMemcpyAsync(g->bin_ptr, bin_ptr.data(), sizeof(int) * bin_ptr.size(), cudaMemcpyHostToDevice, st));
-    if (!bin_rows.empty()) GCNK_CUDA(cudaMemcpyAsync(g->bin_rows, bin_rows.data(), sizeof(int) * bin_rows.size(), cudaMemcpyHostToDevice, st));
+    std::vector<int> indices;
+    if (d_col_keep) {
+        col_keep.resize((size_t)base->n_cols);
+        indices.resize((size_t)base->nnz);
+        GCNK_CUDA(cudaMemcpyAsync(col_keep.data(), d_col_keep, sizeof(int) * (size_t)base->n_cols, cudaMemcpyDeviceToHost, st));
+        if (base->nnz) GCNK_CUDA(cudaMemcpyAsync(indices.data(), base->indices, sizeof(int) * (size_t)base->nnz, cudaMemcpyDeviceToHost, st));
+    }
     GCNK_CUDA(cudaStreamSynchronize(st));
+
+    if (d_col_keep) {
+        // drop the entries whose column is filtered out; row order and the order inside a row are preserved
+        std::vector<int> new_ptr((size_t)n + 1, 0);
+        size_t w = 0;
+        for (int i = 0; i < n; i++) {
+            for (int e = indptr[i]; e < indptr[i + 1]; e++) {
+                const int d = indices[e];
+                if (d >= 0 && d < base->n_cols && col_keep[d]) indices[w++] = d;
+            }
+            new_ptr[i + 1] = (int)w;
+        }
+        indices.resize(w);
+        indptr.swap(new_ptr);
+        GCNK_CUDA(cudaMalloc(&g->own_indptr, sizeof(int) * ((size_t)n + 1)));
+        GCNK_CUDA(cudaMalloc(&g->own_indices, sizeof(int) * std::max<size_t>(w, 1)));
+        GCNK_CUDA(cudaMemcpyAsync(g->own_indptr, indptr.data(), sizeof(int) * ((size_t)n + 1), cudaMemcpyHostToDevice, st));
+        if (w) GCNK_CUDA(cudaMemcpyAsync(g->own_indices, indices.data(), sizeof(int) * w, cudaMemcpyHostToDevice, st));
+        GCNK_CUDA(cudaStreamSynchronize(st));
+        g->indptr = g->own_indptr; g->indices = g->own_indices; g->nnz = (int64_t)w;
+        g->symmetric = 0;
+    }
+    std::vector<int> rows;
+    rows.reserve((size_t)n);
+    for (int i = 0; i < n; i++)
+        if (!d_row_keep || row_keep[i]) rows.push_back(i);
+    if (d_row_keep) {
+        int64_t nnz_rows = 0;
+        for (int i : rows) nnz_rows += indptr[i + 1] - indptr[i];
+        g->nnz = nnz_rows;                    // entries this view's launches actually touch
+    }
+    const int rc = build_schedule(g, indptr, rows, st);
+    if (rc) { gcnk_graph_destroy(g); return rc; }
     *out = g;
     return GCNK_OK;
 }
 
 int gcnk_graph_destroy(gcnk_graph *g) {
     if (!g) return GCNK_OK;
-    cudaFree(g->dinv); cudaFree(g->heavy_rows); cudaFree(g->bin_ptr); cudaFree(g->bin_rows); cudaFree(g->scratch);
+    if (!g->base) cudaFree(g->dinv);
+    cudaFree(g->heavy_rows); cudaFree(g->bin_ptr); cudaFree(g->bin_rows); cudaFree(g->scratch);
+    cudaFree(g->own_indptr); cudaFree(g->own_indices);
     delete g;
     return GCNK_OK;
 }

@@ -26,7 +26,20 @@ struct GCN::Fused {
     gcnk_ce_result *d_result = nullptr, *h_result = nullptr;   // device / pinned host
     float *d_sumsq = nullptr, *h_sumsq = nullptr;
     float sumsq = 0;           // sum(W1^2) of the current weights
+    // Views of the graph for the passes that need only part of A_hat*x (splits are static, so these are built once):
+    //   rows[s]     only the labelled rows of split s are aggregated — the loss, the accuracy and the layer-2
+    //               gradients never look at the logits of any other row (module.cpp:130-133: truth < 0 rows are skipped)
+    //   cols_train  entries pointing at rows outside the training split dropped — their loss gradient is exactly zero
+    gcnk_graph *rows[4] = {nullptr, nullptr, nullptr, nullptr}, *cols_train = nullptr;
+    int *keep[4] = {nullptr, nullptr, nullptr, nullptr};
+    // AX = A_hat * X, computed once when X is dense: without input dropout (every eval pass)
+    // A_hat*(X*W1) = (A_hat*X)*W1 is one streaming pass and no gather
+    float *AX = nullptr;
+    bool ax_valid = false, use_views = true;
     ~Fused() {
+        for (gcnk_graph *g : {rows[1], rows[2], rows[3], cols_train}) if (g) gcnk_graph_destroy(g);
+        for (int *k : keep) if (k) gcnk_free(k);
+        if (AX) gcnk_free(AX);
         for (void *p : {(void *)xw_s, (void *)h1_s, (void *)P, (void *)G, (void *)Gm, (void *)dxw, (void *)keep0, (void *)keep1,
                         (void *)mask, (void *)ws, (void *)d_result, (void *)d_sumsq})
             if (p) gcnk_free(p);
@@ -152,7 +165,28 @@ void GCN::build(GCNPlan plan) {
     GCNK_CHECK(gcnk_memcpy_d2h(fz->h_sumsq, fz->d_sumsq, sizeof(float), nullptr));
     GCNK_CHECK(gcnk_stream_sync(nullptr));
     fz->sumsq = *fz->h_sumsq;
-    (void)data->feature_index.spmat(N, F);                // build the handle (dense detection) up front
+    gcnk_spmat *sp = data->feature_index.spmat(N, F);     // build the handle (dense detection) up front
+
+    const char *nv = getenv("GCN_NO_VIEWS"), *na = getenv("GCN_NO_AX");
+    fz->use_views = !(nv && *nv && strcmp(nv, "0"));
+    if (fz->use_views) {
+        gcnk_graph *g = data->graph.graph();
+        for (int s = 1; s <= 3; s++) {
+            std::vector<int> keep((size_t)N);
+            for (int i = 0; i < N; i++) keep[i] = data->split[i] == s && data->label[i] >= 0;
+            fz->keep[s] = upload(keep);
+            if (s < 3) GCNK_CHECK(gcnk_graph_create_view(&fz->rows[s], g, fz->keep[s], nullptr, nullptr));   // test split: on first use
+        }
+        GCNK_CHECK(gcnk_graph_create_view(&fz->cols_train, g, nullptr, fz->keep[1], nullptr));
+    }
+    int dense = 0;
+    GCNK_CHECK(gcnk_spmat_is_dense(sp, &dense));
+    if (dense && H == 16 && F % 2 == 0 && F <= 1024 && !(na && *na && strcmp(na, "0"))) {
+        GCNK_CHECK(gcnk_malloc((void **)&fz->AX, sizeof(float) * (size_t)N * F));
+        GCNK_CHECK(gcnk_graphsum(data->graph.graph(), d_feature_value, fz->AX, F, nullptr));
+        GCNK_CHECK(gcnk_stream_sync(nullptr));
+        fz->ax_valid = true;
+    }
 }
 
 GCN::~GCN() {
@@ -163,6 +197,7 @@ GCN::~GCN() {
 
 void GCN::set_input_from_host(const float *h_values) {
     GCNK_CHECK(gcnk_memcpy_h2d(d_feature_value, h_values, sizeof(float) * data->feature_index.indices.size(), nullptr));
+    if (fz) fz->ax_valid = false;       // A_hat*X was computed from the old values; eval falls back to the gather path
 }
 
 // ---------------------------------------------------------------------------- modules plan ----
@@ -207,30 +242,49 @@ std::pair<float, float> GCN::fused_pass(int current_split, bool training) {
     GCNK_CHECK(gcnk_graph_dinv(g, &dinv));
     Variable &W1 = variables[2], &W2 = variables[5];
 
-    // M0 Dropout + M1 SparseMatmul: the keep bits are drawn from the shared stream in element order and
-    // applied on read; the stored feature values are never modified, so no set_input() copy is needed
-    if (training) {
-        gpu_timer_begin(TMR_DROPOUT_FW);
-        if (drop) GCNK_CHECK(gcnk_dropout_mask(global_rng(), z.keep0, nnzX, p, nullptr));
-        else GCNK_CHECK(gcnk_rng_skip(global_rng(), (uint64_t)nnzX));     // the reference still consumes the draws
-        gpu_timer_end(TMR_DROPOUT_FW);
+    gcnk_graph *g_rows = g, *g_cols = g;
+    if (z.use_views) {
+        const int sidx = current_split >= 1 && current_split <= 3 ? current_split : 0;
+        if (sidx && !z.rows[sidx]) GCNK_CHECK(gcnk_graph_create_view(&z.rows[sidx], g, z.keep[sidx], nullptr, nullptr));
+        if (sidx) g_rows = z.rows[sidx];
+        g_cols = z.cols_train;
     }
-    gpu_timer_begin(TMR_SPMATMUL_FW);
-    GCNK_CHECK(gcnk_spmm_fw(sp, d_feature_value, W1.data, z.xw_s, H, drop ? z.keep0 : nullptr, scale, dinv, nullptr));
-    gpu_timer_end(TMR_SPMATMUL_FW);
+    auto gather_timer = [&](gcnk_graph *view) { return view == g ? TMR_GATHER_FULL : TMR_GATHER_PART; };
 
-    // M2 GraphSum + M3 ReLU + M4 Dropout in the gather's epilogue, then the layer-2 aggregation at width H
-    if (training) {
-        gpu_timer_begin(TMR_DROPOUT_FW);
-        if (drop) GCNK_CHECK(gcnk_dropout_mask(global_rng(), z.keep1, (int64_t)N * H, p, nullptr));
-        else GCNK_CHECK(gcnk_rng_skip(global_rng(), (uint64_t)N * H));
-        gpu_timer_end(TMR_DROPOUT_FW);
+    if (!training && z.ax_valid) {
+        // eval: A_hat*(X*W1) = (A_hat*X)*W1, ReLU and the pre-scale for the next gather in the epilogue
+        gpu_timer_begin(TMR_SPMATMUL_FW);
+        GCNK_CHECK(gcnk_dense_transform(z.AX, N, F, W1.data, z.h1_s, H, nullptr, 1.0f, dinv, 1, nullptr));
+        gpu_timer_end(TMR_SPMATMUL_FW);
+    } else {
+        // M0 Dropout + M1 SparseMatmul: the keep bits are drawn from the shared stream in element order and
+        // applied on read; the stored feature values are never modified, so no set_input() copy is needed
+        if (training) {
+            gpu_timer_begin(TMR_DROPOUT_FW);
+            if (drop) GCNK_CHECK(gcnk_dropout_mask(global_rng(), z.keep0, nnzX, p, nullptr));
+            else GCNK_CHECK(gcnk_rng_skip(global_rng(), (uint64_t)nnzX));     // the reference still consumes the draws
+            gpu_timer_end(TMR_DROPOUT_FW);
+        }
+        gpu_timer_begin(TMR_SPMATMUL_FW);
+        GCNK_CHECK(gcnk_spmm_fw(sp, d_feature_value, W1.data, z.xw_s, H, drop ? z.keep0 : nullptr, scale, dinv, nullptr));
+        gpu_timer_end(TMR_SPMATMUL_FW);
+
+        // M2 GraphSum + M3 ReLU + M4 Dropout in the gather's epilogue
+        if (training) {
+            gpu_timer_begin(TMR_DROPOUT_FW);
+            if (drop) GCNK_CHECK(gcnk_dropout_mask(global_rng(), z.keep1, (int64_t)N * H, p, nullptr));
+            else GCNK_CHECK(gcnk_rng_skip(global_rng(), (uint64_t)N * H));
+            gpu_timer_end(TMR_DROPOUT_FW);
+        }
+        gpu_timer_begin(TMR_GATHER_FULL);
+        GCNK_CHECK(gcnk_gather_relu_drop(g, z.xw_s, z.h1_s, drop ? z.keep1 : nullptr, training ? z.mask : nullptr,
+                                         training ? scale : 1.0f, H, nullptr));
+        gpu_timer_end(TMR_GATHER_FULL);
     }
-    gpu_timer_begin(TMR_GRAPHSUM_FW);
-    GCNK_CHECK(gcnk_gather_relu_drop(g, z.xw_s, z.h1_s, drop ? z.keep1 : nullptr, training ? z.mask : nullptr,
-                                     training ? scale : 1.0f, H, nullptr));
-    GCNK_CHECK(gcnk_gather_plain(g, z.h1_s, z.P, H, nullptr));
-    gpu_timer_end(TMR_GRAPHSUM_FW);
+    // the layer-2 aggregation at width H, only for the rows whose logits the loss looks at
+    gpu_timer_begin(gather_timer(g_rows));
+    GCNK_CHECK(gcnk_gather_plain(g_rows, z.h1_s, z.P, H, nullptr));
+    gpu_timer_end(gather_timer(g_rows));
 
     // M5 Matmul + M7 CrossEntropyLoss + get_accuracy (+ Matmul backward when training), row-local
     gpu_timer_begin(TMR_LOSS_FW);
@@ -243,10 +297,12 @@ std::pair<float, float> GCN::fused_pass(int current_split, bool training) {
     const float sumsq_before = z.sumsq;
     if (training) {
         // backward of M6/M5 is inside layer2; M4/M3/M2 backward = one masked gather + one plain gather
-        gpu_timer_begin(TMR_GRAPHSUM_BW);
-        GCNK_CHECK(gcnk_gather_mask(g, z.G, z.Gm, z.mask, scale, H, nullptr));
+        gpu_timer_begin(gather_timer(g_cols));
+        GCNK_CHECK(gcnk_gather_mask(g_cols, z.G, z.Gm, z.mask, scale, H, nullptr));
+        gpu_timer_end(gather_timer(g_cols));
+        gpu_timer_begin(TMR_GATHER_FULL);
         GCNK_CHECK(gcnk_gather_plain(g, z.Gm, z.dxw, H, nullptr));
-        gpu_timer_end(TMR_GRAPHSUM_BW);
+        gpu_timer_end(TMR_GATHER_FULL);
         gpu_timer_begin(TMR_SPMATMUL_BW);
         GCNK_CHECK(gcnk_spmm_bw(sp, d_feature_value, z.dxw, W1.grad, H, drop ? z.keep0 : nullptr, scale, nullptr));
         gpu_timer_end(TMR_SPMATMUL_BW);
@@ -355,6 +411,7 @@ void GCN::get_var(int idx, bool grad, float *h_out) {
         if (grad) { memset(h_out, 0, sizeof(float) * (size_t)size); return; }
         float *d_logits = nullptr;
         GCNK_CHECK(gcnk_malloc((void **)&d_logits, sizeof(float) * (size_t)size));
+        GCNK_CHECK(gcnk_gather_plain(data->graph.graph(), z.h1_s, z.P, H, nullptr));   // the passes aggregate only their split's rows
         GCNK_CHECK(gcnk_layer2_fused(z.P, variables[5].data, d_split, d_label, 0, N, H, C, 0, 0, nullptr, nullptr, nullptr, d_logits,
                                      z.d_result, z.ws, z.ws_bytes, nullptr));
         d2h(d_logits, size);

@@ -10,6 +10,7 @@ typedef enum {
     TMR_GRAPHSUM_FW, TMR_GRAPHSUM_BW, TMR_LOSS_FW, TMR_RELU_FW, TMR_RELU_BW, TMR_DROPOUT_FW, TMR_DROPOUT_BW,
     // additions of this engine (not in the reference enum)
     TMR_ADAM, TMR_COMM,
+    TMR_GATHER_FULL, TMR_GATHER_PART,   // GraphSum gather launches over the whole graph / over a row- or column-subset view
     __NUM_TMR
 } timer_instance;
 

@@ -67,6 +67,15 @@ int gcnk_flush_l2(gcnk_stream_t stream);               /* writes a >L2 scratch b
 typedef struct gcnk_graph gcnk_graph;
 int gcnk_graph_create(gcnk_graph **g, const int *d_indptr, const int *d_indices, int n, int64_t nnz,
                       int n_cols, const float *d_dinv_global, gcnk_stream_t stream);
+/* A view of `base` (which must outlive it) for passes that need only part of the product:
+ *   d_row_keep (int[n] flags, NULL = all rows): only rows with a non-zero flag are scheduled; the other rows of
+ *               the output are left untouched (e.g. logits are only needed for the labelled rows of the split);
+ *   d_col_keep (int[n_cols] flags, NULL = all): entries whose column flag is 0 are dropped (e.g. the rows of the
+ *               gathered matrix that are known to be zero: the loss gradient of unlabelled nodes).
+ * Degrees — hence d^-1/2 of rows and columns — remain those of the base graph.  gcnk_graph_stats on a view
+ * reports the entries its launches touch. */
+int gcnk_graph_create_view(gcnk_graph **view, const gcnk_graph *base, const int *d_row_keep, const int *d_col_keep,
+                           gcnk_stream_t stream);
 int gcnk_graph_destroy(gcnk_graph *g);
 int gcnk_graph_dinv(const gcnk_graph *g, const float **d_dinv);   /* [n] d^-1/2 of the local rows */
 int gcnk_graph_stats(const gcnk_graph *g, int *n, int64_t *nnz, int *max_degree, int *is_symmetric, int *n_bins);
@@ -117,6 +126,12 @@ int gcnk_spmm_fw(const gcnk_spmat *sp, const float *values, const float *b, floa
                  const uint32_t *drop_bits, float drop_scale, const float *row_scale, gcnk_stream_t stream);
 int gcnk_spmm_bw(gcnk_spmat *sp, const float *values, const float *c_grad, float *b_grad, int p,
                  const uint32_t *drop_bits, float drop_scale, gcnk_stream_t stream);
+/* The same forward for a plain row-major dense matrix x[m x n] (no index at all), with an optional ReLU in the
+ * epilogue: c = row_scale (.) relu?(drop(x) * w).  Used with x = A_hat*X precomputed once, which turns the
+ * dropout-free layer-1 forward A_hat*(X*W1) into one streaming pass (A_hat*X)*W1 with no gather.
+ * Tensor-core path only (p == 16, n even): other shapes return GCNK_EUNSUPPORTED. */
+int gcnk_dense_transform(const float *x, int m, int n, const float *w, float *c, int p, const uint32_t *drop_bits,
+                         float drop_scale, const float *row_scale, int relu, gcnk_stream_t stream);
 
 /* ---- Matmul: K1/K2/K3, cuda_kernel.cu:6-96 (CPU: module.cpp:11-42) -------------------------------- */
 int gcnk_matmul_fw(const float *a, const float *b, float *c, int m, int n, int p, gcnk_stream_t stream);   /* c = a*b       */
