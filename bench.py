@@ -147,22 +147,35 @@ def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world > 1:
-        raise SystemExit("bench.py: the multi-GPU row-partitioned engine is not wired into bench.py yet")
     abi.require_device(local)
     K = abi.k
     t_gen = time.perf_counter()
-    data = host_api.Data.synth("reddit", args.scale)
+    data = host_api.Data.synth("reddit", args.scale)       # every rank generates the same dataset (deterministic)
     sizes = data.sizes()
     t_gen = time.perf_counter() - t_gen
     N, nnzA, nnzX = sizes["num_nodes"], sizes["graph_nnz"], sizes["feature_nnz"]
     H, C, F = 16, data.params.output_dim, data.params.input_dim
-    eng = host_api.Engine(data, hidden_dim=H, dropout=0.5, seed=1, plan=host_api.PLAN_FUSED, device=local)
+    uid = host_api.rendezvous(rank, world, os.environ.get("MASTER_ADDR", "127.0.0.1"), int(os.environ.get("MASTER_PORT", "29500")))
+    eng = host_api.Engine(data, hidden_dim=H, dropout=0.5, seed=1, plan=host_api.PLAN_FUSED, device=local, rank=rank, world=world,
+                          nccl_id=uid)
     L = host_api.load()
+    if world > 1:
+        mine, r0, r1 = data.slice(rank, world)
+        ms_ = mine.sizes()
+        n_loc, nnzA_loc, nnzX_loc = ms_["num_nodes"], ms_["graph_nnz"], ms_["feature_nnz"]
+        x_local = mine.arrays()["feature_value"]
+    else:
+        n_loc, nnzA_loc, nnzX_loc = N, nnzA, nnzX
+        x_local = data.arrays()["feature_value"]
 
     def step():
         eng.train_epoch()
         return eng.eval(2)
+
+    def barrier():
+        K.gcnk_device_sync()
+        eng.allreduce_host([0.0])                          # NCCL all-reduce + sync: all ranks have reached this point
+        K.gcnk_device_sync()
 
     for _ in range(args.warmup):
         step()
@@ -170,76 +183,84 @@ def run_ours(args):
     L.gcnh_timer_reset()
     L.gcnh_timer_enable_gpu(1)
     clocks = ClockSampler(local)
-    clocks.start()
+    if rank == 0:
+        clocks.start()
     ev0, ev1 = abi.Event(), abi.Event()
     launches0 = abi.load().gcnk_launch_count()
-    K.gcnk_device_sync()
+    barrier()
     ev0.record()
     for _ in range(args.steps):
         last = step()
     ev1.record()
     ev1.sync()
-    K.gcnk_device_sync()
+    barrier()
     ms = ev0.elapsed_ms(ev1)
+    ms = float(eng.allreduce_host([ms], op_max=True)[0])   # max over ranks
     launches = abi.load().gcnk_launch_count() - launches0
-    clk = clocks.stop()
+    clk = clocks.stop() if rank == 0 else None
     timers = host_api.timers()
     L.gcnh_timer_enable_gpu(0)
     value = args.steps / (ms * 1e-3)
 
-    # ---- roofline of the dominant kernel: the GraphSum gather over the whole graph
+    # ---- roofline of the dominant kernel: the GraphSum gather over the whole (local) graph
     peak, peak_src = measured_peak()
     # full-graph gather launches only (each bracketed by its own event pair); the row/column-subset launches are
     # reported in `breakdown` as gather_part
     g_total, g_launches = timers.get("gather_full", (0.0, 0))
-    b_min = 4 * nnzA + 4 * (N + 1) + 8 * N * H
+    b_min = 4 * nnzA_loc + 4 * (n_loc + 1) + 4 * H * (N + n_loc)        # indices + indptr + source read once + rows written once
     t_launch = g_total / max(g_launches, 1)
     achieved = b_min / t_launch / 1e9 if t_launch > 0 else 0.0
     traffic = None
     tp = ROOT / "profiles" / "graphsum_traffic.json"
-    if tp.exists():
+    if tp.exists() and world == 1:
         try:
             traffic = json.loads(tp.read_text()).get("dram_bytes_per_launch")
         except Exception:
             traffic = None
-    roofline = {"bound": "hbm", "kernel": "gather_kernel (GraphSum, dim 16)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": b_min,
-                "avg_launch_us": t_launch * 1e6, "launches_timed": g_launches,
-                "share_of_step": g_total / (ms * 1e-3) if ms > 0 else None}
+    roofline = {"bound": "hbm", "kernel": "gather_kernel (GraphSum, dim 16, all rows of this rank)", "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": b_min, "avg_launch_us": t_launch * 1e6, "launches_timed": g_launches,
+                "share_of_step": g_total / (ms * 1e-3) if ms > 0 else None,
+                "l2_to_sm_gather_bytes_per_launch": 64 * nnzA_loc + 4 * nnzA_loc}
     breakdown = {k: {"ms_per_step": v[0] * 1e3 / args.steps, "calls_per_step": v[1] / args.steps} for k, v in timers.items()
                  if k not in ("train", "test")}
 
-    # ---- e2e: the same step through the C face with the feature matrix uploaded from pinned host memory each step
-    pinned = L.gcnh_alloc_pinned(nnzX)
-    host_view = np.ctypeslib.as_array((abi.C.c_float * nnzX).from_address(pinned))
-    host_view[:] = data.arrays()["feature_value"]
+    # ---- e2e: the same step through the C face with the (local rows of the) feature matrix uploaded from pinned
+    # host memory each step
+    pinned = L.gcnh_alloc_pinned(max(nnzX_loc, 1))
+    host_view = np.ctypeslib.as_array((abi.C.c_float * max(nnzX_loc, 1)).from_address(pinned))
+    host_view[:nnzX_loc] = x_local
     e2e_steps = max(3, min(args.steps, 10))
     eng.set_input_host(pinned); step()                      # warm the copy path
-    K.gcnk_device_sync()
+    barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        eng.set_input_host(pinned)                          # H2D of nnz(X) floats on the engine's stream
+        eng.set_input_host(pinned)                          # H2D of this rank's nnz(X) floats on the engine's stream
         step()                                              # train_epoch + eval(2); each reads its scalars back (D2H)
-    K.gcnk_device_sync()
+    barrier()
     e2e_dt = (time.perf_counter() - t0) / e2e_steps
+    e2e_dt = float(eng.allreduce_host([e2e_dt], op_max=True)[0])
     L.gcnh_free_pinned(pinned)
-    e2e = {"value": 1.0 / e2e_dt, "unit": UNIT, "h2d_bytes_per_step": int(nnzX * 4), "d2h_bytes_per_step": 2 * 16 + 4,
+    e2e = {"value": 1.0 / e2e_dt, "unit": UNIT, "h2d_bytes_per_step": int(nnzX * 4), "d2h_bytes_per_step": world * (2 * 16 + 4),
            "steps": e2e_steps, "api": "gcnh_engine_set_input_host + gcnh_engine_train_epoch + gcnh_engine_eval (include/gcn_host.h)"}
     eng.close()
+    if rank != 0:
+        return
 
     # ---- CPU baseline: the reference engine on a bounded sample (rank 0, N=1)
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:
         v, dt, kind, sample = cpu_reference_run(args.cpu_scale, 1, 0, nnzA, host_api)
         cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": "reference" if kind == "reference" else "port", "sample": sample}
 
-    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic",
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if world > 1 else "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
             "config": {"workload": "reddit-shape 2-layer GCN (train_epoch + eval per step), hidden 16, dropout 0.5, fused plan",
                        "scale": args.scale, "nodes": N, "graph_nnz": nnzA, "feature_nnz": nnzX, "features": F, "classes": C,
                        "max_degree": sizes["max_degree"], "l2": "inputs larger than L2 each step (X 561 MB + CSR indices 459 MB streamed per pass); no flush",
-                       "parallelism": "1 GPU", "generate_s": round(t_gen, 1)},
+                       "parallelism": "1 GPU" if world == 1 else f"{world}-way row partition (nnz-balanced), NCCL all-gather of the gather source + all-reduce of dW",
+                       "generate_s": round(t_gen, 1)},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "cpu_baseline": cpu,
             "breakdown": breakdown, "final": {"val_loss": last[0], "val_acc": last[1]}}
     print(json.dumps(line))

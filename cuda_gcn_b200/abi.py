@@ -55,6 +55,7 @@ SIGNATURES = {
     "gcnk_event_record": (i32, [vp, vp]),
     "gcnk_event_sync": (i32, [vp]),
     "gcnk_event_elapsed_ms": (i32, [vp, vp, C.POINTER(f32)]),
+    "gcnk_stream_wait_event": (i32, [vp, vp]),
     "gcnk_flush_l2": (i32, [vp]),
     "gcnk_graph_create": (i32, [C.POINTER(vp), vp, vp, i32, i64, i32, vp, vp]),
     "gcnk_graph_create_view": (i32, [C.POINTER(vp), vp, vp, vp, vp]),
@@ -96,6 +97,12 @@ SIGNATURES = {
     "gcnk_sum_squares": (i32, [vp, i64, vp, vp]),
     "gcnk_layer2_fused": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, sz, vp]),
     "gcnk_layer2_workspace": (sz, [i32, i32, i32]),
+    "gcnk_comm_unique_id": (i32, [vp]),
+    "gcnk_comm_create": (i32, [C.POINTER(vp), vp, i32, i32, i32]),
+    "gcnk_comm_destroy": (i32, [vp]),
+    "gcnk_comm_rank": (i32, [vp, C.POINTER(i32), C.POINTER(i32)]),
+    "gcnk_comm_allgather_rows": (i32, [vp, vp, vp, i32, vp]),
+    "gcnk_comm_allreduce": (i32, [vp, vp, vp, i32, i32, vp]),
     "gcnk_partition_rows": (i32, [vp, i32, i32, vp]),
 }
 

@@ -41,6 +41,14 @@ __device__ __forceinline__ void split(float x, uint32_t &big, uint32_t &small) {
     big = to_tf32(x);
     small = to_tf32(x - __uint_as_float(big));      // exact difference, then rounded to TF32
 }
+// The same split for the streamed operand (140 M elements per pass), by truncation: two LOP3 and one FADD on the
+// full-rate ALU pipe instead of two conversions.  big = x with the 13 low mantissa bits cleared (a valid TF32),
+// small = x - big exactly, truncated again; what is lost is below 2^-20 of x.
+constexpr uint32_t TF32_MASK = 0xffffe000u;
+__device__ __forceinline__ void split_trunc(float x, uint32_t &big, uint32_t &small) {
+    big = __float_as_uint(x) & TF32_MASK;
+    small = __float_as_uint(x - __uint_as_float(big)) & TF32_MASK;
+}
 __device__ __forceinline__ void mma(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
     asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                  : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
@@ -65,9 +73,12 @@ __device__ __forceinline__ void mma3(Acc3 &d, const uint32_t (&ab)[4], const uin
 }
 __device__ __forceinline__ float2 ld_stream_f2(const float *p) {
     float2 v;
-    asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+    // L1-allocating on purpose: the rows are only 8-byte aligned, so a quad's 32 bytes usually straddle two 32-byte
+    // sectors and the neighbouring k-step wants the other half — it must come from L1, not from L2 again
+    asm volatile("ld.global.nc.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
     return v;
 }
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 // 32 keep bits starting at flat bit position pos (any alignment); words past the end read as 0
 __device__ __forceinline__ uint32_t bit_window(const uint32_t *__restrict__ bits, int64_t words, int64_t pos) {
     const int64_t w = pos >> 5;
@@ -81,6 +92,7 @@ __device__ __forceinline__ uint32_t bit_window(const uint32_t *__restrict__ bits
 // k-step s.  W sits in shared memory already split and already in B-fragment order, one float4 (big)
 // + one float4 (small) per lane per k-step: {b0,b1 of n-tile 0, b0,b1 of n-tile 1}.
 constexpr int FW_BATCH = 4;                 // k-steps (8 columns each) per load batch = 32 columns = one keep window
+constexpr int FW_PF = 4;                    // L2 prefetch distance in batches (512 B ahead in each of the 16 rows)
 
 struct FwBatch {
     float2 a[FW_BATCH], b[FW_BATCH];        // rows g and g+8
@@ -133,26 +145,37 @@ __global__ void __launch_bounds__(THREADS, 2) dense_fw16_tc_kernel(const float *
         fw_load(cur, xa, xb, va, vb, 2 * t, n, bits, bit_words, pa, pb);
 #pragma unroll 1
         for (int b = 0; b < n_batches; b++) {
+            {   // pull the X lines FW_PF batches ahead (wrapping into this warp's next tile) into L2: the register
+                // double buffer then sees L2 latency instead of HBM latency
+                int pb_ = b + FW_PF, ptile = tile;
+                if (pb_ >= n_batches) { pb_ -= n_batches; ptile += gridDim.x * WARPS; }
+                const int pra = ptile * 16 + g, prb = pra + 8, pcol = 32 * pb_ + 2 * t;
+                if (pcol < n) {
+                    if (pra < m) prefetch_l2(x + (size_t)pra * n + pcol);
+                    if (prb < m) prefetch_l2(x + (size_t)prb * n + pcol);
+                }
+            }
             if (b + 1 < n_batches)                                  // next batch in flight while this one is multiplied
                 fw_load(nxt, xa + 32 * (b + 1), xb + 32 * (b + 1), va, vb, 32 * (b + 1) + 2 * t, n, bits, bit_words,
                         pa + 32 * (b + 1), pb + 32 * (b + 1));
+            // keep bits of this lane's two columns, k-step j: bits 8j and 8j+1 of the window shifted by 2t
+            const uint32_t ka = cur.wa >> (2 * t), kb = cur.wb >> (2 * t);
 #pragma unroll
             for (int j = 0; j < FW_BATCH; j++) {
                 const int s = b * FW_BATCH + j;
                 if (s < KS) {
                     float2 fa = cur.a[j], fb = cur.b[j];
-                    if (bits) {
-                        const int sh = 8 * j + 2 * t;
-                        fa.x = (cur.wa >> sh) & 1u ? fa.x * scale : 0.f;
-                        fa.y = (cur.wa >> (sh + 1)) & 1u ? fa.y * scale : 0.f;
-                        fb.x = (cur.wb >> sh) & 1u ? fb.x * scale : 0.f;
-                        fb.y = (cur.wb >> (sh + 1)) & 1u ? fb.y * scale : 0.f;
+                    if (bits) {                                     // the 1/(1-p) factor is applied once, in the epilogue
+                        fa.x = ka & (1u << (8 * j)) ? fa.x : 0.f;
+                        fa.y = ka & (2u << (8 * j)) ? fa.y : 0.f;
+                        fb.x = kb & (1u << (8 * j)) ? fb.x : 0.f;
+                        fb.y = kb & (2u << (8 * j)) ? fb.y : 0.f;
                     }
                     uint32_t ab[4], as[4];
-                    split(fa.x, ab[0], as[0]);      // a0: (row g,   logical k t)   = column 2t
-                    split(fb.x, ab[1], as[1]);      // a1: (row g+8, logical k t)
-                    split(fa.y, ab[2], as[2]);      // a2: (row g,   logical k t+4) = column 2t+1
-                    split(fb.y, ab[3], as[3]);      // a3: (row g+8, logical k t+4)
+                    split_trunc(fa.x, ab[0], as[0]);      // a0: (row g,   logical k t)   = column 2t
+                    split_trunc(fb.x, ab[1], as[1]);      // a1: (row g+8, logical k t)
+                    split_trunc(fa.y, ab[2], as[2]);      // a2: (row g,   logical k t+4) = column 2t+1
+                    split_trunc(fb.y, ab[3], as[3]);      // a3: (row g+8, logical k t+4)
                     const float4 wb4 = sfrag[s * 32 + lane], ws4 = sfrag[(KS + s) * 32 + lane];
                     mma3(acc0, ab, as, __float_as_uint(wb4.x), __float_as_uint(wb4.y), __float_as_uint(ws4.x), __float_as_uint(ws4.y));
                     mma3(acc1, ab, as, __float_as_uint(wb4.z), __float_as_uint(wb4.w), __float_as_uint(ws4.z), __float_as_uint(ws4.w));
@@ -167,14 +190,15 @@ __global__ void __launch_bounds__(THREADS, 2) dense_fw16_tc_kernel(const float *
 #pragma unroll
             for (int e = 0; e < 4; e++) { r0[e] = r0[e] > 0.f ? r0[e] : 0.f; r1[e] = r1[e] > 0.f ? r1[e] : 0.f; }
         }
+        const float post = bits ? scale : 1.f;
         if (va) {
-            const float rs = row_scale ? row_scale[ra] : 1.f;
+            const float rs = post * (row_scale ? row_scale[ra] : 1.f);
             float *o = c + (size_t)ra * P + 2 * t;
             *reinterpret_cast<float2 *>(o) = make_float2(rs * r0[0], rs * r0[1]);
             *reinterpret_cast<float2 *>(o + 8) = make_float2(rs * r1[0], rs * r1[1]);
         }
         if (vb) {
-            const float rs = row_scale ? row_scale[rb] : 1.f;
+            const float rs = post * (row_scale ? row_scale[rb] : 1.f);
             float *o = c + (size_t)rb * P + 2 * t;
             *reinterpret_cast<float2 *>(o) = make_float2(rs * r0[2], rs * r0[3]);
             *reinterpret_cast<float2 *>(o + 8) = make_float2(rs * r1[2], rs * r1[3]);
@@ -189,6 +213,38 @@ __global__ void __launch_bounds__(THREADS, 2) dense_fw16_tc_kernel(const float *
 // a3 = G[row 2t+1][g+8] — logical k = t / t+4 mapped to the adjacent rows 2t / 2t+1), B fragments from X:
 // one 64-bit load X[row][f0 + 2g, +1] feeds n-tile "even" (.x) and n-tile "odd" (.y) of the pair.
 constexpr int BW_PAIRS = 5, BAND = 16 * BW_PAIRS;          // 80 features per warp, 640 per CTA
+constexpr int BW_PF = 6;                                   // L2 prefetch distance in k-steps (8 rows each)
+
+struct BwStep {
+    float2 x0[BW_PAIRS], x1[BW_PAIRS];     // rows k0+2t and k0+2t+1, this lane's column pair of each n-tile pair
+    uint32_t w0[3], w1[3];                 // 96 keep bits from the band start of each row
+    float a[4];                            // G[r0][g], G[r0][g+8], G[r1][g], G[r1][g+8]
+};
+
+__device__ __forceinline__ void bw_load(BwStep &q, const float *__restrict__ x, const float *__restrict__ gmat, int n, int k0, int r_hi,
+                                        int f_band, int t, int g, const uint32_t *__restrict__ bits, int64_t words) {
+    const int r0 = k0 + 2 * t, r1 = r0 + 1;
+    const bool v0 = r0 < r_hi, v1 = r1 < r_hi;
+    const float *p0 = x + (size_t)(v0 ? r0 : 0) * n + f_band + 2 * g, *p1 = x + (size_t)(v1 ? r1 : 0) * n + f_band + 2 * g;
+#pragma unroll
+    for (int p = 0; p < BW_PAIRS; p++) {
+        const bool in = f_band + 16 * p + 2 * g < n;
+        q.x0[p] = (v0 && in) ? ld_stream_f2(p0 + 16 * p) : make_float2(0.f, 0.f);
+        q.x1[p] = (v1 && in) ? ld_stream_f2(p1 + 16 * p) : make_float2(0.f, 0.f);
+    }
+    if (bits) {
+#pragma unroll
+        for (int w = 0; w < 3; w++) {
+            q.w0[w] = v0 ? bit_window(bits, words, (int64_t)r0 * n + f_band + 32 * w) : 0u;
+            q.w1[w] = v1 ? bit_window(bits, words, (int64_t)r1 * n + f_band + 32 * w) : 0u;
+        }
+    }
+    const float *g0 = gmat + (size_t)(v0 ? r0 : 0) * P, *g1 = gmat + (size_t)(v1 ? r1 : 0) * P;
+    q.a[0] = v0 ? __ldg(g0 + g) : 0.f;
+    q.a[1] = v0 ? __ldg(g0 + g + 8) : 0.f;
+    q.a[2] = v1 ? __ldg(g1 + g) : 0.f;
+    q.a[3] = v1 ? __ldg(g1 + g + 8) : 0.f;
+}
 
 __global__ void __launch_bounds__(THREADS, 2) dense_bw16_tc_kernel(const float *__restrict__ x, const float *__restrict__ gmat,
                                                                     float *__restrict__ partials, int m, int n, int rows_per_cta,
@@ -196,78 +252,68 @@ __global__ void __launch_bounds__(THREADS, 2) dense_bw16_tc_kernel(const float *
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, t = lane & 3, g = lane >> 2;
     const int r_lo = blockIdx.x * rows_per_cta, r_hi = min(m, r_lo + rows_per_cta);
     const int f_band = BAND * warp + blockIdx.y * (BAND * WARPS);
-    // two accumulators per n-tile: the dominant big*big chain and the two small cross terms (10 tiles x 2 chains
-    // = 20 independent MMA chains per warp; three per tile would not fit the register budget)
-    float acc[BW_PAIRS][2][4], acs[BW_PAIRS][2][4];
+    // one accumulator per n-tile: the 10 tiles of the band are 10 independent MMA chains
+    float acc[BW_PAIRS][2][4];
 #pragma unroll
     for (int p = 0; p < BW_PAIRS; p++)
 #pragma unroll
         for (int h = 0; h < 2; h++)
 #pragma unroll
-            for (int e = 0; e < 4; e++) acc[p][h][e] = acs[p][h][e] = 0.f;
+            for (int e = 0; e < 4; e++) acc[p][h][e] = 0.f;
 
-    if (f_band < n) {
+    if (f_band < n && r_lo < r_hi) {
+        BwStep cur, nxt;
+        bw_load(cur, x, gmat, n, r_lo, r_hi, f_band, t, g, bits, bit_words);
 #pragma unroll 1
         for (int k0 = r_lo; k0 < r_hi; k0 += 8) {
-            const int r0 = k0 + 2 * t, r1 = r0 + 1;
-            const bool v0 = r0 < r_hi, v1 = r1 < r_hi;
-            // B operands first: the long-latency HBM stream
-            float2 x0[BW_PAIRS], x1[BW_PAIRS];
-            const float *p0 = x + (size_t)(v0 ? r0 : 0) * n + f_band + 2 * g, *p1 = x + (size_t)(v1 ? r1 : 0) * n + f_band + 2 * g;
-#pragma unroll
-            for (int p = 0; p < BW_PAIRS; p++) {
-                const bool in = f_band + 16 * p + 2 * g < n;
-                x0[p] = (v0 && in) ? ld_stream_f2(p0 + 16 * p) : make_float2(0.f, 0.f);
-                x1[p] = (v1 && in) ? ld_stream_f2(p1 + 16 * p) : make_float2(0.f, 0.f);
+            {   // L2 prefetch of this warp's band BW_PF k-steps ahead (the band is 320 B per row: lanes g cover it in 64-B steps)
+                const int pr = k0 + 8 * BW_PF + 2 * t + (g >> 2);
+                const int pf = f_band + 32 * (g & 3) * 1;
+                if (pr < r_hi && pf < n && (g & 3) * 32 < BAND) prefetch_l2(x + (size_t)pr * n + pf);
             }
-            uint32_t w0[3] = {0, 0, 0}, w1[3] = {0, 0, 0};        // 96 keep bits from the band start of each row
-            if (bits) {
-#pragma unroll
-                for (int q = 0; q < 3; q++) {
-                    if (v0) w0[q] = bit_window(bits, bit_words, (int64_t)r0 * n + f_band + 32 * q);
-                    if (v1) w1[q] = bit_window(bits, bit_words, (int64_t)r1 * n + f_band + 32 * q);
-                }
-            }
-            // A fragment (G is small and L2/L1 resident; zero rows beyond the slab)
-            const float *g0 = gmat + (size_t)(v0 ? r0 : 0) * P, *g1 = gmat + (size_t)(v1 ? r1 : 0) * P;
-            const float av[4] = {v0 ? __ldg(g0 + g) : 0.f, v0 ? __ldg(g0 + g + 8) : 0.f, v1 ? __ldg(g1 + g) : 0.f, v1 ? __ldg(g1 + g + 8) : 0.f};
+            if (k0 + 8 < r_hi) bw_load(nxt, x, gmat, n, k0 + 8, r_hi, f_band, t, g, bits, bit_words);   // next 8 rows in flight
             uint32_t ab[4], as[4];
 #pragma unroll
-            for (int e = 0; e < 4; e++) split(av[e], ab[e], as[e]);
+            for (int e = 0; e < 4; e++) split_trunc(cur.a[e], ab[e], as[e]);
 #pragma unroll
             for (int p = 0; p < BW_PAIRS; p++) {
-                float2 f0 = x0[p], f1 = x1[p];
-                if (bits) {
-                    const int sh = 16 * p + 2 * g, q = sh >> 5, s = sh & 31;      // s is even: both bits in one word
-                    f0.x = (w0[q] >> s) & 1u ? f0.x * scale : 0.f;
-                    f0.y = (w0[q] >> (s + 1)) & 1u ? f0.y * scale : 0.f;
-                    f1.x = (w1[q] >> s) & 1u ? f1.x * scale : 0.f;
-                    f1.y = (w1[q] >> (s + 1)) & 1u ? f1.y * scale : 0.f;
+                float2 f0 = cur.x0[p], f1 = cur.x1[p];
+                if (bits) {                                          // the 1/(1-p) factor is applied to the partial sums
+                    // bit 16p + 2g of the 96-bit window; 2g is even, so both bits sit in the same word
+                    const int q = (16 * p) >> 5, s = (16 * p) & 31;
+                    const uint32_t k0w = cur.w0[q] >> (2 * g), k1w = cur.w1[q] >> (2 * g);
+                    // 16p mod 32 is 0 or 16 and 2g <= 14: the pair never straddles a word
+                    f0.x = k0w & (1u << s) ? f0.x : 0.f;
+                    f0.y = k0w & (2u << s) ? f0.y : 0.f;
+                    f1.x = k1w & (1u << s) ? f1.x : 0.f;
+                    f1.y = k1w & (2u << s) ? f1.y : 0.f;
                 }
                 uint32_t bb[4], bs[4];
-                split(f0.x, bb[0], bs[0]);      // even n-tile: b0 (logical k t   = row 2t)
-                split(f1.x, bb[1], bs[1]);      //              b1 (logical k t+4 = row 2t+1)
-                split(f0.y, bb[2], bs[2]);      // odd n-tile
-                split(f1.y, bb[3], bs[3]);
-                mma(acs[p][0], as[0], as[1], as[2], as[3], bb[0], bb[1]);
-                mma(acs[p][1], as[0], as[1], as[2], as[3], bb[2], bb[3]);
+                split_trunc(f0.x, bb[0], bs[0]);      // even n-tile: b0 (logical k t   = row 2t)
+                split_trunc(f1.x, bb[1], bs[1]);      //              b1 (logical k t+4 = row 2t+1)
+                split_trunc(f0.y, bb[2], bs[2]);      // odd n-tile
+                split_trunc(f1.y, bb[3], bs[3]);
+                mma(acc[p][0], as[0], as[1], as[2], as[3], bb[0], bb[1]);
+                mma(acc[p][1], as[0], as[1], as[2], as[3], bb[2], bb[3]);
+                mma(acc[p][0], ab[0], ab[1], ab[2], ab[3], bs[0], bs[1]);
+                mma(acc[p][1], ab[0], ab[1], ab[2], ab[3], bs[2], bs[3]);
                 mma(acc[p][0], ab[0], ab[1], ab[2], ab[3], bb[0], bb[1]);
                 mma(acc[p][1], ab[0], ab[1], ab[2], ab[3], bb[2], bb[3]);
-                mma(acs[p][0], ab[0], ab[1], ab[2], ab[3], bs[0], bs[1]);
-                mma(acs[p][1], ab[0], ab[1], ab[2], ab[3], bs[2], bs[3]);
             }
+            cur = nxt;
         }
     }
     // D fragment of an n-tile: c0 = (h g, n 2t), c1 = (h g, n 2t+1), c2 = (h g+8, n 2t), c3 = (h g+8, n 2t+1);
     // logical column n of the even tile is feature f0 + 2n, of the odd tile f0 + 2n + 1.
+    const float post = bits ? scale : 1.f;
     float *out = partials + (size_t)blockIdx.x * n * P;
 #pragma unroll
     for (int p = 0; p < BW_PAIRS; p++)
 #pragma unroll
         for (int h = 0; h < 2; h++) {
             const int fa = f_band + 16 * p + 2 * (2 * t) + h, fb = f_band + 16 * p + 2 * (2 * t + 1) + h;
-            if (fa < n) { out[(size_t)fa * P + g] = acs[p][h][0] + acc[p][h][0]; out[(size_t)fa * P + g + 8] = acs[p][h][2] + acc[p][h][2]; }
-            if (fb < n) { out[(size_t)fb * P + g] = acs[p][h][1] + acc[p][h][1]; out[(size_t)fb * P + g + 8] = acs[p][h][3] + acc[p][h][3]; }
+            if (fa < n) { out[(size_t)fa * P + g] = post * acc[p][h][0]; out[(size_t)fa * P + g + 8] = post * acc[p][h][2]; }
+            if (fb < n) { out[(size_t)fb * P + g] = post * acc[p][h][1]; out[(size_t)fb * P + g + 8] = post * acc[p][h][3]; }
         }
 }
 

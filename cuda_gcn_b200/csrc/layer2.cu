@@ -266,7 +266,7 @@ __global__ void __launch_bounds__(L2_THREADS) layer2_h16_kernel(const float *__r
 // block 0 also produces the scalar result; every block reduces a slice of dW2 over the CTA partials
 __global__ void __launch_bounds__(256) layer2_finish_kernel(const L2Partial *__restrict__ ce_partials, const float *__restrict__ dw_partials,
                                                              int parts, int hc, int training, float *__restrict__ W2_grad,
-                                                             gcnk_ce_result *__restrict__ result) {
+                                                             gcnk_ce_result *__restrict__ result, float *__restrict__ red4) {
     if (training) {
         const int i = blockIdx.x * blockDim.x + threadIdx.x;
         if (i < hc) {
@@ -293,6 +293,8 @@ __global__ void __launch_bounds__(256) layer2_finish_kernel(const L2Partial *__r
         if (threadIdx.x == 0) {
             result->loss = s_loss[0] / (float)s_count[0];
             result->count = s_count[0]; result->wrong = s_wrong[0]; result->pad = 0;
+            // raw sums as floats (counts < 2^24 are exact): what a row-partitioned run all-reduces across ranks
+            red4[0] = s_loss[0]; red4[1] = (float)s_count[0]; red4[2] = (float)s_wrong[0]; red4[3] = 0.f;
         }
     }
 }
@@ -305,7 +307,7 @@ extern "C" {
 
 size_t gcnk_layer2_workspace(int n, int h, int c) {
     const size_t g = (size_t)l2_grid(n);
-    return g * sizeof(L2Partial) + g * (size_t)h * c * sizeof(float);
+    return 16 + g * sizeof(L2Partial) + g * (size_t)h * c * sizeof(float);
 }
 
 int gcnk_layer2_fused(const float *P, const float *W2, const int *split, const int *label, int current_split, int n, int h,
@@ -317,7 +319,8 @@ int gcnk_layer2_fused(const float *P, const float *W2, const int *split, const i
     GCNK_REQUIRE(workspace && workspace_bytes >= gcnk_layer2_workspace(n, h, c), "workspace too small");
     cudaStream_t st = S(stream);
     const int grid = l2_grid(n);
-    L2Partial *ce_partials = reinterpret_cast<L2Partial *>(workspace);
+    float *red4 = workspace;                                               // {sum of loss terms, count, wrong, 0}
+    L2Partial *ce_partials = reinterpret_cast<L2Partial *>(workspace + 4);
     float *dw_partials = reinterpret_cast<float *>(ce_partials + grid);
     const size_t smem = sizeof(float) * ((size_t)h * c + L2_WARPS * (size_t)c + L2_WARPS * (size_t)h +
                                          (training ? L2_WARPS * (size_t)h * c : 0));
@@ -340,7 +343,7 @@ int gcnk_layer2_fused(const float *P, const float *W2, const int *split, const i
         GCNK_LAUNCHED();
     }
     const int hc = h * c;
-    layer2_finish_kernel<<<training ? (hc + 255) / 256 : 1, 256, 0, st>>>(ce_partials, dw_partials, grid, hc, training, W2_grad, d_result);
+    layer2_finish_kernel<<<training ? (hc + 255) / 256 : 1, 256, 0, st>>>(ce_partials, dw_partials, grid, hc, training, W2_grad, d_result, red4);
     GCNK_LAUNCHED();
     return GCNK_OK;
 }

@@ -121,6 +121,7 @@ int gcnk_event_create(void **ev) {
 int gcnk_event_destroy(void *ev) { if (ev) GCNK_CUDA(cudaEventDestroy((cudaEvent_t)ev)); return GCNK_OK; }
 int gcnk_event_record(void *ev, gcnk_stream_t s) { GCNK_CUDA(cudaEventRecord((cudaEvent_t)ev, S(s))); return GCNK_OK; }
 int gcnk_event_sync(void *ev) { GCNK_CUDA(cudaEventSynchronize((cudaEvent_t)ev)); return GCNK_OK; }
+int gcnk_stream_wait_event(gcnk_stream_t s, void *ev) { GCNK_CUDA(cudaStreamWaitEvent(S(s), (cudaEvent_t)ev, 0)); return GCNK_OK; }
 int gcnk_event_elapsed_ms(void *a, void *b, float *ms) {
     GCNK_CUDA(cudaEventElapsedTime(ms, (cudaEvent_t)a, (cudaEvent_t)b));
     return GCNK_OK;

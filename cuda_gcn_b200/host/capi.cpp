@@ -2,6 +2,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
+#include <vector>
 
 #include "check.h"
 #include "gcn.h"
@@ -12,7 +13,7 @@
 #include "timer.h"
 
 struct gcnh_data { GCNData d; };
-struct gcnh_engine { GCN *g; };
+struct gcnh_engine { GCN *g; gcnk_comm *comm = nullptr; float *d_tmp = nullptr; };
 
 static GCNParams to_cpp(const gcnh_params &p) {
     return GCNParams{p.num_nodes, p.input_dim, p.hidden_dim, p.output_dim, p.dropout, p.learning_rate, p.weight_decay, p.epochs, p.early_stopping};
@@ -65,6 +66,17 @@ int gcnh_data_synth(gcnh_data *d, const char *preset, double scale, uint64_t see
     return 1;
 }
 
+gcnh_data *gcnh_data_slice(const gcnh_data *d, int rank, int world, int *row_begin, int *row_end) {
+    const int n = d->d.graph.rows();
+    std::vector<int> cuts((size_t)world + 1);
+    if (gcnk_partition_rows(d->d.graph.indptr.data(), n, world, cuts.data()) != GCNK_OK || rank < 0 || rank >= world) return nullptr;
+    gcnh_data *out = new gcnh_data;
+    slice_rows(d->d, cuts[rank], cuts[rank + 1] - cuts[rank], out->d);
+    if (row_begin) *row_begin = cuts[rank];
+    if (row_end) *row_end = cuts[rank + 1];
+    return out;
+}
+
 void gcnh_data_sizes(const gcnh_data *d, int64_t *s) {
     const GCNData &x = d->d;
     s[0] = x.graph.rows();
@@ -99,7 +111,46 @@ gcnh_engine *gcnh_engine_create(const gcnh_params *params, gcnh_data *data, long
     return e;
 }
 
-void gcnh_engine_destroy(gcnh_engine *e) { if (e) { delete e->g; delete e; } }
+int gcnh_comm_unique_id(void *id) { return gcnk_comm_unique_id(id) == GCNK_OK; }
+
+gcnh_engine *gcnh_engine_create_dist(const gcnh_params *params, gcnh_data *data, long seed, int device, int rank, int world,
+                                     const void *id128) {
+    GCNK_CHECK(gcnk_set_device(device));
+    if (seed >= 0) {
+        char buf[32];
+        snprintf(buf, sizeof buf, "%ld", seed);
+        setenv("GCN_SEED", buf, 1);
+    }
+    gcnh_engine *e = new gcnh_engine;
+    GCNDist dist;
+    dist.rank = rank; dist.world = world;
+    if (world > 1) {
+        GCNK_CHECK(gcnk_comm_create(&e->comm, id128, rank, world, device));
+        dist.comm = e->comm;
+    }
+    e->g = new GCN(to_cpp(*params), &data->d, PLAN_FUSED, true, dist);
+    return e;
+}
+
+void gcnh_engine_allreduce_host(gcnh_engine *e, float *h, int count, int op_max) {
+    if (!e->comm || count <= 0) return;
+    if (!e->d_tmp) GCNK_CHECK(gcnk_malloc((void **)&e->d_tmp, sizeof(float) * 64));
+    if (count > 64) count = 64;
+    GCNK_CHECK(gcnk_memcpy_h2d(e->d_tmp, h, sizeof(float) * count, nullptr));
+    float *bufs[1] = {e->d_tmp};
+    const size_t counts[1] = {(size_t)count};
+    GCNK_CHECK(gcnk_comm_allreduce(e->comm, bufs, counts, 1, op_max, nullptr));
+    GCNK_CHECK(gcnk_memcpy_d2h(h, e->d_tmp, sizeof(float) * count, nullptr));
+    GCNK_CHECK(gcnk_stream_sync(nullptr));
+}
+
+void gcnh_engine_destroy(gcnh_engine *e) {
+    if (!e) return;
+    delete e->g;
+    if (e->d_tmp) gcnk_free(e->d_tmp);
+    if (e->comm) gcnk_comm_destroy(e->comm);
+    delete e;
+}
 int gcnh_engine_plan(const gcnh_engine *e) { return (int)e->g->plan(); }
 
 void gcnh_engine_train_epoch(gcnh_engine *e, float *loss, float *acc) {

@@ -25,6 +25,8 @@ struct GCN::Fused {
     float *ws = nullptr; size_t ws_bytes = 0;
     gcnk_ce_result *d_result = nullptr, *h_result = nullptr;   // device / pinned host
     float *d_sumsq = nullptr, *h_sumsq = nullptr;
+    float *h_red = nullptr;    // pinned {sum of loss terms, count, wrong, 0} after the cross-rank reduction
+    gcnk_rng *slice_rng = nullptr;   // positions a copy of the shared stream at this rank's rows
     float sumsq = 0;           // sum(W1^2) of the current weights
     // Views of the graph for the passes that need only part of A_hat*x (splits are static, so these are built once):
     //   rows[s]     only the labelled rows of split s are aggregated — the loss, the accuracy and the layer-2
@@ -38,13 +40,15 @@ struct GCN::Fused {
     bool ax_valid = false, use_views = true;
     ~Fused() {
         for (gcnk_graph *g : {rows[1], rows[2], rows[3], cols_train}) if (g) gcnk_graph_destroy(g);
-        for (int *k : keep) if (k) gcnk_free(k);
+        for (int *k : keep) if (k) gcnk_free(k);   // keep[0] = global train-column flags
         if (AX) gcnk_free(AX);
         for (void *p : {(void *)xw_s, (void *)h1_s, (void *)P, (void *)G, (void *)Gm, (void *)dxw, (void *)keep0, (void *)keep1,
                         (void *)mask, (void *)ws, (void *)d_result, (void *)d_sumsq})
             if (p) gcnk_free(p);
         if (h_result) gcnk_free_host(h_result);
         if (h_sumsq) gcnk_free_host(h_sumsq);
+        if (h_red) gcnk_free_host(h_red);
+        if (slice_rng) gcnk_rng_destroy(slice_rng);
     }
 };
 
@@ -60,6 +64,11 @@ static GCNPlan plan_from_env() {
 GCN::GCN(GCNParams params_, GCNData *input_data) : params(params_), data(input_data) { build(plan_from_env()); }
 
 GCN::GCN(GCNParams params_, GCNData *input_data, GCNPlan plan, bool quiet) : params(params_), data(input_data), quiet_(quiet) {
+    build(plan);
+}
+
+GCN::GCN(GCNParams params_, GCNData *input_data, GCNPlan plan, bool quiet, GCNDist dist_)
+    : params(params_), data(input_data), dist(dist_), quiet_(quiet) {
     build(plan);
 }
 
@@ -86,15 +95,24 @@ void GCN::build(GCNPlan plan) {
         exit(EXIT_FAILURE);
     }
     for (int i = 0; i < N; i++)
-        if (data->split[i] >= 1 && data->split[i] <= 3 && data->label[i] >= 0) split_count[data->split[i]]++;   // truth >= 0 rows
+        if (data->split[i] >= 1 && data->split[i] <= 3 && data->label[i] >= 0) split_count[data->split[i]]++;   // truth >= 0 rows (global)
+
+    full_data = data;
+    n_loc = N; r0 = 0;
+    int symmetric = 0;
+    if (dist.world > 1) {
+        if (plan == PLAN_MODULES) { fprintf(stderr, "GCN: the row-partitioned engine runs the fused plan only\n"); exit(EXIT_FAILURE); }
+        GCNK_CHECK(gcnk_graph_stats(full_data->graph.graph(), nullptr, nullptr, nullptr, &symmetric, nullptr));
+        build_partition();                                 // data now points at this rank's row slice
+    } else {
+        GCNK_CHECK(gcnk_graph_stats(data->graph.graph(), nullptr, nullptr, nullptr, &symmetric, nullptr));
+    }
 
     d_feature_value = upload(data->feature_value);
     d_split = upload(data->split);
     d_label = upload(data->label);
     GCNK_CHECK(gcnk_malloc((void **)&d_truth, sizeof(int) * (size_t)N));
 
-    int symmetric = 0;
-    GCNK_CHECK(gcnk_graph_stats(data->graph.graph(), nullptr, nullptr, nullptr, &symmetric, nullptr));
     const bool fusable = symmetric && C <= 128 && (size_t)H * C <= 4096;
     if (plan == PLAN_AUTO) plan = fusable ? PLAN_FUSED : PLAN_MODULES;
     if (plan == PLAN_FUSED && !fusable) {
@@ -150,48 +168,101 @@ void GCN::build(GCNPlan plan) {
     optimizer = Adam({{&variables[2], true}, {&variables[5], false}}, adam_params);
 
     fz.reset(new Fused);
-    const size_t nh = sizeof(float) * (size_t)N * H;
-    for (float **p : {&fz->xw_s, &fz->h1_s, &fz->P, &fz->G, &fz->Gm, &fz->dxw}) GCNK_CHECK(gcnk_malloc((void **)p, nh));
-    GCNK_CHECK(gcnk_malloc((void **)&fz->keep0, sizeof(uint32_t) * (nnzX / 32 + 4)));
-    GCNK_CHECK(gcnk_malloc((void **)&fz->keep1, sizeof(uint32_t) * ((size_t)N * H / 32 + 4)));
-    GCNK_CHECK(gcnk_malloc((void **)&fz->mask, sizeof(uint32_t) * ((size_t)N * gcnk_mask_row_stride_bits(H) / 32 + 4)));
-    fz->ws_bytes = gcnk_layer2_workspace(N, H, C);
+    const size_t nnzX_loc = data->feature_index.indices.size();
+    // gather SOURCES are [N x H] (every rank needs all rows: all-gathered in place), gather OUTPUTS are local
+    const size_t nh_all = sizeof(float) * (size_t)N * H, nh_loc = sizeof(float) * (size_t)n_loc * H;
+    for (float **p : {&fz->xw_s, &fz->h1_s, &fz->G, &fz->Gm}) GCNK_CHECK(gcnk_malloc((void **)p, nh_all));
+    for (float **p : {&fz->P, &fz->dxw}) GCNK_CHECK(gcnk_malloc((void **)p, nh_loc));
+    GCNK_CHECK(gcnk_malloc((void **)&fz->keep0, sizeof(uint32_t) * (nnzX_loc / 32 + 4)));
+    GCNK_CHECK(gcnk_malloc((void **)&fz->keep1, sizeof(uint32_t) * ((size_t)n_loc * H / 32 + 4)));
+    GCNK_CHECK(gcnk_malloc((void **)&fz->mask, sizeof(uint32_t) * ((size_t)n_loc * gcnk_mask_row_stride_bits(H) / 32 + 4)));
+    fz->ws_bytes = gcnk_layer2_workspace(n_loc, H, C);
     GCNK_CHECK(gcnk_malloc((void **)&fz->ws, fz->ws_bytes));
     GCNK_CHECK(gcnk_malloc((void **)&fz->d_result, sizeof(gcnk_ce_result)));
     GCNK_CHECK(gcnk_malloc((void **)&fz->d_sumsq, sizeof(float)));
     GCNK_CHECK(gcnk_malloc_host((void **)&fz->h_result, sizeof(gcnk_ce_result)));
     GCNK_CHECK(gcnk_malloc_host((void **)&fz->h_sumsq, sizeof(float)));
+    GCNK_CHECK(gcnk_malloc_host((void **)&fz->h_red, 4 * sizeof(float)));
+    GCNK_CHECK(gcnk_rng_create(&fz->slice_rng, 1, 2));
     GCNK_CHECK(gcnk_sum_squares(variables[2].data, variables[2].size, fz->d_sumsq, nullptr));
     GCNK_CHECK(gcnk_memcpy_d2h(fz->h_sumsq, fz->d_sumsq, sizeof(float), nullptr));
     GCNK_CHECK(gcnk_stream_sync(nullptr));
     fz->sumsq = *fz->h_sumsq;
-    gcnk_spmat *sp = data->feature_index.spmat(N, F);     // build the handle (dense detection) up front
+    gcnk_spmat *sp = data->feature_index.spmat(n_loc, F);     // build the handle (dense detection) up front
+    gcnk_graph *g = graph_handle();
 
     const char *nv = getenv("GCN_NO_VIEWS"), *na = getenv("GCN_NO_AX");
     fz->use_views = !(nv && *nv && strcmp(nv, "0"));
     if (fz->use_views) {
-        gcnk_graph *g = data->graph.graph();
         for (int s = 1; s <= 3; s++) {
-            std::vector<int> keep((size_t)N);
-            for (int i = 0; i < N; i++) keep[i] = data->split[i] == s && data->label[i] >= 0;
+            std::vector<int> keep((size_t)n_loc);
+            for (int i = 0; i < n_loc; i++) keep[i] = data->split[i] == s && data->label[i] >= 0;
             fz->keep[s] = upload(keep);
             if (s < 3) GCNK_CHECK(gcnk_graph_create_view(&fz->rows[s], g, fz->keep[s], nullptr, nullptr));   // test split: on first use
         }
-        GCNK_CHECK(gcnk_graph_create_view(&fz->cols_train, g, nullptr, fz->keep[1], nullptr));
+        std::vector<int> train_cols((size_t)N);                // column flags are global
+        for (int i = 0; i < N; i++) train_cols[i] = full_data->split[i] == 1 && full_data->label[i] >= 0;
+        fz->keep[0] = upload(train_cols);
+        GCNK_CHECK(gcnk_graph_create_view(&fz->cols_train, g, nullptr, fz->keep[0], nullptr));
     }
     int dense = 0;
     GCNK_CHECK(gcnk_spmat_is_dense(sp, &dense));
     if (dense && H == 16 && F % 2 == 0 && F <= 1024 && !(na && *na && strcmp(na, "0"))) {
-        GCNK_CHECK(gcnk_malloc((void **)&fz->AX, sizeof(float) * (size_t)N * F));
-        GCNK_CHECK(gcnk_graphsum(data->graph.graph(), d_feature_value, fz->AX, F, nullptr));
+        // AX = A_hat * X for this rank's rows; needs all rows of X once
+        float *x_all = d_feature_value;
+        if (dist.world > 1) x_all = upload(full_data->feature_value);
+        GCNK_CHECK(gcnk_malloc((void **)&fz->AX, sizeof(float) * (size_t)n_loc * F));
+        GCNK_CHECK(gcnk_graphsum(g, x_all, fz->AX, F, nullptr));
         GCNK_CHECK(gcnk_stream_sync(nullptr));
+        if (dist.world > 1) GCNK_CHECK(gcnk_free(x_all));
         fz->ax_valid = true;
     }
 }
 
+gcnk_graph *GCN::graph_handle() {
+    return dist.world > 1 ? data->graph.graph_slice(params.num_nodes, d_dinv_global) : data->graph.graph();
+}
+
+void slice_rows(const GCNData &src, int r0, int n_rows, GCNData &dst) {
+    auto slice_csr = [&](const SparseIndex &a, SparseIndex &b) {
+        const int e0 = a.indptr[r0], e1 = a.indptr[r0 + n_rows];
+        b.indptr.resize((size_t)n_rows + 1);
+        for (int i = 0; i <= n_rows; i++) b.indptr[i] = a.indptr[r0 + i] - e0;
+        b.indices.assign(a.indices.begin() + e0, a.indices.begin() + e1);
+    };
+    slice_csr(src.graph, dst.graph);
+    slice_csr(src.feature_index, dst.feature_index);
+    const int x0 = src.feature_index.indptr[r0], x1 = src.feature_index.indptr[r0 + n_rows];
+    dst.feature_value.assign(src.feature_value.begin() + x0, src.feature_value.begin() + x1);
+    dst.split.assign(src.split.begin() + r0, src.split.begin() + r0 + n_rows);
+    dst.label.assign(src.label.begin() + r0, src.label.begin() + r0 + n_rows);
+}
+
+// Row partition: this rank keeps rows [r0, r0 + n_loc) of the graph (column ids stay global), of X, labels and split.
+void GCN::build_partition() {
+    const int N = params.num_nodes;
+    gcnk_graph *gfull = full_data->graph.graph();
+    const float *dinv_full = nullptr;
+    GCNK_CHECK(gcnk_graph_dinv(gfull, &dinv_full));
+    GCNK_CHECK(gcnk_malloc((void **)&d_dinv_global, sizeof(float) * (size_t)N));
+    GCNK_CHECK(gcnk_memcpy_d2d(d_dinv_global, dinv_full, sizeof(float) * (size_t)N, nullptr));
+    GCNK_CHECK(gcnk_stream_sync(nullptr));
+    full_data->graph.release_device();                      // the full CSR is not needed on the device any more
+
+    row_begin.assign((size_t)dist.world + 1, 0);
+    GCNK_CHECK(gcnk_partition_rows(full_data->graph.indptr.data(), N, dist.world, row_begin.data()));
+    r0 = row_begin[dist.rank];
+    n_loc = row_begin[dist.rank + 1] - r0;
+
+    local.reset(new GCNData);
+    slice_rows(*full_data, r0, n_loc, *local);
+    data = local.get();
+}
+
 GCN::~GCN() {
     for (auto m : modules) delete m;
-    for (void *p : {(void *)d_truth, (void *)d_split, (void *)d_label, (void *)d_feature_value})
+    fz.reset();                                             // views before the graph they borrow from
+    for (void *p : {(void *)d_truth, (void *)d_split, (void *)d_label, (void *)d_feature_value, (void *)d_dinv_global})
         if (p) gcnk_free(p);
 }
 
@@ -229,18 +300,28 @@ float GCN::get_l2_penalty() {
 }
 
 // ------------------------------------------------------------------------------ fused plan ----
+void GCN::allgather(float *d_all, int dim) {
+    if (dist.world <= 1) return;
+    gpu_timer_begin(TMR_COMM);
+    GCNK_CHECK(gcnk_comm_allgather_rows(dist.comm, d_all, row_begin.data(), dim, nullptr));
+    gpu_timer_end(TMR_COMM);
+}
+
 std::pair<float, float> GCN::fused_pass(int current_split, bool training) {
     Fused &z = *fz;
     const int N = params.num_nodes, F = params.input_dim, H = params.hidden_dim, C = params.output_dim;
-    const int64_t nnzX = (int64_t)data->feature_index.indices.size();
+    const int64_t nnzX_loc = (int64_t)data->feature_index.indices.size();
+    const int64_t nnzX_all = (int64_t)full_data->feature_index.indices.size();
+    const int64_t x_off = full_data->feature_index.indptr[r0];           // this rank's first feature entry in the global order
     const float p = params.dropout;
     const float scale = 1 / (1 - p);                                      // module.cpp:212
     const bool drop = training && (int)(p * (float)MY_RAND_MAX) > 0;      // threshold 0 keeps everything
-    gcnk_graph *g = data->graph.graph();
-    gcnk_spmat *sp = data->feature_index.spmat(N, F);
-    const float *dinv = nullptr;
+    gcnk_graph *g = graph_handle();
+    gcnk_spmat *sp = data->feature_index.spmat(n_loc, F);
+    const float *dinv = nullptr;                                          // d^-1/2 of the local rows
     GCNK_CHECK(gcnk_graph_dinv(g, &dinv));
     Variable &W1 = variables[2], &W2 = variables[5];
+    const size_t own = (size_t)r0 * H;                                    // this rank's slice of an [N x H] gather source
 
     gcnk_graph *g_rows = g, *g_cols = g;
     if (z.use_views) {
@@ -251,71 +332,93 @@ std::pair<float, float> GCN::fused_pass(int current_split, bool training) {
     }
     auto gather_timer = [&](gcnk_graph *view) { return view == g ? TMR_GATHER_FULL : TMR_GATHER_PART; };
 
+    // The reference draws nnz(X) then N*H values per training pass from ONE stream in element order
+    // (module.cpp:214-218 via gcn.cpp:110-111).  Each rank jumps a copy of the stream to its own rows, so the
+    // masks are the same bits whatever the partition; the shared stream then advances by the global counts.
+    if (training) {
+        gpu_timer_begin(TMR_DROPOUT_FW);
+        if (drop) {
+            uint64_t st[2];
+            GCNK_CHECK(gcnk_rng_get_state(global_rng(), st));
+            GCNK_CHECK(gcnk_rng_set_state(z.slice_rng, st[0], st[1]));
+            GCNK_CHECK(gcnk_rng_skip(z.slice_rng, (uint64_t)x_off));
+            GCNK_CHECK(gcnk_dropout_mask(z.slice_rng, z.keep0, nnzX_loc, p, nullptr));
+            GCNK_CHECK(gcnk_rng_set_state(z.slice_rng, st[0], st[1]));
+            GCNK_CHECK(gcnk_rng_skip(z.slice_rng, (uint64_t)nnzX_all + (uint64_t)r0 * H));
+            GCNK_CHECK(gcnk_dropout_mask(z.slice_rng, z.keep1, (int64_t)n_loc * H, p, nullptr));
+        }
+        GCNK_CHECK(gcnk_rng_skip(global_rng(), (uint64_t)nnzX_all + (uint64_t)N * H));   // consumed even when p == 0
+        gpu_timer_end(TMR_DROPOUT_FW);
+    }
+
     if (!training && z.ax_valid) {
         // eval: A_hat*(X*W1) = (A_hat*X)*W1, ReLU and the pre-scale for the next gather in the epilogue
         gpu_timer_begin(TMR_SPMATMUL_FW);
-        GCNK_CHECK(gcnk_dense_transform(z.AX, N, F, W1.data, z.h1_s, H, nullptr, 1.0f, dinv, 1, nullptr));
+        GCNK_CHECK(gcnk_dense_transform(z.AX, n_loc, F, W1.data, z.h1_s + own, H, nullptr, 1.0f, dinv, 1, nullptr));
         gpu_timer_end(TMR_SPMATMUL_FW);
     } else {
-        // M0 Dropout + M1 SparseMatmul: the keep bits are drawn from the shared stream in element order and
-        // applied on read; the stored feature values are never modified, so no set_input() copy is needed
-        if (training) {
-            gpu_timer_begin(TMR_DROPOUT_FW);
-            if (drop) GCNK_CHECK(gcnk_dropout_mask(global_rng(), z.keep0, nnzX, p, nullptr));
-            else GCNK_CHECK(gcnk_rng_skip(global_rng(), (uint64_t)nnzX));     // the reference still consumes the draws
-            gpu_timer_end(TMR_DROPOUT_FW);
-        }
+        // M0 Dropout + M1 SparseMatmul: keep bits applied on read; the stored feature values are never modified,
+        // so no set_input() copy is needed
         gpu_timer_begin(TMR_SPMATMUL_FW);
-        GCNK_CHECK(gcnk_spmm_fw(sp, d_feature_value, W1.data, z.xw_s, H, drop ? z.keep0 : nullptr, scale, dinv, nullptr));
+        GCNK_CHECK(gcnk_spmm_fw(sp, d_feature_value, W1.data, z.xw_s + own, H, drop ? z.keep0 : nullptr, scale, dinv, nullptr));
         gpu_timer_end(TMR_SPMATMUL_FW);
-
+        allgather(z.xw_s, H);
         // M2 GraphSum + M3 ReLU + M4 Dropout in the gather's epilogue
-        if (training) {
-            gpu_timer_begin(TMR_DROPOUT_FW);
-            if (drop) GCNK_CHECK(gcnk_dropout_mask(global_rng(), z.keep1, (int64_t)N * H, p, nullptr));
-            else GCNK_CHECK(gcnk_rng_skip(global_rng(), (uint64_t)N * H));
-            gpu_timer_end(TMR_DROPOUT_FW);
-        }
         gpu_timer_begin(TMR_GATHER_FULL);
-        GCNK_CHECK(gcnk_gather_relu_drop(g, z.xw_s, z.h1_s, drop ? z.keep1 : nullptr, training ? z.mask : nullptr,
+        GCNK_CHECK(gcnk_gather_relu_drop(g, z.xw_s, z.h1_s + own, drop ? z.keep1 : nullptr, training ? z.mask : nullptr,
                                          training ? scale : 1.0f, H, nullptr));
         gpu_timer_end(TMR_GATHER_FULL);
     }
+    allgather(z.h1_s, H);
     // the layer-2 aggregation at width H, only for the rows whose logits the loss looks at
     gpu_timer_begin(gather_timer(g_rows));
     GCNK_CHECK(gcnk_gather_plain(g_rows, z.h1_s, z.P, H, nullptr));
     gpu_timer_end(gather_timer(g_rows));
 
-    // M5 Matmul + M7 CrossEntropyLoss + get_accuracy (+ Matmul backward when training), row-local
+    // M5 Matmul + M7 CrossEntropyLoss + get_accuracy (+ Matmul backward when training), row-local.
+    // count = labelled rows of the split over ALL ranks: the gradient is divided by it (module.cpp:154-158)
     gpu_timer_begin(TMR_LOSS_FW);
-    GCNK_CHECK(gcnk_layer2_fused(z.P, W2.data, d_split, d_label, current_split, N, H, C, training, split_count[current_split & 3],
-                                 dinv, training ? z.G : nullptr, training ? W2.grad : nullptr, nullptr, z.d_result, z.ws,
-                                 z.ws_bytes, nullptr));
+    GCNK_CHECK(gcnk_layer2_fused(z.P, W2.data, d_split, d_label, current_split, n_loc, H, C, training,
+                                 split_count[current_split & 3], dinv, training ? z.G + own : nullptr,
+                                 training ? W2.grad : nullptr, nullptr, z.d_result, z.ws, z.ws_bytes, nullptr));
     gpu_timer_end(TMR_LOSS_FW);
-    GCNK_CHECK(gcnk_memcpy_d2h(z.h_result, z.d_result, sizeof(gcnk_ce_result), nullptr));
 
     const float sumsq_before = z.sumsq;
     if (training) {
         // backward of M6/M5 is inside layer2; M4/M3/M2 backward = one masked gather + one plain gather
+        allgather(z.G, H);
         gpu_timer_begin(gather_timer(g_cols));
-        GCNK_CHECK(gcnk_gather_mask(g_cols, z.G, z.Gm, z.mask, scale, H, nullptr));
+        GCNK_CHECK(gcnk_gather_mask(g_cols, z.G, z.Gm + own, z.mask, scale, H, nullptr));
         gpu_timer_end(gather_timer(g_cols));
+        allgather(z.Gm, H);
         gpu_timer_begin(TMR_GATHER_FULL);
         GCNK_CHECK(gcnk_gather_plain(g, z.Gm, z.dxw, H, nullptr));
         gpu_timer_end(TMR_GATHER_FULL);
         gpu_timer_begin(TMR_SPMATMUL_BW);
         GCNK_CHECK(gcnk_spmm_bw(sp, d_feature_value, z.dxw, W1.grad, H, drop ? z.keep0 : nullptr, scale, nullptr));
         gpu_timer_end(TMR_SPMATMUL_BW);
+    }
+    if (dist.world > 1) {
+        // sums over nodes: dW1, dW2 and {sum of loss terms, count, wrong}; every rank then applies the same update
+        float *bufs[3] = {z.ws, W1.grad, W2.grad};
+        const size_t counts[3] = {4, (size_t)W1.size, (size_t)W2.size};
+        gpu_timer_begin(TMR_COMM);
+        GCNK_CHECK(gcnk_comm_allreduce(dist.comm, bufs, counts, training ? 3 : 1, 0, nullptr));
+        gpu_timer_end(TMR_COMM);
+    }
+    GCNK_CHECK(gcnk_memcpy_d2h(z.h_red, z.ws, 4 * sizeof(float), nullptr));
+    if (training) {
         optimizer.step(z.d_sumsq);
         GCNK_CHECK(gcnk_memcpy_d2h(z.h_sumsq, z.d_sumsq, sizeof(float), nullptr));
     }
     GCNK_CHECK(gcnk_stream_sync(nullptr));                                // the one host sync of the pass
     gpu_timer_resolve();
     if (training) z.sumsq = *z.h_sumsq;
-    last_count = z.h_result->count;
-    last_wrong = z.h_result->wrong;
+    last_count = (int)z.h_red[1];
+    last_wrong = (int)z.h_red[2];
+    const float mean_loss = z.h_red[0] / (float)last_count;              // count == 0 -> NaN, as the reference
     const float l2 = params.weight_decay * sumsq_before / 2;              // gcn.cpp:98-105, W1 as it was in this forward
-    return {z.h_result->loss + l2, float(last_count - last_wrong) / last_count};
+    return {mean_loss + l2, float(last_count - last_wrong) / last_count};
 }
 
 // -------------------------------------------------------------------------------- the loop ----
@@ -377,6 +480,7 @@ void GCN::run() {
 
 // ------------------------------------------------------------------------------ inspection ----
 long GCN::var_size(int idx) const {
+    if (dist.world > 1 && idx != 2 && idx != 5) return 0;      // a partitioned run exposes the (replicated) weights only
     const long N = params.num_nodes, F = params.input_dim, H = params.hidden_dim, C = params.output_dim;
     switch (idx) {
     case 0: return (long)data->feature_index.indices.size();
@@ -411,7 +515,7 @@ void GCN::get_var(int idx, bool grad, float *h_out) {
         if (grad) { memset(h_out, 0, sizeof(float) * (size_t)size); return; }
         float *d_logits = nullptr;
         GCNK_CHECK(gcnk_malloc((void **)&d_logits, sizeof(float) * (size_t)size));
-        GCNK_CHECK(gcnk_gather_plain(data->graph.graph(), z.h1_s, z.P, H, nullptr));   // the passes aggregate only their split's rows
+        GCNK_CHECK(gcnk_gather_plain(graph_handle(), z.h1_s, z.P, H, nullptr));   // the passes aggregate only their split's rows
         GCNK_CHECK(gcnk_layer2_fused(z.P, variables[5].data, d_split, d_label, 0, N, H, C, 0, 0, nullptr, nullptr, nullptr, d_logits,
                                      z.d_result, z.ws, z.ws_bytes, nullptr));
         d2h(d_logits, size);
@@ -423,7 +527,7 @@ void GCN::get_var(int idx, bool grad, float *h_out) {
     d2h(src, size);
     if (!(idx == 1 && grad)) {
         const float *d_dinv = nullptr;
-        GCNK_CHECK(gcnk_graph_dinv(data->graph.graph(), &d_dinv));
+        GCNK_CHECK(gcnk_graph_dinv(graph_handle(), &d_dinv));
         std::vector<float> dinv((size_t)N);
         GCNK_CHECK(gcnk_memcpy_d2h(dinv.data(), d_dinv, sizeof(float) * (size_t)N, nullptr));
         GCNK_CHECK(gcnk_stream_sync(nullptr));

@@ -38,10 +38,23 @@ public:
 
 enum GCNPlan { PLAN_AUTO = 0, PLAN_MODULES = 1, PLAN_FUSED = 2 };
 
+// Rows [r0, r0 + n_rows) of a dataset: graph rows with GLOBAL column ids, feature rows, labels, split.
+// Pure host integer work; concatenating the slices of a partition reproduces the input bit for bit.
+void slice_rows(const GCNData &src, int r0, int n_rows, GCNData &dst);
+
+// Row-partitioned execution (the reference is single-GPU): rank k of `world` owns the contiguous,
+// nnz-balanced row range gcnk_partition_rows assigns it.  Every rank is constructed from the SAME full GCNData
+// and the same seed; `comm` is an initialised gcnk_comm (include/gcnk.h).  world == 1 is the plain engine.
+struct GCNDist {
+    int rank = 0, world = 1;
+    gcnk_comm *comm = nullptr;
+};
+
 class GCN {
 public:
     GCN(GCNParams params, GCNData *data);                       // plan from $GCN_PLAN (modules|fused), default auto
     GCN(GCNParams params, GCNData *data, GCNPlan plan, bool quiet);
+    GCN(GCNParams params, GCNData *data, GCNPlan plan, bool quiet, GCNDist dist);
     ~GCN();
     GCNParams params;
     void run();
@@ -66,7 +79,16 @@ private:
     float get_l2_penalty();
     std::pair<float, float> fused_pass(int current_split, bool training);
 
-    GCNData *data;
+    void build_partition();
+    gcnk_graph *graph_handle();
+    void allgather(float *d_all, int dim);
+    GCNData *data;                           // what this rank computes on: the caller's data, or `local` (its row slice)
+    GCNData *full_data = nullptr;            // the caller's full data
+    std::unique_ptr<GCNData> local;
+    GCNDist dist;
+    std::vector<int> row_begin;              // [world + 1] partition cuts
+    int n_loc = 0, r0 = 0;                   // rows owned by this rank, first owned row
+    float *d_dinv_global = nullptr;          // [N] d^-1/2 of every node (partitioned runs)
     GCNPlan plan_ = PLAN_MODULES;
     bool quiet_ = false;
     std::vector<Module *> modules;

@@ -5,7 +5,8 @@
 
 #include "check.h"
 
-static gcnk_rng *g_rng = nullptr;
+// one stream per host thread: a process drives one GPU per thread at most (rand.cpp:5 keeps one global state)
+static thread_local gcnk_rng *g_rng = nullptr;
 
 gcnk_rng *global_rng() {
     if (!g_rng) GCNK_CHECK(gcnk_rng_create(&g_rng, 1, 2));

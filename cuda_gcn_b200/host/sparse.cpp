@@ -45,6 +45,14 @@ gcnk_graph *SparseIndex::graph() {
     return graph_;
 }
 
+gcnk_graph *SparseIndex::graph_slice(int n_cols, const float *d_dinv_global) {
+    if (!graph_) {
+        upload();
+        GCNK_CHECK(gcnk_graph_create(&graph_, dev_indptr_, dev_indices_, rows(), nnz(), n_cols, d_dinv_global, nullptr));
+    }
+    return graph_;
+}
+
 gcnk_spmat *SparseIndex::spmat(int m, int n) {
     if (!spmat_) {
         upload();

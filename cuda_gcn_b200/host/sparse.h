@@ -26,6 +26,8 @@ public:
     const int *d_indptr();
     const int *d_indices();
     gcnk_graph *graph();                       // this index as the (square) normalised adjacency
+    // this index as a ROW SLICE of an adjacency with n_cols nodes (column ids global); d_dinv_global = d^-1/2 of all nodes
+    gcnk_graph *graph_slice(int n_cols, const float *d_dinv_global);
     gcnk_spmat *spmat(int m, int n);           // this index as an m x n sparse feature matrix
     void release_device();
 

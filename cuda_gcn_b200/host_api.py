@@ -29,6 +29,7 @@ SIGNATURES = {
     "gcnh_data_parse": (C.c_int, [vp, C.c_char_p, C.c_char_p, C.POINTER(Params), C.c_int]),
     "gcnh_data_fill": (C.c_int, [vp, C.c_int, _i32, _i32, _i32, _i32, _f32, _i32, _i32]),
     "gcnh_data_synth": (C.c_int, [vp, C.c_char_p, C.c_double, C.c_uint64, C.POINTER(Params)]),
+    "gcnh_data_slice": (vp, [vp, C.c_int, C.c_int, ip, ip]),
     "gcnh_data_sizes": (None, [vp, C.POINTER(C.c_int64)]),
     "gcnh_data_graph_indptr": (ip, [vp]),
     "gcnh_data_graph_indices": (ip, [vp]),
@@ -38,6 +39,9 @@ SIGNATURES = {
     "gcnh_data_label": (ip, [vp]),
     "gcnh_data_split": (ip, [vp]),
     "gcnh_engine_create": (vp, [C.POINTER(Params), vp, C.c_long, C.c_int, C.c_int]),
+    "gcnh_comm_unique_id": (C.c_int, [vp]),
+    "gcnh_engine_create_dist": (vp, [C.POINTER(Params), vp, C.c_long, C.c_int, C.c_int, C.c_int, vp]),
+    "gcnh_engine_allreduce_host": (None, [vp, vp, C.c_int, C.c_int]),
     "gcnh_engine_destroy": (None, [vp]),
     "gcnh_engine_plan": (C.c_int, [vp]),
     "gcnh_engine_train_epoch": (None, [vp, fp, fp]),
@@ -108,6 +112,18 @@ class Data:
             raise RuntimeError(f"synthetic preset {preset!r} failed")
         return d
 
+    def slice(self, rank, world):
+        """(Data holding this rank's rows, row_begin, row_end) under the nnz-balanced row partition."""
+        a, b = C.c_int(), C.c_int()
+        out = Data.__new__(Data)
+        out.L = self.L
+        out.h = self.L.gcnh_data_slice(self.h, rank, world, C.byref(a), C.byref(b))
+        if not out.h:
+            raise RuntimeError("gcnh_data_slice failed")
+        out.params = Params.from_buffer_copy(bytes(self.params))
+        out.params.num_nodes = b.value - a.value
+        return out, a.value, b.value
+
     def sizes(self):
         s = (C.c_int64 * 7)()
         self.L.gcnh_data_sizes(self.h, s)
@@ -144,12 +160,23 @@ class Engine:
     """GCN (gcn.h:24-44) on one GPU."""
 
     def __init__(self, data: Data, hidden_dim=16, dropout=0.5, lr=0.01, weight_decay=5e-4, epochs=100, early_stopping=0,
-                 seed=1, plan=PLAN_AUTO, device=0):
+                 seed=1, plan=PLAN_AUTO, device=0, rank=0, world=1, nccl_id=None):
+        """world > 1: row-partitioned engine; every rank passes the same data and seed, nccl_id = the 128 bytes
+        rank 0 got from unique_id() (see rendezvous())."""
         self.L, self.data = load(), data
         p = Params(data.params.num_nodes, data.params.input_dim, hidden_dim, data.params.output_dim, dropout, lr,
                    weight_decay, epochs, early_stopping)
         self.params = p
-        self.h = self.L.gcnh_engine_create(C.byref(p), data.h, seed, plan, device)
+        if world > 1:
+            buf = C.create_string_buffer(bytes(nccl_id), 128)
+            self.h = self.L.gcnh_engine_create_dist(C.byref(p), data.h, seed, device, rank, world, buf)
+        else:
+            self.h = self.L.gcnh_engine_create(C.byref(p), data.h, seed, plan, device)
+
+    def allreduce_host(self, values, op_max=False):
+        a = np.ascontiguousarray(values, dtype=np.float32)
+        self.L.gcnh_engine_allreduce_host(self.h, a.ctypes.data, len(a), int(op_max))
+        return a
 
     @property
     def plan(self):
@@ -192,6 +219,70 @@ class Engine:
             self.close()
         except Exception:
             pass
+
+
+def unique_id() -> bytes:
+    buf = C.create_string_buffer(128)
+    if not load().gcnh_comm_unique_id(buf):
+        raise RuntimeError("ncclGetUniqueId failed")
+    return buf.raw
+
+
+def rendezvous(rank: int, world: int, addr: str = "127.0.0.1", port: int = 29500, timeout: float = 120.0, uid: bytes | None = None) -> bytes:
+    """Share rank 0's ncclUniqueId with the other ranks of ONE node over a loopback TCP socket (stdlib only).
+    Rank 0 listens on the first free port of port+1..port+32; the others probe the same sequence.  A 6-byte
+    magic guards against unrelated services on those ports."""
+    import socket
+    import time
+    magic = b"GCNKID"
+    if world <= 1:
+        return b""
+    if rank == 0:
+        uid = uid if uid is not None else unique_id()
+        srv = None
+        for off in range(1, 33):
+            try:
+                srv = socket.socket(socket.AF_INET, socket.SOCK_STREAM)
+                srv.setsockopt(socket.SOL_SOCKET, socket.SO_REUSEADDR, 1)
+                srv.bind((addr, port + off))
+                break
+            except OSError:
+                srv.close()
+                srv = None
+        if srv is None:
+            raise RuntimeError("rendezvous: no free port")
+        srv.listen(world)
+        srv.settimeout(timeout)
+        served = 0
+        while served < world - 1:
+            conn, _ = srv.accept()
+            conn.settimeout(10)
+            try:
+                if conn.recv(6) == magic:
+                    conn.sendall(magic + uid)
+                    served += 1
+            finally:
+                conn.close()
+        srv.close()
+        return uid
+    deadline = time.time() + timeout
+    while time.time() < deadline:
+        for off in range(1, 33):
+            try:
+                with socket.create_connection((addr, port + off), timeout=2) as c:
+                    c.sendall(magic)
+                    data = b""
+                    while len(data) < 6 + 128:
+                        chunk = c.recv(6 + 128 - len(data))
+                        if not chunk:
+                            break
+                        data += chunk
+                    if len(data) == 6 + 128 and data[:6] == magic:
+                        return data[6:]
+            except OSError:
+                continue
+        time.sleep(0.2)
+    raise RuntimeError("rendezvous: rank 0 did not answer")
 
 
 def timers():

@@ -44,6 +44,9 @@ int gcnh_data_fill(gcnh_data *d, int num_nodes, const int *graph_indptr, const i
 /* seeded synthetic dataset: preset in {cora,citeseer,pubmed,reddit,products}, scale in (0,1] shrinks
  * the node and edge counts; returns 0 on an unknown preset or a degree above the int32-safe 46,340 */
 int gcnh_data_synth(gcnh_data *d, const char *preset, double scale, uint64_t seed, gcnh_params *params);
+/* The row slice rank `rank` of `world` owns under the nnz-balanced partition (gcnk_partition_rows): a new
+ * gcnh_data (free it with gcnh_data_free); *row_begin / *row_end receive the range.  Host-only integer work. */
+gcnh_data *gcnh_data_slice(const gcnh_data *d, int rank, int world, int *row_begin, int *row_end);
 /* sizes[7] = {num_nodes, graph_nnz, feature_nnz, n_label, n_split, max_degree, feature_rows} */
 void gcnh_data_sizes(const gcnh_data *d, int64_t *sizes);
 /* borrowed pointers into the host vectors (valid until the data is freed / refilled) */
@@ -60,6 +63,15 @@ const int   *gcnh_data_split(const gcnh_data *d);
  * seed: the value the reference would get from time(NULL) (rand.cpp:7); < 0 = $GCN_SEED or time(NULL).
  * device: CUDA device index.  The data must outlive the engine (as GCNData* in the reference). */
 gcnh_engine *gcnh_engine_create(const gcnh_params *params, gcnh_data *data, long seed, int plan, int device);
+/* Row-partitioned engine (one process or thread per GPU): every rank passes the SAME full data and seed.
+ * rank 0 obtains the 128-byte id from gcnh_comm_unique_id and shares it with the other ranks (any transport);
+ * all ranks then call gcnh_engine_create_dist, which is collective (NCCL communicator creation). */
+int gcnh_comm_unique_id(void *h_id128);
+gcnh_engine *gcnh_engine_create_dist(const gcnh_params *params, gcnh_data *data, long seed, int device, int rank, int world,
+                                     const void *h_id128);
+/* in-place all-reduce of a small host array over the engine's communicator (sum, or max when op_max != 0):
+ * barrier + max-over-ranks timing for benchmarks; a no-op for a single-GPU engine */
+void gcnh_engine_allreduce_host(gcnh_engine *e, float *h_values, int count, int op_max);
 void gcnh_engine_destroy(gcnh_engine *e);
 int  gcnh_engine_plan(const gcnh_engine *e);
 void gcnh_engine_train_epoch(gcnh_engine *e, float *loss, float *acc);          /* gcn.cpp:107-118 */

@@ -55,6 +55,7 @@ int gcnk_event_destroy(void *event);
 int gcnk_event_record(void *event, gcnk_stream_t stream);
 int gcnk_event_sync(void *event);
 int gcnk_event_elapsed_ms(void *start, void *stop, float *ms);
+int gcnk_stream_wait_event(gcnk_stream_t stream, void *event);   /* work queued on stream after this waits for event */
 int gcnk_flush_l2(gcnk_stream_t stream);               /* writes a >L2 scratch buffer (bench hygiene) */
 
 /* ---- graph preparation ------------------------------------------------------------------------
@@ -190,12 +191,28 @@ int gcnk_sum_squares(const float *w, int64_t n, float *d_out, gcnk_stream_t stre
  *             W2_grad = P^T * dlogits  (= H1^T * A_hat * dlogits for a symmetric A_hat)
  * This is the algebraic re-ordering A_hat*(H1*W2) -> (A_hat*H1)*W2 (hard part 3): the
  * gather runs at width h instead of c.  logits_out may be NULL.  count = #labelled rows (static).
- * d_result as gcnk_softmax_ce.  Requires h*c <= 4096. */
+ * d_result as gcnk_softmax_ce.  Requires h*c <= 4096.  On return the first four floats of `workspace` hold the
+ * raw sums {sum of loss terms, count, wrong, 0} (counts as floats, exact below 2^24) for cross-rank reduction. */
 int gcnk_layer2_fused(const float *P, const float *W2, const int *split, const int *label, int current_split,
                       int n, int h, int c, int training, int count, const float *d_dinv,
                       float *G_scaled, float *W2_grad, float *logits_out, gcnk_ce_result *d_result,
                       float *workspace, size_t workspace_bytes, gcnk_stream_t stream);
 size_t gcnk_layer2_workspace(int n, int h, int c);
+
+/* ---- exchange steps of the row-partitioned engine (NCCL over NVLink; the reference is single-GPU) ------
+ * One process (or thread) per GPU.  Rank 0 calls gcnk_comm_unique_id and shares the 128 bytes with the
+ * other ranks by any means; every rank then calls gcnk_comm_create.  Errors: 1000 + ncclResult_t. */
+typedef struct gcnk_comm gcnk_comm;
+int gcnk_comm_unique_id(void *h_id128);
+int gcnk_comm_create(gcnk_comm **comm, const void *h_id128, int rank, int world, int device);
+int gcnk_comm_destroy(gcnk_comm *comm);
+int gcnk_comm_rank(const gcnk_comm *comm, int *rank, int *world);
+/* In-place all-gather of row blocks: d_all is [h_row_begin[world] x dim]; on entry rank r's rows
+ * [h_row_begin[r], h_row_begin[r+1]) are valid on rank r, on return all rows are valid everywhere. */
+int gcnk_comm_allgather_rows(gcnk_comm *comm, float *d_all, const int *h_row_begin, int dim, gcnk_stream_t stream);
+/* In-place all-reduce (sum, or max when op_max != 0) of n_bufs device buffers in one group. */
+int gcnk_comm_allreduce(gcnk_comm *comm, float *const *d_bufs, const size_t *h_counts, int n_bufs, int op_max,
+                        gcnk_stream_t stream);
 
 /* ---- host-side, bit-exact integer work --------------------------------------------------------------
  * Contiguous nnz-balanced row partition of a CSR: h_row_begin[parts+1] receives the cuts;

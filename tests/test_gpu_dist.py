@@ -1,0 +1,37 @@
+"""Row-partitioned engine == single-GPU engine ("2/4/8-rank run == 1-rank run, loss to 1e-6 rel.,
+integer outputs identical").  Needs >= 2 GPUs: run with `gpurun --gpus 2 -- python -m pytest tests/test_gpu_dist.py -m gpu`."""
+import json
+import subprocess
+import sys
+from pathlib import Path
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def n_gpus():
+    from cuda_gcn_b200 import abi
+    return abi.device_count()
+
+
+@pytest.mark.parametrize("preset,scale,dropout", [("pubmed", 1.0, 0.5), ("cora", 1.0, 0.0), ("reddit", 0.02, 0.5)])
+@pytest.mark.parametrize("world", [2, 4])
+def test_partitioned_equals_single(preset, scale, dropout, world):
+    if n_gpus() < world:
+        pytest.skip(f"needs {world} GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+           "--master-port", str(29600 + world), str(ROOT / "tools" / "dist_check.py"), "--preset", preset, "--scale", str(scale),
+           "--epochs", "6", "--dropout", str(dropout)]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-3000:]
+    line = [l for l in out.stdout.splitlines() if l.startswith("{")][-1]
+    r = json.loads(line)
+    assert r["replicated"], "ranks hold different weights"
+    for d, s in zip(r["dist"], r["single"]):
+        assert abs(d[0] - s[0]) <= 2e-6 * abs(s[0]) + 1e-7 and abs(d[2] - s[2]) <= 2e-6 * abs(s[2]) + 1e-7, (d, s)
+        assert d[4] == s[4] and d[6] == s[6]                       # labelled-row counts: exact
+        assert abs(d[5] - s[5]) <= 1 and abs(d[7] - s[7]) <= 1     # wrong counts: a borderline row at most
+    assert abs(r["dist_test"][0] - r["single_test"][0]) <= 2e-6 * abs(r["single_test"][0]) + 1e-7
+    assert r["w1_maxdiff"] <= 1e-5 * r["w1_scale"] and r["w2_maxdiff"] <= 1e-5 * r["w2_scale"]
