@@ -27,6 +27,10 @@ from pathlib import Path
 
 import numpy as np
 
+# keep NCCL's "NCCL version ..." banner off stdout (the contract is ONE JSON line); INFO/TRACE set by the caller stay
+if os.environ.get("NCCL_DEBUG", "").upper() not in ("INFO", "TRACE"):
+    os.environ["NCCL_DEBUG"] = "WARN"
+
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 

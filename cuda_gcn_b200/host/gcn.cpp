@@ -21,7 +21,17 @@ struct GCN::Fused {
     float *G = nullptr;        // [N x H]  dinv (.) (dlogits * W2^T)
     float *Gm = nullptr;       // [N x H]  dinv (.) dropout'/relu'(A_hat * dlogits W2^T)
     float *dxw = nullptr;      // [N x H]  gradient wrt X W1
-    uint32_t *keep0 = nullptr, *keep1 = nullptr, *mask = nullptr;
+    uint32_t *keep0 = nullptr, *keep1 = nullptr, *mask = nullptr;   // the keep bits this pass reads
+    // Double-buffered keep bits: the masks of the NEXT training pass are drawn on a side stream while this pass
+    // (and the eval pass after it) runs — the generator is ALU-bound, the gathers are L2-bound.  The draws are a
+    // pure function of the stream position, so the bits are identical to drawing them in line; if anything else
+    // consumed the shared stream in between (state mismatch) they are simply drawn again in line.
+    uint32_t *keep0_buf[2] = {nullptr, nullptr}, *keep1_buf[2] = {nullptr, nullptr};
+    int cur = 0;
+    gcnk_stream_t rng_stream = nullptr;
+    void *ev_ready = nullptr, *ev_go = nullptr;
+    bool pre_valid = false;
+    uint64_t pre_state[2] = {0, 0};
     float *ws = nullptr; size_t ws_bytes = 0;
     gcnk_ce_result *d_result = nullptr, *h_result = nullptr;   // device / pinned host
     float *d_sumsq = nullptr, *h_sumsq = nullptr;
@@ -39,10 +49,14 @@ struct GCN::Fused {
     float *AX = nullptr;
     bool ax_valid = false, use_views = true;
     ~Fused() {
+        if (rng_stream) { gcnk_stream_sync(rng_stream); gcnk_stream_destroy(rng_stream); }
+        if (ev_ready) gcnk_event_destroy(ev_ready);
+        if (ev_go) gcnk_event_destroy(ev_go);
+        for (uint32_t *b : {keep0_buf[1], keep1_buf[1]}) if (b) gcnk_free(b);
         for (gcnk_graph *g : {rows[1], rows[2], rows[3], cols_train}) if (g) gcnk_graph_destroy(g);
         for (int *k : keep) if (k) gcnk_free(k);   // keep[0] = global train-column flags
         if (AX) gcnk_free(AX);
-        for (void *p : {(void *)xw_s, (void *)h1_s, (void *)P, (void *)G, (void *)Gm, (void *)dxw, (void *)keep0, (void *)keep1,
+        for (void *p : {(void *)xw_s, (void *)h1_s, (void *)P, (void *)G, (void *)Gm, (void *)dxw, (void *)keep0_buf[0], (void *)keep1_buf[0],
                         (void *)mask, (void *)ws, (void *)d_result, (void *)d_sumsq})
             if (p) gcnk_free(p);
         if (h_result) gcnk_free_host(h_result);
@@ -173,8 +187,19 @@ void GCN::build(GCNPlan plan) {
     const size_t nh_all = sizeof(float) * (size_t)N * H, nh_loc = sizeof(float) * (size_t)n_loc * H;
     for (float **p : {&fz->xw_s, &fz->h1_s, &fz->G, &fz->Gm}) GCNK_CHECK(gcnk_malloc((void **)p, nh_all));
     for (float **p : {&fz->P, &fz->dxw}) GCNK_CHECK(gcnk_malloc((void **)p, nh_loc));
-    GCNK_CHECK(gcnk_malloc((void **)&fz->keep0, sizeof(uint32_t) * (nnzX_loc / 32 + 4)));
-    GCNK_CHECK(gcnk_malloc((void **)&fz->keep1, sizeof(uint32_t) * ((size_t)n_loc * H / 32 + 4)));
+    for (int b = 0; b < 2; b++) {
+        GCNK_CHECK(gcnk_malloc((void **)&fz->keep0_buf[b], sizeof(uint32_t) * (nnzX_loc / 32 + 4)));
+        GCNK_CHECK(gcnk_malloc((void **)&fz->keep1_buf[b], sizeof(uint32_t) * ((size_t)n_loc * H / 32 + 4)));
+    }
+    fz->keep0 = fz->keep0_buf[0]; fz->keep1 = fz->keep1_buf[0];   // freed through keep0/keep1 (buffer 0) and the [1] entries
+    {
+        const char *ns = getenv("GCN_NO_RNG_OVERLAP");
+        if (!(ns && *ns && strcmp(ns, "0"))) {
+            GCNK_CHECK(gcnk_stream_create(&fz->rng_stream));
+            GCNK_CHECK(gcnk_event_create(&fz->ev_ready));
+            GCNK_CHECK(gcnk_event_create(&fz->ev_go));
+        }
+    }
     GCNK_CHECK(gcnk_malloc((void **)&fz->mask, sizeof(uint32_t) * ((size_t)n_loc * gcnk_mask_row_stride_bits(H) / 32 + 4)));
     fz->ws_bytes = gcnk_layer2_workspace(n_loc, H, C);
     GCNK_CHECK(gcnk_malloc((void **)&fz->ws, fz->ws_bytes));
@@ -335,17 +360,24 @@ std::pair<float, float> GCN::fused_pass(int current_split, bool training) {
     // The reference draws nnz(X) then N*H values per training pass from ONE stream in element order
     // (module.cpp:214-218 via gcn.cpp:110-111).  Each rank jumps a copy of the stream to its own rows, so the
     // masks are the same bits whatever the partition; the shared stream then advances by the global counts.
+    auto draw_masks = [&](const uint64_t *st, uint32_t *k0, uint32_t *k1, gcnk_stream_t stream) {
+        GCNK_CHECK(gcnk_rng_set_state(z.slice_rng, st[0], st[1]));
+        GCNK_CHECK(gcnk_rng_skip(z.slice_rng, (uint64_t)x_off));
+        GCNK_CHECK(gcnk_dropout_mask(z.slice_rng, k0, nnzX_loc, p, stream));
+        GCNK_CHECK(gcnk_rng_set_state(z.slice_rng, st[0], st[1]));
+        GCNK_CHECK(gcnk_rng_skip(z.slice_rng, (uint64_t)nnzX_all + (uint64_t)r0 * H));
+        GCNK_CHECK(gcnk_dropout_mask(z.slice_rng, k1, (int64_t)n_loc * H, p, stream));
+    };
     if (training) {
         gpu_timer_begin(TMR_DROPOUT_FW);
+        uint64_t st[2];
+        GCNK_CHECK(gcnk_rng_get_state(global_rng(), st));
         if (drop) {
-            uint64_t st[2];
-            GCNK_CHECK(gcnk_rng_get_state(global_rng(), st));
-            GCNK_CHECK(gcnk_rng_set_state(z.slice_rng, st[0], st[1]));
-            GCNK_CHECK(gcnk_rng_skip(z.slice_rng, (uint64_t)x_off));
-            GCNK_CHECK(gcnk_dropout_mask(z.slice_rng, z.keep0, nnzX_loc, p, nullptr));
-            GCNK_CHECK(gcnk_rng_set_state(z.slice_rng, st[0], st[1]));
-            GCNK_CHECK(gcnk_rng_skip(z.slice_rng, (uint64_t)nnzX_all + (uint64_t)r0 * H));
-            GCNK_CHECK(gcnk_dropout_mask(z.slice_rng, z.keep1, (int64_t)n_loc * H, p, nullptr));
+            z.keep0 = z.keep0_buf[z.cur]; z.keep1 = z.keep1_buf[z.cur];
+            if (z.pre_valid && z.pre_state[0] == st[0] && z.pre_state[1] == st[1])
+                GCNK_CHECK(gcnk_stream_wait_event(nullptr, z.ev_ready));       // drawn ahead on the side stream
+            else
+                draw_masks(st, z.keep0, z.keep1, nullptr);
         }
         GCNK_CHECK(gcnk_rng_skip(global_rng(), (uint64_t)nnzX_all + (uint64_t)N * H));   // consumed even when p == 0
         gpu_timer_end(TMR_DROPOUT_FW);
@@ -362,6 +394,19 @@ std::pair<float, float> GCN::fused_pass(int current_split, bool training) {
         gpu_timer_begin(TMR_SPMATMUL_FW);
         GCNK_CHECK(gcnk_spmm_fw(sp, d_feature_value, W1.data, z.xw_s + own, H, drop ? z.keep0 : nullptr, scale, dinv, nullptr));
         gpu_timer_end(TMR_SPMATMUL_FW);
+        if (drop && z.rng_stream) {
+            // Draw the NEXT training pass's masks now, on the side stream, into the other buffer (its last readers
+            // were in the previous training pass, which has completed: every pass ends with a host sync).  It is
+            // released only after the feature transform above (issue-bound, like the generator) so that it runs
+            // under the L2-bound gathers.
+            GCNK_CHECK(gcnk_event_record(z.ev_go, nullptr));
+            GCNK_CHECK(gcnk_stream_wait_event(z.rng_stream, z.ev_go));
+            GCNK_CHECK(gcnk_rng_get_state(global_rng(), z.pre_state));
+            draw_masks(z.pre_state, z.keep0_buf[z.cur ^ 1], z.keep1_buf[z.cur ^ 1], z.rng_stream);
+            GCNK_CHECK(gcnk_event_record(z.ev_ready, z.rng_stream));
+            z.pre_valid = true;
+            z.cur ^= 1;
+        }
         allgather(z.xw_s, H);
         // M2 GraphSum + M3 ReLU + M4 Dropout in the gather's epilogue
         gpu_timer_begin(TMR_GATHER_FULL);
