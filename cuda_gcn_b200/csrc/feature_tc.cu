@@ -317,20 +317,9 @@ __global__ void __launch_bounds__(THREADS, 2) dense_bw16_tc_kernel(const float *
         }
 }
 
-// sums the per-CTA partials in CTA order (deterministic); 4 independent chains per thread for latency
+// sums the per-CTA partials in a fixed order (deterministic)
 __global__ void __launch_bounds__(256) reduce_parts_kernel(const float *__restrict__ partials, float *__restrict__ out, int elems, int parts) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= elems) return;
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-    int b = 0;
-    for (; b + 3 < parts; b += 4) {
-        s0 += partials[(size_t)b * elems + i];
-        s1 += partials[(size_t)(b + 1) * elems + i];
-        s2 += partials[(size_t)(b + 2) * elems + i];
-        s3 += partials[(size_t)(b + 3) * elems + i];
-    }
-    for (; b < parts; b++) s0 += partials[(size_t)b * elems + i];
-    out[i] = (s0 + s1) + (s2 + s3);
+    reduce_parts_block(partials, out, elems, parts);
 }
 
 }  // namespace gcnk_tc
@@ -376,7 +365,7 @@ int dense_bw16_tc(const float *x, const float *g, float *b_grad, float *partials
     dense_bw16_tc_kernel<<<grid, THREADS, 0, st>>>(x, g, partials, m, n, rows_per_cta, bits, (nnz + 31) / 32, scale);
     GCNK_LAUNCHED();
     const int elems = n * P;
-    reduce_parts_kernel<<<(elems + 255) / 256, 256, 0, st>>>(partials, b_grad, elems, parts);
+    reduce_parts_kernel<<<(elems + 31) / 32, 256, 0, st>>>(partials, b_grad, elems, parts);
     GCNK_LAUNCHED();
     return GCNK_OK;
 }

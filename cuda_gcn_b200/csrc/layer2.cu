@@ -143,46 +143,56 @@ __global__ void __launch_bounds__(L2_THREADS) layer2_h16_kernel(const float *__r
                                                                  float *__restrict__ dw_partials) {
     constexpr int H = 16;
     extern __shared__ __align__(16) float smem[];
-    float *sW = smem;                               // [16][c]
-    float *sDl = sW + H * c;                        // [warps][c]
-    float *sAcc = sDl + L2_WARPS * c;               // [warps][16*c]  (training only; used once, at the end)
+    float *sAcc = smem;                             // [warps][16*c]  (training only; used once, at the end)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int i = threadIdx.x; i < H * c; i += L2_THREADS) sW[i] = W2[i];
-    __syncthreads();
-    float *dl = sDl + warp * c;
-    float dw[CPL][H];
+    // this lane's columns of W2 (classes lane, lane+32) and its slice of the W2 gradient stay in registers
+    float w[CPL][H], dw[CPL][H];
 #pragma unroll
-    for (int t = 0; t < CPL; t++)
+    for (int t = 0; t < CPL; t++) {
+        const int cls = lane + 32 * t;
 #pragma unroll
-        for (int k = 0; k < H; k++) dw[t][k] = 0.f;
+        for (int k = 0; k < H; k++) { w[t][k] = cls < c ? __ldg(W2 + k * c + cls) : 0.f; dw[t][k] = 0.f; }
+    }
 
     float loss = 0.f;
     int count = 0, wrong = 0;
-    const int half = lane >> 4, kk = lane & 15, c_half = (c + 1) >> 1;
     const int total_warps = gridDim.x * L2_WARPS;
-    for (int s = blockIdx.x * L2_WARPS + warp; s < n; s += total_warps) {
-        const int truth = split[s] == current_split ? label[s] : -1;          // set_truth (gcn.cpp:78-81); warp-uniform
+    const float inv_count = 1.0f / count_f;
+    // software pipeline over this warp's rows: the next row's split/label/P are in flight while this row is
+    // processed (a row is a ~1,000-cycle dependent chain: loads, 16-deep FMA chains, five warp reductions)
+    int s = blockIdx.x * L2_WARPS + warp;
+    int n_split = 0, n_label = 0;
+    float4 nq[4] = {};
+    if (s < n) {
+        const float4 *pr = reinterpret_cast<const float4 *>(P + (size_t)s * H);
+        n_split = split[s]; n_label = label[s];
+        nq[0] = __ldg(pr); nq[1] = __ldg(pr + 1); nq[2] = __ldg(pr + 2); nq[3] = __ldg(pr + 3);
+    }
+    for (; s < n; s += total_warps) {
+        const int truth = n_split == current_split ? n_label : -1;            // set_truth (gcn.cpp:78-81); warp-uniform
+        float p[H];
+        p[0] = nq[0].x; p[1] = nq[0].y; p[2] = nq[0].z; p[3] = nq[0].w; p[4] = nq[1].x; p[5] = nq[1].y; p[6] = nq[1].z; p[7] = nq[1].w;
+        p[8] = nq[2].x; p[9] = nq[2].y; p[10] = nq[2].z; p[11] = nq[2].w; p[12] = nq[3].x; p[13] = nq[3].y; p[14] = nq[3].z; p[15] = nq[3].w;
+        {
+            const int sn = s + total_warps;
+            if (sn < n) {
+                const float4 *pr = reinterpret_cast<const float4 *>(P + (size_t)sn * H);
+                n_split = split[sn]; n_label = label[sn];
+                nq[0] = __ldg(pr); nq[1] = __ldg(pr + 1); nq[2] = __ldg(pr + 2); nq[3] = __ldg(pr + 3);
+            }
+        }
         if (truth < 0 && !logits_out) {
             if (training && lane < H) G[(size_t)s * H + lane] = 0.f;          // unlabelled rows carry no gradient
             continue;
-        }
-        float p[H];
-        {
-            const float4 *pr = reinterpret_cast<const float4 *>(P + (size_t)s * H);
-            const float4 a = __ldg(pr), b = __ldg(pr + 1), d = __ldg(pr + 2), e = __ldg(pr + 3);
-            p[0] = a.x; p[1] = a.y; p[2] = a.z; p[3] = a.w; p[4] = b.x; p[5] = b.y; p[6] = b.z; p[7] = b.w;
-            p[8] = d.x; p[9] = d.y; p[10] = d.z; p[11] = d.w; p[12] = e.x; p[13] = e.y; p[14] = e.z; p[15] = e.w;
         }
         float lg[CPL];
 #pragma unroll
         for (int t = 0; t < CPL; t++) {
             const int cls = lane + 32 * t;
             float v = 0.f;
-            if (cls < c) {
 #pragma unroll
-                for (int k = 0; k < H; k++) v = fmaf(p[k], sW[k * c + cls], v);
-                if (logits_out) logits_out[(size_t)s * c + cls] = v;
-            }
+            for (int k = 0; k < H; k++) v = fmaf(p[k], w[t][k], v);
+            if (logits_out && cls < c) logits_out[(size_t)s * c + cls] = v;
             lg[t] = v;
         }
         if (truth < 0) {
@@ -204,34 +214,43 @@ __global__ void __launch_bounds__(L2_THREADS) layer2_h16_kernel(const float *__r
 #pragma unroll
         for (int t = 0; t < CPL; t++) if (t == truth / 32) tl = lg[t];
         tl = __shfl_sync(FULL, tl, truth % 32);
-        bool w = false;
+        bool wr = false;
 #pragma unroll
-        for (int t = 0; t < CPL; t++) w |= (lane + 32 * t < c) && lg[t] > tl;        // strict (gcn.cpp:88-93)
-        w = __any_sync(FULL, w);
+        for (int t = 0; t < CPL; t++) wr |= (lane + 32 * t < c) && lg[t] > tl;       // strict (gcn.cpp:88-93)
+        wr = __any_sync(FULL, wr);
         count++;
-        wrong += w;
+        wrong += wr;
         loss += logf(sum) - (tl - mx);
         if (training) {
+            // dlogits of this lane's classes; dW2 += P^T dlogits; partial of dlogits * W2^T over this lane's classes
+            float pk[H];
+#pragma unroll
+            for (int k = 0; k < H; k++) pk[k] = 0.f;
 #pragma unroll
             for (int t = 0; t < CPL; t++) {
                 const int cls = lane + 32 * t;
+                float g = 0.f;
                 if (cls < c) {
-                    float g = ex[t] / sum;
+                    g = ex[t] / sum;
                     if (cls == truth) g -= 1.0f;
-                    g = g / count_f;                                                 // grad /= count (module.cpp:156-158)
-                    dl[cls] = g;
+                    g = g * inv_count;                                               // grad /= count (module.cpp:156-158)
+                }
 #pragma unroll
-                    for (int k = 0; k < H; k++) dw[t][k] = fmaf(p[k], g, dw[t][k]);  // dW2 += P^T dlogits
+                for (int k = 0; k < H; k++) { dw[t][k] = fmaf(p[k], g, dw[t][k]); pk[k] = fmaf(g, w[t][k], pk[k]); }
+            }
+            // transposing butterfly: 16 per-lane partials -> lane l holds the warp-wide sum for hidden unit l/2
+#pragma unroll
+            for (int half = 8, off = 16; off >= 2; half >>= 1, off >>= 1) {
+                const bool upper = lane & off;
+#pragma unroll
+                for (int i = 0; i < half; i++) {
+                    const float send = upper ? pk[i] : pk[i + half];
+                    const float keep = upper ? pk[i + half] : pk[i];
+                    pk[i] = keep + __shfl_xor_sync(FULL, send, off);
                 }
             }
-            __syncwarp();
-            // dlogits * W2^T: the two half-warps each take half of the classes for hidden unit kk
-            float v = 0.f;
-            const int c_lo = half * c_half, c_hi = min(c, c_lo + c_half);
-            for (int cls = c_lo; cls < c_hi; cls++) v = fmaf(dl[cls], sW[kk * c + cls], v);
-            v += __shfl_xor_sync(FULL, v, 16);
-            if (lane < H) G[(size_t)s * H + lane] = dinv[s] * v;
-            __syncwarp();
+            pk[0] += __shfl_xor_sync(FULL, pk[0], 1);
+            if (!(lane & 1)) G[(size_t)s * H + (lane >> 1)] = dinv[s] * pk[0];
         }
     }
 
@@ -263,39 +282,33 @@ __global__ void __launch_bounds__(L2_THREADS) layer2_h16_kernel(const float *__r
     }
 }
 
-// block 0 also produces the scalar result; every block reduces a slice of dW2 over the CTA partials
+// the last block produces the scalar result; the others reduce 32 elements of dW2 each over the CTA partials
 __global__ void __launch_bounds__(256) layer2_finish_kernel(const L2Partial *__restrict__ ce_partials, const float *__restrict__ dw_partials,
                                                              int parts, int hc, int training, float *__restrict__ W2_grad,
                                                              gcnk_ce_result *__restrict__ result, float *__restrict__ red4) {
-    if (training) {
-        const int i = blockIdx.x * blockDim.x + threadIdx.x;
-        if (i < hc) {
-            float v = 0.f;
-            for (int b = 0; b < parts; b++) v += dw_partials[(size_t)b * hc + i];
-            W2_grad[i] = v;
-        }
+    if (blockIdx.x + 1 < gridDim.x) {
+        reduce_parts_block(dw_partials, W2_grad, hc, parts);
+        return;
     }
-    if (blockIdx.x == 0) {
-        __shared__ float s_loss[256];
-        __shared__ int s_count[256], s_wrong[256];
-        float l = 0.f; int cn = 0, wr = 0;
-        for (int b = threadIdx.x; b < parts; b += 256) { l += ce_partials[b].loss; cn += ce_partials[b].count; wr += ce_partials[b].wrong; }
-        s_loss[threadIdx.x] = l; s_count[threadIdx.x] = cn; s_wrong[threadIdx.x] = wr;
+    __shared__ float s_loss[256];
+    __shared__ int s_count[256], s_wrong[256];
+    float l = 0.f; int cn = 0, wr = 0;
+    for (int b = threadIdx.x; b < parts; b += 256) { l += ce_partials[b].loss; cn += ce_partials[b].count; wr += ce_partials[b].wrong; }
+    s_loss[threadIdx.x] = l; s_count[threadIdx.x] = cn; s_wrong[threadIdx.x] = wr;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) {
+            s_loss[threadIdx.x] += s_loss[threadIdx.x + o];
+            s_count[threadIdx.x] += s_count[threadIdx.x + o];
+            s_wrong[threadIdx.x] += s_wrong[threadIdx.x + o];
+        }
         __syncthreads();
-        for (int o = 128; o > 0; o >>= 1) {
-            if (threadIdx.x < o) {
-                s_loss[threadIdx.x] += s_loss[threadIdx.x + o];
-                s_count[threadIdx.x] += s_count[threadIdx.x + o];
-                s_wrong[threadIdx.x] += s_wrong[threadIdx.x + o];
-            }
-            __syncthreads();
-        }
-        if (threadIdx.x == 0) {
-            result->loss = s_loss[0] / (float)s_count[0];
-            result->count = s_count[0]; result->wrong = s_wrong[0]; result->pad = 0;
-            // raw sums as floats (counts < 2^24 are exact): what a row-partitioned run all-reduces across ranks
-            red4[0] = s_loss[0]; red4[1] = (float)s_count[0]; red4[2] = (float)s_wrong[0]; red4[3] = 0.f;
-        }
+    }
+    if (threadIdx.x == 0) {
+        result->loss = s_loss[0] / (float)s_count[0];
+        result->count = s_count[0]; result->wrong = s_wrong[0]; result->pad = 0;
+        // raw sums as floats (counts < 2^24 are exact): what a row-partitioned run all-reduces across ranks
+        red4[0] = s_loss[0]; red4[1] = (float)s_count[0]; red4[2] = (float)s_wrong[0]; red4[3] = 0.f;
     }
 }
 
@@ -343,7 +356,7 @@ int gcnk_layer2_fused(const float *P, const float *W2, const int *split, const i
         GCNK_LAUNCHED();
     }
     const int hc = h * c;
-    layer2_finish_kernel<<<training ? (hc + 255) / 256 : 1, 256, 0, st>>>(ce_partials, dw_partials, grid, hc, training, W2_grad, d_result, red4);
+    layer2_finish_kernel<<<(training ? (hc + 31) / 32 : 0) + 1, 256, 0, st>>>(ce_partials, dw_partials, grid, hc, training, W2_grad, d_result, red4);
     GCNK_LAUNCHED();
     return GCNK_OK;
 }
