@@ -47,6 +47,7 @@ SIGNATURES = {
     "gcnk_memcpy_d2d": (i32, [vp, vp, sz, vp]),
     "gcnk_memset": (i32, [vp, i32, sz, vp]),
     "gcnk_stream_create": (i32, [C.POINTER(vp)]),
+    "gcnk_stream_create_low_priority": (i32, [C.POINTER(vp)]),
     "gcnk_stream_destroy": (i32, [vp]),
     "gcnk_stream_sync": (i32, [vp]),
     "gcnk_device_sync": (i32, []),
@@ -103,11 +104,19 @@ SIGNATURES = {
     "gcnk_comm_rank": (i32, [vp, C.POINTER(i32), C.POINTER(i32)]),
     "gcnk_comm_allgather_rows": (i32, [vp, vp, vp, i32, vp]),
     "gcnk_comm_allreduce": (i32, [vp, vp, vp, i32, i32, vp]),
+    "gcnk_ipc_export": (i32, [vp, vp]),
+    "gcnk_ipc_import": (i32, [C.POINTER(vp), vp]),
+    "gcnk_ipc_release": (i32, [vp]),
+    "gcnk_comm_allgather_bytes": (i32, [vp, vp, vp, i32]),
+    "gcnk_mirror_next": (i32, [vp, vp, i32]),
+    "gcnk_mirror_pending": (i32, [vp]),
+    "gcnk_peer_push": (i32, [vp, vp, i32, sz, vp]),
+    "gcnk_peer_barrier": (i32, [vp, i32, i32, i32, vp, vp]),
     "gcnk_partition_rows": (i32, [vp, i32, i32, vp]),
 }
 
 # functions whose return value is not an error code
-_NOT_RC = {"gcnk_version", "gcnk_last_error", "gcnk_launch_count", "gcnk_matmul_bw_b_workspace",
+_NOT_RC = {"gcnk_mirror_pending", "gcnk_version", "gcnk_last_error", "gcnk_launch_count", "gcnk_matmul_bw_b_workspace",
            "gcnk_softmax_ce_workspace", "gcnk_layer2_workspace", "gcnk_mask_row_stride_bits"}
 
 _lib = None

@@ -7,6 +7,7 @@
 // the [N x dim] buffer, and one grouped set of ncclBroadcast calls (one root per rank) fills the rest,
 // so there is no staging copy.  The rendezvous (sharing the 128-byte ncclUniqueId) is the caller's job.
 #include <nccl.h>
+#include <string.h>
 
 #include <vector>
 
@@ -28,7 +29,124 @@ struct gcnk_comm {
         }                                                                                     \
     } while (0)
 
+// ------------------------------------------------------------------ peer memory (NVLink P2P) ----
+namespace gcnk {
+static thread_local const float *t_mirror_out = nullptr;
+static thread_local Mirror t_mirror = {};
+
+Mirror take_mirror(const float *out) {
+    Mirror m = {};
+    if (out && t_mirror_out == out) { m = t_mirror; t_mirror_out = nullptr; t_mirror.n = 0; }
+    return m;
+}
+}  // namespace gcnk
+
+namespace {
+
+struct FlagPtrs { int *p[8]; };
+
+// One warp: lane r < world publishes `value` in peer r's flag slot for this rank, then waits until peer r has
+// published it here.  Launched after a producer kernel with mirrored stores: when it completes, every rank's
+// rows of the gather source are in this GPU's buffer.  Each rank runs on its own GPU, so the spin cannot
+// starve the peer it waits for; a ~2 s timeout turns a lost peer into an error instead of a hang.
+__global__ void peer_barrier_kernel(FlagPtrs flags, int rank, int world, int value, int *err) {
+    const int r = threadIdx.x;
+    if (r >= world) return;
+    __threadfence_system();
+    volatile int *remote = flags.p[r] + rank;
+    *remote = value;
+    __threadfence_system();
+    volatile int *mine = flags.p[rank] + r;
+    const long long t0 = clock64();
+    while (*mine < value) {
+        if (clock64() - t0 > (4LL << 30)) { *err = 1; break; }
+    }
+    __threadfence_system();
+}
+
+__global__ void push_rows_kernel(const float4 *__restrict__ src, Mirror m, size_t n_vec) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < n_vec; i += stride) {
+        const float4 v = src[i];
+        for (int p = 0; p < m.n; p++) reinterpret_cast<float4 *>(m.p[p])[i] = v;
+    }
+}
+
+}  // namespace
+
 extern "C" {
+
+int gcnk_ipc_export(const void *dptr, void *h_handle64) {
+    GCNK_REQUIRE(dptr && h_handle64, "null");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    cudaIpcMemHandle_t h;
+    GCNK_CUDA(cudaIpcGetMemHandle(&h, const_cast<void *>(dptr)));
+    memcpy(h_handle64, &h, sizeof h);
+    return GCNK_OK;
+}
+
+int gcnk_ipc_import(void **dptr, const void *h_handle64) {
+    GCNK_REQUIRE(dptr && h_handle64, "null");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, h_handle64, sizeof h);
+    GCNK_CUDA(cudaIpcOpenMemHandle(dptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return GCNK_OK;
+}
+
+int gcnk_ipc_release(void *dptr) {
+    if (dptr) GCNK_CUDA(cudaIpcCloseMemHandle(dptr));
+    return GCNK_OK;
+}
+
+int gcnk_mirror_next(const float *local_out, float *const *peer_out, int n_peers) {
+    GCNK_REQUIRE(local_out && (peer_out || n_peers == 0) && n_peers >= 0 && n_peers <= MAX_PEERS, "bad arguments");
+    t_mirror_out = n_peers ? local_out : nullptr;
+    t_mirror.n = n_peers;
+    for (int i = 0; i < n_peers; i++) t_mirror.p[i] = peer_out[i];
+    return GCNK_OK;
+}
+
+int gcnk_mirror_pending(const float *local_out) {
+    const int pending = local_out && t_mirror_out == local_out && t_mirror.n > 0;
+    if (pending) { t_mirror_out = nullptr; t_mirror.n = 0; }
+    return pending;
+}
+
+int gcnk_peer_push(const float *local_rows, float *const *peer_rows, int n_peers, size_t n_floats, gcnk_stream_t stream) {
+    GCNK_REQUIRE(local_rows && peer_rows && n_peers >= 0 && n_peers <= MAX_PEERS && n_floats % 4 == 0, "bad arguments");
+    if (!n_peers || !n_floats) return GCNK_OK;
+    Mirror m = {};
+    m.n = n_peers;
+    for (int i = 0; i < n_peers; i++) m.p[i] = peer_rows[i];
+    const size_t n_vec = n_floats / 4;
+    const int grid = (int)std::max<size_t>(1, std::min<size_t>((n_vec + 255) / 256, (size_t)sm_count() * 4));
+    push_rows_kernel<<<grid, 256, 0, S(stream)>>>(reinterpret_cast<const float4 *>(local_rows), m, n_vec);
+    GCNK_LAUNCHED();
+    return GCNK_OK;
+}
+
+int gcnk_peer_barrier(int *const *flag_arrays, int rank, int world, int value, int *d_err, gcnk_stream_t stream) {
+    GCNK_REQUIRE(flag_arrays && world >= 1 && world <= 8 && rank >= 0 && rank < world && d_err, "bad arguments");
+    FlagPtrs f = {};
+    for (int r = 0; r < world; r++) f.p[r] = flag_arrays[r];
+    peer_barrier_kernel<<<1, 32, 0, S(stream)>>>(f, rank, world, value, d_err);
+    GCNK_LAUNCHED();
+    return GCNK_OK;
+}
+
+int gcnk_comm_allgather_bytes(gcnk_comm *c, const void *h_send, void *h_recv, int bytes_per_rank) {
+    GCNK_REQUIRE(c && h_send && h_recv && bytes_per_rank > 0, "bad arguments");
+    if (c->world == 1) { memcpy(h_recv, h_send, bytes_per_rank); return GCNK_OK; }
+    char *d = nullptr;
+    GCNK_CUDA(cudaMalloc(&d, (size_t)bytes_per_rank * c->world));
+    GCNK_CUDA(cudaMemcpy(d + (size_t)c->rank * bytes_per_rank, h_send, bytes_per_rank, cudaMemcpyHostToDevice));
+    GCNK_NCCL(ncclAllGather(d + (size_t)c->rank * bytes_per_rank, d, bytes_per_rank, ncclChar, c->comm, nullptr));
+    GCNK_CUDA(cudaStreamSynchronize(nullptr));
+    GCNK_CUDA(cudaMemcpy(h_recv, d, (size_t)bytes_per_rank * c->world, cudaMemcpyDeviceToHost));
+    GCNK_CUDA(cudaFree(d));
+    return GCNK_OK;
+}
 
 int gcnk_comm_unique_id(void *id128) {
     GCNK_REQUIRE(id128, "null");

@@ -36,6 +36,17 @@ inline cudaStream_t S(gcnk_stream_t s) { return reinterpret_cast<cudaStream_t>(s
 
 int sm_count();          // of the current device (cached per device)
 
+// Mirrored output rows (row-partitioned runs): a producer kernel whose output is the input of the next GraphSum
+// on EVERY rank stores each row it writes also at the same offset of the peers' buffers, over NVLink peer
+// mappings — the all-gather is fused into the producer's epilogue instead of being a separate collective.
+constexpr int MAX_PEERS = 7;
+struct Mirror {
+    float *p[MAX_PEERS];
+    int n;
+};
+// the mirror registered with gcnk_mirror_next for `out` (n == 0 if none); consumes the registration
+Mirror take_mirror(const float *out);
+
 constexpr unsigned FULL = 0xffffffffu;
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -52,6 +63,16 @@ __device__ __forceinline__ int warp_sum_int(int v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
     return v;
+}
+
+__device__ __forceinline__ void mirror_store(const Mirror &m, size_t idx, float4 v) {
+    for (int i = 0; i < m.n; i++) *reinterpret_cast<float4 *>(m.p[i] + idx) = v;
+}
+__device__ __forceinline__ void mirror_store(const Mirror &m, size_t idx, float2 v) {
+    for (int i = 0; i < m.n; i++) *reinterpret_cast<float2 *>(m.p[i] + idx) = v;
+}
+__device__ __forceinline__ void mirror_store(const Mirror &m, size_t idx, float v) {
+    for (int i = 0; i < m.n; i++) m.p[i][idx] = v;
 }
 
 // out[i] = sum over b < parts of partials[b*elems + i], deterministically: thread (e, q) of a 32 x 8 CTA sums the

@@ -116,7 +116,8 @@ __device__ __forceinline__ void fw_load(FwBatch &q, const float *xa, const float
 __global__ void __launch_bounds__(THREADS, 2) dense_fw16_tc_kernel(const float *__restrict__ x, const float *__restrict__ w,
                                                                     float *__restrict__ c, int m, int n,
                                                                     const uint32_t *__restrict__ bits, int64_t bit_words,
-                                                                    float scale, const float *__restrict__ row_scale, int relu) {
+                                                                    float scale, const float *__restrict__ row_scale, int relu,
+                                                                    const Mirror mirror) {
     extern __shared__ float4 sfrag[];       // [KS][32] big, then [KS][32] small
     const int KS = (n + 7) / 8;
     for (int i = threadIdx.x; i < KS * 32; i += THREADS) {
@@ -194,14 +195,20 @@ __global__ void __launch_bounds__(THREADS, 2) dense_fw16_tc_kernel(const float *
         if (va) {
             const float rs = post * (row_scale ? row_scale[ra] : 1.f);
             float *o = c + (size_t)ra * P + 2 * t;
-            *reinterpret_cast<float2 *>(o) = make_float2(rs * r0[0], rs * r0[1]);
-            *reinterpret_cast<float2 *>(o + 8) = make_float2(rs * r1[0], rs * r1[1]);
+            const float2 lo = make_float2(rs * r0[0], rs * r0[1]), hi = make_float2(rs * r1[0], rs * r1[1]);
+            *reinterpret_cast<float2 *>(o) = lo;
+            *reinterpret_cast<float2 *>(o + 8) = hi;
+            mirror_store(mirror, (size_t)ra * P + 2 * t, lo);
+            mirror_store(mirror, (size_t)ra * P + 2 * t + 8, hi);
         }
         if (vb) {
             const float rs = post * (row_scale ? row_scale[rb] : 1.f);
             float *o = c + (size_t)rb * P + 2 * t;
-            *reinterpret_cast<float2 *>(o) = make_float2(rs * r0[2], rs * r0[3]);
-            *reinterpret_cast<float2 *>(o + 8) = make_float2(rs * r1[2], rs * r1[3]);
+            const float2 lo = make_float2(rs * r0[2], rs * r0[3]), hi = make_float2(rs * r1[2], rs * r1[3]);
+            *reinterpret_cast<float2 *>(o) = lo;
+            *reinterpret_cast<float2 *>(o + 8) = hi;
+            mirror_store(mirror, (size_t)rb * P + 2 * t, lo);
+            mirror_store(mirror, (size_t)rb * P + 2 * t + 8, hi);
         }
     }
 }
@@ -345,7 +352,7 @@ int dense_fw16_tc(const float *x, const float *w, float *c, int m, int n, const 
     }
     const int n_tiles = (m + 15) / 16;
     const int grid = std::max(1, std::min(sm_count() * 2, (n_tiles + WARPS - 1) / WARPS));
-    dense_fw16_tc_kernel<<<grid, THREADS, smem, st>>>(x, w, c, m, n, bits, (nnz + 31) / 32, scale, row_scale, relu);
+    dense_fw16_tc_kernel<<<grid, THREADS, smem, st>>>(x, w, c, m, n, bits, (nnz + 31) / 32, scale, row_scale, relu, take_mirror(c));
     GCNK_LAUNCHED();
     return GCNK_OK;
 }

@@ -15,6 +15,8 @@
 //
 // Roofline: HBM traffic is 4*nnz (indices) + 8*n*dim; the edge gathers (dim*4 bytes each) are served
 // by L2, where the [n x dim] source is resident (14.9 MB at Reddit shape, dim 16).
+#include <stdlib.h>
+
 #include <algorithm>
 #include <queue>
 #include <vector>
@@ -269,6 +271,10 @@ int launch_gather(const gcnk_graph *g, GatherArgs a, cudaStream_t st) {
     a.indptr = g->indptr; a.indices = g->indices; a.dinv = g->dinv;
     a.heavy_rows = g->heavy_rows; a.n_heavy = g->n_heavy; a.bin_ptr = g->bin_ptr; a.bin_rows = g->bin_rows;
     a.mask_stride = mask_stride_bits(dim);
+    // No mirrored epilogue here on purpose: the 7 extra pointers cost the gather 19 registers (61 -> 80, one CTA per
+    // SM less, +25 % run time measured), and posted 64-byte remote stores back up the load/store unit the row gathers
+    // depend on.  A pending gcnk_mirror_next registration is left for the caller, which pushes the finished rows to
+    // the peers with one coalesced copy kernel (gcnk_peer_push).
     const bool vec4 = dim % 4 == 0 && (reinterpret_cast<uintptr_t>(a.in) % 16 == 0) &&
                       (reinterpret_cast<uintptr_t>(a.out) % 16 == 0);
     if (vec4) {

@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(L2_THREADS) layer2_h16_kernel(const float *__r
                                                                  int current_split, int n, int c, int training, float count_f,
                                                                  const float *__restrict__ dinv, float *__restrict__ G,
                                                                  float *__restrict__ logits_out, L2Partial *__restrict__ ce_partials,
-                                                                 float *__restrict__ dw_partials) {
+                                                                 float *__restrict__ dw_partials, const Mirror mirror) {
     constexpr int H = 16;
     extern __shared__ __align__(16) float smem[];
     float *sAcc = smem;                             // [warps][16*c]  (training only; used once, at the end)
@@ -182,7 +182,7 @@ __global__ void __launch_bounds__(L2_THREADS) layer2_h16_kernel(const float *__r
             }
         }
         if (truth < 0 && !logits_out) {
-            if (training && lane < H) G[(size_t)s * H + lane] = 0.f;          // unlabelled rows carry no gradient
+            if (training && lane < H) { G[(size_t)s * H + lane] = 0.f; mirror_store(mirror, (size_t)s * H + lane, 0.f); }   // unlabelled rows carry no gradient
             continue;
         }
         float lg[CPL];
@@ -196,7 +196,7 @@ __global__ void __launch_bounds__(L2_THREADS) layer2_h16_kernel(const float *__r
             lg[t] = v;
         }
         if (truth < 0) {
-            if (training && lane < H) G[(size_t)s * H + lane] = 0.f;
+            if (training && lane < H) { G[(size_t)s * H + lane] = 0.f; mirror_store(mirror, (size_t)s * H + lane, 0.f); }
             continue;
         }
         float mx = -1e30f;
@@ -250,7 +250,11 @@ __global__ void __launch_bounds__(L2_THREADS) layer2_h16_kernel(const float *__r
                 }
             }
             pk[0] += __shfl_xor_sync(FULL, pk[0], 1);
-            if (!(lane & 1)) G[(size_t)s * H + (lane >> 1)] = dinv[s] * pk[0];
+            if (!(lane & 1)) {
+                const float gv = dinv[s] * pk[0];
+                G[(size_t)s * H + (lane >> 1)] = gv;
+                mirror_store(mirror, (size_t)s * H + (lane >> 1), gv);
+            }
         }
     }
 
@@ -337,16 +341,18 @@ int gcnk_layer2_fused(const float *P, const float *W2, const int *split, const i
     float *dw_partials = reinterpret_cast<float *>(ce_partials + grid);
     const size_t smem = sizeof(float) * ((size_t)h * c + L2_WARPS * (size_t)c + L2_WARPS * (size_t)h +
                                          (training ? L2_WARPS * (size_t)h * c : 0));
+    const Mirror mirror = training ? take_mirror(G_scaled) : Mirror{};
     if (h == 16 && c <= 64) {
         // registers hold the per-lane slice of dW2; the shared accumulator is only the end-of-kernel exchange
         if (c <= 32)
             layer2_h16_kernel<1><<<grid, L2_THREADS, smem, st>>>(P, W2, split, label, current_split, n, c, training, (float)count,
-                                                                d_dinv, G_scaled, logits_out, ce_partials, dw_partials);
+                                                                d_dinv, G_scaled, logits_out, ce_partials, dw_partials, mirror);
         else
             layer2_h16_kernel<2><<<grid, L2_THREADS, smem, st>>>(P, W2, split, label, current_split, n, c, training, (float)count,
-                                                                d_dinv, G_scaled, logits_out, ce_partials, dw_partials);
+                                                                d_dinv, G_scaled, logits_out, ce_partials, dw_partials, mirror);
         GCNK_LAUNCHED();
     } else {
+        GCNK_REQUIRE(mirror.n == 0, "mirrored output is only implemented for hidden width 16");
         if (smem > 48 * 1024) {
             GCNK_REQUIRE(smem <= 200 * 1024, "h*c too large for shared memory");
             GCNK_CUDA(cudaFuncSetAttribute(layer2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -108,6 +108,14 @@ int gcnk_stream_create(gcnk_stream_t *stream) {
     *stream = s;
     return GCNK_OK;
 }
+int gcnk_stream_create_low_priority(gcnk_stream_t *stream) {
+    int least = 0, greatest = 0;
+    GCNK_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+    cudaStream_t s;
+    GCNK_CUDA(cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, least));
+    *stream = s;
+    return GCNK_OK;
+}
 int gcnk_stream_destroy(gcnk_stream_t s) { if (s) GCNK_CUDA(cudaStreamDestroy(S(s))); return GCNK_OK; }
 int gcnk_stream_sync(gcnk_stream_t s) { GCNK_CUDA(cudaStreamSynchronize(S(s))); return GCNK_OK; }
 int gcnk_device_sync(void) { GCNK_CUDA(cudaDeviceSynchronize()); return GCNK_OK; }

@@ -48,7 +48,26 @@ struct GCN::Fused {
     // A_hat*(X*W1) = (A_hat*X)*W1 is one streaming pass and no gather
     float *AX = nullptr;
     bool ax_valid = false, use_views = true;
+    // Row-partitioned runs: the four gather sources live in ONE slab that every peer maps over NVLink (CUDA IPC);
+    // producers mirror their rows into the peers' slabs and a flag barrier replaces the all-gather collective.
+    bool p2p = false;
+    float *slab = nullptr;
+    void *peer_slab[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    int *flag_arrays[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    int barrier_value = 0, world = 1, rank = 0;
+    int *d_err = nullptr, *h_err = nullptr;
+    gcnk_comm *comm = nullptr;
     ~Fused() {
+        gcnk_device_sync();
+        if (slab) {
+            // nobody may still be writing into this slab (or reading ours) when it goes away
+            if (comm) { float *b[1] = {(float *)slab}; const size_t c1[1] = {1}; gcnk_comm_allreduce(comm, b, c1, 1, 1, nullptr); gcnk_device_sync(); }
+            for (int r = 0; r < world; r++) if (r != rank && peer_slab[r]) gcnk_ipc_release(peer_slab[r]);
+            gcnk_free(slab);
+            xw_s = h1_s = G = Gm = nullptr;                 // they were views into the slab
+        }
+        if (d_err) gcnk_free(d_err);
+        if (h_err) gcnk_free_host(h_err);
         if (rng_stream) { gcnk_stream_sync(rng_stream); gcnk_stream_destroy(rng_stream); }
         if (ev_ready) gcnk_event_destroy(ev_ready);
         if (ev_go) gcnk_event_destroy(ev_go);
@@ -185,7 +204,44 @@ void GCN::build(GCNPlan plan) {
     const size_t nnzX_loc = data->feature_index.indices.size();
     // gather SOURCES are [N x H] (every rank needs all rows: all-gathered in place), gather OUTPUTS are local
     const size_t nh_all = sizeof(float) * (size_t)N * H, nh_loc = sizeof(float) * (size_t)n_loc * H;
-    for (float **p : {&fz->xw_s, &fz->h1_s, &fz->G, &fz->Gm}) GCNK_CHECK(gcnk_malloc((void **)p, nh_all));
+    fz->world = dist.world; fz->rank = dist.rank; fz->comm = dist.comm;
+    const char *cm = getenv("GCN_COMM");
+    if (dist.world > 1 && dist.world <= 8 && H % 4 == 0 && !(cm && !strcmp(cm, "nccl"))) {
+        // one slab: [xw_s | h1_s | G | Gm | flags]; export it, import every peer's
+        const size_t buf = (size_t)N * H;
+        GCNK_CHECK(gcnk_malloc((void **)&fz->slab, 4 * nh_all + 256));
+        GCNK_CHECK(gcnk_memset(fz->slab, 0, 4 * nh_all + 256, nullptr));
+        GCNK_CHECK(gcnk_stream_sync(nullptr));
+        unsigned char mine[64], all[64 * 8];
+        GCNK_CHECK(gcnk_ipc_export(fz->slab, mine));
+        GCNK_CHECK(gcnk_comm_allgather_bytes(dist.comm, mine, all, 64));
+        float failed = 0.f;
+        for (int r = 0; r < dist.world; r++) {
+            if (r == dist.rank) { fz->peer_slab[r] = fz->slab; continue; }
+            if (gcnk_ipc_import(&fz->peer_slab[r], all + 64 * r) != GCNK_OK) { fz->peer_slab[r] = nullptr; failed = 1.f; }
+        }
+        // all ranks must agree on the transport
+        float *d_flag = nullptr;
+        GCNK_CHECK(gcnk_malloc((void **)&d_flag, sizeof(float)));
+        GCNK_CHECK(gcnk_memcpy_h2d(d_flag, &failed, sizeof(float), nullptr));
+        float *bufs[1] = {d_flag};
+        const size_t cnt[1] = {1};
+        GCNK_CHECK(gcnk_comm_allreduce(dist.comm, bufs, cnt, 1, 1, nullptr));
+        GCNK_CHECK(gcnk_memcpy_d2h(&failed, d_flag, sizeof(float), nullptr));
+        GCNK_CHECK(gcnk_stream_sync(nullptr));
+        GCNK_CHECK(gcnk_free(d_flag));
+        fz->p2p = failed == 0.f;
+        if (!fz->p2p && !quiet_) fprintf(stderr, "GCN: peer mapping unavailable (%s); using NCCL all-gather\n", gcnk_last_error());
+        fz->xw_s = fz->slab; fz->h1_s = fz->slab + buf; fz->G = fz->slab + 2 * buf; fz->Gm = fz->slab + 3 * buf;
+        for (int r = 0; r < dist.world; r++)
+            fz->flag_arrays[r] = fz->peer_slab[r] ? reinterpret_cast<int *>(static_cast<float *>(fz->peer_slab[r]) + 4 * buf) : nullptr;
+        GCNK_CHECK(gcnk_malloc((void **)&fz->d_err, sizeof(int)));
+        GCNK_CHECK(gcnk_memset(fz->d_err, 0, sizeof(int), nullptr));
+        GCNK_CHECK(gcnk_malloc_host((void **)&fz->h_err, sizeof(int)));
+        *fz->h_err = 0;
+    } else {
+        for (float **p : {&fz->xw_s, &fz->h1_s, &fz->G, &fz->Gm}) GCNK_CHECK(gcnk_malloc((void **)p, nh_all));
+    }
     for (float **p : {&fz->P, &fz->dxw}) GCNK_CHECK(gcnk_malloc((void **)p, nh_loc));
     for (int b = 0; b < 2; b++) {
         GCNK_CHECK(gcnk_malloc((void **)&fz->keep0_buf[b], sizeof(uint32_t) * (nnzX_loc / 32 + 4)));
@@ -195,7 +251,7 @@ void GCN::build(GCNPlan plan) {
     {
         const char *ns = getenv("GCN_NO_RNG_OVERLAP");
         if (!(ns && *ns && strcmp(ns, "0"))) {
-            GCNK_CHECK(gcnk_stream_create(&fz->rng_stream));
+            GCNK_CHECK(gcnk_stream_create_low_priority(&fz->rng_stream));   // fills idle slots under the gathers, never ahead of them
             GCNK_CHECK(gcnk_event_create(&fz->ev_ready));
             GCNK_CHECK(gcnk_event_create(&fz->ev_go));
         }
@@ -325,10 +381,37 @@ float GCN::get_l2_penalty() {
 }
 
 // ------------------------------------------------------------------------------ fused plan ----
+// Before a producer of gather source `d_all`: register the peers' copies so its epilogue mirrors the rows.
+void GCN::mirror(float *d_all, int dim) {
+    if (dist.world <= 1 || !fz->p2p) return;
+    Fused &z = *fz;
+    float *peers[8];
+    int n = 0;
+    const size_t off = (size_t)(d_all - z.slab) + (size_t)r0 * dim;
+    for (int r = 0; r < dist.world; r++)
+        if (r != dist.rank) peers[n++] = static_cast<float *>(z.peer_slab[r]) + off;
+    GCNK_CHECK(gcnk_mirror_next(d_all + (size_t)r0 * dim, peers, n));
+}
+
+// After the producer: every rank's rows of `d_all` must be present before the gather that reads them.
 void GCN::allgather(float *d_all, int dim) {
     if (dist.world <= 1) return;
     gpu_timer_begin(TMR_COMM);
-    GCNK_CHECK(gcnk_comm_allgather_rows(dist.comm, d_all, row_begin.data(), dim, nullptr));
+    if (fz->p2p) {
+        Fused &z = *fz;
+        float *own = d_all + (size_t)r0 * dim;
+        if (gcnk_mirror_pending(own)) {                      // the producer has no mirrored epilogue: copy kernel instead
+            float *peers[8];
+            int n = 0;
+            const size_t off = (size_t)(d_all - z.slab) + (size_t)r0 * dim;
+            for (int r = 0; r < dist.world; r++)
+                if (r != dist.rank) peers[n++] = static_cast<float *>(z.peer_slab[r]) + off;
+            GCNK_CHECK(gcnk_peer_push(own, peers, n, (size_t)n_loc * dim, nullptr));
+        }
+        GCNK_CHECK(gcnk_peer_barrier(z.flag_arrays, dist.rank, dist.world, ++z.barrier_value, z.d_err, nullptr));
+    } else {
+        GCNK_CHECK(gcnk_comm_allgather_rows(dist.comm, d_all, row_begin.data(), dim, nullptr));
+    }
     gpu_timer_end(TMR_COMM);
 }
 
@@ -386,12 +469,14 @@ std::pair<float, float> GCN::fused_pass(int current_split, bool training) {
     if (!training && z.ax_valid) {
         // eval: A_hat*(X*W1) = (A_hat*X)*W1, ReLU and the pre-scale for the next gather in the epilogue
         gpu_timer_begin(TMR_SPMATMUL_FW);
+        mirror(z.h1_s, H);
         GCNK_CHECK(gcnk_dense_transform(z.AX, n_loc, F, W1.data, z.h1_s + own, H, nullptr, 1.0f, dinv, 1, nullptr));
         gpu_timer_end(TMR_SPMATMUL_FW);
     } else {
         // M0 Dropout + M1 SparseMatmul: keep bits applied on read; the stored feature values are never modified,
         // so no set_input() copy is needed
         gpu_timer_begin(TMR_SPMATMUL_FW);
+        mirror(z.xw_s, H);
         GCNK_CHECK(gcnk_spmm_fw(sp, d_feature_value, W1.data, z.xw_s + own, H, drop ? z.keep0 : nullptr, scale, dinv, nullptr));
         gpu_timer_end(TMR_SPMATMUL_FW);
         if (drop && z.rng_stream) {
@@ -410,6 +495,7 @@ std::pair<float, float> GCN::fused_pass(int current_split, bool training) {
         allgather(z.xw_s, H);
         // M2 GraphSum + M3 ReLU + M4 Dropout in the gather's epilogue
         gpu_timer_begin(TMR_GATHER_FULL);
+        mirror(z.h1_s, H);
         GCNK_CHECK(gcnk_gather_relu_drop(g, z.xw_s, z.h1_s + own, drop ? z.keep1 : nullptr, training ? z.mask : nullptr,
                                          training ? scale : 1.0f, H, nullptr));
         gpu_timer_end(TMR_GATHER_FULL);
@@ -423,6 +509,7 @@ std::pair<float, float> GCN::fused_pass(int current_split, bool training) {
     // M5 Matmul + M7 CrossEntropyLoss + get_accuracy (+ Matmul backward when training), row-local.
     // count = labelled rows of the split over ALL ranks: the gradient is divided by it (module.cpp:154-158)
     gpu_timer_begin(TMR_LOSS_FW);
+    if (training) mirror(z.G, H);
     GCNK_CHECK(gcnk_layer2_fused(z.P, W2.data, d_split, d_label, current_split, n_loc, H, C, training,
                                  split_count[current_split & 3], dinv, training ? z.G + own : nullptr,
                                  training ? W2.grad : nullptr, nullptr, z.d_result, z.ws, z.ws_bytes, nullptr));
@@ -433,6 +520,7 @@ std::pair<float, float> GCN::fused_pass(int current_split, bool training) {
         // backward of M6/M5 is inside layer2; M4/M3/M2 backward = one masked gather + one plain gather
         allgather(z.G, H);
         gpu_timer_begin(gather_timer(g_cols));
+        mirror(z.Gm, H);
         GCNK_CHECK(gcnk_gather_mask(g_cols, z.G, z.Gm + own, z.mask, scale, H, nullptr));
         gpu_timer_end(gather_timer(g_cols));
         allgather(z.Gm, H);
@@ -456,7 +544,9 @@ std::pair<float, float> GCN::fused_pass(int current_split, bool training) {
         optimizer.step(z.d_sumsq);
         GCNK_CHECK(gcnk_memcpy_d2h(z.h_sumsq, z.d_sumsq, sizeof(float), nullptr));
     }
+    if (z.p2p) GCNK_CHECK(gcnk_memcpy_d2h(z.h_err, z.d_err, sizeof(int), nullptr));
     GCNK_CHECK(gcnk_stream_sync(nullptr));                                // the one host sync of the pass
+    if (z.p2p && *z.h_err) { fprintf(stderr, "GCN: a peer rank did not reach the exchange barrier\n"); exit(EXIT_FAILURE); }
     gpu_timer_resolve();
     if (training) z.sumsq = *z.h_sumsq;
     last_count = (int)z.h_red[1];

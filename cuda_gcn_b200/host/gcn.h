@@ -81,6 +81,7 @@ private:
 
     void build_partition();
     gcnk_graph *graph_handle();
+    void mirror(float *d_all, int dim);
     void allgather(float *d_all, int dim);
     GCNData *data;                           // what this rank computes on: the caller's data, or `local` (its row slice)
     GCNData *full_data = nullptr;            // the caller's full data

@@ -47,6 +47,7 @@ int gcnk_memcpy_d2h(void *h_dst, const void *src, size_t bytes, gcnk_stream_t st
 int gcnk_memcpy_d2d(void *dst, const void *src, size_t bytes, gcnk_stream_t stream);
 int gcnk_memset(void *dst, int value, size_t bytes, gcnk_stream_t stream);
 int gcnk_stream_create(gcnk_stream_t *stream);
+int gcnk_stream_create_low_priority(gcnk_stream_t *stream);   /* its CTAs are scheduled after those of other streams */
 int gcnk_stream_destroy(gcnk_stream_t stream);
 int gcnk_stream_sync(gcnk_stream_t stream);
 int gcnk_device_sync(void);
@@ -213,6 +214,25 @@ int gcnk_comm_allgather_rows(gcnk_comm *comm, float *d_all, const int *h_row_beg
 /* In-place all-reduce (sum, or max when op_max != 0) of n_bufs device buffers in one group. */
 int gcnk_comm_allreduce(gcnk_comm *comm, float *const *d_bufs, const size_t *h_counts, int n_bufs, int op_max,
                         gcnk_stream_t stream);
+
+/* ---- fused all-gather over NVLink peer memory ----------------------------------------------------------
+ * With one process per GPU, each rank exports the buffer that holds its gather sources (gcnk_ipc_export, a
+ * 64-byte handle), exchanges the handles (gcnk_comm_allgather_bytes) and maps the peers' buffers
+ * (gcnk_ipc_import).  gcnk_mirror_next(out, peer_out, n) then makes the NEXT producer launched on `out`
+ * (gcnk_spmm_fw / gcnk_dense_transform at p == 16, gcnk_gather_*, gcnk_layer2_fused at h == 16) store every row
+ * it writes also at the same offset of each peer_out[i]: the all-gather rides in the producer's epilogue.
+ * gcnk_peer_push is the unfused form (a copy kernel) for producers without a mirrored epilogue.
+ * gcnk_peer_barrier, launched after the producer, returns (in stream order) once every rank has finished the
+ * same step: flag_arrays[r] is rank r's int[world] flag array (own + imported), `value` must increase with
+ * every barrier, *d_err is set to 1 if a peer does not arrive within ~2 s. */
+int gcnk_ipc_export(const void *dptr, void *h_handle64);
+int gcnk_ipc_import(void **dptr, const void *h_handle64);
+int gcnk_ipc_release(void *dptr);
+int gcnk_comm_allgather_bytes(gcnk_comm *comm, const void *h_send, void *h_recv, int bytes_per_rank);
+int gcnk_mirror_next(const float *local_out, float *const *peer_out, int n_peers);
+int gcnk_mirror_pending(const float *local_out);   /* 1 (and cancels it) if the registration was not consumed by a producer */
+int gcnk_peer_push(const float *local_rows, float *const *peer_rows, int n_peers, size_t n_floats, gcnk_stream_t stream);
+int gcnk_peer_barrier(int *const *flag_arrays, int rank, int world, int value, int *d_err, gcnk_stream_t stream);
 
 /* ---- host-side, bit-exact integer work --------------------------------------------------------------
  * Contiguous nnz-balanced row partition of a CSR: h_row_begin[parts+1] receives the cuts;

