@@ -7,6 +7,7 @@
 // the [N x dim] buffer, and one grouped set of ncclBroadcast calls (one root per rank) fills the rest,
 // so there is no staging copy.  The rendezvous (sharing the 128-byte ncclUniqueId) is the caller's job.
 #include <nccl.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
@@ -34,9 +35,14 @@ namespace gcnk {
 static thread_local const float *t_mirror_out = nullptr;
 static thread_local Mirror t_mirror = {};
 
+// Measured on 8 B200 (Reddit shape, 29 K rows per rank): the mirrored epilogues issue 4-16 byte remote stores per
+// lane and made the feature transform 3x and the layer-2 kernel 3.4x slower than their 1/8 share, while one
+// coalesced gcnk_peer_push of the finished rows takes ~10 us.  So the fused epilogues are opt-in
+// (GCNK_MIRROR_EPILOGUE=1); by default a registration stays pending and the caller pushes.
 Mirror take_mirror(const float *out) {
+    static const bool enabled = getenv("GCNK_MIRROR_EPILOGUE") && atoi(getenv("GCNK_MIRROR_EPILOGUE")) != 0;
     Mirror m = {};
-    if (out && t_mirror_out == out) { m = t_mirror; t_mirror_out = nullptr; t_mirror.n = 0; }
+    if (enabled && out && t_mirror_out == out) { m = t_mirror; t_mirror_out = nullptr; t_mirror.n = 0; }
     return m;
 }
 }  // namespace gcnk
@@ -49,7 +55,23 @@ struct FlagPtrs { int *p[8]; };
 // published it here.  Launched after a producer kernel with mirrored stores: when it completes, every rank's
 // rows of the gather source are in this GPU's buffer.  Each rank runs on its own GPU, so the spin cannot
 // starve the peer it waits for; a ~2 s timeout turns a lost peer into an error instead of a hang.
-__global__ void peer_barrier_kernel(FlagPtrs flags, int rank, int world, int value, int *err) {
+// the flag exchange of peer_barrier_kernel, run by the first `world` threads of the LAST CTA of a kernel to finish:
+// every CTA fences its remote stores system-wide and then bumps *counter, so whatever the other CTAs wrote to the
+// peers is visible there before the flag is
+__device__ __forceinline__ bool last_cta_arrives(unsigned *counter) {
+    __shared__ bool s_last;
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned prev = atomicAdd(counter, 1u);
+        s_last = prev == gridDim.x - 1;
+        if (s_last) *counter = 0;                           // ready for the next launch
+    }
+    __syncthreads();
+    return s_last;
+}
+
+__device__ __forceinline__ void flag_exchange(const FlagPtrs &flags, int rank, int world, int value, int *err) {
     const int r = threadIdx.x;
     if (r >= world) return;
     __threadfence_system();
@@ -63,6 +85,52 @@ __global__ void peer_barrier_kernel(FlagPtrs flags, int rank, int world, int val
     }
     __threadfence_system();
 }
+
+// push + barrier in one launch
+__global__ void __launch_bounds__(256) push_barrier_kernel(const float4 *__restrict__ src, Mirror m, size_t n_vec, FlagPtrs flags, int rank,
+                                                           int world, int value, int *err, unsigned *counter) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < n_vec; i += stride) {
+        const float4 v = src[i];
+        for (int p = 0; p < m.n; p++) reinterpret_cast<float4 *>(m.p[p])[i] = v;
+    }
+    if (last_cta_arrives(counter)) flag_exchange(flags, rank, world, value, err);
+}
+
+struct Segs { float *p[4]; unsigned count[4]; int n; };
+struct Areas { float *p[8]; };
+
+// all-reduce step 1: this rank's segments, packed, into slot[rank] of every rank's exchange area; then the barrier
+__global__ void __launch_bounds__(256) allreduce_scatter_kernel(Segs segs, Areas areas, size_t slot_floats, FlagPtrs flags, int rank, int world,
+                                                                int value, int *err, unsigned *counter) {
+    unsigned total = 0;
+    for (int k = 0; k < segs.n; k++) total += segs.count[k];
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        unsigned j = i;
+        int k = 0;
+        while (j >= segs.count[k]) { j -= segs.count[k]; k++; }
+        const float v = segs.p[k][j];
+        for (int r = 0; r < world; r++) areas.p[r][(size_t)rank * slot_floats + i] = v;
+    }
+    if (last_cta_arrives(counter)) flag_exchange(flags, rank, world, value, err);
+}
+
+// all-reduce step 2: the slots summed in rank order (the same order on every rank => bit-identical results)
+__global__ void __launch_bounds__(256) allreduce_gather_kernel(Segs segs, const float *__restrict__ area, size_t slot_floats, int world) {
+    unsigned total = 0;
+    for (int k = 0; k < segs.n; k++) total += segs.count[k];
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        float s = 0.f;
+        for (int r = 0; r < world; r++) s += area[(size_t)r * slot_floats + i];
+        unsigned j = i;
+        int k = 0;
+        while (j >= segs.count[k]) { j -= segs.count[k]; k++; }
+        segs.p[k][j] = s;
+    }
+}
+
+__global__ void peer_barrier_kernel(FlagPtrs flags, int rank, int world, int value, int *err) { flag_exchange(flags, rank, world, value, err); }
 
 __global__ void push_rows_kernel(const float4 *__restrict__ src, Mirror m, size_t n_vec) {
     size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
@@ -122,6 +190,44 @@ int gcnk_peer_push(const float *local_rows, float *const *peer_rows, int n_peers
     const size_t n_vec = n_floats / 4;
     const int grid = (int)std::max<size_t>(1, std::min<size_t>((n_vec + 255) / 256, (size_t)sm_count() * 4));
     push_rows_kernel<<<grid, 256, 0, S(stream)>>>(reinterpret_cast<const float4 *>(local_rows), m, n_vec);
+    GCNK_LAUNCHED();
+    return GCNK_OK;
+}
+
+int gcnk_peer_push_barrier(const float *local_rows, float *const *peer_rows, int n_peers, size_t n_floats, int *const *flag_arrays,
+                           int rank, int world, int value, int *d_err, unsigned *d_counter, gcnk_stream_t stream) {
+    GCNK_REQUIRE(local_rows && peer_rows && n_peers >= 0 && n_peers <= MAX_PEERS && n_floats % 4 == 0 && flag_arrays && d_err && d_counter &&
+                     world >= 1 && world <= 8,
+                 "bad arguments");
+    Mirror m = {};
+    m.n = n_peers;
+    for (int i = 0; i < n_peers; i++) m.p[i] = peer_rows[i];
+    FlagPtrs f = {};
+    for (int r = 0; r < world; r++) f.p[r] = flag_arrays[r];
+    const size_t n_vec = n_floats / 4;
+    const int grid = (int)std::max<size_t>(1, std::min<size_t>((n_vec + 255) / 256, (size_t)sm_count() * 2));
+    push_barrier_kernel<<<grid, 256, 0, S(stream)>>>(reinterpret_cast<const float4 *>(local_rows), m, n_vec, f, rank, world, value, d_err, d_counter);
+    GCNK_LAUNCHED();
+    return GCNK_OK;
+}
+
+int gcnk_peer_allreduce(float *const *d_segs, const size_t *h_counts, int n_segs, float *const *slot_areas, size_t slot_floats,
+                        int *const *flag_arrays, int rank, int world, int value, int *d_err, unsigned *d_counter, gcnk_stream_t stream) {
+    GCNK_REQUIRE(d_segs && h_counts && n_segs > 0 && n_segs <= 4 && slot_areas && flag_arrays && d_err && d_counter && world >= 1 && world <= 8,
+                 "bad arguments");
+    Segs sg = {};
+    sg.n = n_segs;
+    size_t total = 0;
+    for (int k = 0; k < n_segs; k++) { sg.p[k] = d_segs[k]; sg.count[k] = (unsigned)h_counts[k]; total += h_counts[k]; }
+    GCNK_REQUIRE(total <= slot_floats, "segments do not fit the exchange slot");
+    if (world == 1 || total == 0) return GCNK_OK;
+    Areas ar = {};
+    FlagPtrs f = {};
+    for (int r = 0; r < world; r++) { ar.p[r] = slot_areas[r]; f.p[r] = flag_arrays[r]; }
+    const int grid = (int)std::max<size_t>(1, std::min<size_t>((total + 255) / 256, (size_t)sm_count()));
+    allreduce_scatter_kernel<<<grid, 256, 0, S(stream)>>>(sg, ar, slot_floats, f, rank, world, value, d_err, d_counter);
+    GCNK_LAUNCHED();
+    allreduce_gather_kernel<<<grid, 256, 0, S(stream)>>>(sg, slot_areas[rank], slot_floats, world);
     GCNK_LAUNCHED();
     return GCNK_OK;
 }

@@ -56,6 +56,9 @@ struct GCN::Fused {
     int *flag_arrays[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     int barrier_value = 0, world = 1, rank = 0;
     int *d_err = nullptr, *h_err = nullptr;
+    unsigned *d_counter = nullptr;
+    float *areas[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // all-reduce exchange areas
+    size_t slot_floats = 0;
     gcnk_comm *comm = nullptr;
     ~Fused() {
         gcnk_device_sync();
@@ -67,6 +70,7 @@ struct GCN::Fused {
             xw_s = h1_s = G = Gm = nullptr;                 // they were views into the slab
         }
         if (d_err) gcnk_free(d_err);
+        if (d_counter) gcnk_free(d_counter);
         if (h_err) gcnk_free_host(h_err);
         if (rng_stream) { gcnk_stream_sync(rng_stream); gcnk_stream_destroy(rng_stream); }
         if (ev_ready) gcnk_event_destroy(ev_ready);
@@ -207,10 +211,14 @@ void GCN::build(GCNPlan plan) {
     fz->world = dist.world; fz->rank = dist.rank; fz->comm = dist.comm;
     const char *cm = getenv("GCN_COMM");
     if (dist.world > 1 && dist.world <= 8 && H % 4 == 0 && !(cm && !strcmp(cm, "nccl"))) {
-        // one slab: [xw_s | h1_s | G | Gm | flags]; export it, import every peer's
+        // one slab: [xw_s | h1_s | G | Gm | flags (64 ints) | all-reduce area: world slots]; export it, import every peer's
         const size_t buf = (size_t)N * H;
-        GCNK_CHECK(gcnk_malloc((void **)&fz->slab, 4 * nh_all + 256));
-        GCNK_CHECK(gcnk_memset(fz->slab, 0, 4 * nh_all + 256, nullptr));
+        fz->slot_floats = ((size_t)F * H + (size_t)H * C + 4 + 3) / 4 * 4;
+        const size_t slab_bytes = 4 * nh_all + 256 + sizeof(float) * fz->slot_floats * dist.world;
+        GCNK_CHECK(gcnk_malloc((void **)&fz->slab, slab_bytes));
+        GCNK_CHECK(gcnk_memset(fz->slab, 0, slab_bytes, nullptr));
+        GCNK_CHECK(gcnk_malloc((void **)&fz->d_counter, sizeof(unsigned)));
+        GCNK_CHECK(gcnk_memset(fz->d_counter, 0, sizeof(unsigned), nullptr));
         GCNK_CHECK(gcnk_stream_sync(nullptr));
         unsigned char mine[64], all[64 * 8];
         GCNK_CHECK(gcnk_ipc_export(fz->slab, mine));
@@ -233,8 +241,10 @@ void GCN::build(GCNPlan plan) {
         fz->p2p = failed == 0.f;
         if (!fz->p2p && !quiet_) fprintf(stderr, "GCN: peer mapping unavailable (%s); using NCCL all-gather\n", gcnk_last_error());
         fz->xw_s = fz->slab; fz->h1_s = fz->slab + buf; fz->G = fz->slab + 2 * buf; fz->Gm = fz->slab + 3 * buf;
-        for (int r = 0; r < dist.world; r++)
+        for (int r = 0; r < dist.world; r++) {
             fz->flag_arrays[r] = fz->peer_slab[r] ? reinterpret_cast<int *>(static_cast<float *>(fz->peer_slab[r]) + 4 * buf) : nullptr;
+            fz->areas[r] = fz->peer_slab[r] ? static_cast<float *>(fz->peer_slab[r]) + 4 * buf + 64 : nullptr;
+        }
         GCNK_CHECK(gcnk_malloc((void **)&fz->d_err, sizeof(int)));
         GCNK_CHECK(gcnk_memset(fz->d_err, 0, sizeof(int), nullptr));
         GCNK_CHECK(gcnk_malloc_host((void **)&fz->h_err, sizeof(int)));
@@ -400,15 +410,19 @@ void GCN::allgather(float *d_all, int dim) {
     if (fz->p2p) {
         Fused &z = *fz;
         float *own = d_all + (size_t)r0 * dim;
-        if (gcnk_mirror_pending(own)) {                      // the producer has no mirrored epilogue: copy kernel instead
+        if (gcnk_mirror_pending(own)) {
+            // the producer did not mirror its rows: one coalesced copy of the finished rows to every peer, with the
+            // flag exchange done by the last CTA of the same launch
             float *peers[8];
             int n = 0;
             const size_t off = (size_t)(d_all - z.slab) + (size_t)r0 * dim;
             for (int r = 0; r < dist.world; r++)
                 if (r != dist.rank) peers[n++] = static_cast<float *>(z.peer_slab[r]) + off;
-            GCNK_CHECK(gcnk_peer_push(own, peers, n, (size_t)n_loc * dim, nullptr));
+            GCNK_CHECK(gcnk_peer_push_barrier(own, peers, n, (size_t)n_loc * dim, z.flag_arrays, dist.rank, dist.world, ++z.barrier_value,
+                                              z.d_err, z.d_counter, nullptr));
+        } else {
+            GCNK_CHECK(gcnk_peer_barrier(z.flag_arrays, dist.rank, dist.world, ++z.barrier_value, z.d_err, nullptr));
         }
-        GCNK_CHECK(gcnk_peer_barrier(z.flag_arrays, dist.rank, dist.world, ++z.barrier_value, z.d_err, nullptr));
     } else {
         GCNK_CHECK(gcnk_comm_allgather_rows(dist.comm, d_all, row_begin.data(), dim, nullptr));
     }
@@ -536,7 +550,11 @@ std::pair<float, float> GCN::fused_pass(int current_split, bool training) {
         float *bufs[3] = {z.ws, W1.grad, W2.grad};
         const size_t counts[3] = {4, (size_t)W1.size, (size_t)W2.size};
         gpu_timer_begin(TMR_COMM);
-        GCNK_CHECK(gcnk_comm_allreduce(dist.comm, bufs, counts, training ? 3 : 1, 0, nullptr));
+        if (z.p2p)
+            GCNK_CHECK(gcnk_peer_allreduce(bufs, counts, training ? 3 : 1, z.areas, z.slot_floats, z.flag_arrays, dist.rank, dist.world,
+                                           ++z.barrier_value, z.d_err, z.d_counter, nullptr));
+        else
+            GCNK_CHECK(gcnk_comm_allreduce(dist.comm, bufs, counts, training ? 3 : 1, 0, nullptr));
         gpu_timer_end(TMR_COMM);
     }
     GCNK_CHECK(gcnk_memcpy_d2h(z.h_red, z.ws, 4 * sizeof(float), nullptr));

@@ -233,6 +233,16 @@ int gcnk_mirror_next(const float *local_out, float *const *peer_out, int n_peers
 int gcnk_mirror_pending(const float *local_out);   /* 1 (and cancels it) if the registration was not consumed by a producer */
 int gcnk_peer_push(const float *local_rows, float *const *peer_rows, int n_peers, size_t n_floats, gcnk_stream_t stream);
 int gcnk_peer_barrier(int *const *flag_arrays, int rank, int world, int value, int *d_err, gcnk_stream_t stream);
+/* push + barrier in one launch (the last CTA to finish its copies runs the flag exchange); d_counter: a zeroed
+ * device unsigned reserved for these calls */
+int gcnk_peer_push_barrier(const float *local_rows, float *const *peer_rows, int n_peers, size_t n_floats, int *const *flag_arrays,
+                           int rank, int world, int value, int *d_err, unsigned *d_counter, gcnk_stream_t stream);
+/* Deterministic sum all-reduce over peer memory for small vectors (weight gradients, scalars): every rank writes
+ * its n_segs segments, packed, into slot[rank] of every rank's exchange area (slot_areas[r] = rank r's area of
+ * world * slot_floats floats), passes the barrier, and sums the slots in rank order back into the segments —
+ * the same order on every rank, so the replicated weights stay bit-identical. */
+int gcnk_peer_allreduce(float *const *d_segs, const size_t *h_counts, int n_segs, float *const *slot_areas, size_t slot_floats,
+                        int *const *flag_arrays, int rank, int world, int value, int *d_err, unsigned *d_counter, gcnk_stream_t stream);
 
 /* ---- host-side, bit-exact integer work --------------------------------------------------------------
  * Contiguous nnz-balanced row partition of a CSR: h_row_begin[parts+1] receives the cuts;
