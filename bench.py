@@ -173,8 +173,8 @@ def run_ours(args):
         x_local = data.arrays()["feature_value"]
 
     def step():
-        eng.train_epoch()
-        return eng.eval(2)
+        r = eng.epoch(2)                                   # train_epoch + eval(2), one host sync (what GCN::run does per epoch)
+        return r[2], r[3]
 
     def barrier():
         K.gcnk_device_sync()

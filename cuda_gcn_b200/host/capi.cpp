@@ -165,6 +165,15 @@ void gcnh_engine_eval(gcnh_engine *e, int split, float *loss, float *acc) {
     if (acc) *acc = r.second;
 }
 
+void gcnh_engine_epoch(gcnh_engine *e, int split, float *tl, float *ta, float *el, float *ea) {
+    float a, b, c, d;
+    e->g->epoch(split, &a, &b, &c, &d);
+    if (tl) *tl = a;
+    if (ta) *ta = b;
+    if (el) *el = c;
+    if (ea) *ea = d;
+}
+
 void gcnh_engine_last_counts(const gcnh_engine *e, int *count, int *wrong) {
     if (count) *count = e->g->last_count;
     if (wrong) *wrong = e->g->last_wrong;

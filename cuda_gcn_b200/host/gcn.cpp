@@ -35,7 +35,9 @@ struct GCN::Fused {
     float *ws = nullptr; size_t ws_bytes = 0;
     gcnk_ce_result *d_result = nullptr, *h_result = nullptr;   // device / pinned host
     float *d_sumsq = nullptr, *h_sumsq = nullptr;
-    float *h_red = nullptr;    // pinned {sum of loss terms, count, wrong, 0} after the cross-rank reduction
+    float *h_red = nullptr;    // pinned [2][4]: {sum of loss terms, count, wrong, 0} after the cross-rank reduction, per result slot
+    float sumsq_used[2] = {0.f, 0.f};
+    bool sumsq_pending = false;
     gcnk_rng *slice_rng = nullptr;   // positions a copy of the shared stream at this rank's rows
     float sumsq = 0;           // sum(W1^2) of the current weights
     // Views of the graph for the passes that need only part of A_hat*x (splits are static, so these are built once):
@@ -273,7 +275,7 @@ void GCN::build(GCNPlan plan) {
     GCNK_CHECK(gcnk_malloc((void **)&fz->d_sumsq, sizeof(float)));
     GCNK_CHECK(gcnk_malloc_host((void **)&fz->h_result, sizeof(gcnk_ce_result)));
     GCNK_CHECK(gcnk_malloc_host((void **)&fz->h_sumsq, sizeof(float)));
-    GCNK_CHECK(gcnk_malloc_host((void **)&fz->h_red, 4 * sizeof(float)));
+    GCNK_CHECK(gcnk_malloc_host((void **)&fz->h_red, 8 * sizeof(float)));
     GCNK_CHECK(gcnk_rng_create(&fz->slice_rng, 1, 2));
     GCNK_CHECK(gcnk_sum_squares(variables[2].data, variables[2].size, fz->d_sumsq, nullptr));
     GCNK_CHECK(gcnk_memcpy_d2h(fz->h_sumsq, fz->d_sumsq, sizeof(float), nullptr));
@@ -429,7 +431,8 @@ void GCN::allgather(float *d_all, int dim) {
     gpu_timer_end(TMR_COMM);
 }
 
-std::pair<float, float> GCN::fused_pass(int current_split, bool training) {
+// Enqueues one pass on the stream; nothing is read back until fused_collect.  slot: which pinned result slot to use.
+void GCN::fused_enqueue(int current_split, bool training, int slot) {
     Fused &z = *fz;
     const int N = params.num_nodes, F = params.input_dim, H = params.hidden_dim, C = params.output_dim;
     const int64_t nnzX_loc = (int64_t)data->feature_index.indices.size();
@@ -529,7 +532,6 @@ std::pair<float, float> GCN::fused_pass(int current_split, bool training) {
                                  training ? W2.grad : nullptr, nullptr, z.d_result, z.ws, z.ws_bytes, nullptr));
     gpu_timer_end(TMR_LOSS_FW);
 
-    const float sumsq_before = z.sumsq;
     if (training) {
         // backward of M6/M5 is inside layer2; M4/M3/M2 backward = one masked gather + one plain gather
         allgather(z.G, H);
@@ -557,21 +559,53 @@ std::pair<float, float> GCN::fused_pass(int current_split, bool training) {
             GCNK_CHECK(gcnk_comm_allreduce(dist.comm, bufs, counts, training ? 3 : 1, 0, nullptr));
         gpu_timer_end(TMR_COMM);
     }
-    GCNK_CHECK(gcnk_memcpy_d2h(z.h_red, z.ws, 4 * sizeof(float), nullptr));
+    GCNK_CHECK(gcnk_memcpy_d2h(z.h_red + 4 * slot, z.ws, 4 * sizeof(float), nullptr));
+    z.sumsq_used[slot] = -1.f;                                            // eval: the penalty of the weights as they are at collect time
     if (training) {
+        z.sumsq_used[slot] = z.sumsq;                                     // gcn.cpp:98-105: W1 as it was in this forward
         optimizer.step(z.d_sumsq);
         GCNK_CHECK(gcnk_memcpy_d2h(z.h_sumsq, z.d_sumsq, sizeof(float), nullptr));
+        z.sumsq_pending = true;
     }
-    if (z.p2p) GCNK_CHECK(gcnk_memcpy_d2h(z.h_err, z.d_err, sizeof(int), nullptr));
-    GCNK_CHECK(gcnk_stream_sync(nullptr));                                // the one host sync of the pass
-    if (z.p2p && *z.h_err) { fprintf(stderr, "GCN: a peer rank did not reach the exchange barrier\n"); exit(EXIT_FAILURE); }
-    gpu_timer_resolve();
-    if (training) z.sumsq = *z.h_sumsq;
-    last_count = (int)z.h_red[1];
-    last_wrong = (int)z.h_red[2];
-    const float mean_loss = z.h_red[0] / (float)last_count;              // count == 0 -> NaN, as the reference
-    const float l2 = params.weight_decay * sumsq_before / 2;              // gcn.cpp:98-105, W1 as it was in this forward
+}
+
+// The host sync of the enqueued pass(es) and their scalars.
+std::pair<float, float> GCN::fused_collect(int slot, bool sync) {
+    Fused &z = *fz;
+    if (sync) {
+        if (z.p2p) GCNK_CHECK(gcnk_memcpy_d2h(z.h_err, z.d_err, sizeof(int), nullptr));
+        GCNK_CHECK(gcnk_stream_sync(nullptr));
+        if (z.p2p && *z.h_err) { fprintf(stderr, "GCN: a peer rank did not reach the exchange barrier\n"); exit(EXIT_FAILURE); }
+        gpu_timer_resolve();
+        if (z.sumsq_pending) { z.sumsq = *z.h_sumsq; z.sumsq_pending = false; }
+    }
+    const float *red = z.h_red + 4 * slot;
+    last_count = (int)red[1];
+    last_wrong = (int)red[2];
+    const float mean_loss = red[0] / (float)last_count;                  // count == 0 -> NaN, as the reference
+    const float sumsq = z.sumsq_used[slot] >= 0.f ? z.sumsq_used[slot] : z.sumsq;
+    const float l2 = params.weight_decay * sumsq / 2;
     return {mean_loss + l2, float(last_count - last_wrong) / last_count};
+}
+
+std::pair<float, float> GCN::fused_pass(int current_split, bool training) {
+    fused_enqueue(current_split, training, 0);
+    return fused_collect(0, true);
+}
+
+// train_epoch() followed by eval(split) with ONE host synchronisation: the eval pass is enqueued behind the
+// training pass before anything is read back (what GCN::run does every epoch, gcn.cpp:136-138).
+void GCN::epoch(int eval_split, float *train_loss, float *train_acc, float *eval_loss, float *eval_acc) {
+    if (plan_ != PLAN_FUSED) {
+        std::tie(*train_loss, *train_acc) = train_epoch();
+        std::tie(*eval_loss, *eval_acc) = eval(eval_split);
+        return;
+    }
+    fused_enqueue(1, true, 0);
+    fused_enqueue(eval_split, false, 1);
+    std::tie(*train_loss, *train_acc) = fused_collect(0, true);
+    train_count = last_count; train_wrong = last_wrong;
+    std::tie(*eval_loss, *eval_acc) = fused_collect(1, false);
 }
 
 // -------------------------------------------------------------------------------- the loop ----
@@ -606,8 +640,7 @@ void GCN::run() {
     for (; epoch <= params.epochs; epoch++) {
         float train_loss, train_acc, val_loss, val_acc;
         timer_start(TMR_TRAIN);
-        std::tie(train_loss, train_acc) = train_epoch();
-        std::tie(val_loss, val_acc) = eval(2);
+        this->epoch(2, &train_loss, &train_acc, &val_loss, &val_acc);
         const float dt = timer_stop(TMR_TRAIN);
         epochs_run = epoch;
         if (!quiet_)

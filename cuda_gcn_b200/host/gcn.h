@@ -62,6 +62,9 @@ public:
     // ---- beyond the reference's public surface (private there); used by the C face, tests and bench
     std::pair<float, float> train_epoch();
     std::pair<float, float> eval(int current_split);
+    // train_epoch() + eval(split) with one host synchronisation (fused plan); the same numbers as the two calls
+    void epoch(int eval_split, float *train_loss, float *train_acc, float *eval_loss, float *eval_acc);
+    int train_count = 0, train_wrong = 0;                        // integer outputs of the training half of epoch()
     GCNPlan plan() const { return plan_; }
     void set_input_from_host(const float *h_values);            // re-upload the feature values (H2D of nnz(X) floats)
     // Variable idx as constructed in gcn.cpp:21-53 (0 input, 1 X*W1, 2 W1, 3 layer-1 out, 4 H1*W2, 5 W2, 6 logits).
@@ -78,6 +81,8 @@ private:
     float get_accuracy();
     float get_l2_penalty();
     std::pair<float, float> fused_pass(int current_split, bool training);
+    void fused_enqueue(int current_split, bool training, int slot);
+    std::pair<float, float> fused_collect(int slot, bool sync);
 
     void build_partition();
     gcnk_graph *graph_handle();

@@ -46,6 +46,7 @@ SIGNATURES = {
     "gcnh_engine_plan": (C.c_int, [vp]),
     "gcnh_engine_train_epoch": (None, [vp, fp, fp]),
     "gcnh_engine_eval": (None, [vp, C.c_int, fp, fp]),
+    "gcnh_engine_epoch": (None, [vp, C.c_int, fp, fp, fp, fp]),
     "gcnh_engine_last_counts": (None, [vp, ip, ip]),
     "gcnh_engine_run": (C.c_int, [vp, C.c_int]),
     "gcnh_engine_set_input_host": (None, [vp, vp]),
@@ -191,6 +192,12 @@ class Engine:
         a, b = C.c_float(), C.c_float()
         self.L.gcnh_engine_eval(self.h, split, C.byref(a), C.byref(b))
         return a.value, b.value
+
+    def epoch(self, eval_split=2):
+        """train_epoch() + eval(eval_split) with one host sync; returns (train_loss, train_acc, eval_loss, eval_acc)."""
+        v = [C.c_float() for _ in range(4)]
+        self.L.gcnh_engine_epoch(self.h, eval_split, *[C.byref(x) for x in v])
+        return tuple(x.value for x in v)
 
     def last_counts(self):
         a, b = C.c_int(), C.c_int()

@@ -76,6 +76,8 @@ void gcnh_engine_destroy(gcnh_engine *e);
 int  gcnh_engine_plan(const gcnh_engine *e);
 void gcnh_engine_train_epoch(gcnh_engine *e, float *loss, float *acc);          /* gcn.cpp:107-118 */
 void gcnh_engine_eval(gcnh_engine *e, int split, float *loss, float *acc);      /* gcn.cpp:120-128 */
+/* train_epoch followed by eval(split) with one host synchronisation — one epoch as GCN::run times it (gcn.cpp:136-138) */
+void gcnh_engine_epoch(gcnh_engine *e, int eval_split, float *train_loss, float *train_acc, float *eval_loss, float *eval_acc);
 /* integer outputs of the last pass: labelled rows and wrongly classified rows (bit-exact contract) */
 void gcnh_engine_last_counts(const gcnh_engine *e, int *count, int *wrong);
 int  gcnh_engine_run(gcnh_engine *e, int quiet);            /* GCN::run, gcn.cpp:130-158; returns epochs executed */

@@ -131,6 +131,21 @@ def test_fused_equals_modules(host):
         assert abs(ra[2][1] - rb[2][1]) <= 1 and abs(ra[3][1] - rb[3][1]) <= 1
 
 
+def test_epoch_single_sync_equals_two_calls(host):
+    """Engine.epoch() (train + eval enqueued back to back, one host sync) returns exactly what the two calls return."""
+    d = host.Data.synth("pubmed", 0.5)
+    rows = []
+    for fused_epoch in (False, True):
+        e = host.Engine(d, dropout=0.5, seed=5, plan=host.PLAN_FUSED)
+        out = []
+        for _ in range(5):
+            out.append(e.epoch(2) if fused_epoch else (*e.train_epoch(), *e.eval(2)))
+        out.append(e.eval(3))
+        rows.append(out)
+        e.close()
+    assert rows[0] == rows[1]
+
+
 def test_directed_graph_falls_back_to_modules(host, chk):
     """A non-symmetric adjacency: the reference still computes A_hat*grad (not the transpose) in backward
     (module.cpp:103-119); the auto plan must pick the modules chain and match it."""
