@@ -21,6 +21,8 @@
 // denotes as long as A and B agree, so logical k = t and k = t+4 are mapped to the ADJACENT physical
 // columns 2t and 2t+1.  One 64-bit load then feeds two fragment registers, and a quad of lanes reads
 // 32 contiguous bytes.
+#include <stdlib.h>
+
 #include <algorithm>
 
 #include "common.cuh"
@@ -351,8 +353,13 @@ int dense_fw16_tc(const float *x, const float *w, float *c, int m, int n, const 
         attr_set[dev] = true;
     }
     const int n_tiles = (m + 15) / 16;
+    const Mirror mir = take_mirror(c);
+    // (A cp.async variant — 8-byte copies into a 4-stage shared-memory ring per warp, 16 warps/SM — was measured at
+    // 293 us per pass against 176 us for the register double buffer below: with rows that are only 8-byte aligned the
+    // copies cannot be wider than 8 bytes, and LDGSTS.64 costs more issue slots than it frees.  A 16-byte-aligned
+    // re-packed copy of X (row pitch 608 floats) would allow 16-byte cp.async / TMA tiles; not done yet.)
     const int grid = std::max(1, std::min(sm_count() * 2, (n_tiles + WARPS - 1) / WARPS));
-    dense_fw16_tc_kernel<<<grid, THREADS, smem, st>>>(x, w, c, m, n, bits, (nnz + 31) / 32, scale, row_scale, relu, take_mirror(c));
+    dense_fw16_tc_kernel<<<grid, THREADS, smem, st>>>(x, w, c, m, n, bits, (nnz + 31) / 32, scale, row_scale, relu, mir);
     GCNK_LAUNCHED();
     return GCNK_OK;
 }
