@@ -255,7 +255,8 @@ __device__ __forceinline__ void bw_load(BwStep &q, const float *__restrict__ x, 
     q.a[3] = v1 ? __ldg(g1 + g + 8) : 0.f;
 }
 
-__global__ void __launch_bounds__(THREADS, 2) dense_bw16_tc_kernel(const float *__restrict__ x, const float *__restrict__ gmat,
+template <bool PF, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) dense_bw16_tc_kernel(const float *__restrict__ x, const float *__restrict__ gmat,
                                                                     float *__restrict__ partials, int m, int n, int rows_per_cta,
                                                                     const uint32_t *__restrict__ bits, int64_t bit_words, float scale) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, t = lane & 3, g = lane >> 2;
@@ -272,15 +273,16 @@ __global__ void __launch_bounds__(THREADS, 2) dense_bw16_tc_kernel(const float *
 
     if (f_band < n && r_lo < r_hi) {
         BwStep cur, nxt;
-        bw_load(cur, x, gmat, n, r_lo, r_hi, f_band, t, g, bits, bit_words);
+        if (PF) bw_load(cur, x, gmat, n, r_lo, r_hi, f_band, t, g, bits, bit_words);
 #pragma unroll 1
         for (int k0 = r_lo; k0 < r_hi; k0 += 8) {
+            if (!PF) bw_load(cur, x, gmat, n, k0, r_hi, f_band, t, g, bits, bit_words);
             {   // L2 prefetch of this warp's band BW_PF k-steps ahead (the band is 320 B per row: lanes g cover it in 64-B steps)
                 const int pr = k0 + 8 * BW_PF + 2 * t + (g >> 2);
                 const int pf = f_band + 32 * (g & 3) * 1;
                 if (pr < r_hi && pf < n && (g & 3) * 32 < BAND) prefetch_l2(x + (size_t)pr * n + pf);
             }
-            if (k0 + 8 < r_hi) bw_load(nxt, x, gmat, n, k0 + 8, r_hi, f_band, t, g, bits, bit_words);   // next 8 rows in flight
+            if (PF && k0 + 8 < r_hi) bw_load(nxt, x, gmat, n, k0 + 8, r_hi, f_band, t, g, bits, bit_words);   // next 8 rows in flight
             uint32_t ab[4], as[4];
 #pragma unroll
             for (int e = 0; e < 4; e++) split_trunc(cur.a[e], ab[e], as[e]);
@@ -309,7 +311,7 @@ __global__ void __launch_bounds__(THREADS, 2) dense_bw16_tc_kernel(const float *
                 mma(acc[p][0], ab[0], ab[1], ab[2], ab[3], bb[0], bb[1]);
                 mma(acc[p][1], ab[0], ab[1], ab[2], ab[3], bb[2], bb[3]);
             }
-            cur = nxt;
+            if (PF) cur = nxt;
         }
     }
     // D fragment of an n-tile: c0 = (h g, n 2t), c1 = (h g, n 2t+1), c2 = (h g+8, n 2t), c3 = (h g+8, n 2t+1);
@@ -376,7 +378,9 @@ int dense_bw16_tc(const float *x, const float *g, float *b_grad, float *partials
     rows_per_cta = (rows_per_cta + 7) / 8 * 8;
     const int parts = (m + rows_per_cta - 1) / rows_per_cta;
     dim3 grid(parts, f_groups, 1);
-    dense_bw16_tc_kernel<<<grid, THREADS, 0, st>>>(x, g, partials, m, n, rows_per_cta, bits, (nnz + 31) / 32, scale);
+    // (variants without the register prefetch at 3 and 4 CTAs/SM — 80 / 64 registers, some spills — measured the same
+    // 0.28-0.31 ms per pass as this one: occupancy is not what limits this kernel)
+    dense_bw16_tc_kernel<true, 2><<<grid, THREADS, 0, st>>>(x, g, partials, m, n, rows_per_cta, bits, (nnz + 31) / 32, scale);
     GCNK_LAUNCHED();
     const int elems = n * P;
     reduce_parts_kernel<<<(elems + 31) / 32, 256, 0, st>>>(partials, b_grad, elems, parts);
