@@ -170,6 +170,17 @@ def test_reddit_shape_scaled(host, chk):
     ref.close(); eng.close()
 
 
+def test_products_shape_hidden_256(host, chk):
+    """ogbn-products shape (dense 100 features -> hidden 256 -> 47 classes) on a 0.2 % graph: hidden*classes exceeds
+    what the fused layer-2 kernel holds, so the auto plan is the reference's module chain (wide GraphSum, the SIMT
+    Matmul kernels, unfused softmax-CE).  Dropout on, 3 epochs against the checker."""
+    d = host.Data.synth("products", 0.002)
+    assert d.params.input_dim == 100 and d.params.output_dim == 47
+    ref, eng, worst = run_pair(host, chk, d, host.PLAN_AUTO, 0.5, epochs=3, hidden=256)
+    assert eng.plan == host.PLAN_MODULES
+    ref.close(); eng.close()
+
+
 def test_cli_matches_gcn_seq_output_format(host, tmp_path):
     """`./gcn-cuda <dataset>` on text files prints the reference's lines (gcn.cpp:139,152,157; main.cpp:39)."""
     import os, re, subprocess
