@@ -11,13 +11,20 @@
 
 #include "gcn.h"
 
+// Binary dataset cache: the parsed GCNData + the three parser-derived GCNParams fields as one file of
+// raw little-endian arrays, so a Reddit-size dataset loads at file-system speed instead of re-tokenising ~2 GB of text.
+// Parser::parse() uses <root>/<name>.gcnbin when it exists and is at least as new as the three text files, and writes
+// it after a successful text parse unless $GCN_NO_CACHE is set.  The cached arrays are exactly the parser's output.
+bool save_dataset_cache(const std::string &path, const GCNParams &params, const GCNData &data);
+bool load_dataset_cache(const std::string &path, GCNParams *params, GCNData *data);
+
 class Parser {
 public:
     // root defaults to the reference's hard-coded "data/" (parser.cpp:12); $GCN_DATA_DIR overrides it
     Parser(GCNParams *gcnParams, GCNData *gcnData, std::string graph_name, std::string root = "");
     bool parse();
 private:
-    std::string graph_path, split_path, svmlight_path;
+    std::string graph_path, split_path, svmlight_path, cache_path;
     GCNParams *gcnParams;
     GCNData *gcnData;
     bool quiet = false;

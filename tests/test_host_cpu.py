@@ -14,6 +14,8 @@ GOLD = ROOT / "tests" / "golden"
 @pytest.fixture(scope="module")
 def host():
     subprocess.run(["make", "-C", str(ROOT / "cuda_gcn_b200" / "host")], check=True, capture_output=True)
+    import os
+    os.environ["GCN_NO_CACHE"] = "1"      # the golden directories stay free of .gcnbin files; one test opts back in
     from cuda_gcn_b200 import host_api
     host_api.load()
     return host_api
@@ -55,6 +57,35 @@ def test_parser_matches_oracle_on_generated_text(host, oracle, tmp_path):
     assert (got["feature_value"].view(np.uint32) == want["feature_value"].view(np.uint32)).all()
     # and the round trip reproduces the generator's arrays
     assert (got["graph_indices"] == gd.graph_indices).all() and (got["feature_value"] == gd.feature_value).all()
+
+
+def test_binary_cache_round_trip(host, tmp_path, monkeypatch):
+    """The .gcnbin cache written after a text parse reloads to exactly the same arrays, is ignored when a text file is
+    newer, and can be switched off with GCN_NO_CACHE."""
+    import os, time
+    from tests.util import make_dataset, write_text_dataset
+    gd = make_dataset(n=300, f=70, c=5, n_undirected=900, nnz_per_row=7, seed=8, isolated=4)
+    root = write_text_dataset(tmp_path, "c", gd, float_fmt="%.9g")
+    monkeypatch.delenv("GCN_NO_CACHE", raising=False)
+    first = host.Data.parse(root, "c")
+    assert (root / "c.gcnbin").exists()
+    second = host.Data.parse(root, "c")                                  # served from the cache
+    for k, v in first.arrays().items():
+        w = second.arrays()[k]
+        assert v.shape == w.shape and (v.view(np.uint32) == w.view(np.uint32)).all(), k
+    assert (second.params.num_nodes, second.params.input_dim, second.params.output_dim) == \
+           (first.params.num_nodes, first.params.input_dim, first.params.output_dim)
+    # a newer text file invalidates the cache: change one split value
+    lines = (root / "c.split").read_text().splitlines()
+    lines[0] = "3" if lines[0] != "3" else "2"
+    (root / "c.split").write_text("\n".join(lines) + "\n")
+    os.utime(root / "c.split", (time.time() + 5, time.time() + 5))
+    third = host.Data.parse(root, "c")
+    assert third.arrays()["split"][0] == int(lines[0])
+    monkeypatch.setenv("GCN_NO_CACHE", "1")
+    (root / "c.gcnbin").unlink()
+    host.Data.parse(root, "c")
+    assert not (root / "c.gcnbin").exists()
 
 
 def test_parser_failures(host, tmp_path):
