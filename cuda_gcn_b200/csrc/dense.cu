@@ -14,6 +14,11 @@
 
 using namespace gcnk;
 
+namespace gcnk {   // matmul_tc.cu: tcgen05 / TMEM / TMA path for wide reductions
+bool matmul_tc_supported(int m, int k, int n);
+int matmul_tc_fw(const float *a, const float *b, float *c, int m, int k, int n, cudaStream_t st);
+}
+
 namespace {
 
 constexpr int BM = 64, BN = 64, BK = 16, TM = 4, TN = 4;
@@ -95,6 +100,10 @@ extern "C" {
 int gcnk_matmul_fw(const float *a, const float *b, float *c, int m, int n, int p, gcnk_stream_t stream) {
     GCNK_REQUIRE(a && b && c && m >= 0 && n > 0 && p > 0, "bad arguments");
     if (m == 0) return GCNK_OK;
+    if (matmul_tc_supported(m, n, p) && reinterpret_cast<uintptr_t>(a) % 16 == 0) {
+        const int rc = matmul_tc_fw(a, b, c, m, n, p, S(stream));
+        if (rc != GCNK_EUNSUPPORTED) return rc;
+    }
     dim3 grid((p + BN - 1) / BN, (m + BM - 1) / BM, 1);
     gemm_kernel<false, false><<<grid, 256, 0, S(stream)>>>(a, b, c, m, p, n, n);
     GCNK_LAUNCHED();

@@ -251,6 +251,25 @@ def test_matmul(abi, chk, m, n, p):
     close(dbg.numpy(), want_bg, rtol=5e-5, what="matmul bw b")
 
 
+@pytest.mark.parametrize("m,n,p", [(5000, 256, 47), (20001, 256, 47), (4096, 64, 16), (3000, 100, 40), (1025, 68, 8), (2048, 512, 33)])
+def test_matmul_tcgen05(abi, chk, m, n, p):
+    """Matmul forward on the tcgen05 / TMEM / TMA path (wide reductions, e.g. hidden 256 x 47 classes): 3xTF32 keeps
+    fp32 accuracy, so the tolerance is the same as for the SIMT kernel."""
+    rng = np.random.default_rng(m + n + p)
+    a = rng.standard_normal((m, n)).astype(np.float32)
+    b = (rng.standard_normal((n, p)) * 0.3).astype(np.float32)
+    want = chk.matmul_fw(a, b, m, n, p)
+    da, db, dc = abi.dev(a), abi.dev(b), abi.DeviceArray.zeros((m, p), np.float32)
+    abi.k.gcnk_matmul_fw(da.ptr, db.ptr, dc.ptr, m, n, p, None)
+    abi.k.gcnk_device_sync()
+    close(dc.numpy(), want, what=f"tcgen05 matmul {m}x{n}x{p}")
+    # twice in a row (barrier phases, TMEM re-allocation) and with a different B
+    b2 = (rng.standard_normal((n, p)) * 0.3).astype(np.float32)
+    db.upload(b2)
+    abi.k.gcnk_matmul_fw(da.ptr, db.ptr, dc.ptr, m, n, p, None)
+    close(dc.numpy(), chk.matmul_fw(a, b2, m, n, p), what="second call")
+
+
 def test_relu(abi, chk, D):
     n = 10007
     rng = np.random.default_rng(2)
