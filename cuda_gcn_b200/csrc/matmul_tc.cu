@@ -2,7 +2,7 @@
 // for the wide-hidden layer-2 product of the reference (Matmul::forward, module.cpp:11-22, at hidden 256 x 47 classes:
 // the ogbn-products-shape config).  At hidden 16 the product is fused into layer2.cu and never reaches this file.
 //
-// Structure (one CTA per SM, persistent over 128-row tiles of A; 8 warps):
+// Structure (one CTA per SM, persistent over 128-row tiles of A; 12 warps):
 //   warp 0 (one lane)   TMA producer: cp.async.bulk.tensor 2D loads of A tiles [128 rows x 32 floats] into a 3-stage
 //                       ring, 128-byte swizzle, completion on an mbarrier (A's row pitch K*4 bytes is a multiple of 16)
 //   warps 4-7           splitters: fp32 has 24 significant bits, a TF32 operand 11, so every A tile is split IN SHARED
@@ -12,7 +12,8 @@
 //                       three per k-step (small*big, big*small, big*big — 3xTF32, fp32-accurate products), accumulator
 //                       in TMEM; tcgen05.commit releases the ring slot and finally signals the epilogue
 //   warp 2              allocates / frees the TMEM columns
-//   warps 4-7 again     epilogue: tcgen05.ld 32 lanes x 32 bit x 16 columns per warp quadrant -> registers -> C
+//   warps 8-11          epilogue: tcgen05.ld 32 lanes x 32 bit x 16 columns per warp quadrant -> registers -> C; two
+//                       accumulators in TMEM, so the MMAs of the next tile run under the epilogue of this one
 // B (the weights: tiny) is transposed, padded and split once per call by prep_b_kernel into K-major [Npad x Kpad]
 // big / small copies and stays resident in shared memory for the whole kernel (loaded by TMA with the same swizzle).
 //
@@ -28,8 +29,9 @@ using namespace gcnk;
 
 namespace {
 
-constexpr int TC_THREADS = 256;
-constexpr int BM = 128, BK = 32, STAGES = 3;
+constexpr int TC_THREADS = 384;                        // warps 0-3: TMA / MMA / TMEM alloc / idle, 4-7: splitters, 8-11: epilogue
+constexpr int BM = 128, BK = 32, STAGES = 3, ACC_STAGES = 2, TMEM_COLS = 128;   // two 64-column accumulators
+constexpr int EPI_STRIDE = 65;                         // floats per staged row (Npad <= 64; odd => conflict-free column access)
 constexpr int A_TILE_BYTES = BM * BK * 4;              // 16 KB
 constexpr uint32_t TF32_MASK = 0xffffe000u;
 
@@ -78,7 +80,7 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
 }
 
 struct Bars {
-    uint64_t full[STAGES], ready[STAGES], empty[STAGES], b_full, acc_full, acc_empty;
+    uint64_t full[STAGES], ready[STAGES], empty[STAGES], b_full, acc_full[ACC_STAGES], acc_empty[ACC_STAGES];
     uint32_t tmem_base;
 };
 
@@ -104,17 +106,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) matmul_tc_kernel(const __grid_c
     uint8_t *a_big = smem, *a_small = smem + STAGES * A_TILE_BYTES;
     const uint32_t b_block_bytes = (uint32_t)Npad * BK * 4;
     uint8_t *b_big = a_small + STAGES * A_TILE_BYTES, *b_small = b_big + (size_t)kblocks * b_block_bytes;
-    Bars *bars = reinterpret_cast<Bars *>(b_small + (size_t)kblocks * b_block_bytes);
+    float *epi = reinterpret_cast<float *>(b_small + (size_t)kblocks * b_block_bytes);        // [4 warps][32 rows][EPI_STRIDE]
+    Bars *bars = reinterpret_cast<Bars *>(epi + 4 * 32 * EPI_STRIDE);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_tiles = (M + BM - 1) / BM;
 
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; s++) { mbar_init(&bars->full[s], 1); mbar_init(&bars->ready[s], 4); mbar_init(&bars->empty[s], 1); }
-        mbar_init(&bars->b_full, 1); mbar_init(&bars->acc_full, 1); mbar_init(&bars->acc_empty, 4);
+        mbar_init(&bars->b_full, 1);
+        for (int i = 0; i < ACC_STAGES; i++) { mbar_init(&bars->acc_full[i], 1); mbar_init(&bars->acc_empty[i], 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     } else if (warp == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 64;" ::"r"(smem_u32(&bars->tmem_base)) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)), "n"(TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
@@ -143,7 +147,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) matmul_tc_kernel(const __grid_c
         if (!mbar_wait(&bars->b_full, 0, err)) goto teardown;
         uint32_t it = 0, t = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, t++) {
-            if (t > 0 && !mbar_wait(&bars->acc_empty, (t - 1) & 1, err)) goto teardown;   // epilogue drained the accumulator
+            const uint32_t acc = t % ACC_STAGES, d_tmem = tmem + acc * 64;
+            if (t >= ACC_STAGES && !mbar_wait(&bars->acc_empty[acc], ((t / ACC_STAGES) - 1) & 1, err)) goto teardown;   // epilogue drained it
             tc_fence_after();
             for (int kb = 0; kb < kblocks; kb++, it++) {
                 const int s = it % STAGES;
@@ -154,19 +159,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) matmul_tc_kernel(const __grid_c
 #pragma unroll
                 for (int k = 0; k < BK / 8; k++) {
                     const uint32_t off = k * 32;                      // 8 floats inside the 128-byte swizzle atom
-                    tc_mma_tf32(tmem, make_desc(as + off), make_desc(bb + off), idesc, (kb | k) != 0);
-                    tc_mma_tf32(tmem, make_desc(ab + off), make_desc(bs + off), idesc, 1);
-                    tc_mma_tf32(tmem, make_desc(ab + off), make_desc(bb + off), idesc, 1);
+                    tc_mma_tf32(d_tmem, make_desc(as + off), make_desc(bb + off), idesc, (kb | k) != 0);
+                    tc_mma_tf32(d_tmem, make_desc(ab + off), make_desc(bs + off), idesc, 1);
+                    tc_mma_tf32(d_tmem, make_desc(ab + off), make_desc(bb + off), idesc, 1);
                 }
                 tc_commit(&bars->empty[s]);                           // the slot is free once these MMAs have read it
             }
-            tc_commit(&bars->acc_full);
+            tc_commit(&bars->acc_full[acc]);
         }
-    } else if (warp >= 4) {
-        // ======================= splitters, then epilogue (TMEM lane quadrant = warp % 4) =======================
-        const int q = warp - 4, tid = threadIdx.x - 128;
-        uint32_t it = 0, t = 0;
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, t++) {
+    } else if (warp >= 4 && warp < 8) {
+        // ================================ splitters ================================
+        const int tid = threadIdx.x - 128;
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
             for (int kb = 0; kb < kblocks; kb++, it++) {
                 const int s = it % STAGES;
                 if (!mbar_wait(&bars->full[s], (it / STAGES) & 1, err)) goto teardown;
@@ -186,32 +191,50 @@ __global__ void __launch_bounds__(TC_THREADS, 1) matmul_tc_kernel(const __grid_c
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&bars->ready[s]);
             }
-            if (!mbar_wait(&bars->acc_full, t & 1, err)) goto teardown;
+    } else if (warp >= 8) {
+        // ======================= epilogue (TMEM lane quadrant = warp % 4) =======================
+        const int q = warp - 8;
+        uint32_t t = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, t++) {
+            const uint32_t acc = t % ACC_STAGES;
+            if (!mbar_wait(&bars->acc_full[acc], (t / ACC_STAGES) & 1, err)) goto teardown;
             tc_fence_after();
-            const int row = tile * BM + q * 32 + lane;
+            // TMEM -> registers -> this warp's staging rows; then the warp's 32 output rows, which are one contiguous
+            // block of 32*N floats in C, go out with coalesced stores
+            float *stage = epi + q * 32 * EPI_STRIDE;
             for (int c0 = 0; c0 < Npad; c0 += 16) {
                 uint32_t r[16];
-                const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + c0;
+                const uint32_t taddr = tmem + acc * 64 + ((uint32_t)(q * 32) << 16) + c0;
                 asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
                              : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
                                "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
                              : "r"(taddr));
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (row < M) {
 #pragma unroll
-                    for (int j = 0; j < 16; j++)
-                        if (c0 + j < N) c[(size_t)row * N + c0 + j] = __uint_as_float(r[j]);
-                }
+                for (int j = 0; j < 16; j++) stage[lane * EPI_STRIDE + c0 + j] = __uint_as_float(r[j]);
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&bars->acc_empty);
+            if (lane == 0) mbar_arrive(&bars->acc_empty[acc]);          // the accumulator is free as soon as it is in registers/smem
+            {
+                const int row0 = tile * BM + q * 32;
+                const int rows = min(32, M - row0);
+                if (rows > 0) {
+                    float *out = c + (size_t)row0 * N;
+                    const int total = rows * N;
+                    for (int f = lane; f < total; f += 32) {
+                        const int rr = f / N, cc = f - rr * N;
+                        out[f] = stage[rr * EPI_STRIDE + cc];
+                    }
+                }
+            }
+            __syncwarp();                                               // the staging rows are reused by the next tile
         }
     }
 teardown:
     tc_fence_before();
     __syncthreads();
-    if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 64;" ::"r"(tmem) : "memory");
+    if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TMEM_COLS) : "memory");
 }
 
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda)
@@ -247,7 +270,7 @@ bool matmul_tc_supported(int m, int k, int n) {
     static const bool off = getenv("GCNK_NO_TCGEN05") && atoi(getenv("GCNK_NO_TCGEN05")) != 0;
     if (off || m < 1024 || k < 64 || k % 4 || n < 8 || n > 256) return false;
     const int npad = (n + 15) / 16 * 16, kpad = (k + BK - 1) / BK * BK;
-    const size_t smem = 2 * (size_t)STAGES * A_TILE_BYTES + 2 * (size_t)npad * kpad * 4 + sizeof(Bars) + 1024;
+    const size_t smem = 2 * (size_t)STAGES * A_TILE_BYTES + 2 * (size_t)npad * kpad * 4 + 4 * 32 * EPI_STRIDE * sizeof(float) + sizeof(Bars) + 1024;
     return npad <= 64 && smem <= 227 * 1024 && encode_fn() != nullptr;
 }
 
@@ -275,7 +298,7 @@ int matmul_tc_fw(const float *a, const float *b, float *c, int m, int k, int n, 
         set_error("matmul_tc: cuTensorMapEncodeTiled failed");
         return GCNK_EUNSUPPORTED;
     }
-    const size_t smem = 2 * (size_t)STAGES * A_TILE_BYTES + 2 * (size_t)npad * kpad * 4 + sizeof(Bars) + 1024;
+    const size_t smem = 2 * (size_t)STAGES * A_TILE_BYTES + 2 * (size_t)npad * kpad * 4 + 4 * 32 * EPI_STRIDE * sizeof(float) + sizeof(Bars) + 1024;
     static bool attr[64] = {false};
     if (!attr[dev]) {
         GCNK_CUDA(cudaFuncSetAttribute(matmul_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
