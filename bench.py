@@ -35,6 +35,7 @@ ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
 METRIC = "full-batch GCN train epochs/s (Reddit-shape)"
+WORKLOAD = "reddit-shape 2-layer GCN (train_epoch + eval per step), hidden 16, dropout 0.5"
 UNIT = "epochs/s"
 
 
@@ -136,7 +137,7 @@ def run_reference(args):
     value, dt, kind, sample = cpu_reference_run(scale, args.steps, args.warmup, full_nnz, host_api)
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 / value, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": {"workload": "reddit-shape 2-layer GCN, hidden 16, dropout 0.5", "scale": 1.0},
+            "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD, "scale": 1.0, "engine": "reference CPU engine (gcn-seq code), 1 thread, bounded sample"},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "reference" if kind == "reference" else "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line))
@@ -260,7 +261,7 @@ def run_ours(args):
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if world > 1 else "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "reddit-shape 2-layer GCN (train_epoch + eval per step), hidden 16, dropout 0.5, fused plan",
+            "config": {"workload": WORKLOAD, "engine": "fused plan",
                        "scale": args.scale, "nodes": N, "graph_nnz": nnzA, "feature_nnz": nnzX, "features": F, "classes": C,
                        "max_degree": sizes["max_degree"], "l2": "inputs larger than L2 each step (X 561 MB + CSR indices 459 MB streamed per pass); no flush",
                        "parallelism": "1 GPU" if world == 1 else f"{world}-way row partition (nnz-balanced), NCCL all-gather of the gather source + all-reduce of dW",
