@@ -158,32 +158,42 @@ __global__ void __launch_bounds__(L2_THREADS) layer2_h16_kernel(const float *__r
     int count = 0, wrong = 0;
     const int total_warps = gridDim.x * L2_WARPS;
     const float inv_count = 1.0f / count_f;
-    // software pipeline over this warp's rows: the next row's split/label/P are in flight while this row is
-    // processed (a row is a ~1,000-cycle dependent chain: loads, 16-deep FMA chains, five warp reductions)
-    int s = blockIdx.x * L2_WARPS + warp;
-    int n_split = 0, n_label = 0;
-    float4 nq[4] = {};
-    if (s < n) {
-        const float4 *pr = reinterpret_cast<const float4 *>(P + (size_t)s * H);
-        n_split = split[s]; n_label = label[s];
-        nq[0] = __ldg(pr); nq[1] = __ldg(pr + 1); nq[2] = __ldg(pr + 2); nq[3] = __ldg(pr + 3);
-    }
-    for (; s < n; s += total_warps) {
-        const int truth = n_split == current_split ? n_label : -1;            // set_truth (gcn.cpp:78-81); warp-uniform
+    // A warp takes blocks of 32 consecutive rows: split[] / label[] are read coalesced (one row per lane), a ballot gives
+    // the labelled rows, and only those are processed — an eval pass over a 10 % split touches 10 % of the P rows.
+    // The next labelled row's P is in flight while the current one (a ~700-cycle dependent chain) is processed.
+    const int n_blocks = (n + 31) / 32;
+    for (int blk = blockIdx.x * L2_WARPS + warp; blk < n_blocks; blk += total_warps) {
+        const int base = blk * 32, my_row = base + lane;
+        const int my_truth = (my_row < n && split[my_row] == current_split) ? label[my_row] : -1;   // set_truth (gcn.cpp:78-81)
+        unsigned todo = __ballot_sync(FULL, logits_out ? my_row < n : my_truth >= 0);
+        if (training) {
+            // rows without a label carry no gradient: zero their G rows, 32 consecutive floats per store
+            const unsigned labelled = __ballot_sync(FULL, my_truth >= 0);
+#pragma unroll
+            for (int j = 0; j < H; j++) {
+                const int idx = j * 32 + lane, r = idx >> 4;
+                if (base + r < n && !((labelled >> r) & 1u)) {
+                    G[(size_t)base * H + idx] = 0.f;
+                    mirror_store(mirror, (size_t)base * H + idx, 0.f);
+                }
+            }
+        }
+        float4 nq[4] = {};
+        if (todo) {
+            const float4 *pr = reinterpret_cast<const float4 *>(P + (size_t)(base + __ffs(todo) - 1) * H);
+            nq[0] = __ldg(pr); nq[1] = __ldg(pr + 1); nq[2] = __ldg(pr + 2); nq[3] = __ldg(pr + 3);
+        }
+        while (todo) {
+        const int r_in = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const int s = base + r_in;
+        const int truth = __shfl_sync(FULL, my_truth, r_in);                  // warp-uniform
         float p[H];
         p[0] = nq[0].x; p[1] = nq[0].y; p[2] = nq[0].z; p[3] = nq[0].w; p[4] = nq[1].x; p[5] = nq[1].y; p[6] = nq[1].z; p[7] = nq[1].w;
         p[8] = nq[2].x; p[9] = nq[2].y; p[10] = nq[2].z; p[11] = nq[2].w; p[12] = nq[3].x; p[13] = nq[3].y; p[14] = nq[3].z; p[15] = nq[3].w;
-        {
-            const int sn = s + total_warps;
-            if (sn < n) {
-                const float4 *pr = reinterpret_cast<const float4 *>(P + (size_t)sn * H);
-                n_split = split[sn]; n_label = label[sn];
-                nq[0] = __ldg(pr); nq[1] = __ldg(pr + 1); nq[2] = __ldg(pr + 2); nq[3] = __ldg(pr + 3);
-            }
-        }
-        if (truth < 0 && !logits_out) {
-            if (training && lane < H) { G[(size_t)s * H + lane] = 0.f; mirror_store(mirror, (size_t)s * H + lane, 0.f); }   // unlabelled rows carry no gradient
-            continue;
+        if (todo) {
+            const float4 *pr = reinterpret_cast<const float4 *>(P + (size_t)(base + __ffs(todo) - 1) * H);
+            nq[0] = __ldg(pr); nq[1] = __ldg(pr + 1); nq[2] = __ldg(pr + 2); nq[3] = __ldg(pr + 3);
         }
         float lg[CPL];
 #pragma unroll
@@ -195,10 +205,7 @@ __global__ void __launch_bounds__(L2_THREADS) layer2_h16_kernel(const float *__r
             if (logits_out && cls < c) logits_out[(size_t)s * c + cls] = v;
             lg[t] = v;
         }
-        if (truth < 0) {
-            if (training && lane < H) { G[(size_t)s * H + lane] = 0.f; mirror_store(mirror, (size_t)s * H + lane, 0.f); }
-            continue;
-        }
+        if (truth < 0) continue;                                             // logits_out only: the row has no label
         float mx = -1e30f;
 #pragma unroll
         for (int t = 0; t < CPL; t++) if (lane + 32 * t < c) mx = fmaxf(mx, lg[t]);
@@ -256,6 +263,7 @@ __global__ void __launch_bounds__(L2_THREADS) layer2_h16_kernel(const float *__r
                 mirror_store(mirror, (size_t)s * H + (lane >> 1), gv);
             }
         }
+        }   // labelled rows of the block
     }
 
     __shared__ float s_loss[L2_WARPS];
@@ -316,7 +324,11 @@ __global__ void __launch_bounds__(256) layer2_finish_kernel(const L2Partial *__r
     }
 }
 
-int l2_grid(int n) { return std::max(1, std::min(sm_count() * 4, (n + L2_WARPS - 1) / L2_WARPS)); }
+// one 32-row block per warp when that gives at most ~6 waves of CTAs, else a multiple of the SM count
+int l2_grid(int n) {
+    const int blocks = (n + 31) / 32, ctas = (blocks + L2_WARPS - 1) / L2_WARPS;
+    return std::max(1, std::min(ctas, sm_count() * 12));
+}
 
 }  // namespace
 
