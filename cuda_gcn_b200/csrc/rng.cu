@@ -35,7 +35,7 @@ __host__ __device__ inline U128 step_state(U128 s) {
 }
 
 constexpr int N_POW = 64;
-constexpr int CTA_THREADS = 128, DRAWS_PER_THREAD = 512, THREAD_SHIFT = 9, CTA_SHIFT = 16;   // 128 * 512 = 2^16
+constexpr int CTA_THREADS = 128;   // a CTA owns 128 << TS consecutive draws, TS = log2(draws per thread): 9 for long streams, 7 for short ones
 
 struct JumpTables {
     // J[b][j] = M^(2^b) applied to the unit vector e_j  (column j of the matrix)
@@ -87,8 +87,10 @@ __device__ __forceinline__ U128 apply_dev(const U128 *__restrict__ cols, U128 s)
     return U128{lo, hi};
 }
 
+template <int THREAD_SHIFT>
 __global__ void __launch_bounds__(CTA_THREADS) dropout_mask_kernel(const U128 *__restrict__ J, U128 start, uint32_t *__restrict__ keep,
                                                                     int64_t n, int threshold) {
+    constexpr int DRAWS_PER_THREAD = 1 << THREAD_SHIFT, CTA_SHIFT = THREAD_SHIFT + 7;
     __shared__ U128 s_state[CTA_THREADS];
     __shared__ uint64_t s_red[2][CTA_THREADS / 32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -210,9 +212,16 @@ int gcnk_dropout_mask(gcnk_rng *rng, uint32_t *keep_bits, int64_t n, float p, gc
     U128 *tab = device_tables();
     if (!tab) return cuda_fail(cudaGetLastError(), "xorshift jump tables", __FILE__, __LINE__);
     const int threshold = (int)(p * (float)0x7fffffff);                    // int(p * MY_RAND_MAX) (module.cpp:211)
-    const int64_t ctas = (n + (1ll << CTA_SHIFT) - 1) >> CTA_SHIFT;
-    GCNK_REQUIRE(ctas <= 0x7fffffff, "too many draws for one launch");
-    dropout_mask_kernel<<<(unsigned)ctas, CTA_THREADS, 0, S(stream)>>>(tab, rng->s, keep_bits, n, threshold);
+    // short streams (the N x hidden mask: 3.7 M draws at Reddit shape) get 128 draws per thread so that they still
+    // fill the machine; long ones 512 (the per-CTA jump is amortised over more draws)
+    if (n < (16ll << 20)) {
+        const int64_t ctas = (n + (1ll << 14) - 1) >> 14;
+        dropout_mask_kernel<7><<<(unsigned)ctas, CTA_THREADS, 0, S(stream)>>>(tab, rng->s, keep_bits, n, threshold);
+    } else {
+        const int64_t ctas = (n + (1ll << 16) - 1) >> 16;
+        GCNK_REQUIRE(ctas <= 0x7fffffff, "too many draws for one launch");
+        dropout_mask_kernel<9><<<(unsigned)ctas, CTA_THREADS, 0, S(stream)>>>(tab, rng->s, keep_bits, n, threshold);
+    }
     GCNK_LAUNCHED();
     rng->s = skip_host(rng->s, (uint64_t)n);
     return GCNK_OK;
