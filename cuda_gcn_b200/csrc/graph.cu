@@ -44,7 +44,7 @@ struct gcnk_graph {
 namespace {
 
 constexpr int THREADS = 256, WARPS = THREADS / 32;
-constexpr int HEAVY_DEGREE = 2048;     // rows above this get a whole CTA
+constexpr int HEAVY_DEGREE = 2048;     // rows above this get a whole CTA (less for small graphs, see build_schedule)
 constexpr int ROW_OVERHEAD = 24;       // per-row cost in edge-equivalents for the bin balance
 
 enum Mode { MODE_PLAIN = 0, MODE_RELU_DROP = 1, MODE_MASK = 2 };
@@ -354,12 +354,19 @@ __global__ void scale_rows_kernel(const float *__restrict__ dinv, const float *_
 
 // Static schedule over the given rows: heavy rows -> one CTA each; the rest -> LPT bins, one warp per bin.
 int build_schedule(gcnk_graph *g, const std::vector<int> &indptr, const std::vector<int> &rows, cudaStream_t st) {
+    // A warp walks its row 32 entries at a time and every step is an L2 round trip, so the longest single-warp row
+    // is a latency floor (2,048 entries ~ 45 us).  That is invisible when the launch has hundreds of microseconds of
+    // throughput-bound work, but a rank of an 8-way partition has ~100 us in total: the CTA-per-row threshold
+    // therefore shrinks with the work of the launch (8 warps then share the row's 32-entry steps).
+    int64_t work = 0;
+    for (int i : rows) work += indptr[i + 1] - indptr[i];
+    const int heavy_degree = (int)std::max<int64_t>(256, std::min<int64_t>(HEAVY_DEGREE, work / ((int64_t)sm_count() * 128)));
     std::vector<int> heavy, light;
     int max_deg = 0;
     for (int i : rows) {
         const int deg = indptr[i + 1] - indptr[i];
         max_deg = std::max(max_deg, deg);
-        (deg > HEAVY_DEGREE ? heavy : light).push_back(i);
+        (deg > heavy_degree ? heavy : light).push_back(i);
     }
     g->max_degree = max_deg;
     g->n_rows_scheduled = (int)rows.size();
