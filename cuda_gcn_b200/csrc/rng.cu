@@ -214,7 +214,7 @@ int gcnk_dropout_mask(gcnk_rng *rng, uint32_t *keep_bits, int64_t n, float p, gc
     const int threshold = (int)(p * (float)0x7fffffff);                    // int(p * MY_RAND_MAX) (module.cpp:211)
     // short streams (the N x hidden mask: 3.7 M draws at Reddit shape) get 128 draws per thread so that they still
     // fill the machine; long ones 512 (the per-CTA jump is amortised over more draws)
-    if (n < (16ll << 20)) {
+    if (n < (64ll << 20)) {
         const int64_t ctas = (n + (1ll << 14) - 1) >> 14;
         dropout_mask_kernel<7><<<(unsigned)ctas, CTA_THREADS, 0, S(stream)>>>(tab, rng->s, keep_bits, n, threshold);
     } else {
