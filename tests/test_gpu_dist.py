@@ -36,3 +36,28 @@ def test_partitioned_equals_single(preset, scale, dropout, world):
     assert abs(r["dist_test"][0] - r["single_test"][0]) <= 2e-6 * abs(r["single_test"][0]) + 1e-7
     # Adam divides by sqrt(v): a weight whose gradient is ~0 amplifies rounding-level differences of the reduction order
     assert r["w1_maxdiff"] <= 5e-5 * r["w1_scale"] and r["w2_maxdiff"] <= 5e-5 * r["w2_scale"]
+
+
+def test_cli_multi_gpu_matches_single(tmp_path):
+    """`GCN_GPUS=2 ./gcn-cuda <dataset>` (one forked worker per GPU, NCCL id over pipes) prints the same epochs as the
+    single-GPU CLI on the same files and seed."""
+    import os
+    import re
+    if n_gpus() < 2:
+        pytest.skip("needs 2 GPUs")
+    sys.path.insert(0, str(ROOT))
+    from tests.util import make_dataset, write_text_dataset
+    gd = make_dataset(n=3000, f=120, c=6, n_undirected=20000, nnz_per_row=9, seed=12, alpha=1.4)
+    write_text_dataset(tmp_path, "toy", gd)
+    outs = []
+    for gpus in ("1", "2"):
+        env = dict(os.environ, GCN_SEED="9", GCN_GPUS=gpus, GCN_PLAN="fused")
+        r = subprocess.run([str(ROOT / "gcn-cuda"), "toy", "-", "-", "16", "-", "0.5", "0.01", "5e-4", "6"], cwd=tmp_path, env=env,
+                           capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs.append([l for l in r.stdout.splitlines() if l.startswith("epoch=") or l.startswith("test_loss")])
+    assert len(outs[0]) == 7 and len(outs[1]) == 7
+    for a, b in zip(*outs):
+        fa = [float(x) for x in re.findall(r"=(\d+\.\d+)", a)]
+        fb = [float(x) for x in re.findall(r"=(\d+\.\d+)", b)]
+        assert abs(fa[0] - fb[0]) <= 2e-5 and abs(fa[-3] - fb[-3]) <= 2e-5 if a.startswith("epoch") else abs(fa[0] - fb[0]) <= 2e-5, (a, b)
