@@ -75,6 +75,10 @@ SIGNATURES = {
     "gcnk_spmm_fw": (i32, [vp, vp, vp, vp, i32, vp, f32, vp, vp]),
     "gcnk_spmm_bw": (i32, [vp, vp, vp, vp, i32, vp, f32, vp]),
     "gcnk_dense_transform": (i32, [vp, i32, i32, vp, vp, i32, vp, f32, vp, i32, vp]),
+    "gcnk_dense_pack": (i32, [vp, i32, i32, vp, i32, vp]),
+    "gcnk_dense_transform_ld": (i32, [vp, i32, i32, i32, vp, vp, i32, vp, f32, vp, i32, vp]),
+    "gcnk_dense_transform_bw_workspace": (sz, [i32, i32]),
+    "gcnk_dense_transform_bw_ld": (i32, [vp, i32, i32, i32, vp, vp, i32, vp, f32, vp, sz, vp]),
     "gcnk_matmul_fw": (i32, [vp, vp, vp, i32, i32, i32, vp]),
     "gcnk_matmul_bw_a": (i32, [vp, vp, vp, i32, i32, i32, vp]),
     "gcnk_matmul_bw_b": (i32, [vp, vp, vp, i32, i32, i32, vp, sz, vp]),
@@ -118,7 +122,7 @@ SIGNATURES = {
 }
 
 # functions whose return value is not an error code
-_NOT_RC = {"gcnk_mirror_pending", "gcnk_version", "gcnk_last_error", "gcnk_launch_count", "gcnk_matmul_bw_b_workspace",
+_NOT_RC = {"gcnk_dense_transform_bw_workspace", "gcnk_mirror_pending", "gcnk_version", "gcnk_last_error", "gcnk_launch_count", "gcnk_matmul_bw_b_workspace",
            "gcnk_softmax_ce_workspace", "gcnk_layer2_workspace", "gcnk_mask_row_stride_bits"}
 
 _lib = None

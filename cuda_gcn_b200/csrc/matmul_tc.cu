@@ -18,12 +18,11 @@
 // big / small copies and stays resident in shared memory for the whole kernel (loaded by TMA with the same swizzle).
 //
 // Every mbarrier wait has a clock-based bail-out that raises an error flag instead of hanging the GPU.
-#include <cuda.h>
 #include <stdlib.h>
 
 #include <algorithm>
 
-#include "common.cuh"
+#include "tma.cuh"
 
 using namespace gcnk;
 
@@ -35,35 +34,7 @@ constexpr int EPI_STRIDE = 65;                         // floats per staged row 
 constexpr int A_TILE_BYTES = BM * BK * 4;              // 16 KB
 constexpr uint32_t TF32_MASK = 0xffffe000u;
 
-// ---------------------------------------------------------------------------------- PTX wrappers ----
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-// returns false on timeout (~1 s) so that a protocol error cannot hang the device
-__device__ __forceinline__ bool mbar_wait(uint64_t *bar, uint32_t parity, int *err) {
-    const uint32_t addr = smem_u32(bar);
-    const long long t0 = clock64();
-    for (;;) {
-        uint32_t done;
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(done) : "r"(addr), "r"(parity) : "memory");
-        if (done) return true;
-        if (clock64() - t0 > (2LL << 30)) { *err = 2; return false; }
-    }
-}
-__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1) {
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-                 ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// ------------------------------------------------------------------------- tcgen05 PTX wrappers ----
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t *bar) {
@@ -116,7 +87,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) matmul_tc_kernel(const __grid_c
         for (int s = 0; s < STAGES; s++) { mbar_init(&bars->full[s], 1); mbar_init(&bars->ready[s], 4); mbar_init(&bars->empty[s], 1); }
         mbar_init(&bars->b_full, 1);
         for (int i = 0; i < ACC_STAGES; i++) { mbar_init(&bars->acc_full[i], 1); mbar_init(&bars->acc_empty[i], 4); }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_fence_init();
     } else if (warp == 2) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)), "n"(TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -237,11 +208,15 @@ teardown:
     if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TMEM_COLS) : "memory");
 }
 
+}  // namespace
+
+namespace gcnk {
+
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda)
 typedef CUresult (*EncodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                 const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
                                 CUtensorMapFloatOOBfill);
-EncodeTiled encode_fn() {
+static EncodeTiled encode_fn() {
     static EncodeTiled fn = nullptr;
     if (!fn) {
         void *p = nullptr;
@@ -251,19 +226,18 @@ EncodeTiled encode_fn() {
     }
     return fn;
 }
-// 2-D fp32 row-major [rows x cols] with box [box_rows x 32 floats], 128-byte swizzle, zero fill out of bounds
-bool make_map(CUtensorMap *map, const float *base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+bool tensor_maps_available() { return encode_fn() != nullptr; }
+
+bool make_tensor_map_2d(CUtensorMap *map, const float *base, uint64_t rows, uint64_t cols, uint64_t pitch_floats, uint32_t box_rows,
+                        uint32_t box_cols, bool swizzle128) {
     EncodeTiled fn = encode_fn();
     if (!fn) return false;
-    const cuuint64_t dims[2] = {cols, rows}, strides[1] = {cols * sizeof(float)};
-    const cuuint32_t box[2] = {BK, box_rows}, estr[2] = {1, 1};
+    const cuuint64_t dims[2] = {cols, rows}, strides[1] = {pitch_floats * sizeof(float)};
+    const cuuint32_t box[2] = {box_cols, box_rows}, estr[2] = {1, 1};
     return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+              swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
-
-}  // namespace
-
-namespace gcnk {
 
 // shapes this kernel takes: enough rows to matter, A's row pitch a multiple of 16 bytes, both split copies of B resident
 bool matmul_tc_supported(int m, int k, int n) {
@@ -271,7 +245,7 @@ bool matmul_tc_supported(int m, int k, int n) {
     if (off || m < 1024 || k < 64 || k % 4 || n < 8 || n > 256) return false;
     const int npad = (n + 15) / 16 * 16, kpad = (k + BK - 1) / BK * BK;
     const size_t smem = 2 * (size_t)STAGES * A_TILE_BYTES + 2 * (size_t)npad * kpad * 4 + 4 * 32 * EPI_STRIDE * sizeof(float) + sizeof(Bars) + 1024;
-    return npad <= 64 && smem <= 227 * 1024 && encode_fn() != nullptr;
+    return npad <= 64 && smem <= 227 * 1024 && tensor_maps_available();
 }
 
 int matmul_tc_fw(const float *a, const float *b, float *c, int m, int k, int n, cudaStream_t st) {
@@ -293,8 +267,9 @@ int matmul_tc_fw(const float *a, const float *b, float *c, int m, int k, int n, 
     prep_b_kernel<<<(npad * kpad + 255) / 256, 256, 0, st>>>(b, bt_big, bt_small, k, n, kpad, npad);
     GCNK_LAUNCHED();
     CUtensorMap map_a, map_bb, map_bs;
-    if (!make_map(&map_a, a, (uint64_t)m, (uint64_t)k, BM) || !make_map(&map_bb, bt_big, (uint64_t)npad, (uint64_t)kpad, (uint32_t)npad) ||
-        !make_map(&map_bs, bt_small, (uint64_t)npad, (uint64_t)kpad, (uint32_t)npad)) {
+    if (!make_tensor_map_2d(&map_a, a, (uint64_t)m, (uint64_t)k, (uint64_t)k, BM, BK, true) ||
+        !make_tensor_map_2d(&map_bb, bt_big, (uint64_t)npad, (uint64_t)kpad, (uint64_t)kpad, (uint32_t)npad, BK, true) ||
+        !make_tensor_map_2d(&map_bs, bt_small, (uint64_t)npad, (uint64_t)kpad, (uint64_t)kpad, (uint32_t)npad, BK, true)) {
         set_error("matmul_tc: cuTensorMapEncodeTiled failed");
         return GCNK_EUNSUPPORTED;
     }

@@ -135,6 +135,18 @@ int gcnk_spmm_bw(gcnk_spmat *sp, const float *values, const float *c_grad, float
 int gcnk_dense_transform(const float *x, int m, int n, const float *w, float *c, int p, const uint32_t *drop_bits,
                          float drop_scale, const float *row_scale, int relu, gcnk_stream_t stream);
 
+/* TMA-staged variants of the same transform and of its weight gradient (w_grad[n x p] = drop(x)^T * g[m x p]) for a
+ * PACKED matrix: row pitch `ld` floats with ld*4 a multiple of 16 bytes (the reference's 602-float rows are not TMA-
+ * addressable).  gcnk_dense_pack makes the packed copy (zero padded); the keep bits stay in the reference's flat order
+ * (bit row*n + col of the unpadded matrix).  p == 16 only; GCNK_EUNSUPPORTED otherwise.  The backward needs
+ * gcnk_dense_transform_bw_workspace(m, n) bytes of scratch (per-CTA partial sums, reduced in a fixed order). */
+int gcnk_dense_pack(const float *x, int m, int n, float *xp, int ld, gcnk_stream_t stream);
+int gcnk_dense_transform_ld(const float *xp, int ld, int m, int n, const float *w, float *c, int p, const uint32_t *drop_bits,
+                            float drop_scale, const float *row_scale, int relu, gcnk_stream_t stream);
+size_t gcnk_dense_transform_bw_workspace(int m, int n);
+int gcnk_dense_transform_bw_ld(const float *xp, int ld, int m, int n, const float *g, float *w_grad, int p, const uint32_t *drop_bits,
+                               float drop_scale, float *workspace, size_t workspace_bytes, gcnk_stream_t stream);
+
 /* ---- Matmul: K1/K2/K3, cuda_kernel.cu:6-96 (CPU: module.cpp:11-42) -------------------------------- */
 int gcnk_matmul_fw(const float *a, const float *b, float *c, int m, int n, int p, gcnk_stream_t stream);   /* c = a*b       */
 int gcnk_matmul_bw_a(const float *c_grad, const float *b, float *a_grad, int m, int n, int p, gcnk_stream_t stream); /* a_grad = c_grad * b^T */

@@ -231,6 +231,38 @@ def test_spmm_dense_reddit_width(abi, chk, D):
     close(dg.numpy(), chk.spmm_bw(fp, fi, fv, cg, m, f, h), rtol=5e-5, what="dense bw16")
 
 
+@pytest.mark.parametrize("m,f", [(1237, 602), (700, 96), (5000, 602), (129, 40), (16, 8), (40000, 100)])
+@pytest.mark.parametrize("drop", [False, True])
+def test_dense_transform_tma(abi, chk, m, f, drop):
+    """The TMA-staged feature transform and weight gradient on a packed (16-byte pitch) copy == SparseMatmul forward /
+    backward of the reference on the dense CSR, with and without dropout-on-read, ReLU + row scale in the epilogue."""
+    h = 16
+    fp, fi, fv = make_features(m, f, 0, seed=m + f, dense=True)
+    rng = np.random.default_rng(m)
+    w = (rng.standard_normal((f, h)) * 0.1).astype(np.float32)
+    cg = rng.standard_normal((m, h)).astype(np.float32)
+    keep = rng.random(m * f) >= 0.5
+    rs = rng.random(m).astype(np.float32) + 0.5
+    vals = np.where(keep, fv * np.float32(2), 0).astype(np.float32) if drop else fv
+    want_fw = chk.spmm_fw(fp, fi, vals, w, m, f, h).reshape(m, h)
+    want_bw = chk.spmm_bw(fp, fi, vals, cg, m, f, h)
+    ld = (f + 31) // 32 * 32
+    dx, dxp = abi.dev(fv), abi.DeviceArray((m, ld), np.float32)
+    abi.k.gcnk_dense_pack(dx.ptr, m, f, dxp.ptr, ld, None)
+    packed = dxp.numpy()
+    assert (packed[:, :f] == fv.reshape(m, f)).all() and (packed[:, f:] == 0).all()
+    bits = abi.dev(pack_bits(keep)) if drop else None
+    dw, dc, dg, drs = abi.dev(w), abi.DeviceArray((m, h), np.float32), abi.dev(cg), abi.dev(rs)
+    abi.k.gcnk_dense_transform_ld(dxp.ptr, ld, m, f, dw.ptr, dc.ptr, h, bits.ptr if drop else None, 2.0, None, 0, None)
+    close(dc.numpy(), want_fw, what="tma fw")
+    abi.k.gcnk_dense_transform_ld(dxp.ptr, ld, m, f, dw.ptr, dc.ptr, h, bits.ptr if drop else None, 2.0, drs.ptr, 1, None)
+    close(dc.numpy(), np.maximum(want_fw, 0) * rs[:, None], what="tma fw + relu + row scale")
+    wsb = abi.k.gcnk_dense_transform_bw_workspace(m, f)
+    ws, dwg = abi.DeviceArray((wsb // 4 + 4,), np.float32), abi.DeviceArray((f, h), np.float32)
+    abi.k.gcnk_dense_transform_bw_ld(dxp.ptr, ld, m, f, dg.ptr, dwg.ptr, h, bits.ptr if drop else None, 2.0, ws.ptr, wsb, None)
+    close(dwg.numpy(), want_bw, rtol=5e-5, what="tma bw")
+
+
 @pytest.mark.parametrize("m,n,p", [(1, 1, 1), (300, 16, 7), (1000, 16, 41), (777, 256, 47), (5000, 100, 256), (64, 64, 64)])
 def test_matmul(abi, chk, m, n, p):
     rng = np.random.default_rng(m + n + p)
