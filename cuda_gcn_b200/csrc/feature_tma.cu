@@ -49,8 +49,10 @@ __device__ __forceinline__ uint32_t bit_window(const uint32_t *__restrict__ bits
 }
 
 // ================================================================================== forward ====
-// CTA = 8 consumer warps (16 rows each: a 128-row tile) + 1 producer warp.  Stage = one [128 x 32] box (16 KB).
-constexpr int FW_CONSUMERS = 8, FW_THREADS = (FW_CONSUMERS + 1) * 32, FW_BM = 128, FW_STAGES = 8, FW_STAGE_BYTES = FW_BM * 128;
+// CTA = 16 consumer warps (16 rows each: a 256-row tile) + 1 producer warp.  Stage = one [256 x 32] box (32 KB).
+// (8 consumer warps per SM were measured slower than the register-staged kernel: too few warps to hide the
+// shared-memory and MMA latencies of the dependent k-step chains.)
+constexpr int FW_CONSUMERS = 16, FW_THREADS = (FW_CONSUMERS + 1) * 32, FW_BM = 256, FW_STAGES = 4, FW_STAGE_BYTES = FW_BM * 128;
 
 struct FwBars { uint64_t full[FW_STAGES], empty[FW_STAGES]; };
 
@@ -178,7 +180,9 @@ constexpr int BW_MAX_BOXES = 20, BW_ROWS = 16, BW_BOX_BYTES = BW_ROWS * 128, BW_
 
 struct BwBars { uint64_t full[BW_STAGES], empty[BW_STAGES]; };
 
-__global__ void __launch_bounds__(352, 1) dense_bw16_tma_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_g,
+constexpr int BW_THREADS = 21 * 32;     // two groups of 10 consumer warps (k-step 0 / k-step 1 of every stage) + the producer warp
+
+__global__ void __launch_bounds__(BW_THREADS, 1) dense_bw16_tma_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_g,
                                                                  float *__restrict__ partials, int m, int n, int n_boxes, int rows_per_cta,
                                                                  const uint32_t *__restrict__ bits, int64_t bit_words, float scale, int *err) {
     extern __shared__ uint8_t smem_raw[];
@@ -188,14 +192,14 @@ __global__ void __launch_bounds__(352, 1) dense_bw16_tma_kernel(const __grid_con
     const int n_consumers = (n_boxes + 1) / 2;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, t = lane & 3, g = lane >> 2;
     if (threadIdx.x == 0) {
-        for (int s = 0; s < BW_STAGES; s++) { mbar_init(&bars->full[s], 1); mbar_init(&bars->empty[s], n_consumers); }
+        for (int s = 0; s < BW_STAGES; s++) { mbar_init(&bars->full[s], 1); mbar_init(&bars->empty[s], 2 * n_consumers); }
         mbar_fence_init();
     }
     __syncthreads();
     const int r_lo = blockIdx.x * rows_per_cta, r_hi = min(m, r_lo + rows_per_cta);
     const int n_stages = r_lo < r_hi ? (r_hi - r_lo + BW_ROWS - 1) / BW_ROWS : 0;
 
-    if (warp == 10) {
+    if (warp == 20) {
         if (lane == 0) {
             for (int it = 0; it < n_stages; it++) {
                 const int s = it % BW_STAGES;
@@ -209,9 +213,10 @@ __global__ void __launch_bounds__(352, 1) dense_bw16_tma_kernel(const __grid_con
         }
         return;
     }
-    if (warp >= n_consumers) return;
+    const int group = warp / 10, bw = warp % 10;          // group = which k-step of a stage; bw = feature band
+    if (bw >= n_consumers) return;
 
-    const int f_band = 64 * warp;
+    const int f_band = 64 * bw;
     float acc[4][2][4];
 #pragma unroll
     for (int p = 0; p < 4; p++)
@@ -224,24 +229,21 @@ __global__ void __launch_bounds__(352, 1) dense_bw16_tma_kernel(const __grid_con
     for (int it = 0; it < n_stages; it++) {
         const int s = it % BW_STAGES;
         // keep windows of this lane's rows for both k-steps of the stage: 64 + 31 bits -> three windows of 32
-        uint32_t kw[2][2][2];
+        uint32_t kw[2][2];
         if (bits) {
 #pragma unroll
-            for (int ks = 0; ks < 2; ks++)
+            for (int rr = 0; rr < 2; rr++) {
+                const int row = r_lo + it * BW_ROWS + 8 * group + 2 * t + rr;
+                const int64_t pos = (int64_t)row * n + f_band;
 #pragma unroll
-                for (int rr = 0; rr < 2; rr++) {
-                    const int row = r_lo + it * BW_ROWS + 8 * ks + 2 * t + rr;
-                    const int64_t pos = (int64_t)row * n + f_band;
-#pragma unroll
-                    for (int q = 0; q < 2; q++) kw[ks][rr][q] = row < r_hi ? bit_window(bits, bit_words, pos + 32 * q) : 0u;
-                }
+                for (int q = 0; q < 2; q++) kw[rr][q] = row < r_hi ? bit_window(bits, bit_words, pos + 32 * q) : 0u;
+            }
         }
         if (!mbar_wait(&bars->full[s], (it / BW_STAGES) & 1, err)) return;
         const uint8_t *st = smem + s * stage_bytes;
         const float *gs = reinterpret_cast<const float *>(st + n_boxes * BW_BOX_BYTES);          // [16 rows][16]
-#pragma unroll
-        for (int ks = 0; ks < 2; ks++) {
-            const int lr0 = 8 * ks + 2 * t, lr1 = lr0 + 1;                                       // stage-local rows of this lane
+        {
+            const int lr0 = 8 * group + 2 * t, lr1 = lr0 + 1;                                    // stage-local rows of this lane
             uint32_t ab[4], as[4];
             split_trunc(gs[lr0 * P + g], ab[0], as[0]);
             split_trunc(gs[lr0 * P + g + 8], ab[1], as[1]);
@@ -249,14 +251,14 @@ __global__ void __launch_bounds__(352, 1) dense_bw16_tma_kernel(const __grid_con
             split_trunc(gs[lr1 * P + g + 8], ab[3], as[3]);
 #pragma unroll
             for (int p = 0; p < 4; p++) {
-                const int box = 2 * warp + (p >> 1), cc = 16 * (p & 1) + 2 * g;                  // column inside the 32-wide box
+                const int box = 2 * bw + (p >> 1), cc = 16 * (p & 1) + 2 * g;                    // column inside the 32-wide box
                 if (box < n_boxes) {
                     const uint8_t *bx = st + box * BW_BOX_BYTES;
                     float2 f0 = *reinterpret_cast<const float2 *>(bx + sw128_offset(lr0, cc));
                     float2 f1 = *reinterpret_cast<const float2 *>(bx + sw128_offset(lr1, cc));
                     if (bits) {                                                                  // 1/(1-p) goes onto the partial sums
                         const int sh = 16 * (p & 1) + 2 * g;                                     // bit inside the 32-bit window of this box
-                        const uint32_t w0 = kw[ks][0][p >> 1], w1 = kw[ks][1][p >> 1];
+                        const uint32_t w0 = kw[0][p >> 1], w1 = kw[1][p >> 1];
                         f0.x = (w0 >> sh) & 1u ? f0.x : 0.f;
                         f0.y = (w0 >> sh) & 2u ? f0.y : 0.f;
                         f1.x = (w1 >> sh) & 1u ? f1.x : 0.f;
@@ -282,7 +284,7 @@ __global__ void __launch_bounds__(352, 1) dense_bw16_tma_kernel(const __grid_con
     // D fragment of an n-tile: c0 = (h g, n 2t), c1 = (h g, n 2t+1), c2 = (h g+8, n 2t), c3 = (h g+8, n 2t+1); logical column
     // n of the even tile of a pair is feature f0 + 2n, of the odd tile f0 + 2n + 1
     const float post = bits ? scale : 1.f;
-    float *out = partials + (size_t)blockIdx.x * n * P;
+    float *out = partials + ((size_t)blockIdx.x * 2 + group) * n * P;
 #pragma unroll
     for (int p = 0; p < 4; p++)
 #pragma unroll
@@ -364,7 +366,7 @@ int gcnk_dense_transform_ld(const float *xp, int ld, int m, int n, const float *
 
 size_t gcnk_dense_transform_bw_workspace(int m, int n) {
     const int ctas = std::max(1, std::min(sm_count(), (m + 15) / 16));
-    return sizeof(float) * (size_t)ctas * n * P;
+    return sizeof(float) * 2 * (size_t)ctas * n * P;       // two row groups per CTA
 }
 
 int gcnk_dense_transform_bw_ld(const float *xp, int ld, int m, int n, const float *g, float *w_grad, int p, const uint32_t *drop_bits,
@@ -394,11 +396,11 @@ int gcnk_dense_transform_bw_ld(const float *xp, int ld, int m, int n, const floa
     int ctas = std::max(1, std::min(sm_count(), (m + 15) / 16));
     int rows_per_cta = ((m + ctas - 1) / ctas + BW_ROWS - 1) / BW_ROWS * BW_ROWS;
     ctas = (m + rows_per_cta - 1) / rows_per_cta;
-    dense_bw16_tma_kernel<<<ctas, 352, smem, S(stream)>>>(map_x, map_g, workspace, m, n, n_boxes, rows_per_cta, drop_bits,
+    dense_bw16_tma_kernel<<<ctas, BW_THREADS, smem, S(stream)>>>(map_x, map_g, workspace, m, n, n_boxes, rows_per_cta, drop_bits,
                                                           ((int64_t)m * n + 31) / 32, drop_scale, err_flag());
     GCNK_LAUNCHED();
     const int elems = n * P;
-    reduce_parts_tma_kernel<<<(elems + 31) / 32, 256, 0, S(stream)>>>(workspace, w_grad, elems, ctas);
+    reduce_parts_tma_kernel<<<(elems + 31) / 32, 256, 0, S(stream)>>>(workspace, w_grad, elems, 2 * ctas);
     GCNK_LAUNCHED();
     return GCNK_OK;
 }

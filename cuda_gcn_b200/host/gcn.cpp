@@ -50,6 +50,11 @@ struct GCN::Fused {
     // A_hat*(X*W1) = (A_hat*X)*W1 is one streaming pass and no gather
     float *AX = nullptr;
     bool ax_valid = false, use_views = true;
+    // TMA path of the dense feature transform: packed copies (row pitch ld floats, a multiple of 32) of X and A_hat*X
+    float *Xp = nullptr, *AXp = nullptr, *bw_ws = nullptr;
+    size_t bw_ws_bytes = 0;
+    int ld = 0;
+    bool xp_dirty = false;
     // Row-partitioned runs: the four gather sources live in ONE slab that every peer maps over NVLink (CUDA IPC);
     // producers mirror their rows into the peers' slabs and a flag barrier replaces the all-gather collective.
     bool p2p = false;
@@ -81,6 +86,7 @@ struct GCN::Fused {
         for (gcnk_graph *g : {rows[1], rows[2], rows[3], cols_train}) if (g) gcnk_graph_destroy(g);
         for (int *k : keep) if (k) gcnk_free(k);   // keep[0] = global train-column flags
         if (AX) gcnk_free(AX);
+        for (float *b : {Xp, AXp, bw_ws}) if (b) gcnk_free(b);
         for (void *p : {(void *)xw_s, (void *)h1_s, (void *)P, (void *)G, (void *)Gm, (void *)dxw, (void *)keep0_buf[0], (void *)keep1_buf[0],
                         (void *)mask, (void *)ws, (void *)d_result, (void *)d_sumsq})
             if (p) gcnk_free(p);
@@ -310,6 +316,23 @@ void GCN::build(GCNPlan plan) {
         if (dist.world > 1) GCNK_CHECK(gcnk_free(x_all));
         fz->ax_valid = true;
     }
+    const char *nt = getenv("GCN_NO_TMA");
+    if (dense && H == 16 && F <= 640 && n_loc > 0 && !(nt && *nt && strcmp(nt, "0"))) {
+        // packed (16-byte pitch) copies for the TMA-staged kernels; the unpadded originals stay for inspection
+        fz->ld = (F + 31) / 32 * 32;
+        GCNK_CHECK(gcnk_malloc((void **)&fz->Xp, sizeof(float) * (size_t)n_loc * fz->ld));
+        GCNK_CHECK(gcnk_dense_pack(d_feature_value, n_loc, F, fz->Xp, fz->ld, nullptr));
+        if (fz->ax_valid) {
+            GCNK_CHECK(gcnk_malloc((void **)&fz->AXp, sizeof(float) * (size_t)n_loc * fz->ld));
+            GCNK_CHECK(gcnk_dense_pack(fz->AX, n_loc, F, fz->AXp, fz->ld, nullptr));
+            GCNK_CHECK(gcnk_stream_sync(nullptr));
+            GCNK_CHECK(gcnk_free(fz->AX));
+            fz->AX = nullptr;
+        }
+        fz->bw_ws_bytes = gcnk_dense_transform_bw_workspace(n_loc, F);
+        GCNK_CHECK(gcnk_malloc((void **)&fz->bw_ws, fz->bw_ws_bytes));
+        GCNK_CHECK(gcnk_stream_sync(nullptr));
+    }
 }
 
 gcnk_graph *GCN::graph_handle() {
@@ -361,7 +384,7 @@ GCN::~GCN() {
 
 void GCN::set_input_from_host(const float *h_values) {
     GCNK_CHECK(gcnk_memcpy_h2d(d_feature_value, h_values, sizeof(float) * data->feature_index.indices.size(), nullptr));
-    if (fz) fz->ax_valid = false;       // A_hat*X was computed from the old values; eval falls back to the gather path
+    if (fz) { fz->ax_valid = false; fz->xp_dirty = fz->Xp != nullptr; }   // A_hat*X is stale (eval falls back to the gather path); re-pack X
 }
 
 // ---------------------------------------------------------------------------- modules plan ----
@@ -483,18 +506,21 @@ void GCN::fused_enqueue(int current_split, bool training, int slot) {
         gpu_timer_end(TMR_DROPOUT_FW);
     }
 
-    if (!training && z.ax_valid) {
+    if (!training && z.ax_valid && (z.AX || z.AXp)) {
         // eval: A_hat*(X*W1) = (A_hat*X)*W1, ReLU and the pre-scale for the next gather in the epilogue
         gpu_timer_begin(TMR_SPMATMUL_FW);
         mirror(z.h1_s, H);
-        GCNK_CHECK(gcnk_dense_transform(z.AX, n_loc, F, W1.data, z.h1_s + own, H, nullptr, 1.0f, dinv, 1, nullptr));
+        if (z.AXp) GCNK_CHECK(gcnk_dense_transform_ld(z.AXp, z.ld, n_loc, F, W1.data, z.h1_s + own, H, nullptr, 1.0f, dinv, 1, nullptr));
+        else GCNK_CHECK(gcnk_dense_transform(z.AX, n_loc, F, W1.data, z.h1_s + own, H, nullptr, 1.0f, dinv, 1, nullptr));
         gpu_timer_end(TMR_SPMATMUL_FW);
     } else {
         // M0 Dropout + M1 SparseMatmul: keep bits applied on read; the stored feature values are never modified,
         // so no set_input() copy is needed
         gpu_timer_begin(TMR_SPMATMUL_FW);
+        if (z.xp_dirty) { GCNK_CHECK(gcnk_dense_pack(d_feature_value, n_loc, F, z.Xp, z.ld, nullptr)); z.xp_dirty = false; }
         mirror(z.xw_s, H);
-        GCNK_CHECK(gcnk_spmm_fw(sp, d_feature_value, W1.data, z.xw_s + own, H, drop ? z.keep0 : nullptr, scale, dinv, nullptr));
+        if (z.Xp) GCNK_CHECK(gcnk_dense_transform_ld(z.Xp, z.ld, n_loc, F, W1.data, z.xw_s + own, H, drop ? z.keep0 : nullptr, scale, dinv, 0, nullptr));
+        else GCNK_CHECK(gcnk_spmm_fw(sp, d_feature_value, W1.data, z.xw_s + own, H, drop ? z.keep0 : nullptr, scale, dinv, nullptr));
         gpu_timer_end(TMR_SPMATMUL_FW);
         if (drop && z.rng_stream) {
             // Draw the NEXT training pass's masks now, on the side stream, into the other buffer (its last readers
@@ -544,7 +570,8 @@ void GCN::fused_enqueue(int current_split, bool training, int slot) {
         GCNK_CHECK(gcnk_gather_plain(g, z.Gm, z.dxw, H, nullptr));
         gpu_timer_end(TMR_GATHER_FULL);
         gpu_timer_begin(TMR_SPMATMUL_BW);
-        GCNK_CHECK(gcnk_spmm_bw(sp, d_feature_value, z.dxw, W1.grad, H, drop ? z.keep0 : nullptr, scale, nullptr));
+        if (z.Xp) GCNK_CHECK(gcnk_dense_transform_bw_ld(z.Xp, z.ld, n_loc, F, z.dxw, W1.grad, H, drop ? z.keep0 : nullptr, scale, z.bw_ws, z.bw_ws_bytes, nullptr));
+        else GCNK_CHECK(gcnk_spmm_bw(sp, d_feature_value, z.dxw, W1.grad, H, drop ? z.keep0 : nullptr, scale, nullptr));
         gpu_timer_end(TMR_SPMATMUL_BW);
     }
     if (dist.world > 1) {
