@@ -61,7 +61,7 @@ __global__ void __launch_bounds__(FW_THREADS, 1) dense_fw16_tma_kernel(const __g
                                                                         const uint32_t *__restrict__ bits, int64_t bit_words, float scale,
                                                                         const float *__restrict__ row_scale, int relu, int *err) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 1 KB aligned, still a shared-space pointer (LDS, not LD)
     const int KS = (n + 7) / 8, n_batches = (n + 31) / 32;
     uint8_t *ring = smem;                                                        // [FW_STAGES][16 KB]
     float4 *sfrag = reinterpret_cast<float4 *>(smem + FW_STAGES * FW_STAGE_BYTES);   // [KS][32] big, [KS][32] small
@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(BW_THREADS, 1) dense_bw16_tma_kernel(const __g
                                                                  float *__restrict__ partials, int m, int n, int n_boxes, int rows_per_cta,
                                                                  const uint32_t *__restrict__ bits, int64_t bit_words, float scale, int *err) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 1 KB aligned, still a shared-space pointer (LDS, not LD)
     const uint32_t stage_bytes = (uint32_t)n_boxes * BW_BOX_BYTES + 1024;          // X boxes, then G (padded to keep 1 KB alignment)
     BwBars *bars = reinterpret_cast<BwBars *>(smem + BW_STAGES * stage_bytes);
     const int n_consumers = (n_boxes + 1) / 2;

@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) matmul_tc_kernel(const __grid_c
                                                                    const __grid_constant__ CUtensorMap map_bs, float *__restrict__ c,
                                                                    int M, int N, int Npad, int kblocks, int *err) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);   // swizzle atoms are 1 KB
+    uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 1 KB aligned, still a shared-space pointer (LDS, not LD)   // swizzle atoms are 1 KB
     // [A big: STAGES x 16 KB][A small: STAGES x 16 KB][B big: kblocks x Npad x 128 B][B small: same][barriers]
     uint8_t *a_big = smem, *a_small = smem + STAGES * A_TILE_BYTES;
     const uint32_t b_block_bytes = (uint32_t)Npad * BK * 4;
