@@ -181,6 +181,16 @@ def test_products_shape_hidden_256(host, chk):
     ref.close(); eng.close()
 
 
+@pytest.mark.parametrize("toggle", ["GCN_NO_TMA", "GCN_NO_VIEWS", "GCN_NO_AX", "GCN_NO_RNG_OVERLAP"])
+def test_fallback_paths(host, chk, toggle, monkeypatch):
+    """Every optimisation of the fused plan can be switched off (register-staged feature transform, full-graph gathers
+    instead of split views, no A_hat*X precompute, masks drawn in line): the result must not depend on it."""
+    monkeypatch.setenv(toggle, "1")
+    d = host.Data.synth("reddit", 0.02)
+    ref, eng, worst = run_pair(host, chk, d, host.PLAN_FUSED, 0.5, epochs=3)
+    ref.close(); eng.close()
+
+
 def test_cli_matches_gcn_seq_output_format(host, tmp_path):
     """`./gcn-cuda <dataset>` on text files prints the reference's lines (gcn.cpp:139,152,157; main.cpp:39)."""
     import os, re, subprocess
