@@ -37,6 +37,8 @@ SIGNATURES = {
     "gcnk_device_count": (i32, [C.POINTER(i32)]),
     "gcnk_set_device": (i32, [i32]),
     "gcnk_device_info": (i32, [i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(sz), C.POINTER(i32)]),
+    "gcnk_async_error": (i32, [vp]),
+    "gcnk_async_error_flag": (i32, [C.POINTER(vp)]),
     "gcnk_launch_count": (i64, []),
     "gcnk_malloc": (i32, [C.POINTER(vp), sz]),
     "gcnk_free": (i32, [vp]),

@@ -35,6 +35,7 @@ inline cudaStream_t S(gcnk_stream_t s) { return reinterpret_cast<cudaStream_t>(s
     } while (0)
 
 int sm_count();          // of the current device (cached per device)
+int *async_err_flag();   // per-device int raised by pipeline kernels whose mbarrier wait timed out
 
 // Mirrored output rows (row-partitioned runs): a producer kernel whose output is the input of the next GraphSum
 // on EVERY rank stores each row it writes also at the same offset of the peers' buffers, over NVLink peer

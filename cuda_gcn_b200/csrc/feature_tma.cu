@@ -309,17 +309,6 @@ __global__ void pack_rows_kernel(const float *__restrict__ x, float *__restrict_
     }
 }
 
-int *err_flag() {
-    static int *d_err[64] = {nullptr};
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
-    if (!d_err[dev]) {
-        if (cudaMalloc(&d_err[dev], sizeof(int)) != cudaSuccess) return nullptr;
-        cudaMemset(d_err[dev], 0, sizeof(int));
-    }
-    return d_err[dev];
-}
-
 }  // namespace
 
 extern "C" {
@@ -359,7 +348,7 @@ int gcnk_dense_transform_ld(const float *xp, int ld, int m, int n, const float *
     }
     const int n_tiles = (m + FW_BM - 1) / FW_BM;
     dense_fw16_tma_kernel<<<std::min(n_tiles, sm_count()), FW_THREADS, smem, S(stream)>>>(map_x, w, c, m, n, drop_bits, ((int64_t)m * n + 31) / 32,
-                                                                                     drop_scale, row_scale, relu, err_flag());
+                                                                                     drop_scale, row_scale, relu, async_err_flag());
     GCNK_LAUNCHED();
     return GCNK_OK;
 }
@@ -397,7 +386,7 @@ int gcnk_dense_transform_bw_ld(const float *xp, int ld, int m, int n, const floa
     int rows_per_cta = ((m + ctas - 1) / ctas + BW_ROWS - 1) / BW_ROWS * BW_ROWS;
     ctas = (m + rows_per_cta - 1) / rows_per_cta;
     dense_bw16_tma_kernel<<<ctas, BW_THREADS, smem, S(stream)>>>(map_x, map_g, workspace, m, n, n_boxes, rows_per_cta, drop_bits,
-                                                          ((int64_t)m * n + 31) / 32, drop_scale, err_flag());
+                                                          ((int64_t)m * n + 31) / 32, drop_scale, async_err_flag());
     GCNK_LAUNCHED();
     const int elems = n * P;
     reduce_parts_tma_kernel<<<(elems + 31) / 32, 256, 0, S(stream)>>>(workspace, w_grad, elems, 2 * ctas);

@@ -254,7 +254,6 @@ int matmul_tc_fw(const float *a, const float *b, float *c, int m, int k, int n, 
     GCNK_CUDA(cudaGetDevice(&dev));
     static float *bt[64] = {nullptr};
     static size_t bt_elems[64] = {0};
-    static int *d_err[64] = {nullptr};
     const size_t need = 2 * (size_t)npad * kpad;
     if (bt_elems[dev] < need) {
         GCNK_CUDA(cudaStreamSynchronize(st));
@@ -262,7 +261,6 @@ int matmul_tc_fw(const float *a, const float *b, float *c, int m, int k, int n, 
         GCNK_CUDA(cudaMalloc(&bt[dev], sizeof(float) * need));
         bt_elems[dev] = need;
     }
-    if (!d_err[dev]) { GCNK_CUDA(cudaMalloc(&d_err[dev], sizeof(int))); GCNK_CUDA(cudaMemset(d_err[dev], 0, sizeof(int))); }
     float *bt_big = bt[dev], *bt_small = bt[dev] + (size_t)npad * kpad;
     prep_b_kernel<<<(npad * kpad + 255) / 256, 256, 0, st>>>(b, bt_big, bt_small, k, n, kpad, npad);
     GCNK_LAUNCHED();
@@ -280,7 +278,7 @@ int matmul_tc_fw(const float *a, const float *b, float *c, int m, int k, int n, 
         attr[dev] = true;
     }
     const int n_tiles = (m + BM - 1) / BM;
-    matmul_tc_kernel<<<std::min(n_tiles, sm_count()), TC_THREADS, smem, st>>>(map_a, map_bb, map_bs, c, m, n, npad, kblocks, d_err[dev]);
+    matmul_tc_kernel<<<std::min(n_tiles, sm_count()), TC_THREADS, smem, st>>>(map_a, map_bb, map_bs, c, m, n, npad, kblocks, async_err_flag());
     GCNK_LAUNCHED();
     return GCNK_OK;
 }

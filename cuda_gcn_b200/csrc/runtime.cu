@@ -33,6 +33,19 @@ int sm_count() {
     return cached[dev];
 }
 
+// One int per device that the mbarrier/TMA/tcgen05 kernels raise when a wait times out (a protocol error must not
+// hang the GPU, but it must not pass silently either): callers poll it with gcnk_async_error.
+int *async_err_flag() {
+    static int *d_err[64] = {nullptr};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    if (!d_err[dev]) {
+        if (cudaMalloc(&d_err[dev], sizeof(int)) != cudaSuccess) return nullptr;
+        cudaMemset(d_err[dev], 0, sizeof(int));
+    }
+    return d_err[dev];
+}
+
 }  // namespace gcnk
 
 using namespace gcnk;
@@ -41,6 +54,26 @@ extern "C" {
 
 int gcnk_version(void) { return 100; }
 const char *gcnk_last_error(void) { return t_error; }
+
+int gcnk_async_error_flag(const int **d_flag) {
+    GCNK_REQUIRE(d_flag, "null");
+    *d_flag = async_err_flag();
+    if (!*d_flag) return cuda_fail(cudaGetLastError(), "async error flag", __FILE__, __LINE__);
+    return GCNK_OK;
+}
+
+int gcnk_async_error(gcnk_stream_t stream) {
+    int *d = async_err_flag(), h = 0;
+    if (!d) return cuda_fail(cudaGetLastError(), "async error flag", __FILE__, __LINE__);
+    GCNK_CUDA(cudaMemcpyAsync(&h, d, sizeof(int), cudaMemcpyDeviceToHost, S(stream)));
+    GCNK_CUDA(cudaStreamSynchronize(S(stream)));
+    if (h) {
+        GCNK_CUDA(cudaMemsetAsync(d, 0, sizeof(int), S(stream)));
+        set_error("a TMA / tcgen05 pipeline kernel timed out on an mbarrier (code %d): its output is invalid", h);
+        return GCNK_EASYNC;
+    }
+    return GCNK_OK;
+}
 
 int gcnk_device_count(int *count) {
     int n = 0;

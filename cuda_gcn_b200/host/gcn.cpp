@@ -63,6 +63,7 @@ struct GCN::Fused {
     int *flag_arrays[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     int barrier_value = 0, world = 1, rank = 0;
     int *d_err = nullptr, *h_err = nullptr;
+    int *h_async = nullptr;      // pinned copy of the kernel library's async error flag (mbarrier time-outs)
     unsigned *d_counter = nullptr;
     float *areas[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // all-reduce exchange areas
     size_t slot_floats = 0;
@@ -79,6 +80,7 @@ struct GCN::Fused {
         if (d_err) gcnk_free(d_err);
         if (d_counter) gcnk_free(d_counter);
         if (h_err) gcnk_free_host(h_err);
+        if (h_async) gcnk_free_host(h_async);
         if (rng_stream) { gcnk_stream_sync(rng_stream); gcnk_stream_destroy(rng_stream); }
         if (ev_ready) gcnk_event_destroy(ev_ready);
         if (ev_go) gcnk_event_destroy(ev_go);
@@ -282,6 +284,8 @@ void GCN::build(GCNPlan plan) {
     GCNK_CHECK(gcnk_malloc_host((void **)&fz->h_result, sizeof(gcnk_ce_result)));
     GCNK_CHECK(gcnk_malloc_host((void **)&fz->h_sumsq, sizeof(float)));
     GCNK_CHECK(gcnk_malloc_host((void **)&fz->h_red, 8 * sizeof(float)));
+    GCNK_CHECK(gcnk_malloc_host((void **)&fz->h_async, sizeof(int)));
+    *fz->h_async = 0;
     GCNK_CHECK(gcnk_rng_create(&fz->slice_rng, 1, 2));
     GCNK_CHECK(gcnk_sum_squares(variables[2].data, variables[2].size, fz->d_sumsq, nullptr));
     GCNK_CHECK(gcnk_memcpy_d2h(fz->h_sumsq, fz->d_sumsq, sizeof(float), nullptr));
@@ -601,7 +605,11 @@ std::pair<float, float> GCN::fused_collect(int slot, bool sync) {
     Fused &z = *fz;
     if (sync) {
         if (z.p2p) GCNK_CHECK(gcnk_memcpy_d2h(z.h_err, z.d_err, sizeof(int), nullptr));
+        const int *d_async = nullptr;
+        GCNK_CHECK(gcnk_async_error_flag(&d_async));
+        GCNK_CHECK(gcnk_memcpy_d2h(z.h_async, d_async, sizeof(int), nullptr));
         GCNK_CHECK(gcnk_stream_sync(nullptr));
+        if (*z.h_async) { fprintf(stderr, "GCN: a TMA pipeline kernel timed out on an mbarrier (code %d)\n", *z.h_async); exit(EXIT_FAILURE); }
         if (z.p2p && *z.h_err) { fprintf(stderr, "GCN: a peer rank did not reach the exchange barrier\n"); exit(EXIT_FAILURE); }
         gpu_timer_resolve();
         if (z.sumsq_pending) { z.sumsq = *z.h_sumsq; z.sumsq_pending = false; }

@@ -27,7 +27,7 @@ extern "C" {
 
 typedef void *gcnk_stream_t;
 
-enum { GCNK_OK = 0, GCNK_EINVAL = -1, GCNK_ENOMEM = -2, GCNK_EUNSUPPORTED = -3, GCNK_ENODEVICE = -4 };
+enum { GCNK_OK = 0, GCNK_EINVAL = -1, GCNK_ENOMEM = -2, GCNK_EUNSUPPORTED = -3, GCNK_ENODEVICE = -4, GCNK_EASYNC = -5 };
 
 /* ---- library / device ------------------------------------------------------------------------ */
 int         gcnk_version(void);                        /* 10000*major + 100*minor + patch */
@@ -35,6 +35,11 @@ const char *gcnk_last_error(void);
 int         gcnk_device_count(int *count);             /* GCNK_ENODEVICE (and *count = 0) without a GPU */
 int         gcnk_set_device(int device);
 int         gcnk_device_info(int device, int *sm_count, int *cc_major, int *cc_minor, size_t *total_mem, int *l2_bytes);
+/* The TMA / tcgen05 pipeline kernels bound every mbarrier wait (~1 s) and raise a per-device flag instead of hanging the
+ * GPU.  gcnk_async_error synchronises `stream` and returns GCNK_EASYNC (clearing the flag) if any of them timed out since
+ * the last call; gcnk_async_error_flag exposes the device int so that a caller can read it with its own result copies. */
+int         gcnk_async_error(gcnk_stream_t stream);
+int         gcnk_async_error_flag(const int **d_flag);
 int64_t     gcnk_launch_count(void);                   /* kernels launched by this library so far (process-wide) */
 
 /* ---- memory, streams, events (thin, so a C/C++/ctypes host needs no other CUDA binding) -------- */

@@ -261,6 +261,7 @@ def test_dense_transform_tma(abi, chk, m, f, drop):
     ws, dwg = abi.DeviceArray((wsb // 4 + 4,), np.float32), abi.DeviceArray((f, h), np.float32)
     abi.k.gcnk_dense_transform_bw_ld(dxp.ptr, ld, m, f, dg.ptr, dwg.ptr, h, bits.ptr if drop else None, 2.0, ws.ptr, wsb, None)
     close(dwg.numpy(), want_bw, rtol=5e-5, what="tma bw")
+    abi.k.gcnk_async_error(None)                                   # no mbarrier wait timed out
 
 
 @pytest.mark.parametrize("m,n,p", [(1, 1, 1), (300, 16, 7), (1000, 16, 41), (777, 256, 47), (5000, 100, 256), (64, 64, 64)])
@@ -300,6 +301,7 @@ def test_matmul_tcgen05(abi, chk, m, n, p):
     db.upload(b2)
     abi.k.gcnk_matmul_fw(da.ptr, db.ptr, dc.ptr, m, n, p, None)
     close(dc.numpy(), chk.matmul_fw(a, b2, m, n, p), what="second call")
+    abi.k.gcnk_async_error(None)                                   # no mbarrier wait timed out
 
 
 def test_relu(abi, chk, D):
