@@ -184,9 +184,16 @@ def run_ours(args):
 
     for _ in range(args.warmup):
         step()
-    # ---- timed region: K epochs, everything resident
+    # ---- timed region: K epochs, everything resident.  Only the dominant kernel (the full-graph GraphSum gather) is
+    # bracketed by CUDA events inside the timed region — that is what the roofline is computed from, live.  Timing every
+    # op costs an event pair per launch (measured: 0.2 ms of a 1.9 ms step at N = 2), so the full per-op breakdown comes
+    # from a short extra loop after the timed region (--timers keeps everything on inside it).
+    timers_in_region = args.timers
     L.gcnh_timer_reset()
-    L.gcnh_timer_enable_gpu(1)
+    if timers_in_region:
+        L.gcnh_timer_enable_gpu(1)
+    else:
+        L.gcnh_timer_enable_mask(1 << L.gcnh_timer_slot(b"gather_full"))
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
@@ -203,6 +210,15 @@ def run_ours(args):
     ms = float(eng.allreduce_host([ms], op_max=True)[0])   # max over ranks
     launches = abi.load().gcnk_launch_count() - launches0
     clk = clocks.stop() if rank == 0 else None
+    breakdown_steps = args.steps
+    live = host_api.timers()                               # gather_full, timed live inside the region
+    if not timers_in_region:
+        breakdown_steps = min(args.steps, 5)
+        L.gcnh_timer_reset()
+        L.gcnh_timer_enable_gpu(1)
+        for _ in range(breakdown_steps):
+            step()
+        barrier()
     timers = host_api.timers()
     L.gcnh_timer_enable_gpu(0)
     value = args.steps / (ms * 1e-3)
@@ -211,7 +227,7 @@ def run_ours(args):
     peak, peak_src = measured_peak()
     # full-graph gather launches only (each bracketed by its own event pair); the row/column-subset launches are
     # reported in `breakdown` as gather_part
-    g_total, g_launches = timers.get("gather_full", (0.0, 0))
+    g_total, g_launches = live.get("gather_full", (0.0, 0))
     b_min = 4 * nnzA_loc + 4 * (n_loc + 1) + 4 * H * (N + n_loc)        # indices + indptr + source read once + rows written once
     t_launch = g_total / max(g_launches, 1)
     achieved = b_min / t_launch / 1e9 if t_launch > 0 else 0.0
@@ -227,7 +243,7 @@ def run_ours(args):
                 "algorithmic_bytes_per_launch": b_min, "avg_launch_us": t_launch * 1e6, "launches_timed": g_launches,
                 "share_of_step": g_total / (ms * 1e-3) if ms > 0 else None,
                 "l2_to_sm_gather_bytes_per_launch": 64 * nnzA_loc + 4 * nnzA_loc}
-    breakdown = {k: {"ms_per_step": v[0] * 1e3 / args.steps, "calls_per_step": v[1] / args.steps} for k, v in timers.items()
+    breakdown = {k: {"ms_per_step": v[0] * 1e3 / breakdown_steps, "calls_per_step": v[1] / breakdown_steps} for k, v in timers.items()
                  if k not in ("train", "test")}
 
     # ---- e2e: the same step through the C face with the (local rows of the) feature matrix uploaded from pinned
@@ -281,6 +297,7 @@ def main():
     ap.add_argument("--cpu-scale", type=float, default=0.125, help="sample of the workload the CPU baseline runs")
     ap.add_argument("--ref-scale", type=float, default=0.03125, help="--impl reference: sample of the workload per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--timers", action="store_true", help="keep the per-op CUDA-event timers on inside the timed region at N > 1")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

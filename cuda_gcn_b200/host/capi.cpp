@@ -2,6 +2,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <vector>
 
 #include "check.h"
@@ -191,6 +192,12 @@ int64_t gcnh_engine_var_size(const gcnh_engine *e, int idx) { return e->g->var_s
 void gcnh_engine_get_var(gcnh_engine *e, int idx, int grad, float *out) { e->g->get_var(idx, grad != 0, out); }
 
 void gcnh_timer_enable_gpu(int on) { gpu_timer_enable(on != 0); }
+void gcnh_timer_enable_mask(unsigned mask) { gpu_timer_enable_mask(mask); }
+int gcnh_timer_slot(const char *name) {
+    for (int t = 0; t < __NUM_TMR; t++)
+        if (!strcmp(timer_name((timer_instance)t), name)) return t;
+    return -1;
+}
 void gcnh_timer_reset(void) { timer_reset_all(); }
 float gcnh_timer_total(int slot) { return slot >= 0 && slot < __NUM_TMR ? timer_total((timer_instance)slot) : 0.f; }
 int gcnh_timer_calls(int slot) { return slot >= 0 && slot < __NUM_TMR ? timer_calls((timer_instance)slot) : 0; }

@@ -12,6 +12,7 @@ thread_local Slot g_slots[__NUM_TMR];
 
 struct Pending { timer_instance t; void *start, *stop; };
 thread_local bool g_gpu_on = false;
+thread_local unsigned g_gpu_mask = 0xffffffffu;
 thread_local std::vector<Pending> g_pending;
 thread_local std::vector<void *> g_free_events;
 thread_local void *g_open[__NUM_TMR] = {nullptr};
@@ -45,11 +46,12 @@ const char *timer_name(timer_instance t) {
     return t < __NUM_TMR ? names[t] : "?";
 }
 
-void gpu_timer_enable(bool on) { g_gpu_on = on; }
+void gpu_timer_enable(bool on) { g_gpu_on = on; g_gpu_mask = 0xffffffffu; }
+void gpu_timer_enable_mask(unsigned mask) { g_gpu_on = mask != 0; g_gpu_mask = mask; }
 bool gpu_timer_enabled() { return g_gpu_on; }
 
 void gpu_timer_begin(timer_instance t) {
-    if (!g_gpu_on) return;
+    if (!g_gpu_on || !((g_gpu_mask >> t) & 1u)) return;
     void *e = take_event();
     GCNK_CHECK(gcnk_event_record(e, nullptr));
     g_open[t] = e;

@@ -26,6 +26,7 @@ const char *timer_name(timer_instance t);
 // gpu_timer_resolve() must be called after a stream/device synchronisation and folds the elapsed
 // times into the slots.  All three are no-ops while disabled.
 void gpu_timer_enable(bool on);
+void gpu_timer_enable_mask(unsigned mask);   // bit t set = slot t is timed (an event pair per op is not free: ~6 us)
 bool gpu_timer_enabled();
 void gpu_timer_begin(timer_instance t);
 void gpu_timer_end(timer_instance t);

@@ -53,6 +53,8 @@ SIGNATURES = {
     "gcnh_engine_var_size": (C.c_int64, [vp, C.c_int]),
     "gcnh_engine_get_var": (None, [vp, C.c_int, C.c_int, _f32]),
     "gcnh_timer_enable_gpu": (None, [C.c_int]),
+    "gcnh_timer_enable_mask": (None, [C.c_uint]),
+    "gcnh_timer_slot": (C.c_int, [C.c_char_p]),
     "gcnh_timer_reset": (None, []),
     "gcnh_timer_total": (C.c_float, [C.c_int]),
     "gcnh_timer_calls": (C.c_int, [C.c_int]),

@@ -89,6 +89,8 @@ void gcnh_engine_get_var(gcnh_engine *e, int idx, int grad, float *h_out);
 
 /* ---- timers (timer.h:5-26) ---- */
 void  gcnh_timer_enable_gpu(int on);                        /* CUDA-event timing of each op */
+void  gcnh_timer_enable_mask(unsigned mask);                /* ... of the ops whose slot bit is set only (0 = off) */
+int   gcnh_timer_slot(const char *name);                    /* slot index by name ("gather_full", ...), -1 if unknown */
 void  gcnh_timer_reset(void);
 float gcnh_timer_total(int slot);                           /* seconds */
 int   gcnh_timer_calls(int slot);
