@@ -66,6 +66,7 @@ SIGNATURES = {
     "gcnk_graph_dinv": (i32, [vp, C.POINTER(vp)]),
     "gcnk_graph_stats": (i32, [vp, C.POINTER(i32), C.POINTER(i64), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]),
     "gcnk_graphsum": (i32, [vp, vp, vp, i32, vp]),
+    "gcnk_graph_release_scratch": (i32, [vp]),
     "gcnk_mask_row_stride_bits": (i32, [i32]),
     "gcnk_scale_rows": (i32, [vp, vp, vp, i32, i32, vp]),
     "gcnk_gather_plain": (i32, [vp, vp, vp, i32, vp]),

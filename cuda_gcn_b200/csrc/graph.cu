@@ -581,6 +581,13 @@ int gcnk_graphsum(const gcnk_graph *gc, const float *in, float *out, int dim, gc
     return gcnk_gather_plain(g, g->scratch, out, dim, stream);
 }
 
+int gcnk_graph_release_scratch(gcnk_graph *g) {
+    GCNK_REQUIRE(g, "null graph");
+    if (g->scratch) GCNK_CUDA(cudaFree(g->scratch));
+    g->scratch = nullptr; g->scratch_elems = 0;
+    return GCNK_OK;
+}
+
 int gcnk_partition_rows(const int *h_indptr, int n, int parts, int *h_row_begin) {
     GCNK_REQUIRE(h_indptr && h_row_begin && n >= 0 && parts > 0, "bad arguments");
     const int64_t nnz = h_indptr[n];

@@ -317,6 +317,7 @@ void GCN::build(GCNPlan plan) {
         GCNK_CHECK(gcnk_malloc((void **)&fz->AX, sizeof(float) * (size_t)n_loc * F));
         GCNK_CHECK(gcnk_graphsum(g, x_all, fz->AX, F, nullptr));
         GCNK_CHECK(gcnk_stream_sync(nullptr));
+        GCNK_CHECK(gcnk_graph_release_scratch(g));            // the [N x F] pre-scaled copy is not needed again
         if (dist.world > 1) GCNK_CHECK(gcnk_free(x_all));
         fz->ax_valid = true;
     }

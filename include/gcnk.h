@@ -91,6 +91,9 @@ int gcnk_graph_stats(const gcnk_graph *g, int *n, int64_t *nnz, int *max_degree,
  * out[s,:] = sum_{d in row s} in[d,:] / sqrt(deg(s)*deg(d)).  Forward and backward are the same
  * operation on (data) resp. (grad) buffers, exactly as in the reference.  `in` has n_cols rows. */
 int gcnk_graphsum(const gcnk_graph *g, const float *in, float *out, int dim, gcnk_stream_t stream);
+/* gcnk_graphsum keeps a [n_cols x dim] pre-scaled copy of its input inside the handle for the next call; this frees it
+ * (synchronise first): worth it after a one-off wide call such as A_hat*X at dim 602 (561 MB at Reddit shape). */
+int gcnk_graph_release_scratch(gcnk_graph *g);
 
 /* Building blocks of the fused plan (all row-major [rows x dim], `scaled` = already multiplied by
  * d^-1/2 of its own row so the gather needs no per-edge coefficient):
