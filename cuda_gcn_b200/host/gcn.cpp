@@ -167,6 +167,11 @@ void GCN::build(GCNPlan plan) {
         fprintf(stderr, "GCN: fused plan needs a symmetric adjacency, output_dim <= 128 and hidden*output <= 4096\n");
         exit(EXIT_FAILURE);
     }
+    if (dist.world > 1 && plan != PLAN_FUSED) {
+        fprintf(stderr, "GCN: the row-partitioned engine needs the fused plan (symmetric adjacency, output_dim <= 128, "
+                        "hidden*output <= 4096); run this configuration on one GPU\n");
+        exit(EXIT_FAILURE);
+    }
     plan_ = plan;
 
     modules.reserve(8);
