@@ -128,3 +128,19 @@ def test_synth_invariants(host, preset, scale):
     # deterministic
     d2 = host.Data.synth(preset, scale)
     assert np.array_equal(d2.arrays()["graph_indices"], ix) and np.array_equal(d2.arrays()["feature_value"], a["feature_value"])
+
+
+def test_cli_usage_and_missing_input(host, tmp_path):
+    """The CLI's argument errors need no GPU: usage line + exit 1 without a dataset (main.cpp:17-27), `Cannot read
+    input: <name>` + exit 1 for a dataset that is not there (main.cpp:33-36)."""
+    cli = ROOT / "gcn-cuda"
+    r = subprocess.run([str(cli)], capture_output=True, text=True, cwd=tmp_path)
+    assert r.returncode == 1
+    assert r.stdout.startswith("gcn-cuda graph_name [num_nodes input_dim hidden_dim output_dim dropout learning_rate, weight_decay epochs early_stopping]")
+    r = subprocess.run([str(cli), "nope"], capture_output=True, text=True, cwd=tmp_path)
+    assert r.returncode == 1 and "Cannot read input: nope" in r.stderr
+    r = subprocess.run([str(cli), "synth:unknown"], capture_output=True, text=True, cwd=tmp_path)
+    assert r.returncode == 1 and "Cannot read input" in r.stderr
+    import os
+    r = subprocess.run([str(cli), "nope"], capture_output=True, text=True, cwd=tmp_path, env=dict(os.environ, GCN_GPUS="9"))
+    assert r.returncode == 1 and "GCN_GPUS" in r.stderr
