@@ -68,6 +68,7 @@ SIGNATURES = {
     "gcnk_graphsum": (i32, [vp, vp, vp, i32, vp]),
     "gcnk_graph_release_scratch": (i32, [vp]),
     "gcnk_mask_row_stride_bits": (i32, [i32]),
+    "gcnk_gather_variant": (i32, [i32]),
     "gcnk_scale_rows": (i32, [vp, vp, vp, i32, i32, vp]),
     "gcnk_gather_plain": (i32, [vp, vp, vp, i32, vp]),
     "gcnk_gather_relu_drop": (i32, [vp, vp, vp, vp, vp, f32, i32, vp]),
@@ -126,7 +127,7 @@ SIGNATURES = {
 
 # functions whose return value is not an error code
 _NOT_RC = {"gcnk_dense_transform_bw_workspace", "gcnk_mirror_pending", "gcnk_version", "gcnk_last_error", "gcnk_launch_count", "gcnk_matmul_bw_b_workspace",
-           "gcnk_softmax_ce_workspace", "gcnk_layer2_workspace", "gcnk_mask_row_stride_bits"}
+           "gcnk_softmax_ce_workspace", "gcnk_layer2_workspace", "gcnk_mask_row_stride_bits", "gcnk_gather_variant"}
 
 _lib = None
 
@@ -241,7 +242,8 @@ class Graph:
 
     def __init__(self, indptr, indices, n_cols=None, dinv_global=None):
         self.indptr = dev(indptr, np.int32)
-        self.indices = dev(indices if len(indices) else np.zeros(1, np.int32), np.int32)
+        # four entries of padding: the int4 index reads of the gather round the array length up (gcnk_gather_variant)
+        self.indices = dev(np.concatenate([np.asarray(indices, np.int32), np.full(4, -1, np.int32)]), np.int32)
         self.n = len(indptr) - 1
         self.nnz = int(len(indices))
         self.n_cols = self.n if n_cols is None else n_cols
@@ -282,7 +284,8 @@ class Graph:
 class SpMat:
     def __init__(self, indptr, indices, m, n):
         self.indptr = dev(indptr, np.int32)
-        self.indices = dev(indices if len(indices) else np.zeros(1, np.int32), np.int32)
+        # four entries of padding: the int4 index reads of the gather round the array length up (gcnk_gather_variant)
+        self.indices = dev(np.concatenate([np.asarray(indices, np.int32), np.full(4, -1, np.int32)]), np.int32)
         self.m, self.n, self.nnz = m, n, int(len(indices))
         h = vp()
         k.gcnk_spmat_create(C.byref(h), self.indptr.ptr, self.indices.ptr, m, n, self.nnz, None)

@@ -15,7 +15,9 @@
 //
 // Roofline: HBM traffic is 4*nnz (indices) + 8*n*dim; the edge gathers (dim*4 bytes each) are served
 // by L2, where the [n x dim] source is resident (14.9 MB at Reddit shape, dim 16).
+#include <cuda.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include <algorithm>
 #include <queue>
@@ -34,6 +36,7 @@ struct gcnk_graph {
     int *heavy_rows = nullptr; int n_heavy = 0;
     int *bin_ptr = nullptr, *bin_rows = nullptr; int n_bins = 0;   // n_bins is a multiple of WARPS
     int max_degree = 0, symmetric = 0;
+    int idx4_ok = 0;                  // `indices` is 16-byte aligned and readable up to its length rounded up to 4 entries
     float *scratch = nullptr; size_t scratch_elems = 0;            // pre-scaled copy for gcnk_graphsum
     // views (gcnk_graph_create_view): dinv/dinv_cols are borrowed from `base`; a column-filtered view owns its CSR
     const gcnk_graph *base = nullptr;
@@ -127,6 +130,137 @@ __device__ __forceinline__ void accumulate(Acc<VEC> (&acc)[NACC], const GatherAr
     }
 }
 
+// Index fetch for the LPR == 4 layout (dim 13..16, the hidden width of the benchmark): the four lanes of group g read
+// the SAME aligned int4 = the group's four edges of this 32-edge chunk (one 128-byte wavefront per warp, the hardware
+// broadcasts inside the group).  The coalesced-load + 4 x SHFL version above spends 5 wavefronts of the L1TEX data pipe
+// per chunk on indices — SHFL runs on that pipe too, and the pipe is what bounds this kernel (86 % busy, 14 % of it
+// shuffles: profiles/r01h).  Chunks start at the row's begin rounded down to 4 entries; entries of the first and last
+// chunk outside [beg,end) are other rows' entries (or the array's padding, see idx4_ok) and are skipped.
+__device__ __forceinline__ int4 load_idx4(const int *p) {
+    int4 r;
+    asm("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+
+// A chunk wholly inside the row: four unconditional row reads per group.  BATCH issues them back to back (16 registers
+// of rows in flight: the 40-register build); otherwise the compiler staggers reads and adds to stay within 32.
+template <bool BATCH>
+__device__ __forceinline__ void gather4_full(Acc<4> &acc, const float *in_q, int dim, const int4 &idx) {
+    if constexpr (BATCH) {
+        const float4 x0 = GCNK_GATHER_LD4(reinterpret_cast<const float4 *>(in_q + (size_t)(unsigned)idx.x * dim));
+        const float4 x1 = GCNK_GATHER_LD4(reinterpret_cast<const float4 *>(in_q + (size_t)(unsigned)idx.y * dim));
+        const float4 x2 = GCNK_GATHER_LD4(reinterpret_cast<const float4 *>(in_q + (size_t)(unsigned)idx.z * dim));
+        const float4 x3 = GCNK_GATHER_LD4(reinterpret_cast<const float4 *>(in_q + (size_t)(unsigned)idx.w * dim));
+        acc.v.x += x0.x; acc.v.y += x0.y; acc.v.z += x0.z; acc.v.w += x0.w;
+        acc.v.x += x1.x; acc.v.y += x1.y; acc.v.z += x1.z; acc.v.w += x1.w;
+        acc.v.x += x2.x; acc.v.y += x2.y; acc.v.z += x2.z; acc.v.w += x2.w;
+        acc.v.x += x3.x; acc.v.y += x3.y; acc.v.z += x3.z; acc.v.w += x3.w;
+    } else {
+        acc.load_add(in_q + (size_t)(unsigned)idx.x * dim);
+        acc.load_add(in_q + (size_t)(unsigned)idx.y * dim);
+        acc.load_add(in_q + (size_t)(unsigned)idx.z * dim);
+        acc.load_add(in_q + (size_t)(unsigned)idx.w * dim);
+    }
+}
+// The first / last chunk of a row: the group's entries j with lo <= j < rem (same order of additions as above).
+__device__ __forceinline__ void gather4_edge(Acc<4> &acc, const float *in_q, int dim, const int4 &idx, int lo, int rem) {
+    if (lo <= 0 && rem > 0) acc.load_add(in_q + (size_t)(unsigned)idx.x * dim);
+    if (lo <= 1 && rem > 1) acc.load_add(in_q + (size_t)(unsigned)idx.y * dim);
+    if (lo <= 2 && rem > 2) acc.load_add(in_q + (size_t)(unsigned)idx.z * dim);
+    if (lo <= 3 && rem > 3) acc.load_add(in_q + (size_t)(unsigned)idx.w * dim);
+}
+
+// Two chunks wholly inside the row: eight row reads in flight (the 64-register build), added in the same order.
+__device__ __forceinline__ void gather8_full(Acc<4> &acc, const float *in_q, int dim, const int4 &ia, const int4 &ib) {
+    const float4 x0 = GCNK_GATHER_LD4(reinterpret_cast<const float4 *>(in_q + (size_t)(unsigned)ia.x * dim));
+    const float4 x1 = GCNK_GATHER_LD4(reinterpret_cast<const float4 *>(in_q + (size_t)(unsigned)ia.y * dim));
+    const float4 x2 = GCNK_GATHER_LD4(reinterpret_cast<const float4 *>(in_q + (size_t)(unsigned)ia.z * dim));
+    const float4 x3 = GCNK_GATHER_LD4(reinterpret_cast<const float4 *>(in_q + (size_t)(unsigned)ia.w * dim));
+    const float4 x4 = GCNK_GATHER_LD4(reinterpret_cast<const float4 *>(in_q + (size_t)(unsigned)ib.x * dim));
+    const float4 x5 = GCNK_GATHER_LD4(reinterpret_cast<const float4 *>(in_q + (size_t)(unsigned)ib.y * dim));
+    const float4 x6 = GCNK_GATHER_LD4(reinterpret_cast<const float4 *>(in_q + (size_t)(unsigned)ib.z * dim));
+    const float4 x7 = GCNK_GATHER_LD4(reinterpret_cast<const float4 *>(in_q + (size_t)(unsigned)ib.w * dim));
+    acc.v.x += x0.x; acc.v.y += x0.y; acc.v.z += x0.z; acc.v.w += x0.w;
+    acc.v.x += x1.x; acc.v.y += x1.y; acc.v.z += x1.z; acc.v.w += x1.w;
+    acc.v.x += x2.x; acc.v.y += x2.y; acc.v.z += x2.z; acc.v.w += x2.w;
+    acc.v.x += x3.x; acc.v.y += x3.y; acc.v.z += x3.z; acc.v.w += x3.w;
+    acc.v.x += x4.x; acc.v.y += x4.y; acc.v.z += x4.z; acc.v.w += x4.w;
+    acc.v.x += x5.x; acc.v.y += x5.y; acc.v.z += x5.z; acc.v.w += x5.w;
+    acc.v.x += x6.x; acc.v.y += x6.y; acc.v.z += x6.z; acc.v.w += x6.w;
+    acc.v.x += x7.x; acc.v.y += x7.y; acc.v.z += x7.z; acc.v.w += x7.w;
+}
+
+// STEP: chunks between two of this warp's chunks (1: the warp owns the row, WARPS: a CTA shares it).
+template <bool EXACT, int STEP, int BATCH>   // BATCH: row reads in flight together: 0 = compiler's choice, 4, 8
+__device__ __forceinline__ void accumulate_idx4(Acc<4> &acc, const GatherArgs &a, int beg, int end, int first, int lane) {
+    constexpr int STRIDE = 32 * STEP;
+    const int g4 = (lane >> 2) * 4, q = lane & 3;
+    const int dim = EXACT ? 16 : a.dim;                    // a compile-time row pitch when the row is exactly 16 wide
+    const int base = (beg & ~3) + 32 * first;              // warp-uniform start of this warp's first chunk
+    int left = end - base;                                 // warp-uniform: entries from the chunk start to the row's end
+    if (left <= 0) return;
+    const int *ip = a.indices + base + g4;                 // this group's four entries of the current chunk
+    const float *in_q = a.in + q * 4;
+    // a group whose four entries start at or after the row's end does not read (this keeps every read inside the array
+    // length rounded up to 4 entries, which is what idx4_ok has verified)
+    int4 idx = make_int4(0, 0, 0, 0);
+    if (left > g4) idx = load_idx4(ip);
+    if (!EXACT && q * 4 >= dim) return;                    // lanes beyond the row width
+    if constexpr (BATCH == 8) {
+        int4 idx_b = idx;
+        if (left - STRIDE > g4) idx_b = load_idx4(ip + STRIDE);
+        bool head = base < beg;                            // only this warp's first chunk can start before the row
+        for (;;) {
+            int4 next_a = idx, next_b = idx_b;
+            if (left - 2 * STRIDE > g4) next_a = load_idx4(ip + 2 * STRIDE);   // in flight during the row gathers
+            if (left - 3 * STRIDE > g4) next_b = load_idx4(ip + 3 * STRIDE);
+            if (!head && left >= STRIDE + 32) {
+                gather8_full(acc, in_q, dim, idx, idx_b);
+            } else {
+                if (!head && left >= 32) gather4_full<true>(acc, in_q, dim, idx);
+                else gather4_edge(acc, in_q, dim, idx, head ? beg - base - g4 : 0, left - g4);
+                if (left > STRIDE) {
+                    if (left - STRIDE >= 32) gather4_full<true>(acc, in_q, dim, idx_b);
+                    else gather4_edge(acc, in_q, dim, idx_b, 0, left - STRIDE - g4);
+                }
+            }
+            head = false;
+            if (left <= 2 * STRIDE) break;
+            ip += 2 * STRIDE;
+            left -= 2 * STRIDE;
+            idx = next_a;
+            idx_b = next_b;
+        }
+    } else if constexpr (BATCH == 4) {
+        int4 idx_next = idx;
+        if (left - STRIDE > g4) idx_next = load_idx4(ip + STRIDE);   // in flight during this chunk's row gathers
+        if (base >= beg && left >= 32) gather4_full<true>(acc, in_q, dim, idx);
+        else gather4_edge(acc, in_q, dim, idx, beg - base - g4, left - g4);
+#pragma unroll 1
+        while (left > STRIDE) {
+            ip += STRIDE;
+            left -= STRIDE;
+            idx = idx_next;
+            if (left - STRIDE > g4) idx_next = load_idx4(ip + STRIDE);
+            if (left >= 32) gather4_full<true>(acc, in_q, dim, idx);
+            else gather4_edge(acc, in_q, dim, idx, 0, left - g4);
+        }
+    } else {
+        // 32 registers leave no room for a second index vector: the next chunk's indices are requested when this
+        // chunk's rows have been added (the other 63 warps of the SM cover the round trip)
+        if (base >= beg && left >= 32) gather4_full<false>(acc, in_q, dim, idx);
+        else gather4_edge(acc, in_q, dim, idx, beg - base - g4, left - g4);
+#pragma unroll 1
+        while (left > STRIDE) {
+            ip += STRIDE;
+            left -= STRIDE;
+            if (left > g4) idx = load_idx4(ip);
+            if (left >= 32) gather4_full<false>(acc, in_q, dim, idx);
+            else gather4_edge(acc, in_q, dim, idx, 0, left - g4);
+        }
+    }
+}
+
 template <int VEC, int LPR, int NACC>
 __device__ __forceinline__ void reduce_groups(Acc<VEC> (&acc)[NACC]) {
 #pragma unroll
@@ -209,8 +343,14 @@ __device__ __forceinline__ void epilogue(Acc<VEC> (&acc)[NACC], const GatherArgs
 #ifndef GCNK_GATHER_MIN_CTAS
 #define GCNK_GATHER_MIN_CTAS 8
 #endif
-template <int VEC, int LPR, int NACC, bool EXACT>
-__global__ void __launch_bounds__(THREADS, NACC == 1 ? GCNK_GATHER_MIN_CTAS : 1) gather_kernel(const GatherArgs a) {
+#ifndef GCNK_GATHER_DEFAULT_VARIANT
+#define GCNK_GATHER_DEFAULT_VARIANT 2
+#endif
+// IDX4: 0 = coalesced index load + shuffles; 1 = int4 index reads, 32 registers (8 CTAs/SM); 2 = int4 index reads with
+// the four row reads of a chunk in flight together, 40 registers (6 CTAs/SM); 3 = two chunks (eight row reads) in
+// flight, 64 registers (4 CTAs/SM).
+template <int VEC, int LPR, int NACC, bool EXACT, int IDX4>
+__global__ void __launch_bounds__(THREADS, NACC != 1 ? 1 : IDX4 == 3 ? 4 : IDX4 == 2 ? 6 : GCNK_GATHER_MIN_CTAS) gather_kernel(const GatherArgs a) {
     extern __shared__ float smem[];   // heavy rows only: [WARPS][dim]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     Acc<VEC> acc[NACC];
@@ -222,7 +362,8 @@ __global__ void __launch_bounds__(THREADS, NACC == 1 ? GCNK_GATHER_MIN_CTAS : 1)
         const int beg = a.indptr[s], end = a.indptr[s + 1];
 #pragma unroll
         for (int t = 0; t < NACC; t++) acc[t].zero();
-        accumulate<VEC, LPR, NACC, EXACT>(acc, a, beg, end, warp, WARPS, lane);
+        if constexpr (IDX4 != 0) accumulate_idx4<EXACT, WARPS, IDX4 == 3 ? 8 : IDX4 == 2 ? 4 : 0>(acc[0], a, beg, end, warp, lane);
+        else accumulate<VEC, LPR, NACC, EXACT>(acc, a, beg, end, warp, WARPS, lane);
         reduce_groups<VEC, LPR, NACC>(acc);
         const int q = lane % LPR;
         if (lane < LPR) {
@@ -259,10 +400,43 @@ __global__ void __launch_bounds__(THREADS, NACC == 1 ? GCNK_GATHER_MIN_CTAS : 1)
         const int beg = a.indptr[s], end = a.indptr[s + 1];
 #pragma unroll
         for (int t = 0; t < NACC; t++) acc[t].zero();
-        accumulate<VEC, LPR, NACC, EXACT>(acc, a, beg, end, 0, 1, lane);
+        if constexpr (IDX4 != 0) accumulate_idx4<EXACT, 1, IDX4 == 3 ? 8 : IDX4 == 2 ? 4 : 0>(acc[0], a, beg, end, 0, lane);
+        else accumulate<VEC, LPR, NACC, EXACT>(acc, a, beg, end, 0, 1, lane);
         reduce_groups<VEC, LPR, NACC>(acc);
         epilogue<VEC, LPR, NACC>(acc, a, s, lane);
     }
+}
+
+// Which index-fetch variant the dim 13..16 gather uses (see gather_kernel): GCNK_GATHER_IDX4 in the environment, or
+// gcnk_gather_variant() at run time.
+int g_gather_variant = -1;
+int gather_variant() {
+    if (g_gather_variant < 0) {
+        const char *e = getenv("GCNK_GATHER_IDX4");
+        g_gather_variant = (e && *e >= '0' && *e <= '3') ? *e - '0' : GCNK_GATHER_DEFAULT_VARIANT;
+    }
+    return g_gather_variant;
+}
+
+// True iff [p, p + bytes) lies inside one device allocation (cuMemGetAddressRange through the runtime's driver entry
+// point, so libcuda is not a link dependency).
+bool device_readable(const void *p, size_t bytes) {
+    typedef CUresult (*range_fn)(CUdeviceptr *, size_t *, CUdeviceptr);
+    static range_fn fn = [] {
+        void *f = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &f, cudaEnableDefault, &qr) != cudaSuccess || qr != cudaDriverEntryPointSuccess) f = nullptr;
+        cudaGetLastError();
+        return reinterpret_cast<range_fn>(f);
+    }();
+    if (!fn || !p) return false;
+    CUdeviceptr base = 0;
+    size_t size = 0;
+    if (fn(&base, &size, (CUdeviceptr)(uintptr_t)p) != CUDA_SUCCESS) return false;
+    return (uintptr_t)p + bytes <= (uintptr_t)base + size;
+}
+int idx4_readable(const int *indices, int64_t entries) {
+    return reinterpret_cast<uintptr_t>(indices) % 16 == 0 && device_readable(indices, sizeof(int) * (size_t)((entries + 3) / 4 * 4));
 }
 
 template <int VEC, int LPR, int NACC>
@@ -270,8 +444,23 @@ int launch_variant(const gcnk_graph *g, const GatherArgs &a, cudaStream_t st) {
     const int grid = g->n_heavy + g->n_bins / WARPS;
     if (grid == 0) return GCNK_OK;
     const size_t smem = g->n_heavy ? sizeof(float) * WARPS * (size_t)a.dim : 0;
-    if (a.dim == VEC * LPR * NACC) gather_kernel<VEC, LPR, NACC, true><<<grid, THREADS, smem, st>>>(a);
-    else gather_kernel<VEC, LPR, NACC, false><<<grid, THREADS, smem, st>>>(a);
+    if constexpr (LPR == 4 && VEC == 4 && NACC == 1) {
+        const int variant = g->idx4_ok ? gather_variant() : 0;
+        const bool exact = a.dim == VEC * LPR * NACC;
+        if (variant == 1) {
+            if (exact) gather_kernel<VEC, LPR, NACC, true, 1><<<grid, THREADS, smem, st>>>(a);
+            else gather_kernel<VEC, LPR, NACC, false, 1><<<grid, THREADS, smem, st>>>(a);
+        } else if (variant == 2) {
+            if (exact) gather_kernel<VEC, LPR, NACC, true, 2><<<grid, THREADS, smem, st>>>(a);
+            else gather_kernel<VEC, LPR, NACC, false, 2><<<grid, THREADS, smem, st>>>(a);
+        } else if (variant == 3) {
+            if (exact) gather_kernel<VEC, LPR, NACC, true, 3><<<grid, THREADS, smem, st>>>(a);
+            else gather_kernel<VEC, LPR, NACC, false, 3><<<grid, THREADS, smem, st>>>(a);
+        }
+        if (variant) { GCNK_LAUNCHED(); return GCNK_OK; }
+    }
+    if (a.dim == VEC * LPR * NACC) gather_kernel<VEC, LPR, NACC, true, 0><<<grid, THREADS, smem, st>>>(a);
+    else gather_kernel<VEC, LPR, NACC, false, 0><<<grid, THREADS, smem, st>>>(a);
     GCNK_LAUNCHED();
     return GCNK_OK;
 }
@@ -373,8 +562,12 @@ int build_schedule(gcnk_graph *g, const std::vector<int> &indptr, const std::vec
     auto deg_of = [&](int r) { return indptr[r + 1] - indptr[r]; };
     std::stable_sort(heavy.begin(), heavy.end(), [&](int x, int y) { return deg_of(x) > deg_of(y); });
     std::stable_sort(light.begin(), light.end(), [&](int x, int y) { return deg_of(x) > deg_of(y); });
-    // 4 bins per resident warp slot keeps the tail short without shrinking bins below a few rows
-    int n_bins = sm_count() * 64 * 4;
+    // Bins are equal-sized by construction, so a launch runs in waves of (resident warps per SM x SMs) bins: the bin
+    // count is a whole number of waves of the dim-16 kernel (4-5 bins per resident warp keeps the tail short without
+    // shrinking bins below a few rows).  GCNK_GATHER_BINS_PER_SM overrides it for experiments.
+    int bins_per_sm = gather_variant() == 2 ? 6 * WARPS * 5 : 8 * WARPS * 4;   // (variant 3: 4 CTAs/SM, 8 waves)
+    if (const char *e = getenv("GCNK_GATHER_BINS_PER_SM")) { const int v = atoi(e); if (v >= WARPS && v <= 4096) bins_per_sm = v; }
+    int n_bins = sm_count() * bins_per_sm;
     n_bins = std::min<int64_t>(n_bins, std::max<int64_t>((int64_t)light.size(), 1));
     n_bins = (n_bins + WARPS - 1) / WARPS * WARPS;
     if (light.empty()) n_bins = 0;
@@ -432,6 +625,7 @@ int gcnk_graph_create(gcnk_graph **out, const int *d_indptr, const int *d_indice
     GCNK_CUDA(cudaStreamSynchronize(st));
     GCNK_CUDA(cudaFree(d_asym));
     g->symmetric = (n_cols == n) && !asym;
+    g->idx4_ok = nnz > 0 && idx4_readable(d_indices, nnz);
     if (n && indptr[n] != nnz) { delete g; set_error("gcnk_graph_create: indptr[n]=%d != nnz=%lld", indptr[n], (long long)nnz); return GCNK_EINVAL; }
 
     std::vector<int> rows((size_t)n);
@@ -485,11 +679,12 @@ int gcnk_graph_create_view(gcnk_graph **out, const gcnk_graph *base, const int *
         indices.resize(w);
         indptr.swap(new_ptr);
         GCNK_CUDA(cudaMalloc(&g->own_indptr, sizeof(int) * ((size_t)n + 1)));
-        GCNK_CUDA(cudaMalloc(&g->own_indices, sizeof(int) * std::max<size_t>(w, 1)));
+        GCNK_CUDA(cudaMalloc(&g->own_indices, sizeof(int) * (w + 4)));          // + 4: the int4 index reads round up
         GCNK_CUDA(cudaMemcpyAsync(g->own_indptr, indptr.data(), sizeof(int) * ((size_t)n + 1), cudaMemcpyHostToDevice, st));
         if (w) GCNK_CUDA(cudaMemcpyAsync(g->own_indices, indices.data(), sizeof(int) * w, cudaMemcpyHostToDevice, st));
         GCNK_CUDA(cudaStreamSynchronize(st));
         g->indptr = g->own_indptr; g->indices = g->own_indices; g->nnz = (int64_t)w;
+        g->idx4_ok = w > 0 && idx4_readable(g->own_indices, (int64_t)w);
         g->symmetric = 0;
     }
     std::vector<int> rows;
@@ -563,6 +758,12 @@ int gcnk_gather_mask(const gcnk_graph *g, const float *in_scaled, float *out_sca
 }
 
 int gcnk_mask_row_stride_bits(int dim) { return mask_stride_bits(dim); }
+
+int gcnk_gather_variant(int v) {
+    const int before = gather_variant();
+    if (v >= 0 && v <= 3) g_gather_variant = v;
+    return before;
+}
 
 int gcnk_graphsum(const gcnk_graph *gc, const float *in, float *out, int dim, gcnk_stream_t stream) {
     GCNK_REQUIRE(gc && in && out && dim > 0, "bad arguments");

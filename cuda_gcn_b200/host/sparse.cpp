@@ -28,7 +28,7 @@ void SparseIndex::upload() {
     const int *ip = indptr.empty() ? &zero : indptr.data();
     const size_t n_ip = indptr.empty() ? 1 : indptr.size();
     GCNK_CHECK(gcnk_malloc((void **)&dev_indptr_, sizeof(int) * n_ip));
-    GCNK_CHECK(gcnk_malloc((void **)&dev_indices_, sizeof(int) * (indices.size() + 1)));
+    GCNK_CHECK(gcnk_malloc((void **)&dev_indices_, sizeof(int) * (indices.size() + 4)));   // + 4: the gather's int4 index reads round up
     GCNK_CHECK(gcnk_memcpy_h2d(dev_indptr_, ip, sizeof(int) * n_ip, nullptr));
     GCNK_CHECK(gcnk_memcpy_h2d(dev_indices_, indices.data(), sizeof(int) * indices.size(), nullptr));
     GCNK_CHECK(gcnk_stream_sync(nullptr));

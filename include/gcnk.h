@@ -109,6 +109,14 @@ int gcnk_graph_release_scratch(gcnk_graph *g);
  * never share a word: row i starts at bit i*gcnk_mask_row_stride_bits(dim) (8, 16, or dim rounded up
  * to 32), i.e. it holds n*stride/32 words (rounded up). */
 int gcnk_mask_row_stride_bits(int dim);
+/* Tuning knob of the dim 13..16 gather (how a warp fetches its edge indices): 0 = one coalesced index load + warp
+ * shuffles, 1 = aligned int4 index reads (32 registers, 8 CTAs/SM), 2 = int4 index reads with a chunk's four row reads in
+ * flight together (40 registers, 6 CTAs/SM), 3 = two chunks = eight row reads in flight (64 registers, 4 CTAs/SM).
+ * 1..3 need a 16-byte-aligned indices array allocated with its length rounded up to 4 entries (checked at
+ * gcnk_graph_create; otherwise 0 is used) and add a row's entries in a different (still fixed) order.  v in 0..3
+ * selects, anything else only queries; returns the previous value.  Also settable with GCNK_GATHER_IDX4 in the
+ * environment; set it before the graph is created, the static row schedule is sized for the variant's occupancy. */
+int gcnk_gather_variant(int v);
 int gcnk_scale_rows(const float *d_dinv, const float *in, float *out, int rows, int dim, gcnk_stream_t stream);
 int gcnk_gather_plain(const gcnk_graph *g, const float *in_scaled, float *out, int dim, gcnk_stream_t stream);
 int gcnk_gather_relu_drop(const gcnk_graph *g, const float *in_scaled, float *out_scaled, const uint32_t *drop_bits,

@@ -98,6 +98,63 @@ def test_graphsum(abi, chk, gname, dim):
     assert (g.dinv().view(np.uint32) == (np.float32(1) / np.sqrt(deg)).view(np.uint32)).all()
 
 
+@pytest.mark.parametrize("variant", [1, 2, 3])
+@pytest.mark.parametrize("dim", [12, 16])
+def test_graphsum_index_fetch_variants(abi, chk, D, variant, dim):
+    """The int4 index-fetch variants of the dim 13..16 gather (gcnk_gather_variant) give the reference's sums on every
+    graph shape: rows starting at all four alignments, one-entry rows, CTA-per-row hubs, a directed graph, a row slice
+    with global column ids, a row-subset view and a column-filtered view."""
+    before = abi.k.gcnk_gather_variant(variant)
+    try:
+        assert abi.k.gcnk_gather_variant(-1) == variant
+        for gname in GRAPHS:
+            if gname == "tiny":
+                indptr, indices = np.array([0, 1], np.int32), np.array([0], np.int32)
+            else:
+                indptr, indices = make_graph(**GRAPHS[gname])
+            n = len(indptr) - 1
+            x = np.random.default_rng(dim + n).standard_normal((n, dim)).astype(np.float32)
+            want = chk.graphsum(indptr, indices, x, dim)
+            g = abi.Graph(indptr, indices)
+            out = abi.DeviceArray((n, dim), np.float32)
+            abi.k.gcnk_graphsum(g.h, D(x), out.ptr, dim, None)
+            close(out.numpy(), want, what=f"variant {variant} graphsum {gname} dim {dim}")
+        # row slices (n_cols > n) and views of the last graph family
+        indptr, indices = make_graph(n=3000, n_undirected=12000, seed=9, alpha=1.3)
+        n = len(indptr) - 1
+        x = np.random.default_rng(2).standard_normal((n, dim)).astype(np.float32)
+        want = chk.graphsum(indptr, indices, x, dim).reshape(n, dim)
+        dinv = (np.float32(1) / np.sqrt(np.diff(indptr).astype(np.float32))).astype(np.float32)
+        for lo, hi in ((0, 1000), (1000, 1001), (1001, n)):
+            g = abi.Graph((indptr[lo:hi + 1] - indptr[lo]).astype(np.int32), indices[indptr[lo]:indptr[hi]], n_cols=n, dinv_global=dinv)
+            out = abi.DeviceArray((hi - lo, dim), np.float32)
+            abi.k.gcnk_graphsum(g.h, D(x), out.ptr, dim, None)
+            close(out.numpy(), want[lo:hi], what=f"variant {variant} slice {lo}:{hi}")
+        g = abi.Graph(indptr, indices)
+        rng = np.random.default_rng(3)
+        row_keep, col_keep = (rng.random(n) < 0.3).astype(np.int32), (rng.random(n) < 0.6).astype(np.int32)
+        xs = (x * dinv[:, None]).astype(np.float32)
+        for rk, ck in ((row_keep, None), (None, col_keep), (row_keep, col_keep)):
+            h = C.c_void_p()
+            abi.k.gcnk_graph_create_view(C.byref(h), g.h, D(rk) if rk is not None else None, D(ck) if ck is not None else None, None)
+            out = abi.DeviceArray((n, dim), np.float32)
+            abi.k.gcnk_memset(out.ptr, 0, n * dim * 4, None)
+            abi.k.gcnk_gather_plain(h.value, D(xs), out.ptr, dim, None)
+            got = out.numpy().reshape(n, dim)
+            ref = np.zeros((n, dim), np.float64)
+            for i in range(n):
+                if rk is not None and not rk[i]:
+                    continue
+                nb = indices[indptr[i]:indptr[i + 1]]
+                if ck is not None:
+                    nb = nb[ck[nb] != 0]
+                ref[i] = dinv[i] * xs[nb].astype(np.float64).sum(0)
+            assert np.abs(got - ref).max() <= 2e-5 * max(1.0, np.abs(ref).max()), (variant, rk is not None, ck is not None)
+            abi.k.gcnk_graph_destroy(h.value)
+    finally:
+        abi.k.gcnk_gather_variant(before)
+
+
 def test_graphsum_empty(abi):
     g = abi.Graph(np.zeros(1, np.int32), np.zeros(0, np.int32))
     d = abi.DeviceArray((4,), np.float32)
