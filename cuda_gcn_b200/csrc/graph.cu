@@ -130,7 +130,7 @@ __device__ __forceinline__ void accumulate(Acc<VEC> (&acc)[NACC], const GatherAr
     }
 }
 
-// Index fetch for the LPR == 4 layout (dim 13..16, the hidden width of the benchmark): the four lanes of group g read
+// Index fetch for the LPR == 4 layout (dim 12 and 16 — 16 is the hidden width of the benchmark): the four lanes of group g read
 // the SAME aligned int4 = the group's four edges of this 32-edge chunk (one 128-byte wavefront per warp, the hardware
 // broadcasts inside the group).  The coalesced-load + 4 x SHFL version above spends 5 wavefronts of the L1TEX data pipe
 // per chunk on indices — SHFL runs on that pipe too, and the pipe is what bounds this kernel (86 % busy, 14 % of it
@@ -407,7 +407,7 @@ __global__ void __launch_bounds__(THREADS, NACC != 1 ? 1 : IDX4 == 3 ? 4 : IDX4 
     }
 }
 
-// Which index-fetch variant the dim 13..16 gather uses (see gather_kernel): GCNK_GATHER_IDX4 in the environment, or
+// Which index-fetch variant the dim 12 / 16 gather uses (see gather_kernel): GCNK_GATHER_IDX4 in the environment, or
 // gcnk_gather_variant() at run time.
 int g_gather_variant = -1;
 int gather_variant() {

@@ -109,7 +109,7 @@ int gcnk_graph_release_scratch(gcnk_graph *g);
  * never share a word: row i starts at bit i*gcnk_mask_row_stride_bits(dim) (8, 16, or dim rounded up
  * to 32), i.e. it holds n*stride/32 words (rounded up). */
 int gcnk_mask_row_stride_bits(int dim);
-/* Tuning knob of the dim 13..16 gather (how a warp fetches its edge indices): 0 = one coalesced index load + warp
+/* Tuning knob of the dim 12 and dim 16 gather (how a warp fetches its edge indices): 0 = one coalesced index load + warp
  * shuffles, 1 = aligned int4 index reads (32 registers, 8 CTAs/SM), 2 = int4 index reads with a chunk's four row reads in
  * flight together (40 registers, 6 CTAs/SM), 3 = two chunks = eight row reads in flight (64 registers, 4 CTAs/SM).
  * 1..3 need a 16-byte-aligned indices array allocated with its length rounded up to 4 entries (checked at

@@ -101,7 +101,7 @@ def test_graphsum(abi, chk, gname, dim):
 @pytest.mark.parametrize("variant", [1, 2, 3])
 @pytest.mark.parametrize("dim", [12, 16])
 def test_graphsum_index_fetch_variants(abi, chk, D, variant, dim):
-    """The int4 index-fetch variants of the dim 13..16 gather (gcnk_gather_variant) give the reference's sums on every
+    """The int4 index-fetch variants of the dim 12 / 16 gather (gcnk_gather_variant) give the reference's sums on every
     graph shape: rows starting at all four alignments, one-entry rows, CTA-per-row hubs, a directed graph, a row slice
     with global column ids, a row-subset view and a column-filtered view."""
     before = abi.k.gcnk_gather_variant(variant)
