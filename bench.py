@@ -243,6 +243,17 @@ def run_ours(args):
                 "algorithmic_bytes_per_launch": b_min, "avg_launch_us": t_launch * 1e6, "launches_timed": g_launches,
                 "share_of_step": g_total / (ms * 1e-3) if ms > 0 else None,
                 "l2_to_sm_gather_bytes_per_launch": 64 * nnzA_loc + 4 * nnzA_loc}
+    # what actually bounds this kernel: every gathered 64-byte row is one wavefront of the SM's L1TEX
+    # LSU data pipe, one per clock per SM — reported beside the HBM figure, not instead of it
+    try:
+        sms = abi.C.c_int(0)
+        K.gcnk_device_info(local, abi.C.byref(sms), None, None, None, None)
+        mhz = float((clk or {}).get("sm_mhz") or 0) or 1965.0
+        floor_us = nnzA_loc / max(sms.value, 1) / mhz
+        roofline["on_chip_bound"] = {"unit": "L1TEX LSU data-pipe wavefronts (1 per gathered 64-byte row per SM per clock)", "sms": sms.value,
+                                     "sm_mhz": mhz, "floor_us": floor_us, "frac": floor_us / (t_launch * 1e6) if t_launch > 0 else None}
+    except Exception:
+        pass
     breakdown = {k: {"ms_per_step": v[0] * 1e3 / breakdown_steps, "calls_per_step": v[1] / breakdown_steps} for k, v in timers.items()
                  if k not in ("train", "test")}
 
