@@ -9,12 +9,16 @@
 //   * the gather source is pre-scaled by d^-1/2 of its own row (by the producing kernel's epilogue),
 //     so an edge costs one index (streamed, coalesced, L1-bypassing) and one vectorised row gather;
 //     no sqrtf, no division, no second random indptr read per edge.
+//   * at width 16 (and 12) the lanes that share a row fetch their indices as one aligned int4 and issue the
+//     chunk's four row reads back to back: the kernel is bound by the L1TEX LSU data pipe (one wavefront per
+//     gathered 64-byte row), and warp shuffles run on that pipe too.
 //   * each warp keeps the row sum in registers and WRITES the row once (no global +=, no memset).
 //   * the epilogue fuses the degree normalisation with ReLU + Dropout (+ mask) forward, or with the
 //     Dropout/ReLU backward mask, and with the pre-scale for the next gather.
 //
 // Roofline: HBM traffic is 4*nnz (indices) + 8*n*dim; the edge gathers (dim*4 bytes each) are served
-// by L2, where the [n x dim] source is resident (14.9 MB at Reddit shape, dim 16).
+// by L2, where the [n x dim] source is resident (14.9 MB at Reddit shape, dim 16); on chip, one L1TEX
+// wavefront per edge per SM clock is the floor (395 us at Reddit shape; measured 460 us).
 #include <cuda.h>
 #include <stdlib.h>
 #include <string.h>
