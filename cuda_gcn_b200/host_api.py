@@ -134,10 +134,18 @@ class Data:
         return dict(zip(keys, [int(v) for v in s]))
 
     def arrays(self):
+        """Zero-copy numpy views of the GCNData vectors.  Each view keeps this object alive (numpy array -> ctypes
+        array -> Data), so `Data.synth(...).arrays()` is safe; close() while views are in use is not."""
         s = self.sizes()
+        owner = self
 
         def view(ptr, n, dt):
-            return np.ctypeslib.as_array(ptr, shape=(n,)).view(dt) if n else np.zeros(0, dt)
+            if not n:
+                return np.zeros(0, dt)
+            ctype = C.c_float if dt == np.float32 else C.c_int32
+            buf = (ctype * n).from_address(C.cast(ptr, C.c_void_p).value)
+            buf._owner = owner                                # the ctypes array is the numpy view's base
+            return np.frombuffer(buf, dtype=dt)
         L, h = self.L, self.h
         return dict(graph_indptr=view(L.gcnh_data_graph_indptr(h), s["num_nodes"] + 1, np.int32),
                     graph_indices=view(L.gcnh_data_graph_indices(h), s["graph_nnz"], np.int32),
