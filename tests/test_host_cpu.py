@@ -144,3 +144,17 @@ def test_cli_usage_and_missing_input(host, tmp_path):
     import os
     r = subprocess.run([str(cli), "nope"], capture_output=True, text=True, cwd=tmp_path, env=dict(os.environ, GCN_GPUS="9"))
     assert r.returncode == 1 and "GCN_GPUS" in r.stderr
+
+
+def test_array_views_keep_the_dataset_alive(host):
+    """Data.arrays() returns zero-copy views; they must stay valid after the last explicit reference to the Data object
+    is gone (a temporary `Data.synth(...).arrays()` used to dangle)."""
+    import gc
+    a = host.Data.synth("cora", 1.0).arrays()
+    gc.collect()
+    churn = [np.full(200_000, 7, np.int32) for _ in range(50)]     # reuse freed heap blocks, if any were freed
+    ip = a["graph_indptr"]
+    assert ip[0] == 0 and (np.diff(ip) > 0).all() and ip[-1] == len(a["graph_indices"])
+    assert a["graph_indices"].min() >= 0 and a["graph_indices"].max() < len(ip) - 1
+    assert a["feature_value"].dtype == np.float32 and np.isfinite(a["feature_value"]).all()
+    del churn
