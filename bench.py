@@ -267,14 +267,18 @@ def run_ours(args):
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        eng.set_input_host(pinned)                          # H2D of this rank's nnz(X) floats on the engine's stream
-        step()                                              # train_epoch + eval(2); each reads its scalars back (D2H)
+        if args.e2e_prefetch:
+            eng.epoch_prefetch(2, pinned)                   # the step on the current input; H2D of the next step's input under it
+        else:
+            eng.set_input_host(pinned)                      # H2D of this rank's nnz(X) floats on the engine's stream
+            step()                                          # train_epoch + eval(2); each reads its scalars back (D2H)
     barrier()
     e2e_dt = (time.perf_counter() - t0) / e2e_steps
     e2e_dt = float(eng.allreduce_host([e2e_dt], op_max=True)[0])
     L.gcnh_free_pinned(pinned)
     e2e = {"value": 1.0 / e2e_dt, "unit": UNIT, "h2d_bytes_per_step": int(nnzX * 4), "d2h_bytes_per_step": world * (2 * 16 + 4),
-           "steps": e2e_steps, "api": "gcnh_engine_set_input_host + gcnh_engine_train_epoch + gcnh_engine_eval (include/gcn_host.h)"}
+           "steps": e2e_steps, "api": "gcnh_engine_epoch_prefetch (upload of step k+1 under step k; include/gcn_host.h)" if args.e2e_prefetch else
+           "gcnh_engine_set_input_host + gcnh_engine_train_epoch + gcnh_engine_eval (include/gcn_host.h)"}
     eng.close()
     if rank != 0:
         return
@@ -308,6 +312,7 @@ def main():
     ap.add_argument("--cpu-scale", type=float, default=0.125, help="sample of the workload the CPU baseline runs")
     ap.add_argument("--ref-scale", type=float, default=0.03125, help="--impl reference: sample of the workload per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-prefetch", action="store_true", help="e2e loop through gcnh_engine_epoch_prefetch (pipelined upload; not yet validated on a GPU)")
     ap.add_argument("--timers", action="store_true", help="keep the per-op CUDA-event timers on inside the timed region at N > 1")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

@@ -188,6 +188,14 @@ int gcnh_engine_run(gcnh_engine *e, int quiet) {
 }
 
 void gcnh_engine_set_input_host(gcnh_engine *e, const float *h) { e->g->set_input_from_host(h); }
+void gcnh_engine_epoch_prefetch(gcnh_engine *e, int split, const float *h_next, float *tl, float *ta, float *el, float *ea) {
+    float a, b, c, d;
+    e->g->epoch_prefetch(split, h_next, &a, &b, &c, &d);
+    if (tl) *tl = a;
+    if (ta) *ta = b;
+    if (el) *el = c;
+    if (ea) *ea = d;
+}
 int64_t gcnh_engine_var_size(const gcnh_engine *e, int idx) { return e->g->var_size(idx); }
 void gcnh_engine_get_var(gcnh_engine *e, int idx, int grad, float *out) { e->g->get_var(idx, grad != 0, out); }
 

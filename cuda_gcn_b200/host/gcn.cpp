@@ -386,21 +386,65 @@ void GCN::build_partition() {
 }
 
 GCN::~GCN() {
+    if (copy_stream) { gcnk_stream_sync(copy_stream); gcnk_stream_destroy(copy_stream); }   // an upload may still be in flight
+    if (ev_copied) gcnk_event_destroy(ev_copied);
     for (auto m : modules) delete m;
     fz.reset();                                             // views before the graph they borrow from
-    for (void *p : {(void *)d_truth, (void *)d_split, (void *)d_label, (void *)d_feature_value, (void *)d_dinv_global})
+    for (void *p : {(void *)d_truth, (void *)d_split, (void *)d_label, (void *)d_feature_value, (void *)d_feature_spare,
+                    (void *)d_dinv_global})
         if (p) gcnk_free(p);
 }
 
 void GCN::set_input_from_host(const float *h_values) {
+    consume_pending_input();                                // a prefetched input is older than this one: retire it first
     GCNK_CHECK(gcnk_memcpy_h2d(d_feature_value, h_values, sizeof(float) * data->feature_index.indices.size(), nullptr));
     if (fz) { fz->ax_valid = false; fz->xp_dirty = fz->Xp != nullptr; }   // A_hat*X is stale (eval falls back to the gather path); re-pack X
+}
+
+// Upload into the spare buffer on the copy stream.  The spare buffer is not read by anything in flight: it was the
+// input of a pass that has completed (every pass ends with a host synchronisation before its results are returned).
+void GCN::start_input_upload(const float *h_values) {
+    const size_t bytes = sizeof(float) * data->feature_index.indices.size();
+    if (!copy_stream) {
+        GCNK_CHECK(gcnk_stream_create(&copy_stream));
+        GCNK_CHECK(gcnk_event_create(&ev_copied));
+        GCNK_CHECK(gcnk_malloc((void **)&d_feature_spare, std::max<size_t>(bytes, sizeof(float))));
+    }
+    if (input_pending) GCNK_CHECK(gcnk_stream_sync(copy_stream));   // never two uploads into the one spare buffer
+    GCNK_CHECK(gcnk_memcpy_h2d(d_feature_spare, h_values, bytes, copy_stream));
+    GCNK_CHECK(gcnk_event_record(ev_copied, copy_stream));
+    input_pending = true;
+}
+
+// Called at the start of every pass: switch to the prefetched input once its upload has finished (device-side wait).
+void GCN::consume_pending_input() {
+    if (!input_pending) return;
+    GCNK_CHECK(gcnk_stream_wait_event(nullptr, ev_copied));
+    std::swap(d_feature_value, d_feature_spare);
+    input_pending = false;
+    if (fz) { fz->ax_valid = false; fz->xp_dirty = fz->Xp != nullptr; }
+}
+
+void GCN::epoch_prefetch(int eval_split, const float *h_next, float *train_loss, float *train_acc, float *eval_loss, float *eval_acc) {
+    if (plan_ != PLAN_FUSED) {                              // the modules plan synchronises after every operator: no overlap to win
+        std::tie(*train_loss, *train_acc) = train_epoch();
+        std::tie(*eval_loss, *eval_acc) = eval(eval_split);
+        start_input_upload(h_next);
+        return;
+    }
+    fused_enqueue(1, true, 0);
+    fused_enqueue(eval_split, false, 1);
+    start_input_upload(h_next);                             // runs under the two passes just enqueued
+    std::tie(*train_loss, *train_acc) = fused_collect(0, true);
+    train_count = last_count; train_wrong = last_wrong;
+    std::tie(*eval_loss, *eval_acc) = fused_collect(1, false);
 }
 
 // ---------------------------------------------------------------------------- modules plan ----
 void GCN::set_input() {
     // restores the feature values the in-place Dropout of the previous pass destroyed (gcn.cpp:73-76);
     // device-to-device here, where the reference GPU path re-uploads them from the host (cuda_gcn.cu:81-83)
+    consume_pending_input();
     GCNK_CHECK(gcnk_memcpy_d2d(input->data, d_feature_value, sizeof(float) * (size_t)input->size, nullptr));
 }
 
@@ -466,6 +510,7 @@ void GCN::allgather(float *d_all, int dim) {
 
 // Enqueues one pass on the stream; nothing is read back until fused_collect.  slot: which pinned result slot to use.
 void GCN::fused_enqueue(int current_split, bool training, int slot) {
+    consume_pending_input();
     Fused &z = *fz;
     const int N = params.num_nodes, F = params.input_dim, H = params.hidden_dim, C = params.output_dim;
     const int64_t nnzX_loc = (int64_t)data->feature_index.indices.size();

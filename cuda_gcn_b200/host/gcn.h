@@ -67,6 +67,9 @@ public:
     int train_count = 0, train_wrong = 0;                        // integer outputs of the training half of epoch()
     GCNPlan plan() const { return plan_; }
     void set_input_from_host(const float *h_values);            // re-upload the feature values (H2D of nnz(X) floats)
+    // epoch() on the current input while `h_next` (pinned host memory) is uploaded into a second feature buffer on a
+    // copy stream; the next pass of any kind switches to it.  Pipelines a per-epoch re-upload under the compute.
+    void epoch_prefetch(int eval_split, const float *h_next, float *train_loss, float *train_acc, float *eval_loss, float *eval_acc);
     // Variable idx as constructed in gcn.cpp:21-53 (0 input, 1 X*W1, 2 W1, 3 layer-1 out, 4 H1*W2, 5 W2, 6 logits).
     // In the fused plan 4 does not exist (size 0), 1/3/6 are materialised on demand for data only.
     long var_size(int idx) const;
@@ -103,6 +106,12 @@ private:
     CrossEntropyLoss *ce_module = nullptr;
     int *d_truth = nullptr, *d_split = nullptr, *d_label = nullptr;
     float *d_feature_value = nullptr;        // pristine feature values (never modified)
+    float *d_feature_spare = nullptr;        // epoch_prefetch: the buffer the next input is uploaded into
+    gcnk_stream_t copy_stream = nullptr;
+    void *ev_copied = nullptr;
+    bool input_pending = false;              // d_feature_spare holds a newer input (complete when ev_copied has fired)
+    void start_input_upload(const float *h_values);
+    void consume_pending_input();
     Adam optimizer;
     float loss = 0;
     int split_count[4] = {0, 0, 0, 0};

@@ -50,6 +50,7 @@ SIGNATURES = {
     "gcnh_engine_last_counts": (None, [vp, ip, ip]),
     "gcnh_engine_run": (C.c_int, [vp, C.c_int]),
     "gcnh_engine_set_input_host": (None, [vp, vp]),
+    "gcnh_engine_epoch_prefetch": (None, [vp, C.c_int, vp, fp, fp, fp, fp]),
     "gcnh_engine_var_size": (C.c_int64, [vp, C.c_int]),
     "gcnh_engine_get_var": (None, [vp, C.c_int, C.c_int, _f32]),
     "gcnh_timer_enable_gpu": (None, [C.c_int]),
@@ -219,6 +220,12 @@ class Engine:
 
     def set_input_host(self, ptr):
         self.L.gcnh_engine_set_input_host(self.h, ptr)
+
+    def epoch_prefetch(self, eval_split, next_ptr):
+        """epoch() on the current input while the pinned buffer at next_ptr is uploaded for the following pass."""
+        v = [C.c_float() for _ in range(4)]
+        self.L.gcnh_engine_epoch_prefetch(self.h, eval_split, next_ptr, *[C.byref(x) for x in v])
+        return tuple(x.value for x in v)
 
     def var(self, idx, grad=False):
         out = np.zeros(self.L.gcnh_engine_var_size(self.h, idx), np.float32)

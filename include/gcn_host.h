@@ -84,6 +84,12 @@ int  gcnh_engine_run(gcnh_engine *e, int quiet);            /* GCN::run, gcn.cpp
 /* re-upload the feature values from a host buffer (asynchronous H2D of feature_nnz floats on the
  * engine's stream) — what CUDAGCN::set_input does before every pass (cuda_gcn.cu:81-83) */
 void gcnh_engine_set_input_host(gcnh_engine *e, const float *h_values);
+/* gcnh_engine_epoch on the CURRENT input while h_next_values (pinned host memory, gcnh_alloc_pinned) is uploaded into a
+ * second feature buffer on a copy stream; the next pass of any kind switches to it (device-side wait on the copy).
+ * Pipelines the per-epoch re-upload of cuda_gcn.cu:81-83 under the compute.  h_next_values must stay valid and
+ * unchanged until the next pass has started.  [opt-in; bench.py --e2e-prefetch] */
+void gcnh_engine_epoch_prefetch(gcnh_engine *e, int eval_split, const float *h_next_values, float *train_loss, float *train_acc,
+                                float *eval_loss, float *eval_acc);
 int64_t gcnh_engine_var_size(const gcnh_engine *e, int idx);
 void gcnh_engine_get_var(gcnh_engine *e, int idx, int grad, float *h_out);
 
