@@ -158,3 +158,57 @@ def test_array_views_keep_the_dataset_alive(host):
     assert a["graph_indices"].min() >= 0 and a["graph_indices"].max() < len(ip) - 1
     assert a["feature_value"].dtype == np.float32 and np.isfinite(a["feature_value"]).all()
     del churn
+
+
+def _quirky_text_dataset(rng, root, name):
+    """A valid-but-untidy dataset in the accepted input language of SURVEY Appendix B: ragged whitespace, tabs, blank
+    graph lines (self-loop-only nodes), blank feature lines (label -1, no features), unsorted and repeated neighbours,
+    unsorted and repeated feature keys, floats in every spelling strtof/operator>> accepts, a missing final newline
+    (the reference drops that last line), split codes outside 1..3."""
+    n = int(rng.integers(1, 40))
+    f = int(rng.integers(1, 30))
+    c = int(rng.integers(1, 6))
+    sep = lambda: rng.choice([" ", "  ", "\t", " \t "])
+    glines, flines, slines = [], [], []
+    for i in range(n):
+        if rng.random() < 0.15:
+            glines.append(rng.choice(["", " ", "\t"]))
+        else:
+            nb = rng.integers(0, n, int(rng.integers(1, 9)))                 # unsorted, may repeat, may include i itself
+            glines.append(rng.choice(["", " "]) + sep().join(str(int(v)) for v in nb) + rng.choice(["", " ", "\t"]))
+        if rng.random() < 0.1:
+            flines.append("")
+        else:
+            toks = []
+            for _ in range(int(rng.integers(0, 7))):
+                k = int(rng.integers(0, f))
+                v = float(rng.normal()) * 10 ** int(rng.integers(-3, 3))
+                toks.append(f"{k}:" + rng.choice([f"{v:.6g}", f"{v:.3e}", f"{v:.9f}", str(int(v)), f"{abs(v) % 1:.4f}".lstrip("0") or "0"]))
+            flines.append(str(int(rng.integers(0, c))) + "".join(sep() + t for t in toks) + rng.choice(["", " "]))
+        slines.append(str(int(rng.choice([0, 1, 2, 3, 3, 2, 1, 7]))))
+    end = lambda: "" if rng.random() < 0.3 else "\n"
+    root.mkdir(parents=True, exist_ok=True)
+    (root / f"{name}.graph").write_text("\n".join(glines) + end())
+    (root / f"{name}.svmlight").write_text("\n".join(flines) + end())
+    (root / f"{name}.split").write_text("\n".join(slines) + end())
+
+
+def test_parser_fuzz_against_reference(host, oracle, tmp_path):
+    """Bit-exact integer work on untidy inputs: 60 random datasets parse to exactly the arrays the UNMODIFIED reference
+    parser produces (oracle/_ref when it is built, the pinned C restatement otherwise)."""
+    from oracle.checker import Ref, ref_available
+    checker = Ref() if ref_available() else oracle
+    rng = np.random.default_rng(20240611)
+    for case in range(60):
+        name = f"fz{case}"
+        _quirky_text_dataset(rng, tmp_path / "data", name)
+        want = checker.parse(tmp_path, name)
+        d = host.Data.parse(tmp_path / "data", name)
+        assert (d is None) == (want is None), name
+        if want is None:
+            continue
+        got = d.arrays()
+        assert (d.params.num_nodes, d.params.input_dim, d.params.output_dim) == (want["num_nodes"], want["input_dim"], want["output_dim"]), name
+        for k in ("graph_indptr", "graph_indices", "feature_indptr", "feature_indices", "label", "split"):
+            assert got[k].shape == want[k].shape and (got[k] == want[k]).all(), (name, k)
+        assert (got["feature_value"].view(np.uint32) == want["feature_value"].view(np.uint32)).all(), name
