@@ -12,7 +12,13 @@ gather kernel (algorithmic bytes / CUDA-event duration) against the measured HBM
 = the unmodified reference CPU engine (oracle/_ref) on a bounded sample of the same workload.
 
 `--impl reference` times the reference's own CPU implementation (oracle/_ref/libgcnref.so, built from
-/root/reference by oracle/Makefile; the C restatement when that library is absent) on the host cores.
+/root/reference by oracle/Makefile; the C restatement when that library is absent) on the host cores, on the SAME
+workload at FULL size: one step is ~70 s on one core (the engine is single-threaded), so it runs as many of the
+requested steps as fit --ref-budget-s (default 150 s, at least one) and reports the steps it really timed.
+
+Every line carries `parity`: the per-epoch losses/accuracies of this very run (warm-up + timed steps, from a fresh
+engine, seed 1) against tests/golden/reddit_full_trajectory.json — the unmodified reference CPU engine on the same
+workload and seed (tools/make_trajectory_fixture.py) — and, for N > 1, against the committed 1-GPU trajectory.
 """
 from __future__ import annotations
 
@@ -103,27 +109,38 @@ def graph_data(d):
                      a["label"], a["split"], input_dim=d.params.input_dim, output_dim=d.params.output_dim)
 
 
-def cpu_reference_run(scale, steps, warmup, full_nnz, host_api):
-    """The reference CPU engine on a reddit-shape sample (scale of the node and edge counts); returns
-    (epochs/s extrapolated to the full workload by the edge ratio, description)."""
+def cpu_reference_run(scale, steps, budget_s, host_api):
+    """The reference CPU engine (1 thread: it has no threading) on the reddit-shape workload at `scale` (1.0 = the
+    BASELINE configuration).  Runs up to `steps` epochs of train_epoch + eval(2) but stops as soon as another epoch would
+    overrun `budget_s` (at least one epoch is timed).  Returns measured numbers only — nothing is extrapolated."""
     from oracle.checker import best_checker
     chk = best_checker()
     d = host_api.Data.synth("reddit", scale)
     s = d.sizes()
-    ref = chk.gcn(graph_data(d), dropout=0.5, epochs=steps + warmup, seed=1)
-    for _ in range(warmup):
-        ref.train_epoch(); ref.eval(2)
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        ref.train_epoch(); ref.eval(2)
-    dt = (time.perf_counter() - t0) / max(steps, 1)
+    ref = chk.gcn(graph_data(d), dropout=0.5, epochs=max(steps, 1), seed=1)
+    times, last = [], None
+    t_all = time.perf_counter()
+    for _ in range(max(steps, 1)):
+        t0 = time.perf_counter()
+        tr = ref.train_epoch()
+        ev = ref.eval(2)
+        times.append(time.perf_counter() - t0)
+        last = (*tr, *ev)
+        if time.perf_counter() - t_all + max(times) > budget_s:
+            break
     ref.close()
-    ratio = s["graph_nnz"] / full_nnz
-    value = (1.0 / dt) * ratio
-    sample = (f"{steps} epoch(s) of train_epoch+eval(2) by the {chk.name} CPU engine on reddit-shape at scale {scale:g} "
-              f"({s['num_nodes']} nodes, {s['graph_nnz']} graph nnz, dense 602 features): {dt:.2f} s/epoch, scaled to the full "
-              f"workload by the graph-nnz ratio {ratio:.4f}")
-    return value, dt, chk.name, sample
+    dt = sum(times) / len(times)
+    sample = (f"{len(times)} epoch(s) of train_epoch+eval(2) by the {chk.name} CPU engine (gcn-seq code, 1 thread) on reddit-shape at scale "
+              f"{scale:g} ({s['num_nodes']} nodes, {s['graph_nnz']} graph nnz, dense 602 features, hidden 16, dropout 0.5): "
+              f"{dt:.2f} s/epoch measured")
+    return {"value": 1.0 / dt, "s_per_step": dt, "steps": len(times), "kind": chk.name, "sample": sample, "sizes": s, "last": last}
+
+
+def workload_config(scale, sizes, extra):
+    cfg = {"workload": WORKLOAD, "scale": scale, "nodes": sizes["num_nodes"], "graph_nnz": sizes["graph_nnz"],
+           "feature_nnz": sizes["feature_nnz"], "features": 602, "classes": 41}
+    cfg.update(extra)
+    return cfg
 
 
 def run_reference(args):
@@ -131,20 +148,41 @@ def run_reference(args):
     if rank != 0:
         return
     from cuda_gcn_b200 import host_api
-    # the full workload's size without generating it: the generator is deterministic, sizes recorded by a full run
-    full_nnz = FULL_REDDIT_NNZ
-    scale = args.ref_scale
-    value, dt, kind, sample = cpu_reference_run(scale, args.steps, args.warmup, full_nnz, host_api)
-    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1e3 / value, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD, "scale": 1.0, "engine": "reference CPU engine (gcn-seq code), 1 thread, bounded sample"},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "reference" if kind == "reference" else "port", "sample": sample},
-            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    r = cpu_reference_run(args.scale, args.steps, args.ref_budget_s, host_api)
+    kind = "reference" if r["kind"] == "reference" else "port"
+    line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": r["steps"],
+            "warmup": 0, "requested_steps": args.steps, "requested_warmup": args.warmup, "ms_per_step": r["s_per_step"] * 1e3,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args.scale, r["sizes"], {
+                "engine": "reference CPU engine (oracle/_ref/libgcnref.so = unmodified /root/reference/src/seq), 1 thread",
+                "steps_note": f"a step is ~70 s on one core: as many of the requested steps as fit {args.ref_budget_s:g} s are timed, no warm-up",
+                "data_generator": "cuda_gcn_b200/host/synth.cpp through libgcnhost.so (data only; all arithmetic is the reference library's)"}),
+            "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": 1, "kind": kind, "sample": r["sample"]},
+            "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0,
+            "final": {"val_loss": r["last"][2], "val_acc": r["last"][3]}}
     print(json.dumps(line))
 
 
-# graph nnz (incl. self loops) of synth preset "reddit" at scale 1, seed 4 (deterministic generator)
-FULL_REDDIT_NNZ = 114_862_869
+def trajectory_parity(history, fixture_path, loss_rtol=1e-4):
+    """history: [(train_loss, train_acc, val_loss, val_acc)] from a fresh engine; fixture: the committed trajectory."""
+    try:
+        fx = json.loads(Path(fixture_path).read_text())
+    except Exception as e:
+        return {"against": str(fixture_path), "available": False, "why": str(e)}
+    n = min(len(history), len(fx["epochs"]))
+    if n == 0:
+        return {"against": str(fixture_path), "available": False, "why": "no epochs to compare"}
+    rel, acc = 0.0, 0.0
+    for got, want in zip(history[:n], fx["epochs"][:n]):
+        rel = max(rel, abs(got[0] - want[0]) / abs(want[0]), abs(got[2] - want[2]) / abs(want[2]))
+        acc = max(acc, abs(got[1] - want[1]), abs(got[3] - want[3]))
+    return {"against": str(Path(fixture_path).relative_to(ROOT)), "engine": fx.get("engine"), "epochs_compared": n,
+            "max_rel_loss_diff": rel, "max_abs_acc_diff": acc, "loss_rtol": loss_rtol, "ok": bool(rel <= loss_rtol and acc <= 0.002)}
+
+
+def source_sha(path):
+    import hashlib
+    return hashlib.sha256(Path(path).read_bytes()).hexdigest()[:16]
 
 
 def run_ours(args):
@@ -173,8 +211,12 @@ def run_ours(args):
         n_loc, nnzA_loc, nnzX_loc = N, nnzA, nnzX
         x_local = data.arrays()["feature_value"]
 
-    def step():
+    history = []                                           # every epoch of this run, from the fresh engine on
+
+    def step(record=True):
         r = eng.epoch(2)                                   # train_epoch + eval(2), one host sync (what GCN::run does per epoch)
+        if record:
+            history.append(r)
         return r[2], r[3]
 
     def barrier():
@@ -222,6 +264,7 @@ def run_ours(args):
     timers = host_api.timers()
     L.gcnh_timer_enable_gpu(0)
     value = args.steps / (ms * 1e-3)
+    n_resident = len(history)                              # epochs on the generator's own features (the e2e loop re-uploads the same values)
 
     # ---- roofline of the dominant kernel: the GraphSum gather over the whole (local) graph
     peak, peak_src = measured_peak()
@@ -231,15 +274,22 @@ def run_ours(args):
     b_min = 4 * nnzA_loc + 4 * (n_loc + 1) + 4 * H * (N + n_loc)        # indices + indptr + source read once + rows written once
     t_launch = g_total / max(g_launches, 1)
     achieved = b_min / t_launch / 1e9 if t_launch > 0 else 0.0
-    traffic = None
+    # DRAM traffic of the same kernel from the committed `ncu --set full` capture — only if that capture was taken from
+    # the graph.cu that is built now (the record carries the source hash), otherwise null rather than a stale number
+    traffic, traffic_note = None, None
     tp = ROOT / "profiles" / "graphsum_traffic.json"
     if tp.exists() and world == 1:
         try:
-            traffic = json.loads(tp.read_text()).get("dram_bytes_per_launch")
+            rec = json.loads(tp.read_text())
+            if rec.get("graph_cu_sha16") == source_sha(ROOT / "cuda_gcn_b200" / "csrc" / "graph.cu"):
+                traffic = rec.get("dram_bytes_per_launch")
+                traffic_note = rec.get("source")
+            else:
+                traffic_note = "profiles/graphsum_traffic.json was captured from a different csrc/graph.cu; not reported"
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "kernel": "gather_kernel (GraphSum, dim 16, all rows of this rank)", "achieved": achieved, "peak": peak,
-                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_note, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": b_min, "avg_launch_us": t_launch * 1e6, "launches_timed": g_launches,
                 "share_of_step": g_total / (ms * 1e-3) if ms > 0 else None,
                 "l2_to_sm_gather_bytes_per_launch": 64 * nnzA_loc + 4 * nnzA_loc}
@@ -263,7 +313,7 @@ def run_ours(args):
     host_view = np.ctypeslib.as_array((abi.C.c_float * max(nnzX_loc, 1)).from_address(pinned))
     host_view[:nnzX_loc] = x_local
     e2e_steps = max(3, min(args.steps, 10))
-    eng.set_input_host(pinned); step()                      # warm the copy path
+    eng.set_input_host(pinned); step(False)                 # warm the copy path
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
@@ -271,7 +321,7 @@ def run_ours(args):
             eng.epoch_prefetch(2, pinned)                   # the step on the current input; H2D of the next step's input under it
         else:
             eng.set_input_host(pinned)                      # H2D of this rank's nnz(X) floats on the engine's stream
-            step()                                          # train_epoch + eval(2); each reads its scalars back (D2H)
+            step(False)                                     # train_epoch + eval(2); each reads its scalars back (D2H)
     barrier()
     e2e_dt = (time.perf_counter() - t0) / e2e_steps
     e2e_dt = float(eng.allreduce_host([e2e_dt], op_max=True)[0])
@@ -283,23 +333,86 @@ def run_ours(args):
     if rank != 0:
         return
 
-    # ---- CPU baseline: the reference engine on a bounded sample (rank 0, N=1)
+    # ---- parity of THIS run: every epoch since the engine was created against the reference CPU engine's trajectory
+    # on the same workload and seed, and (N > 1) against the committed single-GPU trajectory
+    parity = None
+    if args.scale == 1.0:
+        parity = trajectory_parity(history[:n_resident], ROOT / "tests" / "golden" / "reddit_full_trajectory.json")
+        if world > 1:
+            one = trajectory_parity(history[:n_resident], ROOT / "tests" / "golden" / "reddit_full_trajectory_gpu1.json", loss_rtol=2e-6)
+            parity["parity_vs_single_gpu_rel"] = one.get("max_rel_loss_diff")
+            parity["vs_single_gpu"] = one
+    if args.save_trajectory:
+        Path(args.save_trajectory).write_text(json.dumps({
+            "generator": "bench.py --save-trajectory (this engine, fused plan, 1 GPU)" if world == 1 else f"bench.py, {world} GPUs",
+            "engine": f"cuda_gcn_b200 fused plan, {world} GPU(s)", "preset": "reddit", "scale": args.scale, "seed": 1, "hidden": H,
+            "dropout": 0.5, "nodes": N, "graph_nnz": nnzA, "columns": ["train_loss", "train_acc", "val_loss", "val_acc"],
+            "epochs": [list(r) for r in history[:n_resident]]}, indent=1))
+
+    # ---- GraphSum per call at each width the reference's models use (SURVEY 8d metric 2): forward == backward launch
+    dims = None
+    if world == 1 and not args.no_dims:
+        dims = graphsum_dims(abi, data, peak)
+
+    # ---- CPU baseline: the reference engine on the same workload (rank 0, N=1): ONE full-size epoch (~70 s, 1 core)
     cpu = None
     if not args.no_cpu_baseline and world == 1:
-        v, dt, kind, sample = cpu_reference_run(args.cpu_scale, 1, 0, nnzA, host_api)
-        cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": "reference" if kind == "reference" else "port", "sample": sample}
+        r = cpu_reference_run(args.cpu_scale, 1, 0, host_api)
+        cpu = {"value": r["value"], "unit": UNIT, "cores": 1, "kind": "reference" if r["kind"] == "reference" else "port",
+               "sample": r["sample"], "sample_scale": args.cpu_scale}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if world > 1 else "weak", "vs_baseline": None,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "engine": "fused plan",
-                       "scale": args.scale, "nodes": N, "graph_nnz": nnzA, "feature_nnz": nnzX, "features": F, "classes": C,
-                       "max_degree": sizes["max_degree"], "l2": "inputs larger than L2 each step (X 561 MB + CSR indices 459 MB streamed per pass); no flush",
-                       "parallelism": "1 GPU" if world == 1 else f"{world}-way row partition (nnz-balanced), NCCL all-gather of the gather source + all-reduce of dW",
-                       "generate_s": round(t_gen, 1)},
-            "e2e": e2e, "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "cpu_baseline": cpu,
-            "breakdown": breakdown, "final": {"val_loss": last[0], "val_acc": last[1]}}
+            "config": workload_config(args.scale, sizes, {
+                "engine": "fused plan", "max_degree": sizes["max_degree"],
+                "l2": "inputs larger than L2 each step (X 561 MB + CSR indices 459 MB streamed per pass); no flush",
+                "parallelism": "1 GPU" if world == 1 else
+                f"{world}-way row partition (nnz-balanced); gather sources exchanged by a hand-written push over NVLink peer memory "
+                "(CUDA IPC) with per-rank arrival flags checked inside the consuming GraphSum kernel; dW summed by a peer-memory "
+                "all-reduce in rank order; NCCL only for setup (handle exchange) and as fallback (GCN_COMM=nccl)",
+                "generate_s": round(t_gen, 1)}),
+            "e2e": e2e, "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "graphsum_dims": dims, "cpu_baseline": cpu,
+            "parity": parity, "breakdown": breakdown, "final": {"val_loss": last[0], "val_acc": last[1]}}
     print(json.dumps(line))
+
+
+def graphsum_dims(abi, data, peak, dims=(16, 41, 47, 256), reps=5):
+    """gcnk_graphsum (= what CUDAGraphSum::forward / backward launch, cuda_module.cu:74-101: the same loop for both
+    directions on a symmetric graph) timed per call at each width the reference's models use."""
+    K = abi.k
+    a = data.arrays()
+    indptr, indices = a["graph_indptr"], a["graph_indices"]
+    n, nnz = len(indptr) - 1, len(indices)
+    g = abi.Graph(indptr, indices)
+    out = []
+    for dim in dims:
+        x = abi.dev(np.random.default_rng(dim).standard_normal((n, dim)).astype(np.float32))
+        y = abi.DeviceArray((n, dim), np.float32)
+        xs = abi.DeviceArray((n, dim), np.float32)
+        K.gcnk_scale_rows(g.dinv_ptr(), x.ptr, xs.ptr, n, dim, None)
+        for _ in range(2):
+            K.gcnk_graphsum(g.h, x.ptr, y.ptr, dim, None)
+            K.gcnk_gather_plain(g.h, xs.ptr, y.ptr, dim, None)
+        e0, e1, e2 = abi.Event(), abi.Event(), abi.Event()
+        K.gcnk_device_sync()
+        e0.record()
+        for _ in range(reps):
+            K.gcnk_graphsum(g.h, x.ptr, y.ptr, dim, None)          # module-level call: pre-scale pass + gather
+        e1.record()
+        for _ in range(reps):
+            K.gcnk_gather_plain(g.h, xs.ptr, y.ptr, dim, None)     # the gather alone (what the fused plan launches)
+        e2.record(); e2.sync()
+        us_call, us_gather = e0.elapsed_ms(e1) / reps * 1e3, e1.elapsed_ms(e2) / reps * 1e3
+        b_min = 4 * nnz + 4 * (n + 1) + 8 * n * dim
+        out.append({"dim": dim, "fw_us": us_call, "bw_us": us_call, "gather_only_us": us_gather, "algorithmic_bytes": b_min,
+                    "GBps": b_min / us_call / 1e3, "frac": b_min / us_call / 1e3 / peak,
+                    "gather_only_GBps": b_min / us_gather / 1e3, "gather_only_frac": b_min / us_gather / 1e3 / peak})
+        del x, y, xs
+    K.gcnk_graph_release_scratch(g.h)
+    return {"note": "forward and backward are the same launch (module.cpp:103-119 reuses the forward loop on a symmetric graph); "
+                    "fw_us/bw_us = gcnk_graphsum (pre-scale pass + gather), gather_only = gcnk_gather_plain on a pre-scaled source",
+            "per_dim": out}
 
 
 def main():
@@ -309,9 +422,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--scale", type=float, default=1.0, help="fraction of the Reddit-shape node/edge counts (1.0 = the BASELINE config)")
-    ap.add_argument("--cpu-scale", type=float, default=0.125, help="sample of the workload the CPU baseline runs")
-    ap.add_argument("--ref-scale", type=float, default=0.03125, help="--impl reference: sample of the workload per step")
+    ap.add_argument("--cpu-scale", type=float, default=1.0, help="workload scale of the cpu_baseline leg (1.0 = the real workload: ~70 s)")
+    ap.add_argument("--ref-budget-s", type=float, default=150.0, help="--impl reference: wall budget for the timed full-size epochs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-dims", action="store_true", help="skip the per-width GraphSum timing")
+    ap.add_argument("--save-trajectory", default=None, help="write this run's per-epoch losses/accuracies (JSON) to this path")
     ap.add_argument("--e2e-prefetch", action="store_true", help="e2e loop through gcnh_engine_epoch_prefetch (pipelined upload; not yet validated on a GPU)")
     ap.add_argument("--timers", action="store_true", help="keep the per-op CUDA-event timers on inside the timed region at N > 1")
     args = ap.parse_args()

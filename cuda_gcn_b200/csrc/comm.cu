@@ -47,6 +47,21 @@ Mirror take_mirror(const float *out) {
 }
 }  // namespace gcnk
 
+namespace gcnk {
+// How long a kernel spins on a peer's flag before it raises *err and gives up (so that a lost peer becomes an error,
+// not a hung GPU): GCN_PEER_TIMEOUT_S seconds (default 60; the first exchange of a run also absorbs whatever host-side
+// skew the ranks have — uneven build(), first-use view construction, a paging stall).
+long long peer_spin_cycles() {
+    static const long long cycles = [] {
+        const char *e = getenv("GCN_PEER_TIMEOUT_S");
+        double sec = e && *e ? atof(e) : 60.0;
+        if (!(sec > 0)) sec = 60.0;
+        return (long long)(sec * 2.0e9);                    // clock64 ticks at <= 2 GHz
+    }();
+    return cycles;
+}
+}  // namespace gcnk
+
 namespace {
 
 struct FlagPtrs { int *p[8]; };
@@ -71,7 +86,7 @@ __device__ __forceinline__ bool last_cta_arrives(unsigned *counter) {
     return s_last;
 }
 
-__device__ __forceinline__ void flag_exchange(const FlagPtrs &flags, int rank, int world, int value, int *err) {
+__device__ __forceinline__ void flag_exchange(const FlagPtrs &flags, int rank, int world, int value, int *err, long long limit) {
     const int r = threadIdx.x;
     if (r >= world) return;
     __threadfence_system();
@@ -81,21 +96,59 @@ __device__ __forceinline__ void flag_exchange(const FlagPtrs &flags, int rank, i
     volatile int *mine = flags.p[rank] + r;
     const long long t0 = clock64();
     while (*mine < value) {
-        if (clock64() - t0 > (4LL << 30)) { *err = 1; break; }
+        if (clock64() - t0 > limit) { *err = 1; break; }
     }
     __threadfence_system();
 }
 
 // push + barrier in one launch
 __global__ void __launch_bounds__(256) push_barrier_kernel(const float4 *__restrict__ src, Mirror m, size_t n_vec, FlagPtrs flags, int rank,
-                                                           int world, int value, int *err, unsigned *counter) {
+                                                           int world, int value, int *err, unsigned *counter, long long limit) {
     size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     for (; i < n_vec; i += stride) {
         const float4 v = src[i];
         for (int p = 0; p < m.n; p++) reinterpret_cast<float4 *>(m.p[p])[i] = v;
     }
-    if (last_cta_arrives(counter)) flag_exchange(flags, rank, world, value, err);
+    if (last_cta_arrives(counter)) flag_exchange(flags, rank, world, value, err, limit);
+}
+
+// push + SIGNAL: the rows go to the peers and the last CTA to finish publishes `value` in each peer's flag slot for
+// (this buffer, this rank) — nobody waits here.  The consumer (the next GraphSum gather on each rank) waits for the
+// flags of the ranks it reads from at ITS start (gcnk_gather_wait_next), so a rank that is ahead runs on with its own
+// work instead of idling in a barrier, and the barrier kernel and its launch disappear from the step.
+// rows == nullptr: the contiguous block [0, n_vec) of float4; otherwise n_rows listed rows of vec_per_row float4 each,
+// a separate list per peer (halo exchange: only the rows that peer's columns reference).
+struct RowLists { const int *rows[MAX_PEERS]; int count[MAX_PEERS]; };
+__global__ void __launch_bounds__(256) push_signal_kernel(const float4 *__restrict__ src, Mirror m, size_t n_vec, FlagPtrs peer_flags, int value,
+                                                          unsigned *counter) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < n_vec; i += stride) {
+        const float4 v = src[i];
+        for (int p = 0; p < m.n; p++) reinterpret_cast<float4 *>(m.p[p])[i] = v;
+    }
+    if (last_cta_arrives(counter) && (int)threadIdx.x < m.n) {
+        __threadfence_system();
+        *reinterpret_cast<volatile int *>(peer_flags.p[threadIdx.x]) = value;
+    }
+}
+__global__ void __launch_bounds__(256) push_rows_signal_kernel(const float4 *__restrict__ src, Mirror m, RowLists lists, int vec_per_row,
+                                                               FlagPtrs peer_flags, int value, unsigned *counter) {
+    // one (row, float4) element per thread per step; peers take turns so that every list is walked coalesced
+    for (int p = 0; p < m.n; p++) {
+        const size_t total = (size_t)lists.count[p] * vec_per_row;
+        const int *rows = lists.rows[p];
+        float4 *dst = reinterpret_cast<float4 *>(m.p[p]);
+        for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+            const size_t e = (size_t)rows[i / vec_per_row] * vec_per_row + i % vec_per_row;
+            dst[e] = src[e];
+        }
+    }
+    if (last_cta_arrives(counter) && (int)threadIdx.x < m.n) {
+        __threadfence_system();
+        *reinterpret_cast<volatile int *>(peer_flags.p[threadIdx.x]) = value;
+    }
 }
 
 struct Segs { float *p[4]; unsigned count[4]; int n; };
@@ -103,7 +156,7 @@ struct Areas { float *p[8]; };
 
 // all-reduce step 1: this rank's segments, packed, into slot[rank] of every rank's exchange area; then the barrier
 __global__ void __launch_bounds__(256) allreduce_scatter_kernel(Segs segs, Areas areas, size_t slot_floats, FlagPtrs flags, int rank, int world,
-                                                                int value, int *err, unsigned *counter) {
+                                                                int value, int *err, unsigned *counter, long long limit) {
     unsigned total = 0;
     for (int k = 0; k < segs.n; k++) total += segs.count[k];
     for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
@@ -113,7 +166,7 @@ __global__ void __launch_bounds__(256) allreduce_scatter_kernel(Segs segs, Areas
         const float v = segs.p[k][j];
         for (int r = 0; r < world; r++) areas.p[r][(size_t)rank * slot_floats + i] = v;
     }
-    if (last_cta_arrives(counter)) flag_exchange(flags, rank, world, value, err);
+    if (last_cta_arrives(counter)) flag_exchange(flags, rank, world, value, err, limit);
 }
 
 // all-reduce step 2: the slots summed in rank order (the same order on every rank => bit-identical results)
@@ -130,7 +183,7 @@ __global__ void __launch_bounds__(256) allreduce_gather_kernel(Segs segs, const 
     }
 }
 
-__global__ void peer_barrier_kernel(FlagPtrs flags, int rank, int world, int value, int *err) { flag_exchange(flags, rank, world, value, err); }
+__global__ void peer_barrier_kernel(FlagPtrs flags, int rank, int world, int value, int *err, long long limit) { flag_exchange(flags, rank, world, value, err, limit); }
 
 __global__ void push_rows_kernel(const float4 *__restrict__ src, Mirror m, size_t n_vec) {
     size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
@@ -206,7 +259,31 @@ int gcnk_peer_push_barrier(const float *local_rows, float *const *peer_rows, int
     for (int r = 0; r < world; r++) f.p[r] = flag_arrays[r];
     const size_t n_vec = n_floats / 4;
     const int grid = (int)std::max<size_t>(1, std::min<size_t>((n_vec + 255) / 256, (size_t)sm_count() * 2));
-    push_barrier_kernel<<<grid, 256, 0, S(stream)>>>(reinterpret_cast<const float4 *>(local_rows), m, n_vec, f, rank, world, value, d_err, d_counter);
+    push_barrier_kernel<<<grid, 256, 0, S(stream)>>>(reinterpret_cast<const float4 *>(local_rows), m, n_vec, f, rank, world, value, d_err, d_counter, peer_spin_cycles());
+    GCNK_LAUNCHED();
+    return GCNK_OK;
+}
+
+int gcnk_peer_push_signal(const float *local_rows, float *const *peer_rows, int n_peers, size_t n_floats, const int *const *d_row_lists,
+                          const int *h_row_counts, int dim, int *const *peer_flag_slots, int value, unsigned *d_counter, gcnk_stream_t stream) {
+    GCNK_REQUIRE(local_rows && peer_rows && n_peers >= 0 && n_peers <= MAX_PEERS && n_floats % 4 == 0 && peer_flag_slots && d_counter, "bad arguments");
+    GCNK_REQUIRE(!d_row_lists || (h_row_counts && dim > 0 && dim % 4 == 0), "row lists need counts and a row width that is a multiple of 4");
+    if (!n_peers) return GCNK_OK;
+    Mirror m = {};
+    FlagPtrs f = {};
+    m.n = n_peers;
+    for (int i = 0; i < n_peers; i++) { m.p[i] = peer_rows[i]; f.p[i] = peer_flag_slots[i]; }
+    if (d_row_lists) {
+        RowLists l = {};
+        size_t most = 0;
+        for (int i = 0; i < n_peers; i++) { l.rows[i] = d_row_lists[i]; l.count[i] = h_row_counts[i]; most = std::max(most, (size_t)h_row_counts[i] * (dim / 4)); }
+        const int grid = (int)std::max<size_t>(1, std::min<size_t>((most + 255) / 256, (size_t)sm_count() * 2));
+        push_rows_signal_kernel<<<grid, 256, 0, S(stream)>>>(reinterpret_cast<const float4 *>(local_rows), m, l, dim / 4, f, value, d_counter);
+    } else {
+        const size_t n_vec = n_floats / 4;
+        const int grid = (int)std::max<size_t>(1, std::min<size_t>((n_vec + 255) / 256, (size_t)sm_count() * 2));
+        push_signal_kernel<<<grid, 256, 0, S(stream)>>>(reinterpret_cast<const float4 *>(local_rows), m, n_vec, f, value, d_counter);
+    }
     GCNK_LAUNCHED();
     return GCNK_OK;
 }
@@ -225,7 +302,7 @@ int gcnk_peer_allreduce(float *const *d_segs, const size_t *h_counts, int n_segs
     FlagPtrs f = {};
     for (int r = 0; r < world; r++) { ar.p[r] = slot_areas[r]; f.p[r] = flag_arrays[r]; }
     const int grid = (int)std::max<size_t>(1, std::min<size_t>((total + 255) / 256, (size_t)sm_count()));
-    allreduce_scatter_kernel<<<grid, 256, 0, S(stream)>>>(sg, ar, slot_floats, f, rank, world, value, d_err, d_counter);
+    allreduce_scatter_kernel<<<grid, 256, 0, S(stream)>>>(sg, ar, slot_floats, f, rank, world, value, d_err, d_counter, peer_spin_cycles());
     GCNK_LAUNCHED();
     allreduce_gather_kernel<<<grid, 256, 0, S(stream)>>>(sg, slot_areas[rank], slot_floats, world);
     GCNK_LAUNCHED();
@@ -236,7 +313,7 @@ int gcnk_peer_barrier(int *const *flag_arrays, int rank, int world, int value, i
     GCNK_REQUIRE(flag_arrays && world >= 1 && world <= 8 && rank >= 0 && rank < world && d_err, "bad arguments");
     FlagPtrs f = {};
     for (int r = 0; r < world; r++) f.p[r] = flag_arrays[r];
-    peer_barrier_kernel<<<1, 32, 0, S(stream)>>>(f, rank, world, value, d_err);
+    peer_barrier_kernel<<<1, 32, 0, S(stream)>>>(f, rank, world, value, d_err, peer_spin_cycles());
     GCNK_LAUNCHED();
     return GCNK_OK;
 }

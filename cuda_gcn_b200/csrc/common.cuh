@@ -35,6 +35,7 @@ inline cudaStream_t S(gcnk_stream_t s) { return reinterpret_cast<cudaStream_t>(s
     } while (0)
 
 int sm_count();          // of the current device (cached per device)
+long long peer_spin_cycles();   // clock64 ticks a kernel waits for a peer's flag before raising its error flag (GCN_PEER_TIMEOUT_S)
 int *async_err_flag();   // per-device int raised by pipeline kernels whose mbarrier wait timed out
 
 // Mirrored output rows (row-partitioned runs): a producer kernel whose output is the input of the next GraphSum

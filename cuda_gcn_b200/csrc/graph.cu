@@ -67,7 +67,38 @@ struct GatherArgs {
     uint32_t *mask_out;                    // MODE_RELU_DROP (may be NULL)
     const uint32_t *mask_in;               // MODE_MASK
     float scale;
+    // row-partitioned runs: flags[r] >= wait_value once rank r's rows of the gather source have landed in this GPU's
+    // copy (gcnk_peer_push_signal); every CTA checks them before its first row read.  NULL: no wait.
+    const int *wait_flags;
+    int wait_n, wait_skip, wait_value;
+    int *wait_err;
+    long long wait_limit;
 };
+
+// Registered by gcnk_gather_wait_next for the next gather launched by this thread.
+struct GatherWait { const int *flags; int n, skip, value; int *err; };
+thread_local GatherWait t_wait = {nullptr, 0, -1, 0, nullptr};
+
+// All rows of the source that other ranks produce must be in place before any of them is read: thread r of every CTA
+// polls rank r's flag (an acquire load at system scope: the peer wrote the rows, fenced, then the flag), the CTA
+// barrier orders everybody else's reads after it.  Nothing of the source has been touched by this kernel before, so
+// no stale line can sit in L1.  A peer that never arrives raises *err after wait_limit clocks instead of hanging.
+__device__ __forceinline__ void wait_for_peers(const GatherArgs &a) {
+    if (!a.wait_flags) return;
+    const int r = threadIdx.x;
+    if (r < a.wait_n && r != a.wait_skip) {
+        const int *f = a.wait_flags + r;
+        const long long t0 = clock64();
+        for (;;) {
+            int v;
+            asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+            if (v >= a.wait_value) break;
+            if (clock64() - t0 > a.wait_limit) { *a.wait_err = 1; break; }
+            __nanosleep(64);
+        }
+    }
+    __syncthreads();
+}
 
 __host__ __device__ inline int mask_stride_bits(int dim) { return dim <= 8 ? 8 : dim <= 16 ? 16 : (dim + 31) / 32 * 32; }
 
@@ -358,6 +389,7 @@ __global__ void __launch_bounds__(THREADS, NACC != 1 ? 1 : IDX4 == 3 ? 4 : IDX4 
     extern __shared__ float smem[];   // heavy rows only: [WARPS][dim]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     Acc<VEC> acc[NACC];
+    wait_for_peers(a);
 
     if ((int)blockIdx.x < a.n_heavy) {
         // a whole CTA on one high-degree row: warps take interleaved 32-edge chunks, partials are
@@ -474,6 +506,11 @@ int launch_gather(const gcnk_graph *g, GatherArgs a, cudaStream_t st) {
     a.indptr = g->indptr; a.indices = g->indices; a.dinv = g->dinv;
     a.heavy_rows = g->heavy_rows; a.n_heavy = g->n_heavy; a.bin_ptr = g->bin_ptr; a.bin_rows = g->bin_rows;
     a.mask_stride = mask_stride_bits(dim);
+    if (t_wait.flags) {
+        a.wait_flags = t_wait.flags; a.wait_n = t_wait.n; a.wait_skip = t_wait.skip; a.wait_value = t_wait.value;
+        a.wait_err = t_wait.err; a.wait_limit = peer_spin_cycles();
+        t_wait.flags = nullptr;
+    }
     // No mirrored epilogue here on purpose: the 7 extra pointers cost the gather 19 registers (61 -> 80, one CTA per
     // SM less, +25 % run time measured), and posted 64-byte remote stores back up the load/store unit the row gathers
     // depend on.  A pending gcnk_mirror_next registration is left for the caller, which pushes the finished rows to
@@ -522,10 +559,15 @@ __global__ void dinv_kernel(const int *indptr, float *dinv, int n) {
 __global__ void symmetry_kernel(const int *indptr, const int *indices, int n, int n_cols, int *asym) {
     const int s = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32, lane = threadIdx.x & 31;
     if (s >= n) return;
-    for (int e = indptr[s] + lane; e < indptr[s + 1]; e += 32) {
+    const int row_beg = indptr[s];
+    for (int e = row_beg + lane; e < indptr[s + 1]; e += 32) {
         const int d = indices[e];
         if (d == s) continue;
         if (d < 0 || d >= n_cols || d >= n) { atomicOr(asym, 1); continue; }
+        // A repeated neighbour (the parser keeps duplicates, as the reference's does, parser.cpp:31-40) makes
+        // A_hat[s][d] = k / sqrt(deg_s deg_d): symmetric only if row d repeats s as often.  Multiplicities are not
+        // compared here — any repeated entry reports "not verified", and such inputs run the modules plan.
+        if (e > row_beg + 1 && indices[e - 1] == d) { atomicOr(asym, 1); continue; }
         int lo = indptr[d], hi = indptr[d + 1];
         if (lo < hi && indices[lo] == d) lo++;             // skip the leading self loop
         bool found = false;
@@ -762,6 +804,12 @@ int gcnk_gather_mask(const gcnk_graph *g, const float *in_scaled, float *out_sca
 }
 
 int gcnk_mask_row_stride_bits(int dim) { return mask_stride_bits(dim); }
+
+int gcnk_gather_wait_next(const int *d_flags, int n_flags, int skip, int value, int *d_err) {
+    GCNK_REQUIRE((d_flags && n_flags > 0 && n_flags <= THREADS && d_err) || (!d_flags && n_flags == 0), "bad arguments");
+    t_wait.flags = d_flags; t_wait.n = n_flags; t_wait.skip = skip; t_wait.value = value; t_wait.err = d_err;
+    return GCNK_OK;
+}
 
 int gcnk_gather_variant(int v) {
     const int before = gather_variant();

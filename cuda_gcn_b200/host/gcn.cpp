@@ -62,6 +62,14 @@ struct GCN::Fused {
     void *peer_slab[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     int *flag_arrays[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     int barrier_value = 0, world = 1, rank = 0;
+    // Exchange by push + signal: buffer b of {xw_s, h1_s, G, Gm} has one flag per producing rank in every rank's slab
+    // (ints [64 + 8 b + r] of the flag block); seq[b] counts how often the buffer has been produced, and is the value
+    // the pushes publish and the consuming gather waits for.  halo[p] (optional) lists the local rows peer p references.
+    int seq[4] = {0, 0, 0, 0};
+    int *halo_rows[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    int halo_count[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    bool use_halo = false, signal_exchange = true;
+    gcnk_stream_t stream = nullptr;   // everything the fused plan enqueues runs on this (non-blocking) stream
     int *d_err = nullptr, *h_err = nullptr;
     int *h_async = nullptr;      // pinned copy of the kernel library's async error flag (mbarrier time-outs)
     unsigned *d_counter = nullptr;
@@ -82,6 +90,8 @@ struct GCN::Fused {
         if (h_err) gcnk_free_host(h_err);
         if (h_async) gcnk_free_host(h_async);
         if (rng_stream) { gcnk_stream_sync(rng_stream); gcnk_stream_destroy(rng_stream); }
+        if (stream) { gcnk_stream_sync(stream); gcnk_stream_destroy(stream); }
+        for (int *h : halo_rows) if (h) gcnk_free(h);
         if (ev_ready) gcnk_event_destroy(ev_ready);
         if (ev_go) gcnk_event_destroy(ev_go);
         for (uint32_t *b : {keep0_buf[1], keep1_buf[1]}) if (b) gcnk_free(b);
@@ -220,16 +230,19 @@ void GCN::build(GCNPlan plan) {
     optimizer = Adam({{&variables[2], true}, {&variables[5], false}}, adam_params);
 
     fz.reset(new Fused);
+    GCNK_CHECK(gcnk_stream_create(&fz->stream));
     const size_t nnzX_loc = data->feature_index.indices.size();
     // gather SOURCES are [N x H] (every rank needs all rows: all-gathered in place), gather OUTPUTS are local
     const size_t nh_all = sizeof(float) * (size_t)N * H, nh_loc = sizeof(float) * (size_t)n_loc * H;
     fz->world = dist.world; fz->rank = dist.rank; fz->comm = dist.comm;
-    const char *cm = getenv("GCN_COMM");
+    const char *cm = getenv("GCN_COMM"), *ex = getenv("GCN_EXCHANGE");
+    fz->signal_exchange = !(ex && !strcmp(ex, "barrier"));
     if (dist.world > 1 && dist.world <= 8 && H % 4 == 0 && !(cm && !strcmp(cm, "nccl"))) {
-        // one slab: [xw_s | h1_s | G | Gm | flags (64 ints) | all-reduce area: world slots]; export it, import every peer's
+        // one slab: [xw_s | h1_s | G | Gm | flags (128 ints: 0..7 barrier, 64 + 8 b + r buffer b from rank r) |
+        // all-reduce area: world slots]; export it, import every peer's
         const size_t buf = (size_t)N * H;
         fz->slot_floats = ((size_t)F * H + (size_t)H * C + 4 + 3) / 4 * 4;
-        const size_t slab_bytes = 4 * nh_all + 256 + sizeof(float) * fz->slot_floats * dist.world;
+        const size_t slab_bytes = 4 * nh_all + 512 + sizeof(float) * fz->slot_floats * dist.world;
         GCNK_CHECK(gcnk_malloc((void **)&fz->slab, slab_bytes));
         GCNK_CHECK(gcnk_memset(fz->slab, 0, slab_bytes, nullptr));
         GCNK_CHECK(gcnk_malloc((void **)&fz->d_counter, sizeof(unsigned)));
@@ -258,12 +271,13 @@ void GCN::build(GCNPlan plan) {
         fz->xw_s = fz->slab; fz->h1_s = fz->slab + buf; fz->G = fz->slab + 2 * buf; fz->Gm = fz->slab + 3 * buf;
         for (int r = 0; r < dist.world; r++) {
             fz->flag_arrays[r] = fz->peer_slab[r] ? reinterpret_cast<int *>(static_cast<float *>(fz->peer_slab[r]) + 4 * buf) : nullptr;
-            fz->areas[r] = fz->peer_slab[r] ? static_cast<float *>(fz->peer_slab[r]) + 4 * buf + 64 : nullptr;
+            fz->areas[r] = fz->peer_slab[r] ? static_cast<float *>(fz->peer_slab[r]) + 4 * buf + 128 : nullptr;
         }
         GCNK_CHECK(gcnk_malloc((void **)&fz->d_err, sizeof(int)));
         GCNK_CHECK(gcnk_memset(fz->d_err, 0, sizeof(int), nullptr));
         GCNK_CHECK(gcnk_malloc_host((void **)&fz->h_err, sizeof(int)));
         *fz->h_err = 0;
+        if (fz->p2p) build_halo();
     } else {
         for (float **p : {&fz->xw_s, &fz->h1_s, &fz->G, &fz->Gm}) GCNK_CHECK(gcnk_malloc((void **)p, nh_all));
     }
@@ -343,7 +357,50 @@ void GCN::build(GCNPlan plan) {
         GCNK_CHECK(gcnk_malloc((void **)&fz->bw_ws, fz->bw_ws_bytes));
         GCNK_CHECK(gcnk_stream_sync(nullptr));
     }
+    // Setup ran on the legacy stream and the engine stream does not synchronise with it: finish everything first.  Then
+    // meet the other ranks, so that nobody enters its first exchange while another rank is still building (uneven
+    // build times would otherwise eat into the flag-wait timeout).
+    GCNK_CHECK(gcnk_device_sync());
+    if (dist.world > 1) {
+        float *b[1] = {fz->ws};
+        const size_t c1[1] = {1};
+        GCNK_CHECK(gcnk_comm_allreduce(dist.comm, b, c1, 1, 1, nullptr));
+        GCNK_CHECK(gcnk_device_sync());
+    }
 }
+
+// Halo exchange: peer p only ever reads the rows of a gather source that its columns reference.  Every rank
+// marks the columns of its own CSR slice in an N-bit map, the maps are all-gathered once, and each rank keeps, per
+// peer, the list of its own rows that peer needs.  The lists replace the contiguous push when they save at least 10 %
+// of the rows for some peer (GCN_HALO=1 forces them, =0 disables them); on the dense synthetic graphs every peer
+// references nearly every row and the contiguous (fully coalesced) push stays.
+void GCN::build_halo() {
+    Fused &z = *fz;
+    const int N = params.num_nodes;
+    const size_t bytes = ((size_t)N + 7) / 8;
+    std::vector<unsigned char> mine(bytes, 0), all(bytes * (size_t)dist.world, 0);
+    for (int c : data->graph.indices) mine[(size_t)c >> 3] |= (unsigned char)(1u << (c & 7));
+    GCNK_CHECK(gcnk_comm_allgather_bytes(dist.comm, mine.data(), all.data(), (int)bytes));
+    const char *hv = getenv("GCN_HALO");
+    bool any_saving = false;
+    std::vector<std::vector<int>> lists((size_t)dist.world);
+    for (int p = 0; p < dist.world; p++) {
+        if (p == dist.rank) continue;
+        const unsigned char *map = all.data() + bytes * (size_t)p;
+        for (int i = r0; i < r0 + n_loc; i++)
+            if ((map[(size_t)i >> 3] >> (i & 7)) & 1u) lists[p].push_back(i - r0);
+        if ((double)lists[p].size() < 0.9 * (double)n_loc) any_saving = true;
+    }
+    z.use_halo = hv && *hv ? atoi(hv) != 0 : any_saving;
+    if (!z.use_halo) return;
+    for (int p = 0; p < dist.world; p++) {
+        if (p == dist.rank) continue;
+        z.halo_count[p] = (int)lists[p].size();
+        z.halo_rows[p] = upload(lists[p]);
+    }
+}
+
+gcnk_stream_t GCN::engine_stream() const { return fz ? fz->stream : nullptr; }
 
 gcnk_graph *GCN::graph_handle() {
     return dist.world > 1 ? data->graph.graph_slice(params.num_nodes, d_dinv_global) : data->graph.graph();
@@ -397,7 +454,7 @@ GCN::~GCN() {
 
 void GCN::set_input_from_host(const float *h_values) {
     consume_pending_input();                                // a prefetched input is older than this one: retire it first
-    GCNK_CHECK(gcnk_memcpy_h2d(d_feature_value, h_values, sizeof(float) * data->feature_index.indices.size(), nullptr));
+    GCNK_CHECK(gcnk_memcpy_h2d(d_feature_value, h_values, sizeof(float) * data->feature_index.indices.size(), engine_stream()));
     if (fz) { fz->ax_valid = false; fz->xp_dirty = fz->Xp != nullptr; }   // A_hat*X is stale (eval falls back to the gather path); re-pack X
 }
 
@@ -419,7 +476,7 @@ void GCN::start_input_upload(const float *h_values) {
 // Called at the start of every pass: switch to the prefetched input once its upload has finished (device-side wait).
 void GCN::consume_pending_input() {
     if (!input_pending) return;
-    GCNK_CHECK(gcnk_stream_wait_event(nullptr, ev_copied));
+    GCNK_CHECK(gcnk_stream_wait_event(engine_stream(), ev_copied));
     std::swap(d_feature_value, d_feature_spare);
     input_pending = false;
     if (fz) { fz->ax_valid = false; fz->xp_dirty = fz->Xp != nullptr; }
@@ -470,7 +527,8 @@ float GCN::get_l2_penalty() {
 }
 
 // ------------------------------------------------------------------------------ fused plan ----
-// Before a producer of gather source `d_all`: register the peers' copies so its epilogue mirrors the rows.
+// Before a producer of gather source `d_all`: register the peers' copies so its epilogue mirrors the rows
+// (opt-in, GCNK_MIRROR_EPILOGUE=1; by default the registration stays pending and publish() pushes the rows).
 void GCN::mirror(float *d_all, int dim) {
     if (dist.world <= 1 || !fz->p2p) return;
     Fused &z = *fz;
@@ -482,36 +540,62 @@ void GCN::mirror(float *d_all, int dim) {
     GCNK_CHECK(gcnk_mirror_next(d_all + (size_t)r0 * dim, peers, n));
 }
 
-// After the producer: every rank's rows of `d_all` must be present before the gather that reads them.
-void GCN::allgather(float *d_all, int dim) {
+// After the producer of gather source `d_all` (buffer b of the slab): make this rank's rows available to every rank.
+//   peer memory, default: one push kernel copies the finished rows (all of them, or per peer only the rows that peer's
+//     columns reference — halo exchange) into the peers' slabs over NVLink and publishes seq[b] in their flag slots;
+//     nothing waits here.  await(b) then arms the consuming gather, which checks the flags at its own start.
+//   GCN_EXCHANGE=barrier: the round-1 form, push + flag barrier in one launch (every rank waits for every rank here).
+//   GCN_COMM=nccl / no peer mapping: NCCL all-gather (grouped broadcasts).
+void GCN::publish(float *d_all, int dim) {
     if (dist.world <= 1) return;
+    Fused &z = *fz;
     gpu_timer_begin(TMR_COMM);
-    if (fz->p2p) {
-        Fused &z = *fz;
+    if (z.p2p) {
+        const int b = (int)((d_all - z.slab) / ((size_t)params.num_nodes * dim));
         float *own = d_all + (size_t)r0 * dim;
-        if (gcnk_mirror_pending(own)) {
-            // the producer did not mirror its rows: one coalesced copy of the finished rows to every peer, with the
-            // flag exchange done by the last CTA of the same launch
-            float *peers[8];
-            int n = 0;
-            const size_t off = (size_t)(d_all - z.slab) + (size_t)r0 * dim;
-            for (int r = 0; r < dist.world; r++)
-                if (r != dist.rank) peers[n++] = static_cast<float *>(z.peer_slab[r]) + off;
+        const bool mirrored = !gcnk_mirror_pending(own);               // the producer's epilogue already stored the rows remotely
+        float *peers[8];
+        int *slots[8];
+        const int *lists[8];
+        int counts[8], n = 0;
+        const size_t off = (size_t)(d_all - z.slab) + (size_t)r0 * dim;
+        for (int r = 0; r < dist.world; r++) {
+            if (r == dist.rank) continue;
+            peers[n] = static_cast<float *>(z.peer_slab[r]) + off;
+            slots[n] = z.flag_arrays[r] + 64 + 8 * b + dist.rank;
+            lists[n] = z.halo_rows[r]; counts[n] = z.halo_count[r];
+            n++;
+        }
+        if (z.signal_exchange) {
+            ++z.seq[b];
+            GCNK_CHECK(gcnk_peer_push_signal(own, peers, n, mirrored ? 0 : (size_t)n_loc * dim, z.use_halo && !mirrored ? lists : nullptr, counts, dim,
+                                             slots, z.seq[b], z.d_counter, z.stream));
+        } else if (!mirrored) {
             GCNK_CHECK(gcnk_peer_push_barrier(own, peers, n, (size_t)n_loc * dim, z.flag_arrays, dist.rank, dist.world, ++z.barrier_value,
-                                              z.d_err, z.d_counter, nullptr));
+                                              z.d_err, z.d_counter, z.stream));
         } else {
-            GCNK_CHECK(gcnk_peer_barrier(z.flag_arrays, dist.rank, dist.world, ++z.barrier_value, z.d_err, nullptr));
+            GCNK_CHECK(gcnk_peer_barrier(z.flag_arrays, dist.rank, dist.world, ++z.barrier_value, z.d_err, z.stream));
         }
     } else {
-        GCNK_CHECK(gcnk_comm_allgather_rows(dist.comm, d_all, row_begin.data(), dim, nullptr));
+        GCNK_CHECK(gcnk_comm_allgather_rows(dist.comm, d_all, row_begin.data(), dim, z.stream));
     }
     gpu_timer_end(TMR_COMM);
+}
+
+// Arms the next gather launch: it reads buffer `d_all`, so it must see every rank's rows of production seq[b].
+void GCN::await(float *d_all, int dim) {
+    Fused &z = *fz;
+    if (dist.world <= 1 || !z.p2p || !z.signal_exchange) return;
+    const int b = (int)((d_all - z.slab) / ((size_t)params.num_nodes * dim));
+    GCNK_CHECK(gcnk_gather_wait_next(z.flag_arrays[dist.rank] + 64 + 8 * b, dist.world, dist.rank, z.seq[b], z.d_err));
 }
 
 // Enqueues one pass on the stream; nothing is read back until fused_collect.  slot: which pinned result slot to use.
 void GCN::fused_enqueue(int current_split, bool training, int slot) {
     consume_pending_input();
     Fused &z = *fz;
+    gcnk_stream_t st = z.stream;
+    gpu_timer_set_stream(st);
     const int N = params.num_nodes, F = params.input_dim, H = params.hidden_dim, C = params.output_dim;
     const int64_t nnzX_loc = (int64_t)data->feature_index.indices.size();
     const int64_t nnzX_all = (int64_t)full_data->feature_index.indices.size();
@@ -529,7 +613,10 @@ void GCN::fused_enqueue(int current_split, bool training, int slot) {
     gcnk_graph *g_rows = g, *g_cols = g;
     if (z.use_views) {
         const int sidx = current_split >= 1 && current_split <= 3 ? current_split : 0;
-        if (sidx && !z.rows[sidx]) GCNK_CHECK(gcnk_graph_create_view(&z.rows[sidx], g, z.keep[sidx], nullptr, nullptr));
+        if (sidx && !z.rows[sidx]) {
+            GCNK_CHECK(gcnk_graph_create_view(&z.rows[sidx], g, z.keep[sidx], nullptr, nullptr));
+            GCNK_CHECK(gcnk_stream_sync(nullptr));
+        }
         if (sidx) g_rows = z.rows[sidx];
         g_cols = z.cols_train;
     }
@@ -538,24 +625,26 @@ void GCN::fused_enqueue(int current_split, bool training, int slot) {
     // The reference draws nnz(X) then N*H values per training pass from ONE stream in element order
     // (module.cpp:214-218 via gcn.cpp:110-111).  Each rank jumps a copy of the stream to its own rows, so the
     // masks are the same bits whatever the partition; the shared stream then advances by the global counts.
-    auto draw_masks = [&](const uint64_t *st, uint32_t *k0, uint32_t *k1, gcnk_stream_t stream) {
-        GCNK_CHECK(gcnk_rng_set_state(z.slice_rng, st[0], st[1]));
+    auto draw_masks = [&](const uint64_t *state, uint32_t *k0, uint32_t *k1, gcnk_stream_t stream) {
+        GCNK_CHECK(gcnk_rng_set_state(z.slice_rng, state[0], state[1]));
         GCNK_CHECK(gcnk_rng_skip(z.slice_rng, (uint64_t)x_off));
         GCNK_CHECK(gcnk_dropout_mask(z.slice_rng, k0, nnzX_loc, p, stream));
-        GCNK_CHECK(gcnk_rng_set_state(z.slice_rng, st[0], st[1]));
+        GCNK_CHECK(gcnk_rng_set_state(z.slice_rng, state[0], state[1]));
         GCNK_CHECK(gcnk_rng_skip(z.slice_rng, (uint64_t)nnzX_all + (uint64_t)r0 * H));
         GCNK_CHECK(gcnk_dropout_mask(z.slice_rng, k1, (int64_t)n_loc * H, p, stream));
     };
     if (training) {
         gpu_timer_begin(TMR_DROPOUT_FW);
-        uint64_t st[2];
-        GCNK_CHECK(gcnk_rng_get_state(global_rng(), st));
+        uint64_t state[2];
+        GCNK_CHECK(gcnk_rng_get_state(global_rng(), state));
         if (drop) {
             z.keep0 = z.keep0_buf[z.cur]; z.keep1 = z.keep1_buf[z.cur];
-            if (z.pre_valid && z.pre_state[0] == st[0] && z.pre_state[1] == st[1])
-                GCNK_CHECK(gcnk_stream_wait_event(nullptr, z.ev_ready));       // drawn ahead on the side stream
-            else
-                draw_masks(st, z.keep0, z.keep1, nullptr);
+            const bool ahead = z.pre_valid && z.pre_state[0] == state[0] && z.pre_state[1] == state[1];
+            // Either way the side stream's last draw targets THIS buffer pair: wait for it before reading the bits — or
+            // before redrawing them in line, so that a stale draw still in flight cannot overwrite the fresh bits.
+            if (z.pre_valid) GCNK_CHECK(gcnk_stream_wait_event(st, z.ev_ready));
+            if (!ahead) draw_masks(state, z.keep0, z.keep1, st);
+            z.pre_valid = false;
         }
         GCNK_CHECK(gcnk_rng_skip(global_rng(), (uint64_t)nnzX_all + (uint64_t)N * H));   // consumed even when p == 0
         gpu_timer_end(TMR_DROPOUT_FW);
@@ -565,24 +654,24 @@ void GCN::fused_enqueue(int current_split, bool training, int slot) {
         // eval: A_hat*(X*W1) = (A_hat*X)*W1, ReLU and the pre-scale for the next gather in the epilogue
         gpu_timer_begin(TMR_SPMATMUL_FW);
         mirror(z.h1_s, H);
-        if (z.AXp) GCNK_CHECK(gcnk_dense_transform_ld(z.AXp, z.ld, n_loc, F, W1.data, z.h1_s + own, H, nullptr, 1.0f, dinv, 1, nullptr));
-        else GCNK_CHECK(gcnk_dense_transform(z.AX, n_loc, F, W1.data, z.h1_s + own, H, nullptr, 1.0f, dinv, 1, nullptr));
+        if (z.AXp) GCNK_CHECK(gcnk_dense_transform_ld(z.AXp, z.ld, n_loc, F, W1.data, z.h1_s + own, H, nullptr, 1.0f, dinv, 1, st));
+        else GCNK_CHECK(gcnk_dense_transform(z.AX, n_loc, F, W1.data, z.h1_s + own, H, nullptr, 1.0f, dinv, 1, st));
         gpu_timer_end(TMR_SPMATMUL_FW);
     } else {
         // M0 Dropout + M1 SparseMatmul: keep bits applied on read; the stored feature values are never modified,
         // so no set_input() copy is needed
         gpu_timer_begin(TMR_SPMATMUL_FW);
-        if (z.xp_dirty) { GCNK_CHECK(gcnk_dense_pack(d_feature_value, n_loc, F, z.Xp, z.ld, nullptr)); z.xp_dirty = false; }
+        if (z.xp_dirty) { GCNK_CHECK(gcnk_dense_pack(d_feature_value, n_loc, F, z.Xp, z.ld, st)); z.xp_dirty = false; }
         mirror(z.xw_s, H);
-        if (z.Xp) GCNK_CHECK(gcnk_dense_transform_ld(z.Xp, z.ld, n_loc, F, W1.data, z.xw_s + own, H, drop ? z.keep0 : nullptr, scale, dinv, 0, nullptr));
-        else GCNK_CHECK(gcnk_spmm_fw(sp, d_feature_value, W1.data, z.xw_s + own, H, drop ? z.keep0 : nullptr, scale, dinv, nullptr));
+        if (z.Xp) GCNK_CHECK(gcnk_dense_transform_ld(z.Xp, z.ld, n_loc, F, W1.data, z.xw_s + own, H, drop ? z.keep0 : nullptr, scale, dinv, 0, st));
+        else GCNK_CHECK(gcnk_spmm_fw(sp, d_feature_value, W1.data, z.xw_s + own, H, drop ? z.keep0 : nullptr, scale, dinv, st));
         gpu_timer_end(TMR_SPMATMUL_FW);
         if (drop && z.rng_stream) {
             // Draw the NEXT training pass's masks now, on the side stream, into the other buffer (its last readers
             // were in the previous training pass, which has completed: every pass ends with a host sync).  It is
             // released only after the feature transform above (issue-bound, like the generator) so that it runs
             // under the L2-bound gathers.
-            GCNK_CHECK(gcnk_event_record(z.ev_go, nullptr));
+            GCNK_CHECK(gcnk_event_record(z.ev_go, st));
             GCNK_CHECK(gcnk_stream_wait_event(z.rng_stream, z.ev_go));
             GCNK_CHECK(gcnk_rng_get_state(global_rng(), z.pre_state));
             draw_masks(z.pre_state, z.keep0_buf[z.cur ^ 1], z.keep1_buf[z.cur ^ 1], z.rng_stream);
@@ -590,18 +679,20 @@ void GCN::fused_enqueue(int current_split, bool training, int slot) {
             z.pre_valid = true;
             z.cur ^= 1;
         }
-        allgather(z.xw_s, H);
+        publish(z.xw_s, H);
         // M2 GraphSum + M3 ReLU + M4 Dropout in the gather's epilogue
         gpu_timer_begin(TMR_GATHER_FULL);
         mirror(z.h1_s, H);
+        await(z.xw_s, H);
         GCNK_CHECK(gcnk_gather_relu_drop(g, z.xw_s, z.h1_s + own, drop ? z.keep1 : nullptr, training ? z.mask : nullptr,
-                                         training ? scale : 1.0f, H, nullptr));
+                                         training ? scale : 1.0f, H, st));
         gpu_timer_end(TMR_GATHER_FULL);
     }
-    allgather(z.h1_s, H);
+    publish(z.h1_s, H);
     // the layer-2 aggregation at width H, only for the rows whose logits the loss looks at
     gpu_timer_begin(gather_timer(g_rows));
-    GCNK_CHECK(gcnk_gather_plain(g_rows, z.h1_s, z.P, H, nullptr));
+    await(z.h1_s, H);
+    GCNK_CHECK(gcnk_gather_plain(g_rows, z.h1_s, z.P, H, st));
     gpu_timer_end(gather_timer(g_rows));
 
     // M5 Matmul + M7 CrossEntropyLoss + get_accuracy (+ Matmul backward when training), row-local.
@@ -610,43 +701,47 @@ void GCN::fused_enqueue(int current_split, bool training, int slot) {
     if (training) mirror(z.G, H);
     GCNK_CHECK(gcnk_layer2_fused(z.P, W2.data, d_split, d_label, current_split, n_loc, H, C, training,
                                  split_count[current_split & 3], dinv, training ? z.G + own : nullptr,
-                                 training ? W2.grad : nullptr, nullptr, z.d_result, z.ws, z.ws_bytes, nullptr));
+                                 training ? W2.grad : nullptr, nullptr, z.d_result, z.ws, z.ws_bytes, st));
     gpu_timer_end(TMR_LOSS_FW);
 
     if (training) {
         // backward of M6/M5 is inside layer2; M4/M3/M2 backward = one masked gather + one plain gather
-        allgather(z.G, H);
+        publish(z.G, H);
         gpu_timer_begin(gather_timer(g_cols));
         mirror(z.Gm, H);
-        GCNK_CHECK(gcnk_gather_mask(g_cols, z.G, z.Gm + own, z.mask, scale, H, nullptr));
+        await(z.G, H);
+        GCNK_CHECK(gcnk_gather_mask(g_cols, z.G, z.Gm + own, z.mask, scale, H, st));
         gpu_timer_end(gather_timer(g_cols));
-        allgather(z.Gm, H);
+        publish(z.Gm, H);
         gpu_timer_begin(TMR_GATHER_FULL);
-        GCNK_CHECK(gcnk_gather_plain(g, z.Gm, z.dxw, H, nullptr));
+        await(z.Gm, H);
+        GCNK_CHECK(gcnk_gather_plain(g, z.Gm, z.dxw, H, st));
         gpu_timer_end(TMR_GATHER_FULL);
         gpu_timer_begin(TMR_SPMATMUL_BW);
-        if (z.Xp) GCNK_CHECK(gcnk_dense_transform_bw_ld(z.Xp, z.ld, n_loc, F, z.dxw, W1.grad, H, drop ? z.keep0 : nullptr, scale, z.bw_ws, z.bw_ws_bytes, nullptr));
-        else GCNK_CHECK(gcnk_spmm_bw(sp, d_feature_value, z.dxw, W1.grad, H, drop ? z.keep0 : nullptr, scale, nullptr));
+        if (z.Xp) GCNK_CHECK(gcnk_dense_transform_bw_ld(z.Xp, z.ld, n_loc, F, z.dxw, W1.grad, H, drop ? z.keep0 : nullptr, scale, z.bw_ws, z.bw_ws_bytes, st));
+        else GCNK_CHECK(gcnk_spmm_bw(sp, d_feature_value, z.dxw, W1.grad, H, drop ? z.keep0 : nullptr, scale, st));
         gpu_timer_end(TMR_SPMATMUL_BW);
     }
     if (dist.world > 1) {
-        // sums over nodes: dW1, dW2 and {sum of loss terms, count, wrong}; every rank then applies the same update
+        // sums over nodes: dW1, dW2 and {sum of loss terms, count, wrong}; every rank then applies the same update.
+        // This is also the one true barrier of the pass: nobody starts the next pass (and overwrites a gather source
+        // in a peer's slab) before every rank has finished reading this pass's sources.
         float *bufs[3] = {z.ws, W1.grad, W2.grad};
         const size_t counts[3] = {4, (size_t)W1.size, (size_t)W2.size};
         gpu_timer_begin(TMR_COMM);
         if (z.p2p)
             GCNK_CHECK(gcnk_peer_allreduce(bufs, counts, training ? 3 : 1, z.areas, z.slot_floats, z.flag_arrays, dist.rank, dist.world,
-                                           ++z.barrier_value, z.d_err, z.d_counter, nullptr));
+                                           ++z.barrier_value, z.d_err, z.d_counter, st));
         else
-            GCNK_CHECK(gcnk_comm_allreduce(dist.comm, bufs, counts, training ? 3 : 1, 0, nullptr));
+            GCNK_CHECK(gcnk_comm_allreduce(dist.comm, bufs, counts, training ? 3 : 1, 0, st));
         gpu_timer_end(TMR_COMM);
     }
-    GCNK_CHECK(gcnk_memcpy_d2h(z.h_red + 4 * slot, z.ws, 4 * sizeof(float), nullptr));
+    GCNK_CHECK(gcnk_memcpy_d2h(z.h_red + 4 * slot, z.ws, 4 * sizeof(float), st));
     z.sumsq_used[slot] = -1.f;                                            // eval: the penalty of the weights as they are at collect time
     if (training) {
         z.sumsq_used[slot] = z.sumsq;                                     // gcn.cpp:98-105: W1 as it was in this forward
-        optimizer.step(z.d_sumsq);
-        GCNK_CHECK(gcnk_memcpy_d2h(z.h_sumsq, z.d_sumsq, sizeof(float), nullptr));
+        optimizer.step(z.d_sumsq, st);
+        GCNK_CHECK(gcnk_memcpy_d2h(z.h_sumsq, z.d_sumsq, sizeof(float), st));
         z.sumsq_pending = true;
     }
 }
@@ -655,13 +750,13 @@ void GCN::fused_enqueue(int current_split, bool training, int slot) {
 std::pair<float, float> GCN::fused_collect(int slot, bool sync) {
     Fused &z = *fz;
     if (sync) {
-        if (z.p2p) GCNK_CHECK(gcnk_memcpy_d2h(z.h_err, z.d_err, sizeof(int), nullptr));
+        if (z.p2p) GCNK_CHECK(gcnk_memcpy_d2h(z.h_err, z.d_err, sizeof(int), z.stream));
         const int *d_async = nullptr;
         GCNK_CHECK(gcnk_async_error_flag(&d_async));
-        GCNK_CHECK(gcnk_memcpy_d2h(z.h_async, d_async, sizeof(int), nullptr));
-        GCNK_CHECK(gcnk_stream_sync(nullptr));
+        GCNK_CHECK(gcnk_memcpy_d2h(z.h_async, d_async, sizeof(int), z.stream));
+        GCNK_CHECK(gcnk_stream_sync(z.stream));
         if (*z.h_async) { fprintf(stderr, "GCN: a TMA pipeline kernel timed out on an mbarrier (code %d)\n", *z.h_async); exit(EXIT_FAILURE); }
-        if (z.p2p && *z.h_err) { fprintf(stderr, "GCN: a peer rank did not reach the exchange barrier\n"); exit(EXIT_FAILURE); }
+        if (z.p2p && *z.h_err) { fprintf(stderr, "GCN: a peer rank did not reach the exchange within GCN_PEER_TIMEOUT_S\n"); exit(EXIT_FAILURE); }
         gpu_timer_resolve();
         if (z.sumsq_pending) { z.sumsq = *z.h_sumsq; z.sumsq_pending = false; }
     }

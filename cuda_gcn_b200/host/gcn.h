@@ -89,8 +89,11 @@ private:
 
     void build_partition();
     gcnk_graph *graph_handle();
+    void build_halo();
+    gcnk_stream_t engine_stream() const;
     void mirror(float *d_all, int dim);
-    void allgather(float *d_all, int dim);
+    void publish(float *d_all, int dim);
+    void await(float *d_all, int dim);
     GCNData *data;                           // what this rank computes on: the caller's data, or `local` (its row slice)
     GCNData *full_data = nullptr;            // the caller's full data
     std::unique_ptr<GCNData> local;

@@ -31,7 +31,7 @@ Adam &Adam::operator=(Adam &&o) noexcept {
     return *this;
 }
 
-void Adam::step(float *d_sumsq) {
+void Adam::step(float *d_sumsq, void *stream) {
     step_count++;
     // fp32 powf / sqrtf exactly as optim.cpp:26
     const float step_size = params.lr * sqrtf(1 - powf(params.beta2, step_count)) / (1 - powf(params.beta1, step_count));
@@ -40,6 +40,6 @@ void Adam::step(float *d_sumsq) {
         t[i] = gcnk_adam_tensor{vars[i].var->data, vars[i].var->grad, vars[i].m, vars[i].v, vars[i].size(), vars[i].decay ? 1 : 0};
     gpu_timer_begin(TMR_ADAM);
     GCNK_CHECK(gcnk_adam_step(t.data(), (int)t.size(), step_size, params.beta1, params.beta2, params.eps, params.weight_decay,
-                              d_sumsq, nullptr));
+                              d_sumsq, stream));
     gpu_timer_end(TMR_ADAM);
 }

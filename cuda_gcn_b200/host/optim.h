@@ -38,7 +38,7 @@ public:
 
     // One update of every variable.  d_sumsq (optional, device float) receives sum(w^2) of the FIRST variable after the
     // update: the L2 penalty of the next pass (gcn.cpp:98-105) without another reduction launch.
-    void step(float *d_sumsq = nullptr);
+    void step(float *d_sumsq = nullptr, void *stream = nullptr);   // stream: a gcnk_stream_t (NULL = the legacy stream)
 
 private:
     AdamParams params;

@@ -16,6 +16,7 @@ thread_local unsigned g_gpu_mask = 0xffffffffu;
 thread_local std::vector<Pending> g_pending;
 thread_local std::vector<void *> g_free_events;
 thread_local void *g_open[__NUM_TMR] = {nullptr};
+thread_local void *g_stream = nullptr;        // the stream the event pairs are recorded on
 
 void *take_event() {
     if (!g_free_events.empty()) { void *e = g_free_events.back(); g_free_events.pop_back(); return e; }
@@ -49,18 +50,19 @@ const char *timer_name(timer_instance t) {
 void gpu_timer_enable(bool on) { g_gpu_on = on; g_gpu_mask = 0xffffffffu; }
 void gpu_timer_enable_mask(unsigned mask) { g_gpu_on = mask != 0; g_gpu_mask = mask; }
 bool gpu_timer_enabled() { return g_gpu_on; }
+void gpu_timer_set_stream(void *stream) { g_stream = stream; }
 
 void gpu_timer_begin(timer_instance t) {
     if (!g_gpu_on || !((g_gpu_mask >> t) & 1u)) return;
     void *e = take_event();
-    GCNK_CHECK(gcnk_event_record(e, nullptr));
+    GCNK_CHECK(gcnk_event_record(e, g_stream));
     g_open[t] = e;
 }
 
 void gpu_timer_end(timer_instance t) {
     if (!g_gpu_on || !g_open[t]) return;
     void *e = take_event();
-    GCNK_CHECK(gcnk_event_record(e, nullptr));
+    GCNK_CHECK(gcnk_event_record(e, g_stream));
     g_pending.push_back({t, g_open[t], e});
     g_open[t] = nullptr;
 }

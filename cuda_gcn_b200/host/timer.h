@@ -28,6 +28,7 @@ const char *timer_name(timer_instance t);
 void gpu_timer_enable(bool on);
 void gpu_timer_enable_mask(unsigned mask);   // bit t set = slot t is timed (an event pair per op is not free: ~6 us)
 bool gpu_timer_enabled();
+void gpu_timer_set_stream(void *stream);      // the stream begin/end record on (default: the legacy stream); per host thread
 void gpu_timer_begin(timer_instance t);
 void gpu_timer_end(timer_instance t);
 void gpu_timer_resolve();

@@ -265,6 +265,17 @@ int gcnk_peer_barrier(int *const *flag_arrays, int rank, int world, int value, i
  * device unsigned reserved for these calls */
 int gcnk_peer_push_barrier(const float *local_rows, float *const *peer_rows, int n_peers, size_t n_floats, int *const *flag_arrays,
                            int rank, int world, int value, int *d_err, unsigned *d_counter, gcnk_stream_t stream);
+/* push + SIGNAL, and the matching wait inside the consumer (the form the row-partitioned engine uses by default): the
+ * rows go to the peers (the contiguous block, or — halo exchange — only the rows listed per peer: d_row_lists[i] =
+ * n rows' indices relative to local_rows, h_row_counts[i] of them, `dim` floats each) and the last CTA to finish
+ * stores `value` into peer_flag_slots[i] (an int in peer i's memory); nothing waits in this launch.
+ * gcnk_gather_wait_next(d_flags, n, skip, value, d_err) makes the NEXT gcnk_gather_* launched by this thread wait, at
+ * its start, until d_flags[r] >= value for every r < n except r == skip (this rank) — so a rank that is ahead keeps
+ * running its own work, and no barrier kernel sits between producer and consumer.  A peer that does not arrive within
+ * GCN_PEER_TIMEOUT_S seconds (default 60) sets *d_err = 1 instead of hanging the device. */
+int gcnk_peer_push_signal(const float *local_rows, float *const *peer_rows, int n_peers, size_t n_floats, const int *const *d_row_lists,
+                          const int *h_row_counts, int dim, int *const *peer_flag_slots, int value, unsigned *d_counter, gcnk_stream_t stream);
+int gcnk_gather_wait_next(const int *d_flags, int n_flags, int skip, int value, int *d_err);
 /* Deterministic sum all-reduce over peer memory for small vectors (weight gradients, scalars): every rank writes
  * its n_segs segments, packed, into slot[rank] of every rank's exchange area (slot_areas[r] = rank r's area of
  * world * slot_floats floats), passes the barrier, and sums the slots in rank order back into the segments —
