@@ -102,6 +102,7 @@ int main(int argc, char **argv) {
     } else {
         Parser parser(&params, &data, input_name);
         parser.set_quiet(!chatty);
+        parser.set_cache_write(chatty);                         // rank 0 alone writes data/<name>.gcnbin
         if (!parser.parse()) {
             std::cerr << "Cannot read input: " << input_name << std::endl;
             exit(EXIT_FAILURE);

@@ -1,5 +1,7 @@
 #include "parser.h"
 
+#include <unistd.h>
+
 #include <algorithm>
 #include <climits>
 #include <cstdio>
@@ -79,7 +81,7 @@ Parser::Parser(GCNParams *gcnParams_, GCNData *gcnData_, std::string graph_name,
 
 // ------------------------------------------------------------------------------ binary cache ----
 namespace {
-const char CACHE_MAGIC[8] = {'G', 'C', 'N', 'B', 'I', 'N', '0', '1'};
+const char CACHE_MAGIC[8] = {'G', 'C', 'N', 'B', 'I', 'N', '0', '2'};
 
 template <typename T>
 bool write_vec(FILE *f, const std::vector<T> &v) {
@@ -93,18 +95,29 @@ bool read_vec(FILE *f, std::vector<T> &v) {
     v.resize(n);
     return n == 0 || fread(v.data(), sizeof(T), n, f) == n;
 }
-long mtime_of(const std::string &p) {
-    struct stat st;
-    return stat(p.c_str(), &st) == 0 ? (long)st.st_mtime : -1;
-}
 }  // namespace
 
-bool save_dataset_cache(const std::string &path, const GCNParams &params, const GCNData &data) {
-    const std::string tmp = path + ".tmp";
+// {size, mtime (ns)} of the three text files: the cache is valid only for exactly these files
+bool source_stamp(const std::string &graph, const std::string &split, const std::string &svm, int64_t stamp[6]) {
+    const std::string *files[3] = {&graph, &split, &svm};
+    for (int i = 0; i < 3; i++) {
+        struct stat st;
+        if (stat(files[i]->c_str(), &st) != 0) return false;
+        stamp[2 * i] = (int64_t)st.st_size;
+        stamp[2 * i + 1] = (int64_t)st.st_mtim.tv_sec * 1000000000ll + st.st_mtim.tv_nsec;
+    }
+    return true;
+}
+
+bool save_dataset_cache(const std::string &path, const GCNParams &params, const GCNData &data, const int64_t *stamp) {
+    // a name of its own per writer: concurrent processes (GCN_GPUS=N forks one per GPU) never share a half-written file
+    const std::string tmp = path + ".tmp." + std::to_string((long)getpid());
     FILE *f = fopen(tmp.c_str(), "wb");
     if (!f) return false;
     const int32_t dims[3] = {params.num_nodes, params.input_dim, params.output_dim};
-    bool ok = fwrite(CACHE_MAGIC, 8, 1, f) == 1 && fwrite(dims, sizeof dims, 1, f) == 1 && write_vec(f, data.graph.indptr) &&
+    const int64_t zero[6] = {0, 0, 0, 0, 0, 0};
+    bool ok = fwrite(CACHE_MAGIC, 8, 1, f) == 1 && fwrite(dims, sizeof dims, 1, f) == 1 &&
+              fwrite(stamp ? stamp : zero, sizeof zero, 1, f) == 1 && write_vec(f, data.graph.indptr) &&
               write_vec(f, data.graph.indices) && write_vec(f, data.feature_index.indptr) && write_vec(f, data.feature_index.indices) &&
               write_vec(f, data.feature_value) && write_vec(f, data.label) && write_vec(f, data.split);
     ok = fclose(f) == 0 && ok;
@@ -112,13 +125,15 @@ bool save_dataset_cache(const std::string &path, const GCNParams &params, const 
     return true;
 }
 
-bool load_dataset_cache(const std::string &path, GCNParams *params, GCNData *data) {
+bool load_dataset_cache(const std::string &path, GCNParams *params, GCNData *data, const int64_t *stamp) {
     FILE *f = fopen(path.c_str(), "rb");
     if (!f) return false;
     char magic[8];
     int32_t dims[3];
+    int64_t stored[6];
     GCNData d;
     const bool ok = fread(magic, 8, 1, f) == 1 && !memcmp(magic, CACHE_MAGIC, 8) && fread(dims, sizeof dims, 1, f) == 1 &&
+                    fread(stored, sizeof stored, 1, f) == 1 && (!stamp || !memcmp(stored, stamp, sizeof stored)) &&
                     read_vec(f, d.graph.indptr) && read_vec(f, d.graph.indices) && read_vec(f, d.feature_index.indptr) &&
                     read_vec(f, d.feature_index.indices) && read_vec(f, d.feature_value) && read_vec(f, d.label) && read_vec(f, d.split) &&
                     (int)d.graph.indptr.size() == dims[0] + 1 && d.feature_value.size() == d.feature_index.indices.size();
@@ -232,9 +247,10 @@ bool Parser::parseSplit(const std::string &bytes) {
 bool Parser::parse() {
     const char *nc = getenv("GCN_NO_CACHE");
     const bool use_cache = !(nc && *nc && strcmp(nc, "0"));
-    const long t_text = std::max(mtime_of(graph_path), std::max(mtime_of(split_path), mtime_of(svmlight_path)));
-    if (use_cache && mtime_of(graph_path) >= 0 && mtime_of(split_path) >= 0 && mtime_of(svmlight_path) >= 0 &&
-        mtime_of(cache_path) >= t_text && load_dataset_cache(cache_path, gcnParams, gcnData)) {
+    // the cache header records size and mtime (ns) of the three text files it was made from; anything else is stale
+    int64_t stamp[6];
+    const bool have_text = source_stamp(graph_path, split_path, svmlight_path, stamp);
+    if (use_cache && have_text && load_dataset_cache(cache_path, gcnParams, gcnData, stamp)) {
         // the same three lines: callers (and tests) key on them
         if (!quiet) std::cout << "Parse Graph Succeeded." << std::endl << "Parse Node Succeeded." << std::endl << "Parse Split Succeeded." << std::endl;
         return true;
@@ -247,6 +263,6 @@ bool Parser::parse() {
     if (!quiet) std::cout << "Parse Node Succeeded." << std::endl;
     if (!parseSplit(s)) return false;
     if (!quiet) std::cout << "Parse Split Succeeded." << std::endl;
-    if (use_cache) save_dataset_cache(cache_path, *gcnParams, *gcnData);      // best effort: a read-only data/ is not an error
+    if (use_cache && write_cache) save_dataset_cache(cache_path, *gcnParams, *gcnData, stamp);   // best effort: a read-only data/ is not an error
     return true;
 }

@@ -1,0 +1,5 @@
+set -x
+nvidia-smi -L
+python -m pytest tests -m gpu -x -q > gpurun_out/r02a_gputests.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r02a_gputests.log; tail -5 gpurun_out/r02a_gputests.log
+python bench.py --steps 20 --warmup 5 --no-cpu-baseline --save-trajectory gpurun_out/traj_n1.json > gpurun_out/r02a_bench_n1.json 2> gpurun_out/r02a_bench_n1.err; echo "bench rc=$?"; tail -c 3000 gpurun_out/r02a_bench_n1.json
+bash tools/run_gather_microbench.sh gpurun_out/r02a_gather_microbench.jsonl
