@@ -105,6 +105,8 @@ SIGNATURES = {
     "gcnk_adam_step": (i32, [C.POINTER(AdamTensor), i32, f32, f32, f32, f32, f32, vp, vp]),
     "gcnk_sum_squares": (i32, [vp, i64, vp, vp]),
     "gcnk_layer2_fused": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, sz, vp]),
+    "gcnk_layer2_fused_terms": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, sz, vp, vp, vp]),
+    "gcnk_sequential_sum": (i32, [vp, i32, vp, f32, vp, i32, i32, i32, vp, vp]),
     "gcnk_layer2_workspace": (sz, [i32, i32, i32]),
     "gcnk_comm_unique_id": (i32, [vp]),
     "gcnk_comm_create": (i32, [C.POINTER(vp), vp, i32, i32, i32]),

@@ -120,13 +120,14 @@ __global__ void __launch_bounds__(256) push_barrier_kernel(const float4 *__restr
 // rows == nullptr: the contiguous block [0, n_vec) of float4; otherwise n_rows listed rows of vec_per_row float4 each,
 // a separate list per peer (halo exchange: only the rows that peer's columns reference).
 struct RowLists { const int *rows[MAX_PEERS]; int count[MAX_PEERS]; };
-__global__ void __launch_bounds__(256) push_signal_kernel(const float4 *__restrict__ src, Mirror m, size_t n_vec, FlagPtrs peer_flags, int value,
+template <typename T>
+__global__ void __launch_bounds__(256) push_signal_kernel(const T *__restrict__ src, Mirror m, size_t n_vec, FlagPtrs peer_flags, int value,
                                                           unsigned *counter) {
     size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     for (; i < n_vec; i += stride) {
-        const float4 v = src[i];
-        for (int p = 0; p < m.n; p++) reinterpret_cast<float4 *>(m.p[p])[i] = v;
+        const T v = src[i];
+        for (int p = 0; p < m.n; p++) reinterpret_cast<T *>(m.p[p])[i] = v;
     }
     if (last_cta_arrives(counter) && (int)threadIdx.x < m.n) {
         __threadfence_system();
@@ -266,7 +267,7 @@ int gcnk_peer_push_barrier(const float *local_rows, float *const *peer_rows, int
 
 int gcnk_peer_push_signal(const float *local_rows, float *const *peer_rows, int n_peers, size_t n_floats, const int *const *d_row_lists,
                           const int *h_row_counts, int dim, int *const *peer_flag_slots, int value, unsigned *d_counter, gcnk_stream_t stream) {
-    GCNK_REQUIRE(local_rows && peer_rows && n_peers >= 0 && n_peers <= MAX_PEERS && n_floats % 4 == 0 && peer_flag_slots && d_counter, "bad arguments");
+    GCNK_REQUIRE(local_rows && peer_rows && n_peers >= 0 && n_peers <= MAX_PEERS && peer_flag_slots && d_counter, "bad arguments");
     GCNK_REQUIRE(!d_row_lists || (h_row_counts && dim > 0 && dim % 4 == 0), "row lists need counts and a row width that is a multiple of 4");
     if (!n_peers) return GCNK_OK;
     Mirror m = {};
@@ -280,9 +281,12 @@ int gcnk_peer_push_signal(const float *local_rows, float *const *peer_rows, int 
         const int grid = (int)std::max<size_t>(1, std::min<size_t>((most + 255) / 256, (size_t)sm_count() * 2));
         push_rows_signal_kernel<<<grid, 256, 0, S(stream)>>>(reinterpret_cast<const float4 *>(local_rows), m, l, dim / 4, f, value, d_counter);
     } else {
-        const size_t n_vec = n_floats / 4;
+        bool vec4 = n_floats % 4 == 0 && reinterpret_cast<uintptr_t>(local_rows) % 16 == 0;
+        for (int i = 0; i < n_peers; i++) vec4 = vec4 && reinterpret_cast<uintptr_t>(peer_rows[i]) % 16 == 0;
+        const size_t n_vec = vec4 ? n_floats / 4 : n_floats;      // unaligned blocks (a compact range of loss terms) go float by float
         const int grid = (int)std::max<size_t>(1, std::min<size_t>((n_vec + 255) / 256, (size_t)sm_count() * 2));
-        push_signal_kernel<<<grid, 256, 0, S(stream)>>>(reinterpret_cast<const float4 *>(local_rows), m, n_vec, f, value, d_counter);
+        if (vec4) push_signal_kernel<float4><<<grid, 256, 0, S(stream)>>>(reinterpret_cast<const float4 *>(local_rows), m, n_vec, f, value, d_counter);
+        else push_signal_kernel<float><<<grid, 256, 0, S(stream)>>>(local_rows, m, n_vec, f, value, d_counter);
     }
     GCNK_LAUNCHED();
     return GCNK_OK;

@@ -193,6 +193,83 @@ __global__ void __launch_bounds__(1024) sum_squares_kernel(const float *__restri
 
 int ew_grid(int64_t n) { return (int)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, (int64_t)sm_count() * 16)); }
 
+
+// ---------------------------------------------------------------- sequential-order fp32 summation ----
+// The reference adds the per-row loss terms into ONE float in row order (module.cpp:125-143: `total_loss += ...`).
+// With 153,756 labelled rows whose terms are all close to ln(41) in the first epochs, that sum carries a systematic
+// rounding error of ~1e-4 relative (every addition rounds the term to a multiple of ulp(total) the same way) —
+// more than the 1e-4 parity tolerance, so a more accurate tree sum does NOT match gcn-seq at the headline size.
+// This kernel reproduces the reference's result bit for bit, without the 153,756-deep dependent chain:
+//   while the running sum S stays inside one binade [2^e, 2^(e+1)), S is a multiple of u = ulp(S) = 2^(e-23) and
+//   fl(S + t) = S + u*rint(t/u) for every t that is not an exact tie — independent of S.  So a block of terms is
+//   rounded in parallel (t/u is an exact power-of-two scaling), summed exactly as integers (REDUX), and added to the
+//   mantissa of S in integer arithmetic.  A block that would leave the binade, contains a tie, a negative or huge
+//   term, or starts from S = 0 is replayed with plain sequential additions, 32 terms at a time.
+// One warp; ~100 cycles per 256 terms (the dependent chain is one step per 256 terms instead of per term).
+__device__ __forceinline__ bool seq_fast_block(float &S, const float *t, int cnt) {
+    // cnt terms per lane (lane-major inside a row is irrelevant here: the fast path is order-independent)
+    const uint32_t sb = __float_as_uint(S);
+    const int e = (int)((sb >> 23) & 0xff);                     // biased exponent
+    bool ok = !(sb >> 31) && e >= 30 && e <= 250;               // positive, normal, and u = 2^(e-150) is a normal float too
+    const float inv_u = __uint_as_float((uint32_t)(127 + 150 - e) << 23);     // 2^(150 - e) = 1 / u  (e in [30,250] -> exponent in [27,247])
+    int r_sum = 0;
+    for (int j = 0; j < cnt; j++) {
+        const float x = t[j] * inv_u;                           // exact (power-of-two scaling) unless it over/underflows
+        const float r = rintf(x);
+        // ties, negative contributions, terms of the size of S itself, NaN/Inf: let the sequential path decide
+        if (!(x >= 0.f) || !(x < 1048576.f) || fabsf(x - r) == 0.5f) ok = false;
+        r_sum += (int)r;
+    }
+    ok = __all_sync(FULL, ok);
+    if (!ok) return false;
+    const int R = __reduce_add_sync(FULL, r_sum);               // < 2^20 * 256: exact
+    const uint32_t m = (sb & 0x7fffffu) | 0x800000u;            // S = m * u
+    if (m + (uint32_t)R >= 0x1000000u) return false;            // would cross into the next binade
+    S = __uint_as_float((sb & 0x7f800000u) | ((m + (uint32_t)R) & 0x7fffffu));
+    return true;
+}
+
+__global__ void __launch_bounds__(32) seq_sum_kernel(const float *__restrict__ terms, int n, float *__restrict__ out, float divide_by,
+                                                     const int *wait_flags, int wait_n, int wait_skip, int wait_value, int *wait_err,
+                                                     long long wait_limit) {
+    const int lane = threadIdx.x;
+    if (wait_flags) {                                           // row-partitioned runs: every rank's terms must have landed
+        if (lane < wait_n && lane != wait_skip) {
+            const long long t0 = clock64();
+            for (;;) {
+                int v;
+                asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(wait_flags + lane) : "memory");
+                if (v >= wait_value) break;
+                if (clock64() - t0 > wait_limit) { *wait_err = 1; break; }
+                __nanosleep(64);
+            }
+        }
+        __syncwarp();
+    }
+    constexpr int ROWS = 8;                                     // 8 x 32 = 256 terms per step
+    float S = 0.f;
+    float cur[ROWS], nxt[ROWS];
+    auto load = [&](float (&t)[ROWS], int base) {
+#pragma unroll
+        for (int j = 0; j < ROWS; j++) { const int i = base + j * 32 + lane; t[j] = i < n ? ld_stream_f32(terms + i) : 0.f; }
+    };
+    load(cur, 0);
+    for (int base = 0; base < n; base += ROWS * 32) {
+        if (base + ROWS * 32 < n) load(nxt, base + ROWS * 32);
+        if (!seq_fast_block(S, cur, ROWS)) {
+#pragma unroll
+            for (int j = 0; j < ROWS; j++) {                    // a row of 32 at a time: fast if possible, else the reference's own loop
+                if (seq_fast_block(S, &cur[j], 1)) continue;
+                const int left = min(32, n - (base + j * 32));
+                for (int l = 0; l < left; l++) S = S + __shfl_sync(FULL, cur[j], l);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < ROWS; j++) cur[j] = nxt[j];
+    }
+    if (lane == 0) { out[0] = divide_by != 0.f ? S / divide_by : S; }
+}
+
 }  // namespace
 
 extern "C" {
@@ -271,6 +348,14 @@ int gcnk_accuracy(const float *logits, const int *truth, int n, int c, int *d_wr
     accuracy_kernel<<<parts, 256, 0, st>>>(logits, truth, n, c, scratch[dev]);
     GCNK_LAUNCHED();
     accuracy_finish_kernel<<<1, 256, 0, st>>>(scratch[dev], parts, d_wrong_total2);
+    GCNK_LAUNCHED();
+    return GCNK_OK;
+}
+
+int gcnk_sequential_sum(const float *terms, int n, float *d_out, float divide_by, const int *d_wait_flags, int n_flags, int skip,
+                        int wait_value, int *d_err, gcnk_stream_t stream) {
+    GCNK_REQUIRE(terms && d_out && n >= 0 && (!d_wait_flags || (n_flags > 0 && n_flags <= 32 && d_err)), "bad arguments");
+    seq_sum_kernel<<<1, 32, 0, S(stream)>>>(terms, n, d_out, divide_by, d_wait_flags, n_flags, skip, wait_value, d_err, peer_spin_cycles());
     GCNK_LAUNCHED();
     return GCNK_OK;
 }

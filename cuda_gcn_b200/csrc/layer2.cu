@@ -28,7 +28,8 @@ __global__ void __launch_bounds__(L2_THREADS) layer2_kernel(const float *__restr
                                                              int current_split, int n, int h, int c, int training, float count_f,
                                                              const float *__restrict__ dinv, float *__restrict__ G,
                                                              float *__restrict__ logits_out, L2Partial *__restrict__ ce_partials,
-                                                             float *__restrict__ dw_partials) {
+                                                             float *__restrict__ dw_partials, float *__restrict__ terms,
+                                                             const int *__restrict__ term_index) {
     extern __shared__ __align__(16) float smem[];
     float *sW = smem;                               // [h][c]
     float *sDl = sW + h * c;                        // [warps][c]   dlogits of the warp's current row
@@ -80,7 +81,9 @@ __global__ void __launch_bounds__(L2_THREADS) layer2_kernel(const float *__restr
             w = __any_sync(FULL, w);
             count++;
             wrong += w;
-            loss += logf(sum) - (tl - mx);
+            const float term = logf(sum) - (tl - mx);
+            loss += term;
+            if (terms && lane == 0) terms[term_index ? term_index[s] : s] = term;
             if (training) {
 #pragma unroll
                 for (int t = 0; t < CPL_MAX; t++) {
@@ -101,8 +104,9 @@ __global__ void __launch_bounds__(L2_THREADS) layer2_kernel(const float *__restr
                     G[(size_t)s * h + k] = di * v;
                 }
             }
-        } else if (training) {
-            for (int k = lane; k < h; k += 32) G[(size_t)s * h + k] = 0.f;   // unlabelled rows carry no gradient
+        } else {
+            if (training) for (int k = lane; k < h; k += 32) G[(size_t)s * h + k] = 0.f;   // unlabelled rows carry no gradient
+            if (terms && !term_index && lane == 0) terms[s] = 0.f;
         }
         __syncwarp();
     }
@@ -140,7 +144,8 @@ __global__ void __launch_bounds__(L2_THREADS) layer2_h16_kernel(const float *__r
                                                                  int current_split, int n, int c, int training, float count_f,
                                                                  const float *__restrict__ dinv, float *__restrict__ G,
                                                                  float *__restrict__ logits_out, L2Partial *__restrict__ ce_partials,
-                                                                 float *__restrict__ dw_partials, const Mirror mirror) {
+                                                                 float *__restrict__ dw_partials, const Mirror mirror,
+                                                                 float *__restrict__ terms, const int *__restrict__ term_index) {
     constexpr int H = 16;
     extern __shared__ __align__(16) float smem[];
     float *sAcc = smem;                             // [warps][16*c]  (training only; used once, at the end)
@@ -166,6 +171,7 @@ __global__ void __launch_bounds__(L2_THREADS) layer2_h16_kernel(const float *__r
         const int base = blk * 32, my_row = base + lane;
         const int my_truth = (my_row < n && split[my_row] == current_split) ? label[my_row] : -1;   // set_truth (gcn.cpp:78-81)
         unsigned todo = __ballot_sync(FULL, logits_out ? my_row < n : my_truth >= 0);
+        if (terms && !term_index && my_row < n && my_truth < 0) terms[my_row] = 0.f;
         if (training) {
             // rows without a label carry no gradient: zero their G rows, 32 consecutive floats per store
             const unsigned labelled = __ballot_sync(FULL, my_truth >= 0);
@@ -227,7 +233,9 @@ __global__ void __launch_bounds__(L2_THREADS) layer2_h16_kernel(const float *__r
         wr = __any_sync(FULL, wr);
         count++;
         wrong += wr;
-        loss += logf(sum) - (tl - mx);
+        const float term = logf(sum) - (tl - mx);
+        loss += term;
+        if (terms && lane == 0) terms[term_index ? term_index[s] : s] = term;
         if (training) {
             // dlogits of this lane's classes; dW2 += P^T dlogits; partial of dlogits * W2^T over this lane's classes
             float pk[H];
@@ -342,6 +350,14 @@ size_t gcnk_layer2_workspace(int n, int h, int c) {
 int gcnk_layer2_fused(const float *P, const float *W2, const int *split, const int *label, int current_split, int n, int h,
                       int c, int training, int count, const float *d_dinv, float *G_scaled, float *W2_grad, float *logits_out,
                       gcnk_ce_result *d_result, float *workspace, size_t workspace_bytes, gcnk_stream_t stream) {
+    return gcnk_layer2_fused_terms(P, W2, split, label, current_split, n, h, c, training, count, d_dinv, G_scaled, W2_grad, logits_out,
+                                   d_result, workspace, workspace_bytes, nullptr, nullptr, stream);
+}
+
+int gcnk_layer2_fused_terms(const float *P, const float *W2, const int *split, const int *label, int current_split, int n, int h,
+                            int c, int training, int count, const float *d_dinv, float *G_scaled, float *W2_grad, float *logits_out,
+                            gcnk_ce_result *d_result, float *workspace, size_t workspace_bytes, float *loss_terms,
+                            const int *term_index, gcnk_stream_t stream) {
     GCNK_REQUIRE(P && W2 && split && label && d_result && n >= 0 && h > 0 && c > 0, "bad arguments");
     GCNK_REQUIRE(c <= 32 * CPL_MAX && (size_t)h * c <= 4096, "needs c <= 128 and h*c <= 4096");
     GCNK_REQUIRE(!training || (G_scaled && W2_grad && d_dinv), "training needs G, W2_grad and dinv");
@@ -358,10 +374,10 @@ int gcnk_layer2_fused(const float *P, const float *W2, const int *split, const i
         // registers hold the per-lane slice of dW2; the shared accumulator is only the end-of-kernel exchange
         if (c <= 32)
             layer2_h16_kernel<1><<<grid, L2_THREADS, smem, st>>>(P, W2, split, label, current_split, n, c, training, (float)count,
-                                                                d_dinv, G_scaled, logits_out, ce_partials, dw_partials, mirror);
+                                                                d_dinv, G_scaled, logits_out, ce_partials, dw_partials, mirror, loss_terms, term_index);
         else
             layer2_h16_kernel<2><<<grid, L2_THREADS, smem, st>>>(P, W2, split, label, current_split, n, c, training, (float)count,
-                                                                d_dinv, G_scaled, logits_out, ce_partials, dw_partials, mirror);
+                                                                d_dinv, G_scaled, logits_out, ce_partials, dw_partials, mirror, loss_terms, term_index);
         GCNK_LAUNCHED();
     } else {
         GCNK_REQUIRE(mirror.n == 0, "mirrored output is only implemented for hidden width 16");
@@ -370,7 +386,7 @@ int gcnk_layer2_fused(const float *P, const float *W2, const int *split, const i
             GCNK_CUDA(cudaFuncSetAttribute(layer2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         }
         layer2_kernel<<<grid, L2_THREADS, smem, st>>>(P, W2, split, label, current_split, n, h, c, training, (float)count, d_dinv,
-                                                      G_scaled, logits_out, ce_partials, dw_partials);
+                                                      G_scaled, logits_out, ce_partials, dw_partials, loss_terms, term_index);
         GCNK_LAUNCHED();
     }
     const int hc = h * c;

@@ -37,6 +37,7 @@ struct GCN::Fused {
     float *d_sumsq = nullptr, *h_sumsq = nullptr;
     float *h_red = nullptr;    // pinned [2][4]: {sum of loss terms, count, wrong, 0} after the cross-rank reduction, per result slot
     float sumsq_used[2] = {0.f, 0.f};
+    bool seq_used[2] = {false, false};
     bool sumsq_pending = false;
     gcnk_rng *slice_rng = nullptr;   // positions a copy of the shared stream at this rank's rows
     float sumsq = 0;           // sum(W1^2) of the current weights
@@ -65,7 +66,18 @@ struct GCN::Fused {
     // Exchange by push + signal: buffer b of {xw_s, h1_s, G, Gm} has one flag per producing rank in every rank's slab
     // (ints [64 + 8 b + r] of the flag block); seq[b] counts how often the buffer has been produced, and is the value
     // the pushes publish and the consuming gather waits for.  halo[p] (optional) lists the local rows peer p references.
-    int seq[4] = {0, 0, 0, 0};
+    int seq[5] = {0, 0, 0, 0, 0};          // [4]: the loss-term buffer
+    // Reference-order loss: layer 2 stores every labelled row's loss term at its rank among the labelled rows of the split
+    // (term_index[split][row], global order), and one warp adds them up exactly as the reference's scalar loop does
+    // (gcnk_sequential_sum) on a side stream, under the backward pass.  Row-partitioned: every rank pushes its compact
+    // range to the peers and every rank computes the same global sum.  GCN_TREE_LOSS=1: the plain parallel sum instead.
+    bool seq_loss = true;
+    float *terms = nullptr, *d_seq = nullptr, *h_seq = nullptr;
+    bool terms_owned = false;
+    int *term_index[4] = {nullptr, nullptr, nullptr, nullptr};
+    int term_c0[4] = {0, 0, 0, 0}, term_cnt[4] = {0, 0, 0, 0};
+    gcnk_stream_t seq_stream = nullptr;
+    void *ev_l2 = nullptr, *ev_seq = nullptr;
     int *halo_rows[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     int halo_count[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     bool use_halo = false, signal_exchange = true;
@@ -90,7 +102,14 @@ struct GCN::Fused {
         if (h_err) gcnk_free_host(h_err);
         if (h_async) gcnk_free_host(h_async);
         if (rng_stream) { gcnk_stream_sync(rng_stream); gcnk_stream_destroy(rng_stream); }
+        if (seq_stream) { gcnk_stream_sync(seq_stream); gcnk_stream_destroy(seq_stream); }
         if (stream) { gcnk_stream_sync(stream); gcnk_stream_destroy(stream); }
+        if (ev_l2) gcnk_event_destroy(ev_l2);
+        if (ev_seq) gcnk_event_destroy(ev_seq);
+        if (terms_owned && terms) gcnk_free(terms);
+        if (d_seq) gcnk_free(d_seq);
+        if (h_seq) gcnk_free_host(h_seq);
+        for (int *t : term_index) if (t) gcnk_free(t);
         for (int *h : halo_rows) if (h) gcnk_free(h);
         if (ev_ready) gcnk_event_destroy(ev_ready);
         if (ev_go) gcnk_event_destroy(ev_go);
@@ -242,7 +261,9 @@ void GCN::build(GCNPlan plan) {
         // all-reduce area: world slots]; export it, import every peer's
         const size_t buf = (size_t)N * H;
         fz->slot_floats = ((size_t)F * H + (size_t)H * C + 4 + 3) / 4 * 4;
-        const size_t slab_bytes = 4 * nh_all + 512 + sizeof(float) * fz->slot_floats * dist.world;
+        const int max_terms = std::max(split_count[1], std::max(split_count[2], split_count[3]));
+        const size_t terms_off = 4 * buf + 128 + fz->slot_floats * dist.world;         // in floats, a multiple of 4
+        const size_t slab_bytes = sizeof(float) * (terms_off + (size_t)max_terms + 4);
         GCNK_CHECK(gcnk_malloc((void **)&fz->slab, slab_bytes));
         GCNK_CHECK(gcnk_memset(fz->slab, 0, slab_bytes, nullptr));
         GCNK_CHECK(gcnk_malloc((void **)&fz->d_counter, sizeof(unsigned)));
@@ -277,7 +298,7 @@ void GCN::build(GCNPlan plan) {
         GCNK_CHECK(gcnk_memset(fz->d_err, 0, sizeof(int), nullptr));
         GCNK_CHECK(gcnk_malloc_host((void **)&fz->h_err, sizeof(int)));
         *fz->h_err = 0;
-        if (fz->p2p) build_halo();
+        if (fz->p2p) { build_halo(); fz->terms = fz->slab + terms_off; }
     } else {
         for (float **p : {&fz->xw_s, &fz->h1_s, &fz->G, &fz->Gm}) GCNK_CHECK(gcnk_malloc((void **)p, nh_all));
     }
@@ -305,6 +326,35 @@ void GCN::build(GCNPlan plan) {
     GCNK_CHECK(gcnk_malloc_host((void **)&fz->h_red, 8 * sizeof(float)));
     GCNK_CHECK(gcnk_malloc_host((void **)&fz->h_async, sizeof(int)));
     *fz->h_async = 0;
+    {
+        const char *tl = getenv("GCN_TREE_LOSS");
+        fz->seq_loss = !(tl && *tl && strcmp(tl, "0")) && (dist.world == 1 || fz->p2p);
+        if (fz->seq_loss) {
+            if (!fz->terms) {
+                const int max_terms = std::max(split_count[1], std::max(split_count[2], split_count[3]));
+                GCNK_CHECK(gcnk_malloc((void **)&fz->terms, sizeof(float) * ((size_t)max_terms + 4)));
+                fz->terms_owned = true;
+            }
+            GCNK_CHECK(gcnk_malloc((void **)&fz->d_seq, 2 * sizeof(float)));
+            GCNK_CHECK(gcnk_malloc_host((void **)&fz->h_seq, 2 * sizeof(float)));
+            GCNK_CHECK(gcnk_stream_create(&fz->seq_stream));
+            GCNK_CHECK(gcnk_event_create(&fz->ev_l2));
+            GCNK_CHECK(gcnk_event_create(&fz->ev_seq));
+            for (int sp = 1; sp <= 3; sp++) {
+                // rank of every local labelled row among the labelled rows of its split, in global row order
+                std::vector<int> index((size_t)n_loc, 0);
+                int c = 0;
+                for (int i = 0; i < r0; i++) c += full_data->split[i] == sp && full_data->label[i] >= 0;
+                fz->term_c0[sp] = c;
+                for (int i = 0; i < n_loc; i++) {
+                    index[i] = c;
+                    c += data->split[i] == sp && data->label[i] >= 0;
+                }
+                fz->term_cnt[sp] = c - fz->term_c0[sp];
+                fz->term_index[sp] = upload(index);
+            }
+        }
+    }
     GCNK_CHECK(gcnk_rng_create(&fz->slice_rng, 1, 2));
     GCNK_CHECK(gcnk_sum_squares(variables[2].data, variables[2].size, fz->d_sumsq, nullptr));
     GCNK_CHECK(gcnk_memcpy_d2h(fz->h_sumsq, fz->d_sumsq, sizeof(float), nullptr));
@@ -699,10 +749,39 @@ void GCN::fused_enqueue(int current_split, bool training, int slot) {
     // count = labelled rows of the split over ALL ranks: the gradient is divided by it (module.cpp:154-158)
     gpu_timer_begin(TMR_LOSS_FW);
     if (training) mirror(z.G, H);
-    GCNK_CHECK(gcnk_layer2_fused(z.P, W2.data, d_split, d_label, current_split, n_loc, H, C, training,
-                                 split_count[current_split & 3], dinv, training ? z.G + own : nullptr,
-                                 training ? W2.grad : nullptr, nullptr, z.d_result, z.ws, z.ws_bytes, st));
+    const int sidx_l = current_split >= 1 && current_split <= 3 ? current_split : 0;
+    const bool seq = z.seq_loss && sidx_l != 0;
+    GCNK_CHECK(gcnk_layer2_fused_terms(z.P, W2.data, d_split, d_label, current_split, n_loc, H, C, training,
+                                       split_count[current_split & 3], dinv, training ? z.G + own : nullptr,
+                                       training ? W2.grad : nullptr, nullptr, z.d_result, z.ws, z.ws_bytes,
+                                       seq ? z.terms : nullptr, seq ? z.term_index[sidx_l] : nullptr, st));
     gpu_timer_end(TMR_LOSS_FW);
+    if (seq) {
+        // the reference's own summation order for the printed loss (module.cpp:125-143), off the critical path
+        const int *flags = nullptr;
+        if (dist.world > 1) {
+            float *peers[8];
+            int *slots[8], n = 0;
+            const size_t off = (size_t)(z.terms - z.slab) + (size_t)z.term_c0[sidx_l];
+            for (int r = 0; r < dist.world; r++) {
+                if (r == dist.rank) continue;
+                peers[n] = static_cast<float *>(z.peer_slab[r]) + off;
+                slots[n] = z.flag_arrays[r] + 64 + 8 * 4 + dist.rank;
+                n++;
+            }
+            ++z.seq[4];
+            GCNK_CHECK(gcnk_peer_push_signal(z.terms + z.term_c0[sidx_l], peers, n, (size_t)z.term_cnt[sidx_l], nullptr, nullptr, 1, slots,
+                                             z.seq[4], z.d_counter, st));
+            flags = z.flag_arrays[dist.rank] + 64 + 8 * 4;
+        }
+        GCNK_CHECK(gcnk_event_record(z.ev_l2, st));
+        GCNK_CHECK(gcnk_stream_wait_event(z.seq_stream, z.ev_l2));
+        GCNK_CHECK(gcnk_sequential_sum(z.terms, split_count[sidx_l], z.d_seq + slot, 0.f, flags, flags ? dist.world : 0, dist.rank, z.seq[4],
+                                       z.d_err, z.seq_stream));
+        GCNK_CHECK(gcnk_memcpy_d2h(z.h_seq + slot, z.d_seq + slot, sizeof(float), z.seq_stream));
+        GCNK_CHECK(gcnk_event_record(z.ev_seq, z.seq_stream));
+    }
+    z.seq_used[slot] = seq;
 
     if (training) {
         // backward of M6/M5 is inside layer2; M4/M3/M2 backward = one masked gather + one plain gather
@@ -722,6 +801,9 @@ void GCN::fused_enqueue(int current_split, bool training, int slot) {
         else GCNK_CHECK(gcnk_spmm_bw(sp, d_feature_value, z.dxw, W1.grad, H, drop ? z.keep0 : nullptr, scale, st));
         gpu_timer_end(TMR_SPMATMUL_BW);
     }
+    // the pass is complete only with its loss; and (row-partitioned) no peer may overwrite the loss terms in this rank's
+    // slab — which it can do as soon as it has passed the barrier below — before they have been added up
+    if (seq) GCNK_CHECK(gcnk_stream_wait_event(st, z.ev_seq));
     if (dist.world > 1) {
         // sums over nodes: dW1, dW2 and {sum of loss terms, count, wrong}; every rank then applies the same update.
         // This is also the one true barrier of the pass: nobody starts the next pass (and overwrites a gather source
@@ -763,7 +845,8 @@ std::pair<float, float> GCN::fused_collect(int slot, bool sync) {
     const float *red = z.h_red + 4 * slot;
     last_count = (int)red[1];
     last_wrong = (int)red[2];
-    const float mean_loss = red[0] / (float)last_count;                  // count == 0 -> NaN, as the reference
+    const float loss_sum = z.seq_used[slot] ? z.h_seq[slot] : red[0];
+    const float mean_loss = loss_sum / (float)last_count;                // count == 0 -> NaN, as the reference
     const float sumsq = z.sumsq_used[slot] >= 0.f ? z.sumsq_used[slot] : z.sumsq;
     const float l2 = params.weight_decay * sumsq / 2;
     return {mean_loss + l2, float(last_count - last_wrong) / last_count};

@@ -227,6 +227,19 @@ int gcnk_layer2_fused(const float *P, const float *W2, const int *split, const i
                       float *G_scaled, float *W2_grad, float *logits_out, gcnk_ce_result *d_result,
                       float *workspace, size_t workspace_bytes, gcnk_stream_t stream);
 size_t gcnk_layer2_workspace(int n, int h, int c);
+/* The same, also storing every labelled row's loss term: loss_terms[term_index ? term_index[s] : s] = log(sum exp) - logit
+ * [truth] (without term_index the rows without a label get 0).  For gcnk_sequential_sum. */
+int gcnk_layer2_fused_terms(const float *P, const float *W2, const int *split, const int *label, int current_split,
+                            int n, int h, int c, int training, int count, const float *d_dinv,
+                            float *G_scaled, float *W2_grad, float *logits_out, gcnk_ce_result *d_result,
+                            float *workspace, size_t workspace_bytes, float *loss_terms, const int *term_index,
+                            gcnk_stream_t stream);
+/* d_out[0] = ((((0 + terms[0]) + terms[1]) + ...) + terms[n-1]) [/ divide_by if non-zero] in fp32, bit for bit what a scalar
+ * loop computes — the reference accumulates its loss that way (module.cpp:125-143), and at 10^5 labelled rows the rounding
+ * of that loop is larger than the parity tolerance — but evaluated block-parallel by one warp (~0.4 cycles per term).
+ * Optional d_wait_flags as in gcnk_gather_wait_next (row-partitioned runs: the terms of the other ranks arrive by push). */
+int gcnk_sequential_sum(const float *terms, int n, float *d_out, float divide_by, const int *d_wait_flags, int n_flags, int skip,
+                        int wait_value, int *d_err, gcnk_stream_t stream);
 
 /* ---- exchange steps of the row-partitioned engine (NCCL over NVLink; the reference is single-GPU) ------
  * One process (or thread) per GPU.  Rank 0 calls gcnk_comm_unique_id and shares the 128 bytes with the

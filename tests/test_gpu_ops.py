@@ -521,6 +521,39 @@ def test_layer2_fused(abi, chk, D, n, h, c, training):
         close(Wg.numpy(), bg, rtol=5e-5, what="W2 grad")
 
 
+def _seq_sum_cases():
+    rng = np.random.default_rng(5)
+    ln41 = np.float32(np.log(41.0))
+    cases = {
+        "near_constant_153756": (ln41 + rng.normal(0, 0.01, 153756)).astype(np.float32),     # epoch-1 loss terms at Reddit shape
+        "uniform_100003": rng.random(100003).astype(np.float32) * 5,
+        "wide_range": np.exp(rng.normal(0, 6, 50000)).astype(np.float32),
+        "ties": (rng.integers(0, 9, 70000) * 0.5).astype(np.float32),                          # multiples of 0.5: exact ties once ulp(S) = 1
+        "mostly_zero": np.where(rng.random(60000) < 0.1, rng.random(60000) * 4, 0).astype(np.float32),
+        "small_negative": (rng.random(30000) * 3 - 1e-7).astype(np.float32),
+        "with_negatives": rng.normal(0.5, 2.0, 20000).astype(np.float32),
+        "one": np.array([3.5], np.float32), "empty": np.zeros(0, np.float32),
+        "n_255": rng.random(255).astype(np.float32), "n_257": rng.random(257).astype(np.float32),
+        "huge_then_small": np.concatenate([[1e30], rng.random(5000)]).astype(np.float32),
+    }
+    return cases
+
+
+@pytest.mark.parametrize("name", list(_seq_sum_cases()))
+def test_sequential_sum_bit_exact(abi, D, name):
+    """gcnk_sequential_sum == the scalar fp32 loop `for t: total += t` (module.cpp:125-143), bit for bit, although it is
+    evaluated block-parallel (binade-wise integer rounding); np.add.accumulate in float32 is that scalar loop."""
+    x = _seq_sum_cases()[name]
+    want = np.add.accumulate(x, dtype=np.float32)[-1] if len(x) else np.float32(0)
+    out = abi.DeviceArray.zeros((2,), np.float32)
+    abi.k.gcnk_sequential_sum(D(x) if len(x) else D(np.zeros(4, np.float32)), len(x), out.ptr, 0.0, None, 0, -1, 0, None, None)
+    got = out.numpy()[0]
+    assert got.view(np.uint32) == np.float32(want).view(np.uint32), (name, got, want)
+    if len(x):
+        abi.k.gcnk_sequential_sum(D(x), len(x), out.ptr, float(len(x)), None, 0, -1, 0, None, None)
+        assert out.numpy()[0] == np.float32(want) / np.float32(len(x))
+
+
 def test_error_convention(abi):
     """Bad arguments return GCNK_EINVAL with a message; nothing falls back."""
     L = abi.load()
