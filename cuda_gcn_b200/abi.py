@@ -106,6 +106,13 @@ SIGNATURES = {
     "gcnk_sum_squares": (i32, [vp, i64, vp, vp]),
     "gcnk_layer2_fused": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, sz, vp]),
     "gcnk_layer2_fused_terms": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, sz, vp, vp, vp]),
+    "gcnk_drop_scale_rows": (i32, [vp, i32, i32, vp, f32, vp, vp, vp]),
+    "gcnk_relu_dropout_fw": (i32, [vp, i64, vp, f32, vp, vp]),
+    "gcnk_mask_scale_bw": (i32, [vp, i64, vp, f32, vp]),
+    "gcnk_pad_cols": (i32, [vp, vp, i32, i32, i32, vp]),
+    "gcnk_unpad_cols": (i32, [vp, vp, i32, i32, i32, vp]),
+    "gcnk_ce_rows_workspace": (sz, [i32]),
+    "gcnk_ce_rows": (i32, [vp, i32, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp, sz, vp, vp, vp]),
     "gcnk_sequential_sum": (i32, [vp, i32, vp, f32, vp, i32, i32, i32, vp, vp]),
     "gcnk_layer2_workspace": (sz, [i32, i32, i32]),
     "gcnk_comm_unique_id": (i32, [vp]),

@@ -774,12 +774,17 @@ void GCN::fused_enqueue(int current_split, bool training, int slot) {
                                              z.seq[4], z.d_counter, st));
             flags = z.flag_arrays[dist.rank] + 64 + 8 * 4;
         }
-        GCNK_CHECK(gcnk_event_record(z.ev_l2, st));
-        GCNK_CHECK(gcnk_stream_wait_event(z.seq_stream, z.ev_l2));
+        // training: on the side stream, under the backward pass; eval: nothing follows that could hide it, and the stream
+        // hop would cost more than the ~10 us the sum takes for a validation split
+        gcnk_stream_t ss = training ? z.seq_stream : st;
+        if (training) {
+            GCNK_CHECK(gcnk_event_record(z.ev_l2, st));
+            GCNK_CHECK(gcnk_stream_wait_event(z.seq_stream, z.ev_l2));
+        }
         GCNK_CHECK(gcnk_sequential_sum(z.terms, split_count[sidx_l], z.d_seq + slot, 0.f, flags, flags ? dist.world : 0, dist.rank, z.seq[4],
-                                       z.d_err, z.seq_stream));
-        GCNK_CHECK(gcnk_memcpy_d2h(z.h_seq + slot, z.d_seq + slot, sizeof(float), z.seq_stream));
-        GCNK_CHECK(gcnk_event_record(z.ev_seq, z.seq_stream));
+                                       z.d_err, ss));
+        GCNK_CHECK(gcnk_memcpy_d2h(z.h_seq + slot, z.d_seq + slot, sizeof(float), ss));
+        if (training) GCNK_CHECK(gcnk_event_record(z.ev_seq, z.seq_stream));
     }
     z.seq_used[slot] = seq;
 
@@ -803,7 +808,7 @@ void GCN::fused_enqueue(int current_split, bool training, int slot) {
     }
     // the pass is complete only with its loss; and (row-partitioned) no peer may overwrite the loss terms in this rank's
     // slab — which it can do as soon as it has passed the barrier below — before they have been added up
-    if (seq) GCNK_CHECK(gcnk_stream_wait_event(st, z.ev_seq));
+    if (seq && training) GCNK_CHECK(gcnk_stream_wait_event(st, z.ev_seq));
     if (dist.world > 1) {
         // sums over nodes: dW1, dW2 and {sum of loss terms, count, wrong}; every rank then applies the same update.
         // This is also the one true barrier of the pass: nobody starts the next pass (and overwrites a gather source

@@ -241,6 +241,29 @@ int gcnk_layer2_fused_terms(const float *P, const float *W2, const int *split, c
 int gcnk_sequential_sum(const float *terms, int n, float *d_out, float divide_by, const int *d_wait_flags, int n_flags, int skip,
                         int wait_value, int *d_err, gcnk_stream_t stream);
 
+/* ---- row-local pieces of the wide-hidden plan (hidden*classes too large for gcnk_layer2_fused; csrc/wide.cu) ------
+ * The wide plan computes layer 1 as (A_hat * drop(X)) * W1 (gather at the input width, result reused for dW1) and layer 2
+ * in the reference's order at the class width, stored with pitch ld = classes rounded up to 4 (zero padding columns).
+ *   gcnk_drop_scale_rows   out[i,:] = dinv[i] * (keep bit(i*f+j) ? x[i,j]*scale : 0): Dropout forward (module.cpp:207-224) +
+ *                          the GraphSum pre-scale, from the pristine features; keep_bits NULL keeps everything (f % 4 == 0)
+ *   gcnk_relu_dropout_fw   in place h = (z > 0 && keep) ? z*scale : 0, mask bit = (z > 0) && keep  (K10 + K12)
+ *   gcnk_mask_scale_bw     in place g = mask ? g*scale : 0                                         (K13 + K11)
+ *   gcnk_pad_cols / gcnk_unpad_cols   [rows x c] <-> [rows x ld] with zero padding columns
+ *   gcnk_ce_rows           softmax-CE + accuracy over rows of pitch ld, labelled rows of `current_split` only; training:
+ *                          grad_scaled[s,:] = dinv[s] * (softmax - onehot)/count (pitch ld; zero rows for the others);
+ *                          workspace as gcnk_layer2_fused (first four floats = raw sums); loss_terms/term_index as
+ *                          gcnk_layer2_fused_terms. */
+int gcnk_drop_scale_rows(const float *x, int rows, int f, const uint32_t *keep_bits, float scale, const float *d_dinv, float *out,
+                         gcnk_stream_t stream);
+int gcnk_relu_dropout_fw(float *z, int64_t n, const uint32_t *keep_bits, float scale, uint32_t *mask_bits, gcnk_stream_t stream);
+int gcnk_mask_scale_bw(float *g, int64_t n, const uint32_t *mask_bits, float scale, gcnk_stream_t stream);
+int gcnk_pad_cols(const float *src, float *dst, int rows, int c, int ld, gcnk_stream_t stream);
+int gcnk_unpad_cols(const float *src, float *dst, int rows, int c, int ld, gcnk_stream_t stream);
+size_t gcnk_ce_rows_workspace(int n);
+int gcnk_ce_rows(const float *logits, int ld, const int *split, const int *label, int current_split, int n, int c, int training,
+                 int count, const float *d_dinv, float *grad_scaled, gcnk_ce_result *d_result, float *workspace,
+                 size_t workspace_bytes, float *loss_terms, const int *term_index, gcnk_stream_t stream);
+
 /* ---- exchange steps of the row-partitioned engine (NCCL over NVLink; the reference is single-GPU) ------
  * One process (or thread) per GPU.  Rank 0 calls gcnk_comm_unique_id and shares the 128 bytes with the
  * other ranks by any means; every rank then calls gcnk_comm_create.  Errors: 1000 + ncclResult_t. */
