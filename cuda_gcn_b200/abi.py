@@ -106,6 +106,10 @@ SIGNATURES = {
     "gcnk_sum_squares": (i32, [vp, i64, vp, vp]),
     "gcnk_layer2_fused": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, sz, vp]),
     "gcnk_layer2_fused_terms": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, sz, vp, vp, vp]),
+    "gcnk_matmul_nn": (i32, [vp, i32, vp, i32, vp, i32, i32, i32, i32, vp, vp]),
+    "gcnk_matmul_nt": (i32, [vp, i32, vp, i32, vp, i32, i32, i32, i32, vp]),
+    "gcnk_matmul_tn_workspace": (sz, [i32, i32, i32]),
+    "gcnk_matmul_tn": (i32, [vp, i32, vp, i32, vp, i32, i32, i32, i32, vp, sz, vp]),
     "gcnk_drop_scale_rows": (i32, [vp, i32, i32, vp, f32, vp, vp, vp]),
     "gcnk_relu_dropout_fw": (i32, [vp, i64, vp, f32, vp, vp]),
     "gcnk_mask_scale_bw": (i32, [vp, i64, vp, f32, vp]),

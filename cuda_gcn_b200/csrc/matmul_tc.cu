@@ -17,6 +17,16 @@
 // B (the weights: tiny) is transposed, padded and split once per call by prep_b_kernel into K-major [Npad x Kpad]
 // big / small copies and stays resident in shared memory for the whole kernel (loaded by TMA with the same swizzle).
 //
+//
+// Generalised for the wide-hidden plan (host/gcn_wide.cpp) to the three products of a layer (csrc/gemm.cu dispatches):
+//   nn / nt  C[m x n] (pitch ldc) = A[m x k] (pitch lda) * B, B given as [k x n] or as [n x k]; n is covered by tiles of
+//            at most 64 columns, each CTA keeps ITS tile of B resident and walks the row tiles (the CTAs of one row tile
+//            run side by side, so A is re-read from L2, not from HBM); optional row scale in the epilogue.
+//   tn       C[ka x n] = A[m x ka]^T * B[m x n]: the node dimension m is the contraction.  Both operands are MN-major
+//            for the tensor core (instruction-descriptor bits 15/16; shared-memory descriptors with LBO = the distance of
+//            two 32-float column groups, exactly what a [32 rows x 32 floats] TMA box with the 128-byte swizzle lays down),
+//            so the row-major tiles are fed as they are — no transposed copies.  Split over m across CTAs, partial tiles
+//            reduced in a fixed order (deterministic).
 // Every mbarrier wait has a clock-based bail-out that raises an error flag instead of hanging the GPU.
 #include <stdlib.h>
 
@@ -56,12 +66,13 @@ struct Bars {
 };
 
 // B[K x N] row-major  ->  Bt_big / Bt_small [Npad x Kpad], K contiguous, zero padded, split into two TF32 values
-__global__ void prep_b_kernel(const float *__restrict__ b, float *__restrict__ bt_big, float *__restrict__ bt_small, int K, int N,
+// (b_is_nk: B is already stored [N x K], pitch ldb — the nt product)
+__global__ void prep_b_kernel(const float *__restrict__ b, int ldb, int b_is_nk, float *__restrict__ bt_big, float *__restrict__ bt_small, int K, int N,
                               int Kpad, int Npad) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= Kpad * Npad) return;
     const int n = i / Kpad, k = i % Kpad;
-    const float v = (n < N && k < K) ? b[(size_t)k * N + n] : 0.f;
+    const float v = (n < N && k < K) ? (b_is_nk ? b[(size_t)n * ldb + k] : b[(size_t)k * ldb + n]) : 0.f;
     const uint32_t big = __float_as_uint(v) & TF32_MASK;
     bt_big[i] = __uint_as_float(big);
     bt_small[i] = __uint_as_float(__float_as_uint(v - __uint_as_float(big)) & TF32_MASK);
@@ -70,7 +81,10 @@ __global__ void prep_b_kernel(const float *__restrict__ b, float *__restrict__ b
 __global__ void __launch_bounds__(TC_THREADS, 1) matmul_tc_kernel(const __grid_constant__ CUtensorMap map_a,
                                                                    const __grid_constant__ CUtensorMap map_bb,
                                                                    const __grid_constant__ CUtensorMap map_bs, float *__restrict__ c,
-                                                                   int M, int N, int Npad, int kblocks, int *err) {
+                                                                   int ldc, const float *__restrict__ row_scale, int M, int N, int Npad,
+                                                                   int ntn, int kblocks, int *err) {
+    // Npad = columns of one n tile (a multiple of 16, <= 64); this CTA owns n tile `nt` and walks row tiles
+    // tile0, tile0 + tstep, ...
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 1 KB aligned, still a shared-space pointer (LDS, not LD)   // swizzle atoms are 1 KB
     // [A big: STAGES x 16 KB][A small: STAGES x 16 KB][B big: kblocks x Npad x 128 B][B small: same][barriers]
@@ -82,6 +96,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) matmul_tc_kernel(const __grid_c
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_tiles = (M + BM - 1) / BM;
+    const int nt = blockIdx.x % ntn, tile0 = blockIdx.x / ntn, tstep = gridDim.x / ntn;   // gridDim.x is a multiple of ntn
 
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; s++) { mbar_init(&bars->full[s], 1); mbar_init(&bars->ready[s], 4); mbar_init(&bars->empty[s], 1); }
@@ -101,11 +116,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) matmul_tc_kernel(const __grid_c
         // ================================ TMA producer ================================
         mbar_expect_tx(&bars->b_full, 2u * kblocks * b_block_bytes);
         for (int kb = 0; kb < kblocks; kb++) {
-            tma_load_2d(b_big + (size_t)kb * b_block_bytes, &map_bb, &bars->b_full, kb * BK, 0);
-            tma_load_2d(b_small + (size_t)kb * b_block_bytes, &map_bs, &bars->b_full, kb * BK, 0);
+            tma_load_2d(b_big + (size_t)kb * b_block_bytes, &map_bb, &bars->b_full, kb * BK, nt * Npad);
+            tma_load_2d(b_small + (size_t)kb * b_block_bytes, &map_bs, &bars->b_full, kb * BK, nt * Npad);
         }
         uint32_t it = 0;
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
+        for (int tile = tile0; tile < n_tiles; tile += tstep)
             for (int kb = 0; kb < kblocks; kb++, it++) {
                 const int s = it % STAGES;
                 if (it >= STAGES && !mbar_wait(&bars->empty[s], ((it / STAGES) - 1) & 1, err)) goto teardown;
@@ -117,7 +132,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) matmul_tc_kernel(const __grid_c
         const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(Npad >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
         if (!mbar_wait(&bars->b_full, 0, err)) goto teardown;
         uint32_t it = 0, t = 0;
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, t++) {
+        for (int tile = tile0; tile < n_tiles; tile += tstep, t++) {
             const uint32_t acc = t % ACC_STAGES, d_tmem = tmem + acc * 64;
             if (t >= ACC_STAGES && !mbar_wait(&bars->acc_empty[acc], ((t / ACC_STAGES) - 1) & 1, err)) goto teardown;   // epilogue drained it
             tc_fence_after();
@@ -142,7 +157,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) matmul_tc_kernel(const __grid_c
         // ================================ splitters ================================
         const int tid = threadIdx.x - 128;
         uint32_t it = 0;
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
+        for (int tile = tile0; tile < n_tiles; tile += tstep)
             for (int kb = 0; kb < kblocks; kb++, it++) {
                 const int s = it % STAGES;
                 if (!mbar_wait(&bars->full[s], (it / STAGES) & 1, err)) goto teardown;
@@ -166,7 +181,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) matmul_tc_kernel(const __grid_c
         // ======================= epilogue (TMEM lane quadrant = warp % 4) =======================
         const int q = warp - 8;
         uint32_t t = 0;
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, t++) {
+        for (int tile = tile0; tile < n_tiles; tile += tstep, t++) {
             const uint32_t acc = t % ACC_STAGES;
             if (!mbar_wait(&bars->acc_full[acc], (t / ACC_STAGES) & 1, err)) goto teardown;
             tc_fence_after();
@@ -190,12 +205,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) matmul_tc_kernel(const __grid_c
             {
                 const int row0 = tile * BM + q * 32;
                 const int rows = min(32, M - row0);
-                if (rows > 0) {
-                    float *out = c + (size_t)row0 * N;
-                    const int total = rows * N;
+                const int n0 = nt * Npad, cols = min(Npad, N - n0);          // this tile's share of the N real columns
+                if (rows > 0 && cols > 0) {
+                    float *out = c + (size_t)row0 * ldc + n0;
+                    const int total = rows * cols;
                     for (int f = lane; f < total; f += 32) {
-                        const int rr = f / N, cc = f - rr * N;
-                        out[f] = stage[rr * EPI_STRIDE + cc];
+                        const int rr = f / cols, cc = f - rr * cols;
+                        const float v = stage[rr * EPI_STRIDE + cc];
+                        out[(size_t)rr * ldc + cc] = row_scale ? row_scale[row0 + rr] * v : v;
                     }
                 }
             }
@@ -206,6 +223,151 @@ teardown:
     tc_fence_before();
     __syncthreads();
     if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TMEM_COLS) : "memory");
+}
+
+
+// ================================================================================== tn kernel ====
+// C[ka x n] = A[m x ka]^T * B[m x n], contraction over the rows m.  CTA = (128-feature tile of A, n tile of B, part of m).
+// Stage = 32 rows: A as four [32 x 32-float] TMA boxes (one per 32-feature group, 4 KB each, 128-byte swizzle) and B as
+// up to four such boxes; in this layout both operands are MN-major for tcgen05 (the contiguous direction is M resp. N):
+// 8 rows = one 1 KB swizzle atom = the K = 8 of one tf32 MMA, column groups LBO = 4096 bytes apart.
+constexpr int TN_ROWS = 32, TN_STAGES = 3, TN_BOX_BYTES = TN_ROWS * 128, TN_OPERAND_BYTES = 4 * TN_BOX_BYTES;   // 16 KB
+constexpr int TN_STAGE_BYTES = 4 * TN_OPERAND_BYTES;                     // A big, A small, B big, B small
+
+struct TnBars {
+    uint64_t full[TN_STAGES], ready[TN_STAGES], empty[TN_STAGES], acc_full;
+    uint32_t tmem_base;
+};
+
+// MN-major operand, 128-byte swizzle: leading-dimension byte offset (between 32-float column groups) 4096, stride byte
+// offset (between 8-row groups along K) 1024, descriptor version 1
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr & 0x3ffff) >> 4) | ((uint64_t)(TN_BOX_BYTES >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
+           ((uint64_t)2 << 61);
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1) matmul_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                                                                   float *__restrict__ ws, int ld_ws, int rows_ws, int M, int rows_per_part, int mt,
+                                                                   int ntn, int nt_cols, int *err) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    TnBars *bars = reinterpret_cast<TnBars *>(smem + (size_t)TN_STAGES * TN_STAGE_BYTES);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tiles = mt * ntn, tile = blockIdx.x % tiles, part = blockIdx.x / tiles;
+    const int m_tile = tile / ntn, n_tile = tile % ntn;
+    const int r_lo = part * rows_per_part, r_hi = min(M, r_lo + rows_per_part);
+    const int steps = (r_hi - r_lo + TN_ROWS - 1) / TN_ROWS;             // >= 1 by construction of the grid
+    const int b_boxes = (nt_cols + 31) / 32;
+    (void)mt;
+
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < TN_STAGES; s++) { mbar_init(&bars->full[s], 1); mbar_init(&bars->ready[s], 4); mbar_init(&bars->empty[s], 1); }
+        mbar_init(&bars->acc_full, 1);
+        mbar_fence_init();
+    } else if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)), "n"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = bars->tmem_base;
+
+    if (warp == 0 && lane == 0) {
+        // ================================ TMA producer ================================
+        for (int it = 0; it < steps; it++) {
+            const int s = it % TN_STAGES;
+            if (it >= TN_STAGES && !mbar_wait(&bars->empty[s], ((it / TN_STAGES) - 1) & 1, err)) goto teardown;
+            uint8_t *st = smem + (size_t)s * TN_STAGE_BYTES;
+            mbar_expect_tx(&bars->full[s], (uint32_t)(4 + b_boxes) * TN_BOX_BYTES);
+            const int row = r_lo + it * TN_ROWS;
+            for (int fg = 0; fg < 4; fg++) tma_load_2d(st + fg * TN_BOX_BYTES, &map_a, &bars->full[s], m_tile * 128 + fg * 32, row);
+            for (int fb = 0; fb < b_boxes; fb++)
+                tma_load_2d(st + 2 * TN_OPERAND_BYTES + fb * TN_BOX_BYTES, &map_b, &bars->full[s], n_tile * nt_cols + fb * 32, row);
+        }
+    } else if (warp == 1 && lane == 0) {
+        // ================================ MMA issuer ================================
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(nt_cols >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        for (int it = 0; it < steps; it++) {
+            const int s = it % TN_STAGES;
+            if (!mbar_wait(&bars->ready[s], (it / TN_STAGES) & 1, err)) goto teardown;
+            tc_fence_after();
+            const uint32_t ab = smem_u32(smem + (size_t)s * TN_STAGE_BYTES), as = ab + TN_OPERAND_BYTES, bb = ab + 2 * TN_OPERAND_BYTES, bs = ab + 3 * TN_OPERAND_BYTES;
+#pragma unroll
+            for (int k = 0; k < TN_ROWS / 8; k++) {
+                const uint32_t off = k * 1024;                            // the next 8 rows = the next swizzle atom
+                tc_mma_tf32(tmem, make_desc_mn(as + off), make_desc_mn(bb + off), idesc, (it | k) != 0);
+                tc_mma_tf32(tmem, make_desc_mn(ab + off), make_desc_mn(bs + off), idesc, 1);
+                tc_mma_tf32(tmem, make_desc_mn(ab + off), make_desc_mn(bb + off), idesc, 1);
+            }
+            tc_commit(&bars->empty[s]);
+        }
+        tc_commit(&bars->acc_full);
+    } else if (warp >= 4 && warp < 8) {
+        // ================================ splitters (both operands) ================================
+        const int tid = threadIdx.x - 128;
+        const int b_vec = b_boxes * TN_BOX_BYTES / 16;
+        for (int it = 0; it < steps; it++) {
+            const int s = it % TN_STAGES;
+            if (!mbar_wait(&bars->full[s], (it / TN_STAGES) & 1, err)) goto teardown;
+            uint8_t *st = smem + (size_t)s * TN_STAGE_BYTES;
+            auto split = [&](float4 *big, float4 *sm, int n_vec) {
+                for (int i = tid; i < n_vec; i += 128) {
+                    const float4 v = big[i];
+                    float4 hi, lo;
+                    hi.x = __uint_as_float(__float_as_uint(v.x) & TF32_MASK); lo.x = __uint_as_float(__float_as_uint(v.x - hi.x) & TF32_MASK);
+                    hi.y = __uint_as_float(__float_as_uint(v.y) & TF32_MASK); lo.y = __uint_as_float(__float_as_uint(v.y - hi.y) & TF32_MASK);
+                    hi.z = __uint_as_float(__float_as_uint(v.z) & TF32_MASK); lo.z = __uint_as_float(__float_as_uint(v.z - hi.z) & TF32_MASK);
+                    hi.w = __uint_as_float(__float_as_uint(v.w) & TF32_MASK); lo.w = __uint_as_float(__float_as_uint(v.w - hi.w) & TF32_MASK);
+                    big[i] = hi;
+                    sm[i] = lo;
+                }
+            };
+            split(reinterpret_cast<float4 *>(st), reinterpret_cast<float4 *>(st + TN_OPERAND_BYTES), TN_OPERAND_BYTES / 16);
+            split(reinterpret_cast<float4 *>(st + 2 * TN_OPERAND_BYTES), reinterpret_cast<float4 *>(st + 3 * TN_OPERAND_BYTES), b_vec);
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars->ready[s]);
+        }
+    } else if (warp >= 8) {
+        // ======================= epilogue: the partial tile of this part -> workspace =======================
+        const int q = warp - 8;
+        if (!mbar_wait(&bars->acc_full, 0, err)) goto teardown;
+        tc_fence_after();
+        float *out = ws + ((size_t)part * rows_ws + m_tile * 128 + q * 32 + lane) * ld_ws + n_tile * nt_cols;
+        for (int c0 = 0; c0 < nt_cols; c0 += 16) {
+            uint32_t r[16];
+            const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + c0;
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                         : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                           "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                         : "r"(taddr));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int j = 0; j < 16; j += 4)
+                *reinterpret_cast<float4 *>(out + c0 + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+        }
+        tc_fence_before();
+    }
+teardown:
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TMEM_COLS) : "memory");
+}
+
+// C[r, c] (pitch ldc) = sum over parts of ws[part][r][c], in part order
+__global__ void reduce_tn_kernel(const float *__restrict__ ws, float *__restrict__ c, int ka, int n, int ld_ws, int rows_ws, int ldc, int parts) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ka * n) return;
+    const int r = i / n, cc = i % n;
+    float s0 = 0.f, s1 = 0.f;
+    int b = 0;
+    for (; b + 1 < parts; b += 2) {
+        s0 += ws[((size_t)b * rows_ws + r) * ld_ws + cc];
+        s1 += ws[((size_t)(b + 1) * rows_ws + r) * ld_ws + cc];
+    }
+    if (b < parts) s0 += ws[((size_t)b * rows_ws + r) * ld_ws + cc];
+    c[(size_t)r * ldc + cc] = s0 + s1;
 }
 
 }  // namespace
@@ -239,46 +401,106 @@ bool make_tensor_map_2d(CUtensorMap *map, const float *base, uint64_t rows, uint
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-// shapes this kernel takes: enough rows to matter, A's row pitch a multiple of 16 bytes, both split copies of B resident
-bool matmul_tc_supported(int m, int k, int n) {
+// ------------------------------------------------------------------------------------ nn / nt ----
+static bool tc_disabled() {
     static const bool off = getenv("GCNK_NO_TCGEN05") && atoi(getenv("GCNK_NO_TCGEN05")) != 0;
-    if (off || m < 1024 || k < 64 || k % 4 || n < 8 || n > 256) return false;
-    const int npad = (n + 15) / 16 * 16, kpad = (k + BK - 1) / BK * BK;
-    const size_t smem = 2 * (size_t)STAGES * A_TILE_BYTES + 2 * (size_t)npad * kpad * 4 + 4 * 32 * EPI_STRIDE * sizeof(float) + sizeof(Bars) + 1024;
-    return npad <= 64 && smem <= 227 * 1024 && tensor_maps_available();
+    return off;
+}
+// n tile: all of n when its padding fits 64 columns, else 64-column tiles
+static int nn_tile(int n) { const int npad = (n + 15) / 16 * 16; return npad <= 64 ? npad : 64; }
+static size_t nn_smem(int k, int nt_cols) {
+    const int kpad = (k + BK - 1) / BK * BK;
+    return 2 * (size_t)STAGES * A_TILE_BYTES + 2 * (size_t)nt_cols * kpad * 4 + 4 * 32 * EPI_STRIDE * sizeof(float) + sizeof(Bars) + 1024;
 }
 
-int matmul_tc_fw(const float *a, const float *b, float *c, int m, int k, int n, cudaStream_t st) {
-    const int npad = (n + 15) / 16 * 16, kpad = (k + BK - 1) / BK * BK, kblocks = kpad / BK;
+// shapes the kernel takes: enough rows to matter, A's row pitch a multiple of 16 bytes, both split copies of the CTA's B tile resident
+bool matmul_tc_nn_supported(int m, int k, int n, int lda, int ldc, bool b_is_nk) {
+    (void)ldc; (void)b_is_nk;
+    if (tc_disabled() || m < 1024 || k < 16 || lda % 4 || n < 8) return false;
+    return nn_smem(k, nn_tile(n)) <= 227 * 1024 && tensor_maps_available();
+}
+bool matmul_tc_supported(int m, int k, int n) { return k >= 64 && k % 4 == 0 && n <= 64 && matmul_tc_nn_supported(m, k, n, k, n, false); }
+
+int matmul_tc_nn(const float *a, int lda, const float *b, int ldb, bool b_is_nk, float *c, int ldc, int m, int k, int n, const float *row_scale,
+                 cudaStream_t st) {
+    const int nt_cols = nn_tile(n), ntn = (n + nt_cols - 1) / nt_cols, npad_all = ntn * nt_cols;
+    const int kpad = (k + BK - 1) / BK * BK, kblocks = kpad / BK;
     int dev = 0;
     GCNK_CUDA(cudaGetDevice(&dev));
     static float *bt[64] = {nullptr};
     static size_t bt_elems[64] = {0};
-    const size_t need = 2 * (size_t)npad * kpad;
+    const size_t need = 2 * (size_t)npad_all * kpad;
     if (bt_elems[dev] < need) {
         GCNK_CUDA(cudaStreamSynchronize(st));
         if (bt[dev]) GCNK_CUDA(cudaFree(bt[dev]));
         GCNK_CUDA(cudaMalloc(&bt[dev], sizeof(float) * need));
         bt_elems[dev] = need;
     }
-    float *bt_big = bt[dev], *bt_small = bt[dev] + (size_t)npad * kpad;
-    prep_b_kernel<<<(npad * kpad + 255) / 256, 256, 0, st>>>(b, bt_big, bt_small, k, n, kpad, npad);
+    float *bt_big = bt[dev], *bt_small = bt[dev] + (size_t)npad_all * kpad;
+    prep_b_kernel<<<(npad_all * kpad + 255) / 256, 256, 0, st>>>(b, ldb, b_is_nk ? 1 : 0, bt_big, bt_small, k, n, kpad, npad_all);
     GCNK_LAUNCHED();
     CUtensorMap map_a, map_bb, map_bs;
-    if (!make_tensor_map_2d(&map_a, a, (uint64_t)m, (uint64_t)k, (uint64_t)k, BM, BK, true) ||
-        !make_tensor_map_2d(&map_bb, bt_big, (uint64_t)npad, (uint64_t)kpad, (uint64_t)kpad, (uint32_t)npad, BK, true) ||
-        !make_tensor_map_2d(&map_bs, bt_small, (uint64_t)npad, (uint64_t)kpad, (uint64_t)kpad, (uint32_t)npad, BK, true)) {
+    if (!make_tensor_map_2d(&map_a, a, (uint64_t)m, (uint64_t)k, (uint64_t)lda, BM, BK, true) ||
+        !make_tensor_map_2d(&map_bb, bt_big, (uint64_t)npad_all, (uint64_t)kpad, (uint64_t)kpad, (uint32_t)nt_cols, BK, true) ||
+        !make_tensor_map_2d(&map_bs, bt_small, (uint64_t)npad_all, (uint64_t)kpad, (uint64_t)kpad, (uint32_t)nt_cols, BK, true)) {
         set_error("matmul_tc: cuTensorMapEncodeTiled failed");
         return GCNK_EUNSUPPORTED;
     }
-    const size_t smem = 2 * (size_t)STAGES * A_TILE_BYTES + 2 * (size_t)npad * kpad * 4 + 4 * 32 * EPI_STRIDE * sizeof(float) + sizeof(Bars) + 1024;
+    const size_t smem = nn_smem(k, nt_cols);
     static bool attr[64] = {false};
     if (!attr[dev]) {
         GCNK_CUDA(cudaFuncSetAttribute(matmul_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr[dev] = true;
     }
     const int n_tiles = (m + BM - 1) / BM;
-    matmul_tc_kernel<<<std::min(n_tiles, sm_count()), TC_THREADS, smem, st>>>(map_a, map_bb, map_bs, c, m, n, npad, kblocks, async_err_flag());
+    const int grid = std::max(1, std::min(n_tiles, sm_count() / ntn)) * ntn;      // a multiple of ntn: every CTA owns one n tile
+    matmul_tc_kernel<<<grid, TC_THREADS, smem, st>>>(map_a, map_bb, map_bs, c, ldc, row_scale, m, n, nt_cols, ntn, kblocks, async_err_flag());
+    GCNK_LAUNCHED();
+    return GCNK_OK;
+}
+
+int matmul_tc_fw(const float *a, const float *b, float *c, int m, int k, int n, cudaStream_t st) {
+    return matmul_tc_nn(a, k, b, n, false, c, n, m, k, n, nullptr, st);
+}
+
+// ----------------------------------------------------------------------------------------- tn ----
+static int tn_tile_n(int n) { const int npad = (n + 15) / 16 * 16; return npad <= 128 ? npad : 128; }
+static int tn_parts(int m, int tiles) { return std::max(1, std::min(sm_count() / tiles, (m + 4 * TN_ROWS - 1) / (4 * TN_ROWS))); }
+bool matmul_tc_tn_supported(int m, int ka, int n, int lda, int ldb) {
+    if (tc_disabled() || m < 2048 || lda % 4 || ldb % 4 || ka < 8 || n < 8) return false;
+    const int tiles = ((ka + 127) / 128) * ((n + tn_tile_n(n) - 1) / tn_tile_n(n));
+    return tiles <= sm_count() && tensor_maps_available();
+}
+size_t matmul_tc_tn_workspace(int m, int ka, int n) {
+    const int nt_cols = tn_tile_n(n), mt = (ka + 127) / 128, ntn = (n + nt_cols - 1) / nt_cols;
+    return sizeof(float) * (size_t)tn_parts(m, mt * ntn) * (mt * 128) * (ntn * nt_cols);
+}
+
+int matmul_tc_tn(const float *a, int lda, const float *b, int ldb, float *c, int ldc, int m, int ka, int n, float *ws, size_t ws_bytes, cudaStream_t st) {
+    const int nt_cols = tn_tile_n(n), mt = (ka + 127) / 128, ntn = (n + nt_cols - 1) / nt_cols, tiles = mt * ntn;
+    const int parts = tn_parts(m, tiles);
+    if (!ws || ws_bytes < matmul_tc_tn_workspace(m, ka, n)) { set_error("matmul_tc_tn: workspace too small"); return GCNK_EINVAL; }
+    CUtensorMap map_a, map_b;
+    if (!make_tensor_map_2d(&map_a, a, (uint64_t)m, (uint64_t)ka, (uint64_t)lda, TN_ROWS, 32, true) ||
+        !make_tensor_map_2d(&map_b, b, (uint64_t)m, (uint64_t)n, (uint64_t)ldb, TN_ROWS, 32, true)) {
+        set_error("matmul_tc_tn: cuTensorMapEncodeTiled failed");
+        return GCNK_EUNSUPPORTED;
+    }
+    int dev = 0;
+    GCNK_CUDA(cudaGetDevice(&dev));
+    static bool attr[64] = {false};
+    if (!attr[dev]) {
+        GCNK_CUDA(cudaFuncSetAttribute(matmul_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr[dev] = true;
+    }
+    const int ld_ws = ntn * nt_cols, rows_ws = mt * 128;
+    // rows of m per part: whole 32-row stages
+    int rows_per_part = ((m + parts - 1) / parts + TN_ROWS - 1) / TN_ROWS * TN_ROWS;
+    const int parts_used = (m + rows_per_part - 1) / rows_per_part;
+    const size_t smem = (size_t)TN_STAGES * TN_STAGE_BYTES + sizeof(TnBars) + 1024;
+    matmul_tn_kernel<<<tiles * parts_used, TC_THREADS, smem, st>>>(map_a, map_b, ws, ld_ws, rows_ws, m, rows_per_part, mt, ntn, nt_cols, async_err_flag());
+    GCNK_LAUNCHED();
+    reduce_tn_kernel<<<(ka * n + 255) / 256, 256, 0, st>>>(ws, c, ka, n, ld_ws, rows_ws, ldc, parts_used);
     GCNK_LAUNCHED();
     return GCNK_OK;
 }

@@ -7,126 +7,11 @@
 #include <tuple>
 
 #include "check.h"
+#include "gcn_fused.h"
 #include "rand.h"
 #include "timer.h"
 
 GCNParams GCNParams::get_default() { return {2708, 1433, 16, 7, 0.5f, 0.01f, 5e-4f, 100, 0}; }   // gcn.cpp:9-11
-
-// Buffers of the fused plan.  "_s" = already multiplied by d^-1/2 of its own row (the gather kernels
-// take pre-scaled sources, so an edge costs one index and one row read; see csrc/graph.cu).
-struct GCN::Fused {
-    float *xw_s = nullptr;     // [N x H]  dinv (.) (dropout(X) * W1)
-    float *h1_s = nullptr;     // [N x H]  dinv (.) dropout(relu(A_hat * X W1))
-    float *P = nullptr;        // [N x H]  A_hat * H1
-    float *G = nullptr;        // [N x H]  dinv (.) (dlogits * W2^T)
-    float *Gm = nullptr;       // [N x H]  dinv (.) dropout'/relu'(A_hat * dlogits W2^T)
-    float *dxw = nullptr;      // [N x H]  gradient wrt X W1
-    uint32_t *keep0 = nullptr, *keep1 = nullptr, *mask = nullptr;   // the keep bits this pass reads
-    // Double-buffered keep bits: the masks of the NEXT training pass are drawn on a side stream while this pass
-    // (and the eval pass after it) runs — the generator is ALU-bound, the gathers are L2-bound.  The draws are a
-    // pure function of the stream position, so the bits are identical to drawing them in line; if anything else
-    // consumed the shared stream in between (state mismatch) they are simply drawn again in line.
-    uint32_t *keep0_buf[2] = {nullptr, nullptr}, *keep1_buf[2] = {nullptr, nullptr};
-    int cur = 0;
-    gcnk_stream_t rng_stream = nullptr;
-    void *ev_ready = nullptr, *ev_go = nullptr;
-    bool pre_valid = false;
-    uint64_t pre_state[2] = {0, 0};
-    float *ws = nullptr; size_t ws_bytes = 0;
-    gcnk_ce_result *d_result = nullptr, *h_result = nullptr;   // device / pinned host
-    float *d_sumsq = nullptr, *h_sumsq = nullptr;
-    float *h_red = nullptr;    // pinned [2][4]: {sum of loss terms, count, wrong, 0} after the cross-rank reduction, per result slot
-    float sumsq_used[2] = {0.f, 0.f};
-    bool seq_used[2] = {false, false};
-    bool sumsq_pending = false;
-    gcnk_rng *slice_rng = nullptr;   // positions a copy of the shared stream at this rank's rows
-    float sumsq = 0;           // sum(W1^2) of the current weights
-    // Views of the graph for the passes that need only part of A_hat*x (splits are static, so these are built once):
-    //   rows[s]     only the labelled rows of split s are aggregated — the loss, the accuracy and the layer-2
-    //               gradients never look at the logits of any other row (module.cpp:130-133: truth < 0 rows are skipped)
-    //   cols_train  entries pointing at rows outside the training split dropped — their loss gradient is exactly zero
-    gcnk_graph *rows[4] = {nullptr, nullptr, nullptr, nullptr}, *cols_train = nullptr;
-    int *keep[4] = {nullptr, nullptr, nullptr, nullptr};
-    // AX = A_hat * X, computed once when X is dense: without input dropout (every eval pass)
-    // A_hat*(X*W1) = (A_hat*X)*W1 is one streaming pass and no gather
-    float *AX = nullptr;
-    bool ax_valid = false, use_views = true;
-    // TMA path of the dense feature transform: packed copies (row pitch ld floats, a multiple of 32) of X and A_hat*X
-    float *Xp = nullptr, *AXp = nullptr, *bw_ws = nullptr;
-    size_t bw_ws_bytes = 0;
-    int ld = 0;
-    bool xp_dirty = false;
-    // Row-partitioned runs: the four gather sources live in ONE slab that every peer maps over NVLink (CUDA IPC);
-    // producers mirror their rows into the peers' slabs and a flag barrier replaces the all-gather collective.
-    bool p2p = false;
-    float *slab = nullptr;
-    void *peer_slab[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    int *flag_arrays[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    int barrier_value = 0, world = 1, rank = 0;
-    // Exchange by push + signal: buffer b of {xw_s, h1_s, G, Gm} has one flag per producing rank in every rank's slab
-    // (ints [64 + 8 b + r] of the flag block); seq[b] counts how often the buffer has been produced, and is the value
-    // the pushes publish and the consuming gather waits for.  halo[p] (optional) lists the local rows peer p references.
-    int seq[5] = {0, 0, 0, 0, 0};          // [4]: the loss-term buffer
-    // Reference-order loss: layer 2 stores every labelled row's loss term at its rank among the labelled rows of the split
-    // (term_index[split][row], global order), and one warp adds them up exactly as the reference's scalar loop does
-    // (gcnk_sequential_sum) on a side stream, under the backward pass.  Row-partitioned: every rank pushes its compact
-    // range to the peers and every rank computes the same global sum.  GCN_TREE_LOSS=1: the plain parallel sum instead.
-    bool seq_loss = true;
-    float *terms = nullptr, *d_seq = nullptr, *h_seq = nullptr;
-    bool terms_owned = false;
-    int *term_index[4] = {nullptr, nullptr, nullptr, nullptr};
-    int term_c0[4] = {0, 0, 0, 0}, term_cnt[4] = {0, 0, 0, 0};
-    gcnk_stream_t seq_stream = nullptr;
-    void *ev_l2 = nullptr, *ev_seq = nullptr;
-    int *halo_rows[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    int halo_count[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    bool use_halo = false, signal_exchange = true;
-    gcnk_stream_t stream = nullptr;   // everything the fused plan enqueues runs on this (non-blocking) stream
-    int *d_err = nullptr, *h_err = nullptr;
-    int *h_async = nullptr;      // pinned copy of the kernel library's async error flag (mbarrier time-outs)
-    unsigned *d_counter = nullptr;
-    float *areas[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // all-reduce exchange areas
-    size_t slot_floats = 0;
-    gcnk_comm *comm = nullptr;
-    ~Fused() {
-        gcnk_device_sync();
-        if (slab) {
-            // nobody may still be writing into this slab (or reading ours) when it goes away
-            if (comm) { float *b[1] = {(float *)slab}; const size_t c1[1] = {1}; gcnk_comm_allreduce(comm, b, c1, 1, 1, nullptr); gcnk_device_sync(); }
-            for (int r = 0; r < world; r++) if (r != rank && peer_slab[r]) gcnk_ipc_release(peer_slab[r]);
-            gcnk_free(slab);
-            xw_s = h1_s = G = Gm = nullptr;                 // they were views into the slab
-        }
-        if (d_err) gcnk_free(d_err);
-        if (d_counter) gcnk_free(d_counter);
-        if (h_err) gcnk_free_host(h_err);
-        if (h_async) gcnk_free_host(h_async);
-        if (rng_stream) { gcnk_stream_sync(rng_stream); gcnk_stream_destroy(rng_stream); }
-        if (seq_stream) { gcnk_stream_sync(seq_stream); gcnk_stream_destroy(seq_stream); }
-        if (stream) { gcnk_stream_sync(stream); gcnk_stream_destroy(stream); }
-        if (ev_l2) gcnk_event_destroy(ev_l2);
-        if (ev_seq) gcnk_event_destroy(ev_seq);
-        if (terms_owned && terms) gcnk_free(terms);
-        if (d_seq) gcnk_free(d_seq);
-        if (h_seq) gcnk_free_host(h_seq);
-        for (int *t : term_index) if (t) gcnk_free(t);
-        for (int *h : halo_rows) if (h) gcnk_free(h);
-        if (ev_ready) gcnk_event_destroy(ev_ready);
-        if (ev_go) gcnk_event_destroy(ev_go);
-        for (uint32_t *b : {keep0_buf[1], keep1_buf[1]}) if (b) gcnk_free(b);
-        for (gcnk_graph *g : {rows[1], rows[2], rows[3], cols_train}) if (g) gcnk_graph_destroy(g);
-        for (int *k : keep) if (k) gcnk_free(k);   // keep[0] = global train-column flags
-        if (AX) gcnk_free(AX);
-        for (float *b : {Xp, AXp, bw_ws}) if (b) gcnk_free(b);
-        for (void *p : {(void *)xw_s, (void *)h1_s, (void *)P, (void *)G, (void *)Gm, (void *)dxw, (void *)keep0_buf[0], (void *)keep1_buf[0],
-                        (void *)mask, (void *)ws, (void *)d_result, (void *)d_sumsq})
-            if (p) gcnk_free(p);
-        if (h_result) gcnk_free_host(h_result);
-        if (h_sumsq) gcnk_free_host(h_sumsq);
-        if (h_red) gcnk_free_host(h_red);
-        if (slice_rng) gcnk_rng_destroy(slice_rng);
-    }
-};
 
 static GCNPlan plan_from_env() {
     const char *s = getenv("GCN_PLAN");
@@ -146,15 +31,6 @@ GCN::GCN(GCNParams params_, GCNData *input_data, GCNPlan plan, bool quiet) : par
 GCN::GCN(GCNParams params_, GCNData *input_data, GCNPlan plan, bool quiet, GCNDist dist_)
     : params(params_), data(input_data), dist(dist_), quiet_(quiet) {
     build(plan);
-}
-
-template <typename T>
-static T *upload(const std::vector<T> &h) {
-    T *d = nullptr;
-    GCNK_CHECK(gcnk_malloc((void **)&d, sizeof(T) * h.size()));
-    GCNK_CHECK(gcnk_memcpy_h2d(d, h.data(), sizeof(T) * h.size(), nullptr));
-    GCNK_CHECK(gcnk_stream_sync(nullptr));
-    return d;
 }
 
 void GCN::build(GCNPlan plan) {
@@ -189,19 +65,33 @@ void GCN::build(GCNPlan plan) {
     d_label = upload(data->label);
     GCNK_CHECK(gcnk_malloc((void **)&d_truth, sizeof(int) * (size_t)N));
 
-    const bool fusable = symmetric && C <= 128 && (size_t)H * C <= 4096;
+    // Two fused forms: hidden 16-style (layer 2 row-local in one kernel: needs hidden*classes <= 4096) and the WIDE form
+    // (gcn_wide.cpp: real GEMMs on the tensor cores, layer 1 re-ordered to (A_hat drop(X)) W1; needs dense features whose
+    // width is a multiple of 4 and not above the hidden width).  Both need A_hat = A_hat^T (the backward GraphSum of the
+    // reference multiplies by A_hat, not its transpose, module.cpp:103-119) and at most 128 classes.
+    const bool narrow_ok = symmetric && C <= 128 && (size_t)H * C <= 4096;
+    bool wide_ok = symmetric && C <= 128 && F % 4 == 0 && F <= 1024 && F <= H && nnzX == (size_t)N * F;
+    if (wide_ok) {                                         // dense layout: every row stores columns 0..F-1 in order
+        const std::vector<int> &fi = full_data->feature_index.indices, &fp = full_data->feature_index.indptr;
+        for (int i = 0; i <= N && wide_ok; i++) wide_ok = fp[i] == i * F;
+        for (size_t k = 0; k < fi.size() && wide_ok; k += 1 + (k % 97)) wide_ok = fi[k] == (int)(k % (size_t)F);   // sampled: rows are sorted, so a full row of F distinct keys below F is 0..F-1
+    }
+    const char *fw = getenv("GCN_WIDE");
+    const bool force_wide = fw && *fw && strcmp(fw, "0");
+    const bool fusable = narrow_ok || wide_ok;
     if (plan == PLAN_AUTO) plan = fusable ? PLAN_FUSED : PLAN_MODULES;
     if (plan == PLAN_FUSED && !fusable) {
-        // the layer-2 re-ordering needs A_hat = A_hat^T for the W2 gradient (csrc/layer2.cu)
-        fprintf(stderr, "GCN: fused plan needs a symmetric adjacency, output_dim <= 128 and hidden*output <= 4096\n");
+        fprintf(stderr, "GCN: the fused plans need a symmetric adjacency and output_dim <= 128, and either hidden*output <= 4096 or dense "
+                        "features (width a multiple of 4, at most the hidden width)\n");
         exit(EXIT_FAILURE);
     }
     if (dist.world > 1 && plan != PLAN_FUSED) {
-        fprintf(stderr, "GCN: the row-partitioned engine needs the fused plan (symmetric adjacency, output_dim <= 128, "
-                        "hidden*output <= 4096); run this configuration on one GPU\n");
+        fprintf(stderr, "GCN: the row-partitioned engine needs a fused plan (symmetric adjacency, output_dim <= 128, and hidden*output "
+                        "<= 4096 or dense features no wider than the hidden layer); run this configuration on one GPU\n");
         exit(EXIT_FAILURE);
     }
     plan_ = plan;
+    const bool wide = plan == PLAN_FUSED && wide_ok && (!narrow_ok || force_wide);
 
     modules.reserve(8);
     variables.reserve(8);
@@ -249,20 +139,24 @@ void GCN::build(GCNPlan plan) {
     optimizer = Adam({{&variables[2], true}, {&variables[5], false}}, adam_params);
 
     fz.reset(new Fused);
+    fz->wide = wide;
+    fz->Cp = (C + 3) / 4 * 4;
     GCNK_CHECK(gcnk_stream_create(&fz->stream));
     const size_t nnzX_loc = data->feature_index.indices.size();
-    // gather SOURCES are [N x H] (every rank needs all rows: all-gathered in place), gather OUTPUTS are local
-    const size_t nh_all = sizeof(float) * (size_t)N * H, nh_loc = sizeof(float) * (size_t)n_loc * H;
+    // gather SOURCES are [N x H] ([N x Cp] in the wide plan; every rank needs all rows: exchanged in place), gather OUTPUTS are local
+    const size_t buf = wide ? (size_t)N * fz->Cp : (size_t)N * H;
+    const int nbuf = wide ? 2 : 4;
+    fz->buf_floats = buf;
+    const size_t nh_all = sizeof(float) * buf, nh_loc = sizeof(float) * (size_t)n_loc * H;
     fz->world = dist.world; fz->rank = dist.rank; fz->comm = dist.comm;
     const char *cm = getenv("GCN_COMM"), *ex = getenv("GCN_EXCHANGE");
     fz->signal_exchange = !(ex && !strcmp(ex, "barrier"));
-    if (dist.world > 1 && dist.world <= 8 && H % 4 == 0 && !(cm && !strcmp(cm, "nccl"))) {
-        // one slab: [xw_s | h1_s | G | Gm | flags (128 ints: 0..7 barrier, 64 + 8 b + r buffer b from rank r) |
-        // all-reduce area: world slots]; export it, import every peer's
-        const size_t buf = (size_t)N * H;
+    if (dist.world > 1 && dist.world <= 8 && (wide || H % 4 == 0) && !(cm && !strcmp(cm, "nccl"))) {
+        // one slab: [xw_s | h1_s | G | Gm  (wide: T_s | D_s) | flags (128 ints: 0..7 barrier, 64 + 8 b + r buffer b from rank r) |
+        // all-reduce area: world slots | loss terms]; export it, import every peer's
         fz->slot_floats = ((size_t)F * H + (size_t)H * C + 4 + 3) / 4 * 4;
         const int max_terms = std::max(split_count[1], std::max(split_count[2], split_count[3]));
-        const size_t terms_off = 4 * buf + 128 + fz->slot_floats * dist.world;         // in floats, a multiple of 4
+        const size_t terms_off = nbuf * buf + 128 + fz->slot_floats * dist.world;         // in floats, a multiple of 4
         const size_t slab_bytes = sizeof(float) * (terms_off + (size_t)max_terms + 4);
         GCNK_CHECK(gcnk_malloc((void **)&fz->slab, slab_bytes));
         GCNK_CHECK(gcnk_memset(fz->slab, 0, slab_bytes, nullptr));
@@ -289,35 +183,42 @@ void GCN::build(GCNPlan plan) {
         GCNK_CHECK(gcnk_free(d_flag));
         fz->p2p = failed == 0.f;
         if (!fz->p2p && !quiet_) fprintf(stderr, "GCN: peer mapping unavailable (%s); using NCCL all-gather\n", gcnk_last_error());
-        fz->xw_s = fz->slab; fz->h1_s = fz->slab + buf; fz->G = fz->slab + 2 * buf; fz->Gm = fz->slab + 3 * buf;
+        if (wide) { fz->T_s = fz->slab; fz->D_s = fz->slab + buf; }
+        else { fz->xw_s = fz->slab; fz->h1_s = fz->slab + buf; fz->G = fz->slab + 2 * buf; fz->Gm = fz->slab + 3 * buf; }
         for (int r = 0; r < dist.world; r++) {
-            fz->flag_arrays[r] = fz->peer_slab[r] ? reinterpret_cast<int *>(static_cast<float *>(fz->peer_slab[r]) + 4 * buf) : nullptr;
-            fz->areas[r] = fz->peer_slab[r] ? static_cast<float *>(fz->peer_slab[r]) + 4 * buf + 128 : nullptr;
+            fz->flag_arrays[r] = fz->peer_slab[r] ? reinterpret_cast<int *>(static_cast<float *>(fz->peer_slab[r]) + nbuf * buf) : nullptr;
+            fz->areas[r] = fz->peer_slab[r] ? static_cast<float *>(fz->peer_slab[r]) + nbuf * buf + 128 : nullptr;
         }
         GCNK_CHECK(gcnk_malloc((void **)&fz->d_err, sizeof(int)));
         GCNK_CHECK(gcnk_memset(fz->d_err, 0, sizeof(int), nullptr));
         GCNK_CHECK(gcnk_malloc_host((void **)&fz->h_err, sizeof(int)));
         *fz->h_err = 0;
         if (fz->p2p) { build_halo(); fz->terms = fz->slab + terms_off; }
+    } else if (wide) {
+        GCNK_CHECK(gcnk_malloc((void **)&fz->T_s, 2 * nh_all));
+        fz->D_s = fz->T_s + buf;
+        fz->wide_sources_owned = true;
     } else {
         for (float **p : {&fz->xw_s, &fz->h1_s, &fz->G, &fz->Gm}) GCNK_CHECK(gcnk_malloc((void **)p, nh_all));
     }
-    for (float **p : {&fz->P, &fz->dxw}) GCNK_CHECK(gcnk_malloc((void **)p, nh_loc));
-    for (int b = 0; b < 2; b++) {
-        GCNK_CHECK(gcnk_malloc((void **)&fz->keep0_buf[b], sizeof(uint32_t) * (nnzX_loc / 32 + 4)));
-        GCNK_CHECK(gcnk_malloc((void **)&fz->keep1_buf[b], sizeof(uint32_t) * ((size_t)n_loc * H / 32 + 4)));
-    }
-    fz->keep0 = fz->keep0_buf[0]; fz->keep1 = fz->keep1_buf[0];   // freed through keep0/keep1 (buffer 0) and the [1] entries
-    {
+    if (!wide) {
+        for (float **p : {&fz->P, &fz->dxw}) GCNK_CHECK(gcnk_malloc((void **)p, nh_loc));
+        for (int b = 0; b < 2; b++) {
+            GCNK_CHECK(gcnk_malloc((void **)&fz->keep0_buf[b], sizeof(uint32_t) * (nnzX_loc / 32 + 4)));
+            GCNK_CHECK(gcnk_malloc((void **)&fz->keep1_buf[b], sizeof(uint32_t) * ((size_t)n_loc * H / 32 + 4)));
+        }
+        fz->keep0 = fz->keep0_buf[0]; fz->keep1 = fz->keep1_buf[0];   // freed through keep0/keep1 (buffer 0) and the [1] entries
         const char *ns = getenv("GCN_NO_RNG_OVERLAP");
         if (!(ns && *ns && strcmp(ns, "0"))) {
             GCNK_CHECK(gcnk_stream_create_low_priority(&fz->rng_stream));   // fills idle slots under the gathers, never ahead of them
             GCNK_CHECK(gcnk_event_create(&fz->ev_ready));
             GCNK_CHECK(gcnk_event_create(&fz->ev_go));
         }
+        GCNK_CHECK(gcnk_malloc((void **)&fz->mask, sizeof(uint32_t) * ((size_t)n_loc * gcnk_mask_row_stride_bits(H) / 32 + 4)));
+        fz->ws_bytes = gcnk_layer2_workspace(n_loc, H, C);
+    } else {
+        fz->ws_bytes = gcnk_ce_rows_workspace(n_loc);
     }
-    GCNK_CHECK(gcnk_malloc((void **)&fz->mask, sizeof(uint32_t) * ((size_t)n_loc * gcnk_mask_row_stride_bits(H) / 32 + 4)));
-    fz->ws_bytes = gcnk_layer2_workspace(n_loc, H, C);
     GCNK_CHECK(gcnk_malloc((void **)&fz->ws, fz->ws_bytes));
     GCNK_CHECK(gcnk_malloc((void **)&fz->d_result, sizeof(gcnk_ce_result)));
     GCNK_CHECK(gcnk_malloc((void **)&fz->d_sumsq, sizeof(float)));
@@ -360,6 +261,7 @@ void GCN::build(GCNPlan plan) {
     GCNK_CHECK(gcnk_memcpy_d2h(fz->h_sumsq, fz->d_sumsq, sizeof(float), nullptr));
     GCNK_CHECK(gcnk_stream_sync(nullptr));
     fz->sumsq = *fz->h_sumsq;
+    if (wide) { build_wide(); finish_build(); return; }
     gcnk_spmat *sp = data->feature_index.spmat(n_loc, F);     // build the handle (dense detection) up front
     gcnk_graph *g = graph_handle();
 
@@ -407,6 +309,10 @@ void GCN::build(GCNPlan plan) {
         GCNK_CHECK(gcnk_malloc((void **)&fz->bw_ws, fz->bw_ws_bytes));
         GCNK_CHECK(gcnk_stream_sync(nullptr));
     }
+    finish_build();
+}
+
+void GCN::finish_build() {
     // Setup ran on the legacy stream and the engine stream does not synchronise with it: finish everything first.  Then
     // meet the other ranks, so that nobody enters its first exchange while another rank is still building (uneven
     // build times would otherwise eat into the flag-wait timeout).
@@ -503,6 +409,10 @@ GCN::~GCN() {
 }
 
 void GCN::set_input_from_host(const float *h_values) {
+    if (fz && fz->wide && dist.world > 1) {
+        fprintf(stderr, "GCN: the row-partitioned wide plan keeps every node's features on every rank; re-upload is single-GPU only\n");
+        exit(EXIT_FAILURE);
+    }
     consume_pending_input();                                // a prefetched input is older than this one: retire it first
     GCNK_CHECK(gcnk_memcpy_h2d(d_feature_value, h_values, sizeof(float) * data->feature_index.indices.size(), engine_stream()));
     if (fz) { fz->ax_valid = false; fz->xp_dirty = fz->Xp != nullptr; }   // A_hat*X is stale (eval falls back to the gather path); re-pack X
@@ -601,7 +511,7 @@ void GCN::publish(float *d_all, int dim) {
     Fused &z = *fz;
     gpu_timer_begin(TMR_COMM);
     if (z.p2p) {
-        const int b = (int)((d_all - z.slab) / ((size_t)params.num_nodes * dim));
+        const int b = (int)((size_t)(d_all - z.slab) / z.buf_floats);
         float *own = d_all + (size_t)r0 * dim;
         const bool mirrored = !gcnk_mirror_pending(own);               // the producer's epilogue already stored the rows remotely
         float *peers[8];
@@ -636,12 +546,84 @@ void GCN::publish(float *d_all, int dim) {
 void GCN::await(float *d_all, int dim) {
     Fused &z = *fz;
     if (dist.world <= 1 || !z.p2p || !z.signal_exchange) return;
-    const int b = (int)((d_all - z.slab) / ((size_t)params.num_nodes * dim));
+    const int b = (int)((size_t)(d_all - z.slab) / z.buf_floats);
+    (void)dim;
     GCNK_CHECK(gcnk_gather_wait_next(z.flag_arrays[dist.rank] + 64 + 8 * b, dist.world, dist.rank, z.seq[b], z.d_err));
+}
+
+// The reference's own summation order for the printed loss (module.cpp:125-143), off the critical path: the per-row loss
+// terms of split `sidx` (written by the layer-2 / CE kernel just enqueued) are pushed to the peers and added up by
+// gcnk_sequential_sum.
+void GCN::enqueue_loss_sum(int sidx_l, bool training, int slot) {
+    Fused &z = *fz;
+    gcnk_stream_t st = z.stream;
+    {
+        // the reference's own summation order for the printed loss (module.cpp:125-143), off the critical path
+        const int *flags = nullptr;
+        if (dist.world > 1) {
+            float *peers[8];
+            int *slots[8], n = 0;
+            const size_t off = (size_t)(z.terms - z.slab) + (size_t)z.term_c0[sidx_l];
+            for (int r = 0; r < dist.world; r++) {
+                if (r == dist.rank) continue;
+                peers[n] = static_cast<float *>(z.peer_slab[r]) + off;
+                slots[n] = z.flag_arrays[r] + 64 + 8 * 4 + dist.rank;
+                n++;
+            }
+            ++z.seq[4];
+            GCNK_CHECK(gcnk_peer_push_signal(z.terms + z.term_c0[sidx_l], peers, n, (size_t)z.term_cnt[sidx_l], nullptr, nullptr, 1, slots,
+                                             z.seq[4], z.d_counter, st));
+            flags = z.flag_arrays[dist.rank] + 64 + 8 * 4;
+        }
+        // training: on the side stream, under the backward pass; eval: nothing follows that could hide it, and the stream
+        // hop would cost more than the ~10 us the sum takes for a validation split
+        gcnk_stream_t ss = training ? z.seq_stream : st;
+        if (training) {
+            GCNK_CHECK(gcnk_event_record(z.ev_l2, st));
+            GCNK_CHECK(gcnk_stream_wait_event(z.seq_stream, z.ev_l2));
+        }
+        GCNK_CHECK(gcnk_sequential_sum(z.terms, split_count[sidx_l], z.d_seq + slot, 0.f, flags, flags ? dist.world : 0, dist.rank, z.seq[4],
+                                       z.d_err, ss));
+        GCNK_CHECK(gcnk_memcpy_d2h(z.h_seq + slot, z.d_seq + slot, sizeof(float), ss));
+        if (training) GCNK_CHECK(gcnk_event_record(z.ev_seq, z.seq_stream));
+    }
+}
+
+// The end of every fused pass: cross-rank sums, the scalars to the host, the optimiser step.
+void GCN::finish_pass(bool training, bool seq, int slot) {
+    Fused &z = *fz;
+    gcnk_stream_t st = z.stream;
+    Variable &W1 = variables[2], &W2 = variables[5];
+    // the pass is complete only with its loss; and (row-partitioned) no peer may overwrite the loss terms in this rank's
+    // slab — which it can do as soon as it has passed the barrier below — before they have been added up
+    if (seq && training) GCNK_CHECK(gcnk_stream_wait_event(st, z.ev_seq));
+    if (dist.world > 1) {
+        // sums over nodes: dW1, dW2 and {sum of loss terms, count, wrong}; every rank then applies the same update.
+        // This is also the one true barrier of the pass: nobody starts the next pass (and overwrites a gather source
+        // in a peer's slab) before every rank has finished reading this pass's sources.
+        float *bufs[3] = {z.ws, W1.grad, W2.grad};
+        const size_t counts[3] = {4, (size_t)W1.size, (size_t)W2.size};
+        gpu_timer_begin(TMR_COMM);
+        if (z.p2p)
+            GCNK_CHECK(gcnk_peer_allreduce(bufs, counts, training ? 3 : 1, z.areas, z.slot_floats, z.flag_arrays, dist.rank, dist.world,
+                                           ++z.barrier_value, z.d_err, z.d_counter, st));
+        else
+            GCNK_CHECK(gcnk_comm_allreduce(dist.comm, bufs, counts, training ? 3 : 1, 0, st));
+        gpu_timer_end(TMR_COMM);
+    }
+    GCNK_CHECK(gcnk_memcpy_d2h(z.h_red + 4 * slot, z.ws, 4 * sizeof(float), st));
+    z.sumsq_used[slot] = -1.f;                                            // eval: the penalty of the weights as they are at collect time
+    if (training) {
+        z.sumsq_used[slot] = z.sumsq;                                     // gcn.cpp:98-105: W1 as it was in this forward
+        optimizer.step(z.d_sumsq, st);
+        GCNK_CHECK(gcnk_memcpy_d2h(z.h_sumsq, z.d_sumsq, sizeof(float), st));
+        z.sumsq_pending = true;
+    }
 }
 
 // Enqueues one pass on the stream; nothing is read back until fused_collect.  slot: which pinned result slot to use.
 void GCN::fused_enqueue(int current_split, bool training, int slot) {
+    if (fz->wide) { wide_enqueue(current_split, training, slot); return; }
     consume_pending_input();
     Fused &z = *fz;
     gcnk_stream_t st = z.stream;
@@ -756,36 +738,7 @@ void GCN::fused_enqueue(int current_split, bool training, int slot) {
                                        training ? W2.grad : nullptr, nullptr, z.d_result, z.ws, z.ws_bytes,
                                        seq ? z.terms : nullptr, seq ? z.term_index[sidx_l] : nullptr, st));
     gpu_timer_end(TMR_LOSS_FW);
-    if (seq) {
-        // the reference's own summation order for the printed loss (module.cpp:125-143), off the critical path
-        const int *flags = nullptr;
-        if (dist.world > 1) {
-            float *peers[8];
-            int *slots[8], n = 0;
-            const size_t off = (size_t)(z.terms - z.slab) + (size_t)z.term_c0[sidx_l];
-            for (int r = 0; r < dist.world; r++) {
-                if (r == dist.rank) continue;
-                peers[n] = static_cast<float *>(z.peer_slab[r]) + off;
-                slots[n] = z.flag_arrays[r] + 64 + 8 * 4 + dist.rank;
-                n++;
-            }
-            ++z.seq[4];
-            GCNK_CHECK(gcnk_peer_push_signal(z.terms + z.term_c0[sidx_l], peers, n, (size_t)z.term_cnt[sidx_l], nullptr, nullptr, 1, slots,
-                                             z.seq[4], z.d_counter, st));
-            flags = z.flag_arrays[dist.rank] + 64 + 8 * 4;
-        }
-        // training: on the side stream, under the backward pass; eval: nothing follows that could hide it, and the stream
-        // hop would cost more than the ~10 us the sum takes for a validation split
-        gcnk_stream_t ss = training ? z.seq_stream : st;
-        if (training) {
-            GCNK_CHECK(gcnk_event_record(z.ev_l2, st));
-            GCNK_CHECK(gcnk_stream_wait_event(z.seq_stream, z.ev_l2));
-        }
-        GCNK_CHECK(gcnk_sequential_sum(z.terms, split_count[sidx_l], z.d_seq + slot, 0.f, flags, flags ? dist.world : 0, dist.rank, z.seq[4],
-                                       z.d_err, ss));
-        GCNK_CHECK(gcnk_memcpy_d2h(z.h_seq + slot, z.d_seq + slot, sizeof(float), ss));
-        if (training) GCNK_CHECK(gcnk_event_record(z.ev_seq, z.seq_stream));
-    }
+    if (seq) enqueue_loss_sum(sidx_l, training, slot);
     z.seq_used[slot] = seq;
 
     if (training) {
@@ -806,31 +759,7 @@ void GCN::fused_enqueue(int current_split, bool training, int slot) {
         else GCNK_CHECK(gcnk_spmm_bw(sp, d_feature_value, z.dxw, W1.grad, H, drop ? z.keep0 : nullptr, scale, st));
         gpu_timer_end(TMR_SPMATMUL_BW);
     }
-    // the pass is complete only with its loss; and (row-partitioned) no peer may overwrite the loss terms in this rank's
-    // slab — which it can do as soon as it has passed the barrier below — before they have been added up
-    if (seq && training) GCNK_CHECK(gcnk_stream_wait_event(st, z.ev_seq));
-    if (dist.world > 1) {
-        // sums over nodes: dW1, dW2 and {sum of loss terms, count, wrong}; every rank then applies the same update.
-        // This is also the one true barrier of the pass: nobody starts the next pass (and overwrites a gather source
-        // in a peer's slab) before every rank has finished reading this pass's sources.
-        float *bufs[3] = {z.ws, W1.grad, W2.grad};
-        const size_t counts[3] = {4, (size_t)W1.size, (size_t)W2.size};
-        gpu_timer_begin(TMR_COMM);
-        if (z.p2p)
-            GCNK_CHECK(gcnk_peer_allreduce(bufs, counts, training ? 3 : 1, z.areas, z.slot_floats, z.flag_arrays, dist.rank, dist.world,
-                                           ++z.barrier_value, z.d_err, z.d_counter, st));
-        else
-            GCNK_CHECK(gcnk_comm_allreduce(dist.comm, bufs, counts, training ? 3 : 1, 0, st));
-        gpu_timer_end(TMR_COMM);
-    }
-    GCNK_CHECK(gcnk_memcpy_d2h(z.h_red + 4 * slot, z.ws, 4 * sizeof(float), st));
-    z.sumsq_used[slot] = -1.f;                                            // eval: the penalty of the weights as they are at collect time
-    if (training) {
-        z.sumsq_used[slot] = z.sumsq;                                     // gcn.cpp:98-105: W1 as it was in this forward
-        optimizer.step(z.d_sumsq, st);
-        GCNK_CHECK(gcnk_memcpy_d2h(z.h_sumsq, z.d_sumsq, sizeof(float), st));
-        z.sumsq_pending = true;
-    }
+    finish_pass(training, seq, slot);
 }
 
 // The host sync of the enqueued pass(es) and their scalars.
@@ -935,7 +864,7 @@ void GCN::run() {
 
 // ------------------------------------------------------------------------------ inspection ----
 long GCN::var_size(int idx) const {
-    if (dist.world > 1 && idx != 2 && idx != 5) return 0;      // a partitioned run exposes the (replicated) weights only
+    if ((dist.world > 1 || (fz && fz->wide)) && idx != 2 && idx != 5) return 0;   // partitioned / wide runs expose the weights only
     const long N = params.num_nodes, F = params.input_dim, H = params.hidden_dim, C = params.output_dim;
     switch (idx) {
     case 0: return (long)data->feature_index.indices.size();

@@ -90,6 +90,11 @@ private:
     void build_partition();
     gcnk_graph *graph_handle();
     void build_halo();
+    void build_wide();
+    void finish_build();
+    void wide_enqueue(int current_split, bool training, int slot);
+    void enqueue_loss_sum(int split_index, bool training, int slot);
+    void finish_pass(bool training, bool seq, int slot);
     gcnk_stream_t engine_stream() const;
     void mirror(float *d_all, int dim);
     void publish(float *d_all, int dim);

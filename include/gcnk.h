@@ -170,6 +170,21 @@ int gcnk_matmul_bw_b(const float *a, const float *c_grad, float *b_grad, int m, 
                      float *workspace, size_t workspace_bytes, gcnk_stream_t stream);                      /* b_grad = a^T * c_grad */
 size_t gcnk_matmul_bw_b_workspace(int m, int n, int p);
 
+/* The same three products for operands inside padded buffers (explicit row pitches lda/ldb/ldc, in floats):
+ *   nn: C[m x n] = A[m x k] * B[k x n], optional row_scale (C[i,:] *= row_scale[i]: the GraphSum pre-scale)   Matmul::forward
+ *   nt: C[m x n] = A[m x k] * B[n x k]^T                                                                      dA = dC * B^T
+ *   tn: C[ka x n] = A[m x ka]^T * B[m x n], contraction over the node dimension m (split across CTAs, partial tiles summed
+ *       in a fixed order); needs gcnk_matmul_tn_workspace(m, ka, n) bytes                                     dB = A^T * dC
+ * Large shapes with 16-byte-aligned pitches run on the tensor cores (tcgen05.mma kind::tf32 with 3xTF32 split products,
+ * accumulators in TMEM, operands staged by TMA: csrc/matmul_tc.cu); anything else on the fp32 SIMT kernel.  GCNK_NO_TCGEN05=1
+ * forces the latter. */
+int gcnk_matmul_nn(const float *a, int lda, const float *b, int ldb, float *c, int ldc, int m, int k, int n,
+                   const float *row_scale, gcnk_stream_t stream);
+int gcnk_matmul_nt(const float *a, int lda, const float *b, int ldb, float *c, int ldc, int m, int k, int n, gcnk_stream_t stream);
+size_t gcnk_matmul_tn_workspace(int m, int ka, int n);
+int gcnk_matmul_tn(const float *a, int lda, const float *b, int ldb, float *c, int ldc, int m, int ka, int n,
+                   float *workspace, size_t workspace_bytes, gcnk_stream_t stream);
+
 /* ---- ReLU: K10/K11, cuda_kernel.cu:204-219 (CPU: module.cpp:175-194) ------------------------------- */
 int gcnk_relu_fw(float *x, uint32_t *mask_bits, int64_t n, int training, gcnk_stream_t stream);  /* mask untouched when !training */
 int gcnk_relu_bw(float *grad, const uint32_t *mask_bits, int64_t n, gcnk_stream_t stream);

@@ -16,14 +16,15 @@ def n_gpus():
     return abi.device_count()
 
 
-@pytest.mark.parametrize("preset,scale,dropout", [("pubmed", 1.0, 0.5), ("cora", 1.0, 0.0), ("reddit", 0.02, 0.5)])
+@pytest.mark.parametrize("preset,scale,dropout,hidden", [("pubmed", 1.0, 0.5, 16), ("cora", 1.0, 0.0, 16), ("reddit", 0.02, 0.5, 16),
+                                                         ("products", 0.004, 0.5, 256)])    # hidden 256: the wide plan
 @pytest.mark.parametrize("world", [2, 4])
-def test_partitioned_equals_single(preset, scale, dropout, world):
+def test_partitioned_equals_single(preset, scale, dropout, hidden, world):
     if n_gpus() < world:
         pytest.skip(f"needs {world} GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
            "--master-port", str(29600 + world), str(ROOT / "tools" / "dist_check.py"), "--preset", preset, "--scale", str(scale),
-           "--epochs", "6", "--dropout", str(dropout)]
+           "--epochs", "6", "--dropout", str(dropout), "--hidden", str(hidden)]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert out.returncode == 0, out.stderr[-3000:]
     line = [l for l in out.stdout.splitlines() if l.startswith("{")][-1]

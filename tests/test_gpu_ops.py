@@ -521,6 +521,105 @@ def test_layer2_fused(abi, chk, D, n, h, c, training):
         close(Wg.numpy(), bg, rtol=5e-5, what="W2 grad")
 
 
+@pytest.mark.parametrize("m", [700, 5000])          # 700: fp32 SIMT kernel; 5000: tcgen05 (tensor cores, 3xTF32 split)
+@pytest.mark.parametrize("k,n", [(100, 256), (48, 256), (256, 48), (16, 41)])
+def test_matmul_pitched_nn_nt(abi, D, m, k, n):
+    """gcnk_matmul_nn / _nt (Matmul::forward and the dA half of Matmul::backward, module.cpp:11-30) for operands inside
+    padded buffers, with the optional row scale; fp64 numpy as the yardstick, same tolerance as the unpitched kernels."""
+    rng = np.random.default_rng(m + k + n)
+    lda, ldc = (k + 7) // 4 * 4, (n + 11) // 4 * 4
+    a = np.zeros((m, lda), np.float32); a[:, :k] = rng.standard_normal((m, k))
+    a[:, k:] = 77.0                                           # padding must never be read as data
+    b = rng.standard_normal((k, n)).astype(np.float32)
+    rs = (rng.random(m) + 0.5).astype(np.float32)
+    want = (a[:, :k].astype(np.float64) @ b.astype(np.float64))
+    c = abi.DeviceArray.zeros((m, ldc), np.float32)
+    abi.k.gcnk_matmul_nn(D(a), lda, D(b), n, c.ptr, ldc, m, k, n, D(rs), None)
+    got = c.numpy()
+    close(got[:, :n], want * rs[:, None], what="nn")
+    assert (got[:, n:] == 0).all()                            # columns beyond n are not written
+    bt = np.zeros((n, k + 4), np.float32); bt[:, :k] = b.T
+    c2 = abi.DeviceArray.zeros((m, ldc), np.float32)
+    abi.k.gcnk_matmul_nt(D(a), lda, D(bt), k + 4, c2.ptr, ldc, m, k, n, None)
+    close(c2.numpy()[:, :n], want, what="nt")
+
+
+@pytest.mark.parametrize("m", [900, 6000, 40000])    # 900: SIMT split-K; 6000 / 40000: tcgen05 with MN-major operands
+@pytest.mark.parametrize("ka,n", [(100, 256), (256, 48), (16, 41)])
+def test_matmul_pitched_tn(abi, D, m, ka, n):
+    """gcnk_matmul_tn: dB = A^T dC (module.cpp:31-42), contraction over the node dimension, partial tiles reduced in a
+    fixed order — two runs must agree bit for bit."""
+    rng = np.random.default_rng(m + ka + n)
+    lda, ldb, ldc = (ka + 7) // 4 * 4, (n + 7) // 4 * 4, n + 3
+    a = np.full((m, lda), 55.0, np.float32); a[:, :ka] = rng.standard_normal((m, ka))
+    b = np.full((m, ldb), -33.0, np.float32); b[:, :n] = rng.standard_normal((m, n))
+    want = a[:, :ka].astype(np.float64).T @ b[:, :n].astype(np.float64)
+    ws_bytes = abi.k.gcnk_matmul_tn_workspace(m, ka, n)
+    ws = abi.DeviceArray((max(ws_bytes, 16) // 4,), np.float32)
+    outs = []
+    for _ in range(2):
+        c = abi.DeviceArray.zeros((ka, ldc), np.float32)
+        abi.k.gcnk_matmul_tn(D(a), lda, D(b), ldb, c.ptr, ldc, m, ka, n, ws.ptr, ws_bytes, None)
+        outs.append(c.numpy())
+    close(outs[0][:, :n], want, what="tn")
+    assert (outs[0][:, n:] == 0).all()
+    assert (outs[0].view(np.uint32) == outs[1].view(np.uint32)).all()
+    assert abi.k.gcnk_async_error(None) == 0
+
+
+def test_wide_rowlocal_kernels(abi, chk, D):
+    """csrc/wide.cu against the checker's Dropout / ReLU / CrossEntropyLoss on the same bits and rows."""
+    rng = np.random.default_rng(9)
+    n, f, h, c, ld = 777, 100, 64, 47, 48
+    x = rng.standard_normal((n, f)).astype(np.float32)
+    dinv = (rng.random(n) + 0.1).astype(np.float32)
+    keep = rng.random(n * f) < 0.5
+    out = abi.DeviceArray((n, f), np.float32)
+    abi.k.gcnk_drop_scale_rows(D(x), n, f, D(pack_bits(keep)), 2.0, D(dinv), out.ptr, None)
+    want = np.where(keep.reshape(n, f), x * np.float32(2.0) * dinv[:, None], 0)
+    close(out.numpy(), want, rtol=1e-6, what="drop_scale_rows")
+    abi.k.gcnk_drop_scale_rows(D(x), n, f, None, 2.0, D(dinv), out.ptr, None)
+    close(out.numpy(), x * dinv[:, None], rtol=1e-6, what="scale_rows only")
+    # ReLU + dropout forward and backward: same mask bits as applying the reference's two modules in turn
+    z = rng.standard_normal(n * h + 5).astype(np.float32)            # not a multiple of 32
+    keep1 = rng.random(len(z)) < 0.5
+    zd = abi.dev(z)
+    mask = abi.DeviceArray.zeros(((len(z) + 31) // 32,), np.uint32)
+    abi.k.gcnk_relu_dropout_fw(zd.ptr, len(z), D(pack_bits(keep1)), 2.0, mask.ptr, None)
+    r, rmask, _ = chk.relu(z)
+    want_mask = (rmask.astype(bool)) & keep1
+    assert (unpack_bits(mask.numpy(), len(z)) == want_mask).all()
+    assert (zd.numpy() == np.where(want_mask, z * np.float32(2.0), 0).astype(np.float32)).all()
+    g = rng.standard_normal(len(z)).astype(np.float32)
+    gd = abi.dev(g)
+    abi.k.gcnk_mask_scale_bw(gd.ptr, len(z), mask.ptr, 2.0, None)
+    assert (gd.numpy() == np.where(want_mask, g * np.float32(2.0), 0).astype(np.float32)).all()
+    # softmax-CE on pitch-48 rows of 47 classes, one split's labelled rows only
+    logits = np.zeros((n, ld), np.float32); logits[:, :c] = rng.standard_normal((n, c)) * 3
+    logits[:, c:] = 1e9                                               # the padding column must not take part
+    split = rng.integers(0, 4, n).astype(np.int32)
+    label = rng.integers(0, c, n).astype(np.int32); label[::13] = -1
+    truth = chk.set_truth(split, label, 1)
+    ref_loss, _, ref_grad = chk.cross_entropy(logits[:, :c].copy(), truth, c, training=True)
+    count = int((truth >= 0).sum())
+    grad = abi.DeviceArray.zeros((n, ld), np.float32)
+    res = abi.DeviceArray.zeros((4,), np.int32)
+    ws_bytes = abi.k.gcnk_ce_rows_workspace(n)
+    ws = abi.DeviceArray.zeros((ws_bytes // 4 + 4,), np.float32)
+    terms = abi.DeviceArray.zeros((n,), np.float32)
+    abi.k.gcnk_ce_rows(D(logits), ld, D(split), D(label), 1, n, c, 1, count, D(dinv), grad.ptr, res.ptr, ws.ptr, ws_bytes, terms.ptr, None, None)
+    r4 = res.numpy()
+    assert r4[1] == count
+    assert abs(r4[0:1].view(np.float32)[0] - ref_loss) <= 2e-5 * abs(ref_loss)
+    gg = grad.numpy()
+    close(gg[:, :c], ref_grad.reshape(n, c) * dinv[:, None], what="ce grad")
+    assert (gg[:, c:] == 0).all() and (gg[truth < 0] == 0).all()
+    t = terms.numpy()
+    assert (t[truth < 0] == 0).all() and abs(t.sum() / count - ref_loss) <= 2e-5 * abs(ref_loss)
+    _, wrong, total = chk.accuracy(logits[:, :c].copy(), truth, c)
+    assert r4[2] == wrong and total == count
+
+
 def _seq_sum_cases():
     rng = np.random.default_rng(5)
     ln41 = np.float32(np.log(41.0))

@@ -36,12 +36,13 @@ def main():
     ap.add_argument("--epochs", type=int, default=5)
     ap.add_argument("--dropout", type=float, default=0.5)
     ap.add_argument("--seed", type=int, default=3)
+    ap.add_argument("--hidden", type=int, default=16)
     a = ap.parse_args()
     rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", "0"), ("WORLD_SIZE", "1"), ("LOCAL_RANK", "0")))
     abi.require_device(local)
     data = host_api.Data.synth(a.preset, a.scale)
     uid = host_api.rendezvous(rank, world, os.environ.get("MASTER_ADDR", "127.0.0.1"), int(os.environ.get("MASTER_PORT", "29500")))
-    eng = host_api.Engine(data, dropout=a.dropout, seed=a.seed, plan=host_api.PLAN_FUSED, device=local, rank=rank, world=world, nccl_id=uid)
+    eng = host_api.Engine(data, hidden_dim=a.hidden, dropout=a.dropout, seed=a.seed, plan=host_api.PLAN_FUSED, device=local, rank=rank, world=world, nccl_id=uid)
     dist_series, dist_test = series(eng, a.epochs)
     w1, w2 = eng.var(2), eng.var(5)
     # every rank must hold bit-identical replicated weights
@@ -49,7 +50,7 @@ def main():
     replicated = bool(chk[0] == -chk[1])
     eng.close()
     if rank == 0:
-        single = host_api.Engine(data, dropout=a.dropout, seed=a.seed, plan=host_api.PLAN_FUSED, device=local)
+        single = host_api.Engine(data, hidden_dim=a.hidden, dropout=a.dropout, seed=a.seed, plan=host_api.PLAN_FUSED, device=local)
         one_series, one_test = series(single, a.epochs)
         v1, v2 = single.var(2), single.var(5)
         single.close()
