@@ -43,6 +43,13 @@ sys.path.insert(0, str(ROOT))
 METRIC = "full-batch GCN train epochs/s (Reddit-shape)"
 WORKLOAD = "reddit-shape 2-layer GCN (train_epoch + eval per step), hidden 16, dropout 0.5"
 UNIT = "epochs/s"
+# --workload products: BASELINE configs[4] (ogbn-products shape, hidden 256: the wide plan with the tcgen05 GEMMs); the
+# default (and the headline metric) is the Reddit shape
+WORKLOADS = {
+    "reddit": {"preset": "reddit", "hidden": 16, "metric": METRIC, "workload": WORKLOAD, "features": 602, "classes": 41},
+    "products": {"preset": "products", "hidden": 256, "metric": "full-batch GCN train epochs/s (ogbn-products-shape)",
+                 "workload": "ogbn-products-shape 2-layer GCN (train_epoch + eval per step), hidden 256, dropout 0.5", "features": 100, "classes": 47},
+}
 
 
 def measured_peak():
@@ -109,15 +116,16 @@ def graph_data(d):
                      a["label"], a["split"], input_dim=d.params.input_dim, output_dim=d.params.output_dim)
 
 
-def cpu_reference_run(scale, steps, budget_s, host_api):
+def cpu_reference_run(scale, steps, budget_s, host_api, wl=None):
     """The reference CPU engine (1 thread: it has no threading) on the reddit-shape workload at `scale` (1.0 = the
     BASELINE configuration).  Runs up to `steps` epochs of train_epoch + eval(2) but stops as soon as another epoch would
     overrun `budget_s` (at least one epoch is timed).  Returns measured numbers only — nothing is extrapolated."""
     from oracle.checker import best_checker
     chk = best_checker()
-    d = host_api.Data.synth("reddit", scale)
+    wl = wl or WORKLOADS["reddit"]
+    d = host_api.Data.synth(wl["preset"], scale)
     s = d.sizes()
-    ref = chk.gcn(graph_data(d), dropout=0.5, epochs=max(steps, 1), seed=1)
+    ref = chk.gcn(graph_data(d), hidden_dim=wl["hidden"], dropout=0.5, epochs=max(steps, 1), seed=1)
     times, last = [], None
     t_all = time.perf_counter()
     for _ in range(max(steps, 1)):
@@ -130,15 +138,16 @@ def cpu_reference_run(scale, steps, budget_s, host_api):
             break
     ref.close()
     dt = sum(times) / len(times)
-    sample = (f"{len(times)} epoch(s) of train_epoch+eval(2) by the {chk.name} CPU engine (gcn-seq code, 1 thread) on reddit-shape at scale "
-              f"{scale:g} ({s['num_nodes']} nodes, {s['graph_nnz']} graph nnz, dense 602 features, hidden 16, dropout 0.5): "
+    sample = (f"{len(times)} epoch(s) of train_epoch+eval(2) by the {chk.name} CPU engine (gcn-seq code, 1 thread) on {wl['preset']}-shape at scale "
+              f"{scale:g} ({s['num_nodes']} nodes, {s['graph_nnz']} graph nnz, dense {wl['features']} features, hidden {wl['hidden']}, dropout 0.5): "
               f"{dt:.2f} s/epoch measured")
     return {"value": 1.0 / dt, "s_per_step": dt, "steps": len(times), "kind": chk.name, "sample": sample, "sizes": s, "last": last}
 
 
-def workload_config(scale, sizes, extra):
-    cfg = {"workload": WORKLOAD, "scale": scale, "nodes": sizes["num_nodes"], "graph_nnz": sizes["graph_nnz"],
-           "feature_nnz": sizes["feature_nnz"], "features": 602, "classes": 41}
+def workload_config(scale, sizes, extra, wl=None):
+    wl = wl or WORKLOADS["reddit"]
+    cfg = {"workload": wl["workload"], "scale": scale, "nodes": sizes["num_nodes"], "graph_nnz": sizes["graph_nnz"],
+           "feature_nnz": sizes["feature_nnz"], "features": wl["features"], "classes": wl["classes"], "hidden": wl["hidden"]}
     cfg.update(extra)
     return cfg
 
@@ -148,15 +157,16 @@ def run_reference(args):
     if rank != 0:
         return
     from cuda_gcn_b200 import host_api
-    r = cpu_reference_run(args.scale, args.steps, args.ref_budget_s, host_api)
+    wl = WORKLOADS[args.workload]
+    r = cpu_reference_run(args.scale, args.steps, args.ref_budget_s, host_api, wl)
     kind = "reference" if r["kind"] == "reference" else "port"
-    line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": r["steps"],
+    line = {"impl": "reference", "metric": wl["metric"], "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": r["steps"],
             "warmup": 0, "requested_steps": args.steps, "requested_warmup": args.warmup, "ms_per_step": r["s_per_step"] * 1e3,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args.scale, r["sizes"], {
                 "engine": "reference CPU engine (oracle/_ref/libgcnref.so = unmodified /root/reference/src/seq), 1 thread",
                 "steps_note": f"a step is ~70 s on one core: as many of the requested steps as fit {args.ref_budget_s:g} s are timed, no warm-up",
-                "data_generator": "cuda_gcn_b200/host/synth.cpp through libgcnhost.so (data only; all arithmetic is the reference library's)"}),
+                "data_generator": "cuda_gcn_b200/host/synth.cpp through libgcnhost.so (data only; all arithmetic is the reference library's)"}, wl),
             "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": 1, "kind": kind, "sample": r["sample"]},
             "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0,
             "final": {"val_loss": r["last"][2], "val_acc": r["last"][3]}}
@@ -193,11 +203,13 @@ def run_ours(args):
     abi.require_device(local)
     K = abi.k
     t_gen = time.perf_counter()
-    data = host_api.Data.synth("reddit", args.scale)       # every rank generates the same dataset (deterministic)
+    wl = WORKLOADS[args.workload]
+    wide = wl["hidden"] != 16
+    data = host_api.Data.synth(wl["preset"], args.scale)   # every rank generates the same dataset (deterministic)
     sizes = data.sizes()
     t_gen = time.perf_counter() - t_gen
     N, nnzA, nnzX = sizes["num_nodes"], sizes["graph_nnz"], sizes["feature_nnz"]
-    H, C, F = 16, data.params.output_dim, data.params.input_dim
+    H, C, F = wl["hidden"], data.params.output_dim, data.params.input_dim
     uid = host_api.rendezvous(rank, world, os.environ.get("MASTER_ADDR", "127.0.0.1"), int(os.environ.get("MASTER_PORT", "29500")))
     eng = host_api.Engine(data, hidden_dim=H, dropout=0.5, seed=1, plan=host_api.PLAN_FUSED, device=local, rank=rank, world=world,
                           nccl_id=uid)
@@ -235,7 +247,7 @@ def run_ours(args):
     if timers_in_region:
         L.gcnh_timer_enable_gpu(1)
     else:
-        L.gcnh_timer_enable_mask(1 << L.gcnh_timer_slot(b"gather_full"))
+        L.gcnh_timer_enable_mask(1 << L.gcnh_timer_slot(b"graphsum_fw" if wide else b"gather_full"))
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
@@ -270,8 +282,11 @@ def run_ours(args):
     peak, peak_src = measured_peak()
     # full-graph gather launches only (each bracketed by its own event pair); the row/column-subset launches are
     # reported in `breakdown` as gather_part
-    g_total, g_launches = live.get("gather_full", (0.0, 0))
-    b_min = 4 * nnzA_loc + 4 * (n_loc + 1) + 4 * H * (N + n_loc)        # indices + indptr + source read once + rows written once
+    g_total, g_launches = live.get("graphsum_fw" if wide else "gather_full", (0.0, 0))
+    gw = F if wide else H                                                # width of the dominant gather: the input width in the wide plan
+    b_min = 4 * nnzA_loc + 4 * (n_loc + 1) + 4 * gw * (N + n_loc)       # indices + indptr + source read once + rows written once
+    if wide:
+        b_min += 4 * F * 2 * N + N * F // 8                              # + the dropout/pre-scale pass in the same timer: X read, source written, keep bits
     t_launch = g_total / max(g_launches, 1)
     achieved = b_min / t_launch / 1e9 if t_launch > 0 else 0.0
     # DRAM traffic of the same kernel from the committed `ncu --set full` capture — only if that capture was taken from
@@ -288,11 +303,12 @@ def run_ours(args):
                 traffic_note = "profiles/graphsum_traffic.json was captured from a different csrc/graph.cu; not reported"
         except Exception:
             traffic = None
-    roofline = {"bound": "hbm", "kernel": "gather_kernel (GraphSum, dim 16, all rows of this rank)", "achieved": achieved, "peak": peak,
+    roofline = {"bound": "hbm", "kernel": ("drop_scale_rows + gather_kernel (GraphSum at the input width 100: A_hat*drop(X), all rows of this rank)" if wide
+                                           else "gather_kernel (GraphSum, dim 16, all rows of this rank)"), "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_note, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": b_min, "avg_launch_us": t_launch * 1e6, "launches_timed": g_launches,
                 "share_of_step": g_total / (ms * 1e-3) if ms > 0 else None,
-                "l2_to_sm_gather_bytes_per_launch": 64 * nnzA_loc + 4 * nnzA_loc}
+                "l2_to_sm_gather_bytes_per_launch": 4 * gw * nnzA_loc + 4 * nnzA_loc}
     # what actually bounds this kernel: every gathered 64-byte row is one wavefront of the SM's L1TEX
     # LSU data pipe, one per clock per SM — reported beside the HBM figure, not instead of it
     try:
@@ -309,26 +325,31 @@ def run_ours(args):
 
     # ---- e2e: the same step through the C face with the (local rows of the) feature matrix uploaded from pinned
     # host memory each step
-    pinned = L.gcnh_alloc_pinned(max(nnzX_loc, 1))
-    host_view = np.ctypeslib.as_array((abi.C.c_float * max(nnzX_loc, 1)).from_address(pinned))
-    host_view[:nnzX_loc] = x_local
-    e2e_steps = max(3, min(args.steps, 10))
-    eng.set_input_host(pinned); step(False)                 # warm the copy path
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        if args.e2e_prefetch:
-            eng.epoch_prefetch(2, pinned)                   # the step on the current input; H2D of the next step's input under it
-        else:
-            eng.set_input_host(pinned)                      # H2D of this rank's nnz(X) floats on the engine's stream
-            step(False)                                     # train_epoch + eval(2); each reads its scalars back (D2H)
-    barrier()
-    e2e_dt = (time.perf_counter() - t0) / e2e_steps
-    e2e_dt = float(eng.allreduce_host([e2e_dt], op_max=True)[0])
-    L.gcnh_free_pinned(pinned)
-    e2e = {"value": 1.0 / e2e_dt, "unit": UNIT, "h2d_bytes_per_step": int(nnzX * 4), "d2h_bytes_per_step": world * (2 * 16 + 4),
-           "steps": e2e_steps, "api": "gcnh_engine_epoch_prefetch (upload of step k+1 under step k; include/gcn_host.h)" if args.e2e_prefetch else
-           "gcnh_engine_set_input_host + gcnh_engine_train_epoch + gcnh_engine_eval (include/gcn_host.h)"}
+    e2e = None
+    if wide and world > 1:
+        # the row-partitioned wide plan keeps every node's features on every rank: no per-step re-upload path
+        e2e = {"value": None, "unit": UNIT, "note": "not measured: the partitioned wide plan has no feature re-upload entry point"}
+    else:
+        pinned = L.gcnh_alloc_pinned(max(nnzX_loc, 1))
+        host_view = np.ctypeslib.as_array((abi.C.c_float * max(nnzX_loc, 1)).from_address(pinned))
+        host_view[:nnzX_loc] = x_local
+        e2e_steps = max(3, min(args.steps, 10))
+        eng.set_input_host(pinned); step(False)                 # warm the copy path
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            if args.e2e_prefetch:
+                eng.epoch_prefetch(2, pinned)                   # the step on the current input; H2D of the next step's input under it
+            else:
+                eng.set_input_host(pinned)                      # H2D of this rank's nnz(X) floats on the engine's stream
+                step(False)                                     # train_epoch + eval(2); each reads its scalars back (D2H)
+        barrier()
+        e2e_dt = (time.perf_counter() - t0) / e2e_steps
+        e2e_dt = float(eng.allreduce_host([e2e_dt], op_max=True)[0])
+        L.gcnh_free_pinned(pinned)
+        e2e = {"value": 1.0 / e2e_dt, "unit": UNIT, "h2d_bytes_per_step": int(nnzX * 4), "d2h_bytes_per_step": world * (2 * 16 + 4),
+               "steps": e2e_steps, "api": "gcnh_engine_epoch_prefetch (upload of step k+1 under step k; include/gcn_host.h)" if args.e2e_prefetch else
+               "gcnh_engine_set_input_host + gcnh_engine_train_epoch + gcnh_engine_eval (include/gcn_host.h)"}
     eng.close()
     if rank != 0:
         return
@@ -337,41 +358,42 @@ def run_ours(args):
     # on the same workload and seed, and (N > 1) against the committed single-GPU trajectory
     parity = None
     if args.scale == 1.0:
-        parity = trajectory_parity(history[:n_resident], ROOT / "tests" / "golden" / "reddit_full_trajectory.json")
+        parity = trajectory_parity(history[:n_resident], ROOT / "tests" / "golden" / f"{wl['preset']}_full_trajectory.json")
         if world > 1:
-            one = trajectory_parity(history[:n_resident], ROOT / "tests" / "golden" / "reddit_full_trajectory_gpu1.json", loss_rtol=2e-6)
+            one = trajectory_parity(history[:n_resident], ROOT / "tests" / "golden" / f"{wl['preset']}_full_trajectory_gpu1.json", loss_rtol=2e-6)
             parity["parity_vs_single_gpu_rel"] = one.get("max_rel_loss_diff")
             parity["vs_single_gpu"] = one
     if args.save_trajectory:
         Path(args.save_trajectory).write_text(json.dumps({
             "generator": "bench.py --save-trajectory (this engine, fused plan, 1 GPU)" if world == 1 else f"bench.py, {world} GPUs",
-            "engine": f"cuda_gcn_b200 fused plan, {world} GPU(s)", "preset": "reddit", "scale": args.scale, "seed": 1, "hidden": H,
+            "engine": f"cuda_gcn_b200 fused plan, {world} GPU(s)", "preset": wl["preset"], "scale": args.scale, "seed": 1, "hidden": H,
             "dropout": 0.5, "nodes": N, "graph_nnz": nnzA, "columns": ["train_loss", "train_acc", "val_loss", "val_acc"],
             "epochs": [list(r) for r in history[:n_resident]]}, indent=1))
 
     # ---- GraphSum per call at each width the reference's models use (SURVEY 8d metric 2): forward == backward launch
     dims = None
-    if world == 1 and not args.no_dims:
+    if world == 1 and not args.no_dims and not wide:
         dims = graphsum_dims(abi, data, peak)
 
     # ---- CPU baseline: the reference engine on the same workload (rank 0, N=1): ONE full-size epoch (~70 s, 1 core)
     cpu = None
     if not args.no_cpu_baseline and world == 1:
-        r = cpu_reference_run(args.cpu_scale, 1, 0, host_api)
+        r = cpu_reference_run(args.cpu_scale, 1, 0, host_api, wl)
         cpu = {"value": r["value"], "unit": UNIT, "cores": 1, "kind": "reference" if r["kind"] == "reference" else "port",
                "sample": r["sample"], "sample_scale": args.cpu_scale}
 
-    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+    line = {"metric": wl["metric"], "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": workload_config(args.scale, sizes, {
-                "engine": "fused plan", "max_degree": sizes["max_degree"],
-                "l2": "inputs larger than L2 each step (X 561 MB + CSR indices 459 MB streamed per pass); no flush",
+                "engine": "fused plan (wide: host/gcn_wide.cpp)" if wide else "fused plan", "max_degree": sizes["max_degree"],
+                "l2": ("inputs larger than L2 each step (X 980 MB + CSR indices 500 MB streamed per pass); no flush" if wide else
+                       "inputs larger than L2 each step (X 561 MB + CSR indices 459 MB streamed per pass); no flush"),
                 "parallelism": "1 GPU" if world == 1 else
                 f"{world}-way row partition (nnz-balanced); gather sources exchanged by a hand-written push over NVLink peer memory "
                 "(CUDA IPC) with per-rank arrival flags checked inside the consuming GraphSum kernel; dW summed by a peer-memory "
                 "all-reduce in rank order; NCCL only for setup (handle exchange) and as fallback (GCN_COMM=nccl)",
-                "generate_s": round(t_gen, 1)}),
+                "generate_s": round(t_gen, 1)}, wl),
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "graphsum_dims": dims, "cpu_baseline": cpu,
             "parity": parity, "breakdown": breakdown, "final": {"val_loss": last[0], "val_acc": last[1]}}
     print(json.dumps(line))
@@ -421,6 +443,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="reddit", choices=sorted(WORKLOADS), help="reddit = the headline metric; products = BASELINE configs[4]")
     ap.add_argument("--scale", type=float, default=1.0, help="fraction of the Reddit-shape node/edge counts (1.0 = the BASELINE config)")
     ap.add_argument("--cpu-scale", type=float, default=1.0, help="workload scale of the cpu_baseline leg (1.0 = the real workload: ~70 s)")
     ap.add_argument("--ref-budget-s", type=float, default=150.0, help="--impl reference: wall budget for the timed full-size epochs")

@@ -142,7 +142,8 @@ SIGNATURES = {
 
 # functions whose return value is not an error code
 _NOT_RC = {"gcnk_dense_transform_bw_workspace", "gcnk_mirror_pending", "gcnk_version", "gcnk_last_error", "gcnk_launch_count", "gcnk_matmul_bw_b_workspace",
-           "gcnk_softmax_ce_workspace", "gcnk_layer2_workspace", "gcnk_mask_row_stride_bits", "gcnk_gather_variant"}
+           "gcnk_softmax_ce_workspace", "gcnk_layer2_workspace", "gcnk_mask_row_stride_bits", "gcnk_gather_variant", "gcnk_matmul_tn_workspace",
+           "gcnk_ce_rows_workspace", "gcnk_async_error"}
 
 _lib = None
 

@@ -24,7 +24,8 @@
 //            run side by side, so A is re-read from L2, not from HBM); optional row scale in the epilogue.
 //   tn       C[ka x n] = A[m x ka]^T * B[m x n]: the node dimension m is the contraction.  Both operands are MN-major
 //            for the tensor core (instruction-descriptor bits 15/16; shared-memory descriptors with LBO = the distance of
-//            two 32-float column groups, exactly what a [32 rows x 32 floats] TMA box with the 128-byte swizzle lays down),
+//            two 32-float column groups, exactly what a [32 rows x 32 floats] TMA box with the 128-byte / 32-byte-atom
+//            swizzle lays down — the one layout tcgen05 accepts for MN-major 32-bit operands),
 //            so the row-major tiles are fed as they are — no transposed copies.  Split over m across CTAs, partial tiles
 //            reduced in a fixed order (deterministic).
 // Every mbarrier wait has a clock-based bail-out that raises an error flag instead of hanging the GPU.
@@ -228,9 +229,9 @@ teardown:
 
 // ================================================================================== tn kernel ====
 // C[ka x n] = A[m x ka]^T * B[m x n], contraction over the rows m.  CTA = (128-feature tile of A, n tile of B, part of m).
-// Stage = 32 rows: A as four [32 x 32-float] TMA boxes (one per 32-feature group, 4 KB each, 128-byte swizzle) and B as
-// up to four such boxes; in this layout both operands are MN-major for tcgen05 (the contiguous direction is M resp. N):
-// 8 rows = one 1 KB swizzle atom = the K = 8 of one tf32 MMA, column groups LBO = 4096 bytes apart.
+// Stage = 32 rows: A as four [32 x 32-float] TMA boxes (one per 32-feature group, 4 KB each, 128-byte swizzle with 32-byte
+// atoms) and B as up to four such boxes; in this layout both operands are MN-major for tcgen05 (the contiguous direction
+// is M resp. N): 8 rows = two 512-byte swizzle atoms = the K = 8 of one tf32 MMA, column groups LBO = 4096 bytes apart.
 constexpr int TN_ROWS = 32, TN_STAGES = 3, TN_BOX_BYTES = TN_ROWS * 128, TN_OPERAND_BYTES = 4 * TN_BOX_BYTES;   // 16 KB
 constexpr int TN_STAGE_BYTES = 4 * TN_OPERAND_BYTES;                     // A big, A small, B big, B small
 
@@ -239,11 +240,14 @@ struct TnBars {
     uint32_t tmem_base;
 };
 
-// MN-major operand, 128-byte swizzle: leading-dimension byte offset (between 32-float column groups) 4096, stride byte
-// offset (between 8-row groups along K) 1024, descriptor version 1
+// MN-major tf32 operand.  The only shared-memory layout the tensor core takes for 32-bit MN-major operands is the
+// 128-byte swizzle with a 32-byte base (layout type 1: 32-byte chunks of a 128-byte row XORed with the row index mod 4,
+// atoms of 4 rows = 512 bytes) — what a TMA box written with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B looks like.
+// Leading-dimension byte offset (between 32-float column groups) = one box = 4096; stride byte offset (between 4-row
+// groups along K) = 512; descriptor version 1.
 __device__ __forceinline__ uint64_t make_desc_mn(uint32_t smem_addr) {
-    return (uint64_t)((smem_addr & 0x3ffff) >> 4) | ((uint64_t)(TN_BOX_BYTES >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
-           ((uint64_t)2 << 61);
+    return (uint64_t)((smem_addr & 0x3ffff) >> 4) | ((uint64_t)(TN_BOX_BYTES >> 4) << 16) | ((uint64_t)(512 >> 4) << 32) | ((uint64_t)1 << 46) |
+           ((uint64_t)1 << 61);
 }
 
 __global__ void __launch_bounds__(TC_THREADS, 1) matmul_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
@@ -390,15 +394,19 @@ static EncodeTiled encode_fn() {
 }
 bool tensor_maps_available() { return encode_fn() != nullptr; }
 
-bool make_tensor_map_2d(CUtensorMap *map, const float *base, uint64_t rows, uint64_t cols, uint64_t pitch_floats, uint32_t box_rows,
-                        uint32_t box_cols, bool swizzle128) {
+static bool make_tensor_map_2d_mode(CUtensorMap *map, const float *base, uint64_t rows, uint64_t cols, uint64_t pitch_floats, uint32_t box_rows,
+                                    uint32_t box_cols, CUtensorMapSwizzle swizzle) {
     EncodeTiled fn = encode_fn();
     if (!fn) return false;
     const cuuint64_t dims[2] = {cols, rows}, strides[1] = {pitch_floats * sizeof(float)};
     const cuuint32_t box[2] = {box_cols, box_rows}, estr[2] = {1, 1};
     return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-              swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+              swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+bool make_tensor_map_2d(CUtensorMap *map, const float *base, uint64_t rows, uint64_t cols, uint64_t pitch_floats, uint32_t box_rows,
+                        uint32_t box_cols, bool swizzle128) {
+    return make_tensor_map_2d_mode(map, base, rows, cols, pitch_floats, box_rows, box_cols,
+                                   swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE);
 }
 
 // ------------------------------------------------------------------------------------ nn / nt ----
@@ -481,8 +489,8 @@ int matmul_tc_tn(const float *a, int lda, const float *b, int ldb, float *c, int
     const int parts = tn_parts(m, tiles);
     if (!ws || ws_bytes < matmul_tc_tn_workspace(m, ka, n)) { set_error("matmul_tc_tn: workspace too small"); return GCNK_EINVAL; }
     CUtensorMap map_a, map_b;
-    if (!make_tensor_map_2d(&map_a, a, (uint64_t)m, (uint64_t)ka, (uint64_t)lda, TN_ROWS, 32, true) ||
-        !make_tensor_map_2d(&map_b, b, (uint64_t)m, (uint64_t)n, (uint64_t)ldb, TN_ROWS, 32, true)) {
+    if (!make_tensor_map_2d_mode(&map_a, a, (uint64_t)m, (uint64_t)ka, (uint64_t)lda, TN_ROWS, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B) ||
+        !make_tensor_map_2d_mode(&map_b, b, (uint64_t)m, (uint64_t)n, (uint64_t)ldb, TN_ROWS, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) {
         set_error("matmul_tc_tn: cuTensorMapEncodeTiled failed");
         return GCNK_EUNSUPPORTED;
     }

@@ -864,7 +864,8 @@ void GCN::run() {
 
 // ------------------------------------------------------------------------------ inspection ----
 long GCN::var_size(int idx) const {
-    if ((dist.world > 1 || (fz && fz->wide)) && idx != 2 && idx != 5) return 0;   // partitioned / wide runs expose the weights only
+    if (dist.world > 1 && idx != 2 && idx != 5) return 0;      // a partitioned run exposes the (replicated) weights only
+    if (fz && fz->wide && idx != 2 && idx != 5 && idx != 3 && idx != 6) return 0;   // wide plan: weights, layer-1 output, logits
     const long N = params.num_nodes, F = params.input_dim, H = params.hidden_dim, C = params.output_dim;
     switch (idx) {
     case 0: return (long)data->feature_index.indices.size();
@@ -893,6 +894,18 @@ void GCN::get_var(int idx, bool grad, float *h_out) {
     Fused &z = *fz;
     const int N = params.num_nodes, H = params.hidden_dim, C = params.output_dim;
     if (idx == 2 || idx == 5) { d2h(grad ? variables[idx].grad : variables[idx].data, size); return; }
+    if (z.wide) {
+        // layer-1 output (data: after ReLU/dropout; grad: the masked gradient that reached it) and the logits of the rows the
+        // last pass aggregated (the other rows keep whatever an earlier pass left there)
+        if (idx == 3) { d2h(grad ? z.dH1 : z.H1, size); return; }
+        if (grad) { memset(h_out, 0, sizeof(float) * (size_t)size); return; }
+        float *d_tmp = nullptr;
+        GCNK_CHECK(gcnk_malloc((void **)&d_tmp, sizeof(float) * (size_t)size));
+        GCNK_CHECK(gcnk_unpad_cols(z.logits, d_tmp, N, C, z.Cp, nullptr));
+        d2h(d_tmp, size);
+        GCNK_CHECK(gcnk_free(d_tmp));
+        return;
+    }
     if (idx == 0) { if (grad) memset(h_out, 0, sizeof(float) * (size_t)size); else d2h(d_feature_value, size); return; }
     if (idx == 6) {
         // the logits are never stored by the fused plan: recompute them from the last pass's P with the CURRENT W2

@@ -214,9 +214,13 @@ def test_products_shape_wide_hidden(host, chk, plan, hidden, dropout):
     plan_id = host.PLAN_MODULES if plan == "modules" else host.PLAN_FUSED
     ref, eng, worst = run_pair(host, chk, d, plan_id, dropout, epochs=4, hidden=hidden)
     assert eng.plan == plan_id
+    # weights after 4 Adam steps.  Adam's update is lr * m / (sqrt(v) + eps): where a gradient element is at rounding level
+    # (dead ReLU units at hidden 128-256) its SIGN decides a +-lr step, so single elements may differ by a few 1e-5
+    # although every gradient agrees to ~1e-6 of the gradient's scale (tools/debug_wide.py prints them)
     for idx in (2, 5):
         w, g = ref.var(idx), eng.var(idx)
-        assert np.abs(w - g).max() <= 2e-4 * np.abs(w).max(), idx
+        assert np.abs(w - g).max() <= 1e-3 * np.abs(w).max(), idx
+        assert np.mean(np.abs(w - g)) <= 2e-5 * np.abs(w).max(), idx
     ref.close(); eng.close()
 
 
