@@ -334,11 +334,12 @@ def run_ours(args):
         host_view = np.ctypeslib.as_array((abi.C.c_float * max(nnzX_loc, 1)).from_address(pinned))
         host_view[:nnzX_loc] = x_local
         e2e_steps = max(3, min(args.steps, 10))
+        prefetch = not args.e2e_serial
         eng.set_input_host(pinned); step(False)                 # warm the copy path
         barrier()
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
-            if args.e2e_prefetch:
+            if prefetch:
                 eng.epoch_prefetch(2, pinned)                   # the step on the current input; H2D of the next step's input under it
             else:
                 eng.set_input_host(pinned)                      # H2D of this rank's nnz(X) floats on the engine's stream
@@ -348,7 +349,7 @@ def run_ours(args):
         e2e_dt = float(eng.allreduce_host([e2e_dt], op_max=True)[0])
         L.gcnh_free_pinned(pinned)
         e2e = {"value": 1.0 / e2e_dt, "unit": UNIT, "h2d_bytes_per_step": int(nnzX * 4), "d2h_bytes_per_step": world * (2 * 16 + 4),
-               "steps": e2e_steps, "api": "gcnh_engine_epoch_prefetch (upload of step k+1 under step k; include/gcn_host.h)" if args.e2e_prefetch else
+               "steps": e2e_steps, "api": "gcnh_engine_epoch_prefetch (upload of step k+1 under step k; include/gcn_host.h)" if prefetch else
                "gcnh_engine_set_input_host + gcnh_engine_train_epoch + gcnh_engine_eval (include/gcn_host.h)"}
     eng.close()
     if rank != 0:
@@ -450,7 +451,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-dims", action="store_true", help="skip the per-width GraphSum timing")
     ap.add_argument("--save-trajectory", default=None, help="write this run's per-epoch losses/accuracies (JSON) to this path")
-    ap.add_argument("--e2e-prefetch", action="store_true", help="e2e loop through gcnh_engine_epoch_prefetch (pipelined upload; not yet validated on a GPU)")
+    ap.add_argument("--e2e-serial", action="store_true", help="e2e loop as set_input_host + epoch (upload, then compute) instead of the pipelined "
+                    "gcnh_engine_epoch_prefetch (upload of step k+1 on a copy stream under step k; tests/test_gpu_train.py::test_epoch_prefetch_equals_serial)")
     ap.add_argument("--timers", action="store_true", help="keep the per-op CUDA-event timers on inside the timed region at N > 1")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

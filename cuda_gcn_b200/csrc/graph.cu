@@ -54,7 +54,7 @@ constexpr int THREADS = 256, WARPS = THREADS / 32;
 constexpr int HEAVY_DEGREE = 2048;     // rows above this get a whole CTA (less for small graphs, see build_schedule)
 constexpr int ROW_OVERHEAD = 24;       // per-row cost in edge-equivalents for the bin balance
 
-enum Mode { MODE_PLAIN = 0, MODE_RELU_DROP = 1, MODE_MASK = 2 };
+enum Mode { MODE_PLAIN = 0, MODE_RELU_DROP = 1, MODE_MASK = 2, MODE_RAW = 3 };   // RAW: the unscaled row sum (a partial result)
 
 struct GatherArgs {
     const int *indptr, *indices;
@@ -73,11 +73,14 @@ struct GatherArgs {
     int wait_n, wait_skip, wait_value;
     int *wait_err;
     long long wait_limit;
+    // accumulate: the row sum starts from init[s, :] (the raw partial sum an earlier launch over other columns left there)
+    const float *init;
 };
 
 // Registered by gcnk_gather_wait_next for the next gather launched by this thread.
 struct GatherWait { const int *flags; int n, skip, value; int *err; };
 thread_local GatherWait t_wait = {nullptr, 0, -1, 0, nullptr};
+thread_local const float *t_init = nullptr;     // gcnk_gather_init_next
 
 // All rows of the source that other ranks produce must be in place before any of them is read: thread r of every CTA
 // polls rank r's flag (an acquire load at system scope: the peer wrote the rows, fenced, then the flag), the CTA
@@ -116,6 +119,7 @@ template <> struct Acc<4> {
         v.x += x.x; v.y += x.y; v.z += x.z; v.w += x.w;
     }
     __device__ void add(const Acc &o) { v.x += o.v.x; v.y += o.v.y; v.z += o.v.z; v.w += o.v.w; }
+    __device__ void load(const float *p) { v = *reinterpret_cast<const float4 *>(p); }
     __device__ void shfl_xor_add(int off) {
         v.x += __shfl_xor_sync(FULL, v.x, off); v.y += __shfl_xor_sync(FULL, v.y, off);
         v.z += __shfl_xor_sync(FULL, v.z, off); v.w += __shfl_xor_sync(FULL, v.w, off);
@@ -128,6 +132,7 @@ template <> struct Acc<1> {
     __device__ void zero() { v = 0.f; }
     __device__ void load_add(const float *p) { v += __ldg(p); }
     __device__ void add(const Acc &o) { v += o.v; }
+    __device__ void load(const float *p) { v = *p; }
     __device__ void shfl_xor_add(int off) { v += __shfl_xor_sync(FULL, v, off); }
     __device__ float get(int) const { return v; }
     __device__ void set(int, float f) { v = f; }
@@ -312,8 +317,9 @@ __device__ __forceinline__ void epilogue(Acc<VEC> (&acc)[NACC], const GatherArgs
     const bool owner = lane < LPR;
     const float di = a.dinv[s];
     float *orow = a.out + (size_t)s * dim;
-    if (a.mode == MODE_PLAIN) {
+    if (a.mode == MODE_PLAIN || a.mode == MODE_RAW) {
         if (owner) {
+            const float di = a.mode == MODE_RAW ? 1.0f : a.dinv[s];
 #pragma unroll
             for (int t = 0; t < NACC; t++) {
                 const int u = (q + LPR * t) * VEC;
@@ -397,7 +403,11 @@ __global__ void __launch_bounds__(THREADS, NACC != 1 ? 1 : IDX4 == 3 ? 4 : IDX4 
         const int s = a.heavy_rows[blockIdx.x];
         const int beg = a.indptr[s], end = a.indptr[s + 1];
 #pragma unroll
-        for (int t = 0; t < NACC; t++) acc[t].zero();
+        for (int t = 0; t < NACC; t++) {
+            acc[t].zero();
+            const int u = (lane % LPR + LPR * t) * VEC;
+            if (a.init && warp == 0 && lane < LPR && u < a.dim) acc[t].load(a.init + (size_t)s * a.dim + u);   // the partial sum so far
+        }
         if constexpr (IDX4 != 0) accumulate_idx4<EXACT, WARPS, IDX4 == 3 ? 8 : IDX4 == 2 ? 4 : 0>(acc[0], a, beg, end, warp, lane);
         else accumulate<VEC, LPR, NACC, EXACT>(acc, a, beg, end, warp, WARPS, lane);
         reduce_groups<VEC, LPR, NACC>(acc);
@@ -435,7 +445,11 @@ __global__ void __launch_bounds__(THREADS, NACC != 1 ? 1 : IDX4 == 3 ? 4 : IDX4 
         const int s = a.bin_rows[r];
         const int beg = a.indptr[s], end = a.indptr[s + 1];
 #pragma unroll
-        for (int t = 0; t < NACC; t++) acc[t].zero();
+        for (int t = 0; t < NACC; t++) {
+            acc[t].zero();
+            const int u = (lane % LPR + LPR * t) * VEC;
+            if (a.init && lane < LPR && u < a.dim) acc[t].load(a.init + (size_t)s * a.dim + u);                  // the partial sum so far
+        }
         if constexpr (IDX4 != 0) accumulate_idx4<EXACT, 1, IDX4 == 3 ? 8 : IDX4 == 2 ? 4 : 0>(acc[0], a, beg, end, 0, lane);
         else accumulate<VEC, LPR, NACC, EXACT>(acc, a, beg, end, 0, 1, lane);
         reduce_groups<VEC, LPR, NACC>(acc);
@@ -506,6 +520,8 @@ int launch_gather(const gcnk_graph *g, GatherArgs a, cudaStream_t st) {
     a.indptr = g->indptr; a.indices = g->indices; a.dinv = g->dinv;
     a.heavy_rows = g->heavy_rows; a.n_heavy = g->n_heavy; a.bin_ptr = g->bin_ptr; a.bin_rows = g->bin_rows;
     a.mask_stride = mask_stride_bits(dim);
+    a.init = t_init;
+    t_init = nullptr;
     if (t_wait.flags) {
         a.wait_flags = t_wait.flags; a.wait_n = t_wait.n; a.wait_skip = t_wait.skip; a.wait_value = t_wait.value;
         a.wait_err = t_wait.err; a.wait_limit = peer_spin_cycles();
@@ -585,6 +601,36 @@ __global__ void scale_rows_kernel(const float *__restrict__ dinv, const float *_
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (; i < total; i += stride) out[i] = dinv[i / dim] * in[i];
+}
+
+// Column-filtered views (gcnk_graph_create_view): a warp per row counts / compacts the entries whose column flag is set,
+// in order (ballot + prefix popcount)
+__global__ void view_count_kernel(const int *__restrict__ indptr, const int *__restrict__ indices, const int *__restrict__ col_keep, int n, int n_cols,
+                                  int *__restrict__ cnt) {
+    const int s = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32, lane = threadIdx.x & 31;
+    if (s >= n) return;
+    int c = 0;
+    for (int e = indptr[s] + lane; e < indptr[s + 1]; e += 32) {
+        const int d = indices[e];
+        c += d >= 0 && d < n_cols && col_keep[d] != 0;
+    }
+    c = warp_sum_int(c);
+    if (lane == 0) cnt[s] = c;
+}
+__global__ void view_fill_kernel(const int *__restrict__ indptr, const int *__restrict__ indices, const int *__restrict__ col_keep,
+                                 const int *__restrict__ new_ptr, int n, int n_cols, int *__restrict__ out) {
+    const int s = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32, lane = threadIdx.x & 31;
+    if (s >= n) return;
+    int w = new_ptr[s];
+    const int beg = indptr[s], end = indptr[s + 1];
+    for (int e0 = beg; e0 < end; e0 += 32) {
+        const int e = e0 + lane;
+        const int d = e < end ? indices[e] : -1;
+        const bool keep = d >= 0 && d < n_cols && col_keep[d] != 0;
+        const unsigned m = __ballot_sync(FULL, keep);
+        if (keep) out[w + __popc(m & ((1u << lane) - 1u))] = d;
+        w += __popc(m);
+    }
 }
 
 // Static schedule over the given rows: heavy rows -> one CTA each; the rest -> LPT bins, one warp per bin.
@@ -687,51 +733,47 @@ int gcnk_graph_create(gcnk_graph **out, const int *d_indptr, const int *d_indice
 
 int gcnk_graph_create_view(gcnk_graph **out, const gcnk_graph *base, const int *d_row_keep, const int *d_col_keep,
                            gcnk_stream_t stream) {
-    GCNK_REQUIRE(out && base && !base->base, "needs a base graph (not itself a view)");
+    GCNK_REQUIRE(out && base, "needs a base graph");
+    GCNK_REQUIRE(!base->base || !d_col_keep, "a view of a view can only restrict the rows (it shares the parent's filtered CSR)");
     cudaStream_t st = S(stream);
     const int n = base->n;
     gcnk_graph *g = new gcnk_graph;
     *g = *base;
-    g->base = base;
+    g->base = base->base ? base->base : base;        // d^-1/2 always comes from the root graph
     g->heavy_rows = nullptr; g->bin_ptr = nullptr; g->bin_rows = nullptr; g->scratch = nullptr; g->scratch_elems = 0;
-    g->own_indptr = nullptr; g->own_indices = nullptr;
+    g->own_indptr = nullptr; g->own_indices = nullptr;   // (a row view of a column view borrows that view's CSR: it must outlive this one)
 
-    std::vector<int> indptr((size_t)n + 1, 0), row_keep, col_keep;
-    GCNK_CUDA(cudaMemcpyAsync(indptr.data(), base->indptr, sizeof(int) * ((size_t)n + 1), cudaMemcpyDeviceToHost, st));
+    std::vector<int> indptr((size_t)n + 1, 0), row_keep;
     if (d_row_keep) {
         row_keep.resize((size_t)n);
         GCNK_CUDA(cudaMemcpyAsync(row_keep.data(), d_row_keep, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, st));
     }
-    std::vector<int> indices;
     if (d_col_keep) {
-        col_keep.resize((size_t)base->n_cols);
-        indices.resize((size_t)base->nnz);
-        GCNK_CUDA(cudaMemcpyAsync(col_keep.data(), d_col_keep, sizeof(int) * (size_t)base->n_cols, cudaMemcpyDeviceToHost, st));
-        if (base->nnz) GCNK_CUDA(cudaMemcpyAsync(indices.data(), base->indices, sizeof(int) * (size_t)base->nnz, cudaMemcpyDeviceToHost, st));
-    }
-    GCNK_CUDA(cudaStreamSynchronize(st));
-
-    if (d_col_keep) {
-        // drop the entries whose column is filtered out; row order and the order inside a row are preserved
-        std::vector<int> new_ptr((size_t)n + 1, 0);
-        size_t w = 0;
-        for (int i = 0; i < n; i++) {
-            for (int e = indptr[i]; e < indptr[i + 1]; e++) {
-                const int d = indices[e];
-                if (d >= 0 && d < base->n_cols && col_keep[d]) indices[w++] = d;
-            }
-            new_ptr[i + 1] = (int)w;
-        }
-        indices.resize(w);
-        indptr.swap(new_ptr);
+        // Drop the entries whose column is filtered out; row order and the order inside a row are preserved.  Counted and
+        // compacted on the device (a warp per row); only the n + 1 row offsets travel to the host, for the prefix sum and
+        // the schedule — not the index array (459 MB at Reddit shape).
+        int *d_cnt = nullptr;
+        GCNK_CUDA(cudaMalloc(&d_cnt, sizeof(int) * ((size_t)n + 1)));
         GCNK_CUDA(cudaMalloc(&g->own_indptr, sizeof(int) * ((size_t)n + 1)));
-        GCNK_CUDA(cudaMalloc(&g->own_indices, sizeof(int) * (w + 4)));          // + 4: the int4 index reads round up
-        GCNK_CUDA(cudaMemcpyAsync(g->own_indptr, indptr.data(), sizeof(int) * ((size_t)n + 1), cudaMemcpyHostToDevice, st));
-        if (w) GCNK_CUDA(cudaMemcpyAsync(g->own_indices, indices.data(), sizeof(int) * w, cudaMemcpyHostToDevice, st));
+        if (n) { view_count_kernel<<<(n + 7) / 8, 256, 0, st>>>(base->indptr, base->indices, d_col_keep, n, base->n_cols, d_cnt); GCNK_LAUNCHED(); }
+        std::vector<int> cnt((size_t)n + 1, 0);
+        GCNK_CUDA(cudaMemcpyAsync(cnt.data(), d_cnt, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, st));
         GCNK_CUDA(cudaStreamSynchronize(st));
-        g->indptr = g->own_indptr; g->indices = g->own_indices; g->nnz = (int64_t)w;
-        g->idx4_ok = w > 0 && idx4_readable(g->own_indices, (int64_t)w);
+        int64_t w = 0;
+        for (int i = 0; i < n; i++) { indptr[i] = (int)w; w += cnt[i]; }
+        indptr[n] = (int)w;
+        GCNK_CUDA(cudaMalloc(&g->own_indices, sizeof(int) * ((size_t)w + 4)));     // + 4: the int4 index reads round up
+        GCNK_CUDA(cudaMemsetAsync(g->own_indices + w, 0, sizeof(int) * 4, st));
+        GCNK_CUDA(cudaMemcpyAsync(g->own_indptr, indptr.data(), sizeof(int) * ((size_t)n + 1), cudaMemcpyHostToDevice, st));
+        if (n) { view_fill_kernel<<<(n + 7) / 8, 256, 0, st>>>(base->indptr, base->indices, d_col_keep, g->own_indptr, n, base->n_cols, g->own_indices); GCNK_LAUNCHED(); }
+        GCNK_CUDA(cudaStreamSynchronize(st));
+        GCNK_CUDA(cudaFree(d_cnt));
+        g->indptr = g->own_indptr; g->indices = g->own_indices; g->nnz = w;
+        g->idx4_ok = w > 0 && idx4_readable(g->own_indices, w);
         g->symmetric = 0;
+    } else {
+        GCNK_CUDA(cudaMemcpyAsync(indptr.data(), base->indptr, sizeof(int) * ((size_t)n + 1), cudaMemcpyDeviceToHost, st));
+        GCNK_CUDA(cudaStreamSynchronize(st));
     }
     std::vector<int> rows;
     rows.reserve((size_t)n);
@@ -750,7 +792,7 @@ int gcnk_graph_create_view(gcnk_graph **out, const gcnk_graph *base, const int *
 
 int gcnk_graph_destroy(gcnk_graph *g) {
     if (!g) return GCNK_OK;
-    if (!g->base) cudaFree(g->dinv);
+    if (!g->base) cudaFree(g->dinv);                  // views borrow d^-1/2 from the root graph
     cudaFree(g->heavy_rows); cudaFree(g->bin_ptr); cudaFree(g->bin_rows); cudaFree(g->scratch);
     cudaFree(g->own_indptr); cudaFree(g->own_indices);
     delete g;
@@ -804,6 +846,18 @@ int gcnk_gather_mask(const gcnk_graph *g, const float *in_scaled, float *out_sca
 }
 
 int gcnk_mask_row_stride_bits(int dim) { return mask_stride_bits(dim); }
+
+int gcnk_gather_init_next(const float *d_partial) {
+    t_init = d_partial;
+    return GCNK_OK;
+}
+
+int gcnk_gather_raw(const gcnk_graph *g, const float *in_scaled, float *out_raw, int dim, gcnk_stream_t stream) {
+    GCNK_REQUIRE(g && in_scaled && out_raw && dim > 0, "bad arguments");
+    GatherArgs a = {};
+    a.in = in_scaled; a.out = out_raw; a.dim = dim; a.mode = MODE_RAW; a.scale = 1.f;
+    return launch_gather(g, a, S(stream));
+}
 
 int gcnk_gather_wait_next(const int *d_flags, int n_flags, int skip, int value, int *d_err) {
     GCNK_REQUIRE((d_flags && n_flags > 0 && n_flags <= THREADS && d_err) || (!d_flags && n_flags == 0), "bad arguments");

@@ -41,7 +41,8 @@ namespace {
 
 constexpr int TC_THREADS = 384;                        // warps 0-3: TMA / MMA / TMEM alloc / idle, 4-7: splitters, 8-11: epilogue
 constexpr int BM = 128, BK = 32, STAGES = 3, ACC_STAGES = 2, TMEM_COLS = 128;   // two 64-column accumulators
-constexpr int EPI_STRIDE = 65;                         // floats per staged row (Npad <= 64; odd => conflict-free column access)
+constexpr int EPI_STRIDE = 68;                         // floats per staged row (Npad <= 64): 16-byte aligned rows, and 68 = 4 mod 32 keeps the
+                                                       // quarter-warp float4 accesses of eight different rows on distinct banks
 constexpr int A_TILE_BYTES = BM * BK * 4;              // 16 KB
 constexpr uint32_t TF32_MASK = 0xffffe000u;
 
@@ -198,7 +199,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) matmul_tc_kernel(const __grid_c
                              : "r"(taddr));
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-                for (int j = 0; j < 16; j++) stage[lane * EPI_STRIDE + c0 + j] = __uint_as_float(r[j]);
+                for (int j = 0; j < 16; j += 4)
+                    *reinterpret_cast<float4 *>(stage + lane * EPI_STRIDE + c0 + j) =
+                        make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
             }
             tc_fence_before();
             __syncwarp();
@@ -209,11 +212,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1) matmul_tc_kernel(const __grid_c
                 const int n0 = nt * Npad, cols = min(Npad, N - n0);          // this tile's share of the N real columns
                 if (rows > 0 && cols > 0) {
                     float *out = c + (size_t)row0 * ldc + n0;
-                    const int total = rows * cols;
-                    for (int f = lane; f < total; f += 32) {
-                        const int rr = f / cols, cc = f - rr * cols;
-                        const float v = stage[rr * EPI_STRIDE + cc];
-                        out[(size_t)rr * ldc + cc] = row_scale ? row_scale[row0 + rr] * v : v;
+                    if (((ldc | cols) & 3) == 0 && (reinterpret_cast<uintptr_t>(c) & 15) == 0) {
+                        // two output rows per step, one float4 per lane: 128-bit shared loads and coalesced 128-bit stores
+                        const int c4 = lane & 15, cpr = cols >> 2;
+#pragma unroll 4
+                        for (int it = 0; it < 16; it++) {
+                            const int rr = 2 * it + (lane >> 4);
+                            if (c4 < cpr && rr < rows) {
+                                float4 v = *reinterpret_cast<const float4 *>(stage + rr * EPI_STRIDE + 4 * c4);
+                                if (row_scale) { const float rs = row_scale[row0 + rr]; v.x *= rs; v.y *= rs; v.z *= rs; v.w *= rs; }
+                                *reinterpret_cast<float4 *>(out + (size_t)rr * ldc + 4 * c4) = v;
+                            }
+                        }
+                    } else {
+                        const int total = rows * cols;
+                        for (int f = lane; f < total; f += 32) {
+                            const int rr = f / cols, cc = f - rr * cols;
+                            const float v = stage[rr * EPI_STRIDE + cc];
+                            out[(size_t)rr * ldc + cc] = row_scale ? row_scale[row0 + rr] * v : v;
+                        }
                     }
                 }
             }

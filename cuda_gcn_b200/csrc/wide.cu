@@ -37,59 +37,42 @@ __global__ void __launch_bounds__(256) drop_scale_rows_kernel(const float4 *__re
     }
 }
 
-// in place: h = (z > 0 && keep) ? z * scale : 0; mask bit = (z > 0) && keep.  One 32-element mask word per thread.
-__global__ void __launch_bounds__(256) relu_dropout_fw_kernel(float *__restrict__ z, const uint32_t *__restrict__ keep, uint32_t *__restrict__ mask,
-                                                              int64_t n, float scale) {
-    const int64_t words = (n + 31) / 32;
-    int64_t w = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+// in place: h = (z > 0 && keep) ? z * scale : 0; mask bit = (z > 0) && keep.  One float4 per thread (coalesced); the eight
+// lanes that share a 32-element mask word combine their nibbles with three shuffles.  n % 4 == 0.
+__global__ void __launch_bounds__(256) relu_dropout_fw_kernel(float4 *__restrict__ z, const uint32_t *__restrict__ keep, uint32_t *__restrict__ mask,
+                                                              int64_t n_vec, float scale) {
+    const int lane = threadIdx.x & 31;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (; w < words; w += stride) {
-        const int64_t base = w * 32;
-        const uint32_t kb = keep ? keep[w] : 0xffffffffu;
-        uint32_t bits = 0;
-        if (base + 32 <= n) {
-            float4 *p = reinterpret_cast<float4 *>(z + base);
-#pragma unroll
-            for (int q = 0; q < 8; q++) {
-                float4 v = p[q];
-                const uint32_t k = kb >> (4 * q);
-                const bool a = v.x > 0.f && (k & 1u), b = v.y > 0.f && (k & 2u), c = v.z > 0.f && (k & 4u), d = v.w > 0.f && (k & 8u);
-                v.x = a ? v.x * scale : 0.f; v.y = b ? v.y * scale : 0.f; v.z = c ? v.z * scale : 0.f; v.w = d ? v.w * scale : 0.f;
-                bits |= ((uint32_t)a | (uint32_t)b << 1 | (uint32_t)c << 2 | (uint32_t)d << 3) << (4 * q);
-                p[q] = v;
-            }
-        } else {
-            for (int i = 0; base + i < n; i++) {
-                const float v = z[base + i];
-                const bool a = v > 0.f && ((kb >> i) & 1u);
-                z[base + i] = a ? v * scale : 0.f;
-                bits |= (uint32_t)a << i;
-            }
+    for (int64_t base = blockIdx.x * (int64_t)blockDim.x + (threadIdx.x & ~31); base < n_vec; base += stride) {
+        const int64_t i = base + lane;
+        uint32_t nib = 0;
+        if (i < n_vec) {
+            float4 v = z[i];
+            const int64_t bit = i * 4;
+            const uint32_t k = keep ? (keep[bit >> 5] >> (bit & 31)) & 0xfu : 0xfu;
+            const bool a = v.x > 0.f && (k & 1u), b = v.y > 0.f && (k & 2u), c = v.z > 0.f && (k & 4u), d = v.w > 0.f && (k & 8u);
+            v.x = a ? v.x * scale : 0.f; v.y = b ? v.y * scale : 0.f; v.z = c ? v.z * scale : 0.f; v.w = d ? v.w * scale : 0.f;
+            z[i] = v;
+            nib = (uint32_t)a | (uint32_t)b << 1 | (uint32_t)c << 2 | (uint32_t)d << 3;
         }
-        if (mask) mask[w] = bits;
+        uint32_t word = nib << (4 * (lane & 7));
+        word |= __shfl_xor_sync(FULL, word, 1);
+        word |= __shfl_xor_sync(FULL, word, 2);
+        word |= __shfl_xor_sync(FULL, word, 4);
+        if (mask && (lane & 7) == 0 && i < n_vec) mask[i >> 3] = word;
     }
 }
 
 // in place: g = mask bit ? g * scale : 0     (Dropout backward then ReLU backward, module.cpp:186-194,226-233)
-__global__ void __launch_bounds__(256) mask_scale_bw_kernel(float *__restrict__ g, const uint32_t *__restrict__ mask, int64_t n, float scale) {
-    const int64_t words = (n + 31) / 32;
-    int64_t w = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256) mask_scale_bw_kernel(float4 *__restrict__ g, const uint32_t *__restrict__ mask, int64_t n_vec, float scale) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (; w < words; w += stride) {
-        const int64_t base = w * 32;
-        const uint32_t mb = mask[w];
-        if (base + 32 <= n) {
-            float4 *p = reinterpret_cast<float4 *>(g + base);
-#pragma unroll
-            for (int q = 0; q < 8; q++) {
-                float4 v = p[q];
-                const uint32_t k = mb >> (4 * q);
-                v.x = (k & 1u) ? v.x * scale : 0.f; v.y = (k & 2u) ? v.y * scale : 0.f; v.z = (k & 4u) ? v.z * scale : 0.f; v.w = (k & 8u) ? v.w * scale : 0.f;
-                p[q] = v;
-            }
-        } else {
-            for (int i = 0; base + i < n; i++) g[base + i] = ((mb >> i) & 1u) ? g[base + i] * scale : 0.f;
-        }
+    for (; i < n_vec; i += stride) {
+        float4 v = g[i];
+        const int64_t bit = i * 4;
+        const uint32_t k = (mask[bit >> 5] >> (bit & 31)) & 0xfu;
+        v.x = (k & 1u) ? v.x * scale : 0.f; v.y = (k & 2u) ? v.y * scale : 0.f; v.z = (k & 4u) ? v.z * scale : 0.f; v.w = (k & 8u) ? v.w * scale : 0.f;
+        g[i] = v;
     }
 }
 
@@ -235,21 +218,21 @@ int gcnk_drop_scale_rows(const float *x, int rows, int f, const uint32_t *keep_b
 }
 
 int gcnk_relu_dropout_fw(float *z, int64_t n, const uint32_t *keep_bits, float scale, uint32_t *mask_bits, gcnk_stream_t stream) {
-    GCNK_REQUIRE(z && n >= 0 && reinterpret_cast<uintptr_t>(z) % 16 == 0, "bad arguments");
+    GCNK_REQUIRE(z && n >= 0 && n % 4 == 0 && reinterpret_cast<uintptr_t>(z) % 16 == 0, "bad arguments (n must be a multiple of 4)");
     if (!n) return GCNK_OK;
-    const int64_t words = (n + 31) / 32;
-    const int grid = (int)std::min<int64_t>((words + 255) / 256, (int64_t)sm_count() * 16);
-    relu_dropout_fw_kernel<<<grid, 256, 0, S(stream)>>>(z, keep_bits, mask_bits, n, scale);
+    const int64_t n_vec = n / 4;
+    const int grid = (int)std::min<int64_t>((n_vec + 255) / 256, (int64_t)sm_count() * 16);
+    relu_dropout_fw_kernel<<<grid, 256, 0, S(stream)>>>(reinterpret_cast<float4 *>(z), keep_bits, mask_bits, n_vec, scale);
     GCNK_LAUNCHED();
     return GCNK_OK;
 }
 
 int gcnk_mask_scale_bw(float *g, int64_t n, const uint32_t *mask_bits, float scale, gcnk_stream_t stream) {
-    GCNK_REQUIRE(g && mask_bits && n >= 0 && reinterpret_cast<uintptr_t>(g) % 16 == 0, "bad arguments");
+    GCNK_REQUIRE(g && mask_bits && n >= 0 && n % 4 == 0 && reinterpret_cast<uintptr_t>(g) % 16 == 0, "bad arguments (n must be a multiple of 4)");
     if (!n) return GCNK_OK;
-    const int64_t words = (n + 31) / 32;
-    const int grid = (int)std::min<int64_t>((words + 255) / 256, (int64_t)sm_count() * 16);
-    mask_scale_bw_kernel<<<grid, 256, 0, S(stream)>>>(g, mask_bits, n, scale);
+    const int64_t n_vec = n / 4;
+    const int grid = (int)std::min<int64_t>((n_vec + 255) / 256, (int64_t)sm_count() * 16);
+    mask_scale_bw_kernel<<<grid, 256, 0, S(stream)>>>(reinterpret_cast<float4 *>(g), mask_bits, n_vec, scale);
     GCNK_LAUNCHED();
     return GCNK_OK;
 }

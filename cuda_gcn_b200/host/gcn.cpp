@@ -279,6 +279,36 @@ void GCN::build(GCNPlan plan) {
         fz->keep[0] = upload(train_cols);
         GCNK_CHECK(gcnk_graph_create_view(&fz->cols_train, g, nullptr, fz->keep[0], nullptr));
     }
+    {
+        const char *ov = getenv("GCN_OVERLAP");
+        const bool want = !(ov && *ov && !strcmp(ov, "0"));
+        if (dist.world > 1 && fz->p2p && fz->signal_exchange && fz->use_views && want) {
+            // column blocks of this rank's CSR slice: the columns it owns itself / the columns the peers own, each also
+            // restricted to training columns (the backward GraphSum); row-subset views of both per split on top
+            std::vector<int> own_f((size_t)N, 0), rem_f((size_t)N, 1), town((size_t)N, 0), trem((size_t)N, 0);
+            for (int i = 0; i < N; i++) {
+                const bool mine = i >= r0 && i < r0 + n_loc, train = full_data->split[i] == 1 && full_data->label[i] >= 0;
+                own_f[i] = mine; rem_f[i] = !mine; town[i] = mine && train; trem[i] = !mine && train;
+            }
+            int *d_f[4] = {upload(own_f), upload(rem_f), upload(town), upload(trem)};
+            GCNK_CHECK(gcnk_graph_create_view(&fz->g_own, g, nullptr, d_f[0], nullptr));
+            GCNK_CHECK(gcnk_graph_create_view(&fz->g_rem, g, nullptr, d_f[1], nullptr));
+            GCNK_CHECK(gcnk_graph_create_view(&fz->gt_own, g, nullptr, d_f[2], nullptr));
+            GCNK_CHECK(gcnk_graph_create_view(&fz->gt_rem, g, nullptr, d_f[3], nullptr));
+            for (int s = 1; s <= 2; s++) {
+                GCNK_CHECK(gcnk_graph_create_view(&fz->rows_own[s], fz->g_own, fz->keep[s], nullptr, nullptr));
+                GCNK_CHECK(gcnk_graph_create_view(&fz->rows_rem[s], fz->g_rem, fz->keep[s], nullptr, nullptr));
+            }
+            GCNK_CHECK(gcnk_stream_sync(nullptr));
+            for (int *f : d_f) GCNK_CHECK(gcnk_free(f));
+            GCNK_CHECK(gcnk_malloc((void **)&fz->partial, nh_loc));
+            GCNK_CHECK(gcnk_malloc((void **)&fz->d_counter2, sizeof(unsigned)));
+            GCNK_CHECK(gcnk_memset(fz->d_counter2, 0, sizeof(unsigned), nullptr));
+            GCNK_CHECK(gcnk_stream_create(&fz->comm_stream));
+            GCNK_CHECK(gcnk_event_create(&fz->ev_prod));
+            fz->overlap = true;
+        }
+    }
     int dense = 0;
     GCNK_CHECK(gcnk_spmat_is_dense(sp, &dense));
     if (dense && H == 16 && F % 2 == 0 && F <= 1024 && !(na && *na && strcmp(na, "0"))) {
@@ -440,6 +470,7 @@ void GCN::consume_pending_input() {
     std::swap(d_feature_value, d_feature_spare);
     input_pending = false;
     if (fz) { fz->ax_valid = false; fz->xp_dirty = fz->Xp != nullptr; }
+    if (fz && fz->wide && !fz->x_all_owned) fz->X_all = d_feature_value;   // single-GPU wide plan: X_all aliases the feature buffer
 }
 
 void GCN::epoch_prefetch(int eval_split, const float *h_next, float *train_loss, float *train_acc, float *eval_loss, float *eval_acc) {
@@ -506,14 +537,18 @@ void GCN::mirror(float *d_all, int dim) {
 //     nothing waits here.  await(b) then arms the consuming gather, which checks the flags at its own start.
 //   GCN_EXCHANGE=barrier: the round-1 form, push + flag barrier in one launch (every rank waits for every rank here).
 //   GCN_COMM=nccl / no peer mapping: NCCL all-gather (grouped broadcasts).
-void GCN::publish(float *d_all, int dim) {
+void GCN::publish(float *d_all, int dim, bool on_comm_stream) {
     if (dist.world <= 1) return;
     Fused &z = *fz;
-    gpu_timer_begin(TMR_COMM);
+    gcnk_stream_t ps = on_comm_stream ? z.comm_stream : z.stream;
+    unsigned *counter = on_comm_stream ? z.d_counter2 : z.d_counter;   // the push kernels' last-CTA counter: one per stream
+    if (!on_comm_stream) gpu_timer_begin(TMR_COMM);
     if (z.p2p) {
         const int b = (int)((size_t)(d_all - z.slab) / z.buf_floats);
         float *own = d_all + (size_t)r0 * dim;
-        const bool mirrored = !gcnk_mirror_pending(own);               // the producer's epilogue already stored the rows remotely
+        // hidden-16 plan: a producer with a mirrored epilogue (opt-in) has consumed the registration made by mirror() and
+        // stored the rows remotely itself; the wide plan's producers never do
+        const bool mirrored = !z.wide && !gcnk_mirror_pending(own);
         float *peers[8];
         int *slots[8];
         const int *lists[8];
@@ -529,7 +564,7 @@ void GCN::publish(float *d_all, int dim) {
         if (z.signal_exchange) {
             ++z.seq[b];
             GCNK_CHECK(gcnk_peer_push_signal(own, peers, n, mirrored ? 0 : (size_t)n_loc * dim, z.use_halo && !mirrored ? lists : nullptr, counts, dim,
-                                             slots, z.seq[b], z.d_counter, z.stream));
+                                             slots, z.seq[b], counter, ps));
         } else if (!mirrored) {
             GCNK_CHECK(gcnk_peer_push_barrier(own, peers, n, (size_t)n_loc * dim, z.flag_arrays, dist.rank, dist.world, ++z.barrier_value,
                                               z.d_err, z.d_counter, z.stream));
@@ -539,7 +574,26 @@ void GCN::publish(float *d_all, int dim) {
     } else {
         GCNK_CHECK(gcnk_comm_allgather_rows(dist.comm, d_all, row_begin.data(), dim, z.stream));
     }
-    gpu_timer_end(TMR_COMM);
+    if (!on_comm_stream) gpu_timer_end(TMR_COMM);
+}
+
+// Exchange of gather source `buf` overlapped with the local part of the GraphSum that consumes it (north star:
+// "communication overlapped with local-row aggregation"): the push of this rank's rows to the peers runs on the
+// communication stream while the compute stream already aggregates the columns this rank owns (view v_own; raw partial row
+// sums).  The rest of the sum — the columns other ranks own (v_rem) — starts from those partials and waits, inside the
+// kernel, for the peers' arrival flags.  Own columns first, remote second: a fixed order.  `final_gather(view)` launches
+// the consumer (with its epilogue) on the given view.  Returns false when the overlap is off: the caller runs the plain
+// publish / await / gather sequence.
+bool GCN::exchange_overlapped(float *buf, int dim, gcnk_graph *v_own, gcnk_graph *v_rem) {
+    Fused &z = *fz;
+    if (!z.overlap || !v_own || !v_rem) return false;
+    GCNK_CHECK(gcnk_event_record(z.ev_prod, z.stream));
+    GCNK_CHECK(gcnk_stream_wait_event(z.comm_stream, z.ev_prod));
+    publish(buf, dim, true);
+    GCNK_CHECK(gcnk_gather_raw(v_own, buf, z.partial, dim, z.stream));
+    await(buf, dim);
+    GCNK_CHECK(gcnk_gather_init_next(z.partial));
+    return true;
 }
 
 // Arms the next gather launch: it reads buffer `d_all`, so it must see every rank's rows of production seq[b].
@@ -711,20 +765,30 @@ void GCN::fused_enqueue(int current_split, bool training, int slot) {
             z.pre_valid = true;
             z.cur ^= 1;
         }
-        publish(z.xw_s, H);
         // M2 GraphSum + M3 ReLU + M4 Dropout in the gather's epilogue
         gpu_timer_begin(TMR_GATHER_FULL);
+        gcnk_graph *v = g;
+        if (exchange_overlapped(z.xw_s, H, z.g_own, z.g_rem)) v = z.g_rem;
+        else { publish(z.xw_s, H); await(z.xw_s, H); }
         mirror(z.h1_s, H);
-        await(z.xw_s, H);
-        GCNK_CHECK(gcnk_gather_relu_drop(g, z.xw_s, z.h1_s + own, drop ? z.keep1 : nullptr, training ? z.mask : nullptr,
+        GCNK_CHECK(gcnk_gather_relu_drop(v, z.xw_s, z.h1_s + own, drop ? z.keep1 : nullptr, training ? z.mask : nullptr,
                                          training ? scale : 1.0f, H, st));
         gpu_timer_end(TMR_GATHER_FULL);
     }
-    publish(z.h1_s, H);
     // the layer-2 aggregation at width H, only for the rows whose logits the loss looks at
     gpu_timer_begin(gather_timer(g_rows));
-    await(z.h1_s, H);
-    GCNK_CHECK(gcnk_gather_plain(g_rows, z.h1_s, z.P, H, st));
+    {
+        const int sv = current_split >= 1 && current_split <= 3 ? current_split : 0;
+        gcnk_graph *v = g_rows;
+        if (sv && z.overlap && !z.rows_own[sv]) {              // test split: on first use
+            GCNK_CHECK(gcnk_graph_create_view(&z.rows_own[sv], z.g_own, z.keep[sv], nullptr, nullptr));
+            GCNK_CHECK(gcnk_graph_create_view(&z.rows_rem[sv], z.g_rem, z.keep[sv], nullptr, nullptr));
+            GCNK_CHECK(gcnk_stream_sync(nullptr));
+        }
+        if (exchange_overlapped(z.h1_s, H, sv ? z.rows_own[sv] : z.g_own, sv ? z.rows_rem[sv] : z.g_rem)) v = sv ? z.rows_rem[sv] : z.g_rem;
+        else { publish(z.h1_s, H); await(z.h1_s, H); }
+        GCNK_CHECK(gcnk_gather_plain(v, z.h1_s, z.P, H, st));
+    }
     gpu_timer_end(gather_timer(g_rows));
 
     // M5 Matmul + M7 CrossEntropyLoss + get_accuracy (+ Matmul backward when training), row-local.
@@ -743,16 +807,18 @@ void GCN::fused_enqueue(int current_split, bool training, int slot) {
 
     if (training) {
         // backward of M6/M5 is inside layer2; M4/M3/M2 backward = one masked gather + one plain gather
-        publish(z.G, H);
         gpu_timer_begin(gather_timer(g_cols));
+        gcnk_graph *v = g_cols;
+        if (exchange_overlapped(z.G, H, z.gt_own, z.gt_rem)) v = z.gt_rem;
+        else { publish(z.G, H); await(z.G, H); }
         mirror(z.Gm, H);
-        await(z.G, H);
-        GCNK_CHECK(gcnk_gather_mask(g_cols, z.G, z.Gm + own, z.mask, scale, H, st));
+        GCNK_CHECK(gcnk_gather_mask(v, z.G, z.Gm + own, z.mask, scale, H, st));
         gpu_timer_end(gather_timer(g_cols));
-        publish(z.Gm, H);
         gpu_timer_begin(TMR_GATHER_FULL);
-        await(z.Gm, H);
-        GCNK_CHECK(gcnk_gather_plain(g, z.Gm, z.dxw, H, st));
+        v = g;
+        if (exchange_overlapped(z.Gm, H, z.g_own, z.g_rem)) v = z.g_rem;
+        else { publish(z.Gm, H); await(z.Gm, H); }
+        GCNK_CHECK(gcnk_gather_plain(v, z.Gm, z.dxw, H, st));
         gpu_timer_end(TMR_GATHER_FULL);
         gpu_timer_begin(TMR_SPMATMUL_BW);
         if (z.Xp) GCNK_CHECK(gcnk_dense_transform_bw_ld(z.Xp, z.ld, n_loc, F, z.dxw, W1.grad, H, drop ? z.keep0 : nullptr, scale, z.bw_ws, z.bw_ws_bytes, st));

@@ -108,6 +108,16 @@ struct GCN::Fused {
     int halo_count[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     bool use_halo = false, signal_exchange = true;
     gcnk_stream_t stream = nullptr;   // everything the fused plan enqueues runs on this (non-blocking) stream
+    // Overlap of the exchange with the local part of the consuming GraphSum (GCN::exchange_overlapped; GCN_OVERLAP=0 turns
+    // it off): own-columns / remote-columns views of the CSR slice (gt_*: training columns only; rows_*: per split), the
+    // raw partial sums, and the communication stream the pushes run on.
+    bool overlap = false;
+    gcnk_graph *g_own = nullptr, *g_rem = nullptr, *gt_own = nullptr, *gt_rem = nullptr;
+    gcnk_graph *rows_own[4] = {nullptr, nullptr, nullptr, nullptr}, *rows_rem[4] = {nullptr, nullptr, nullptr, nullptr};
+    float *partial = nullptr;
+    gcnk_stream_t comm_stream = nullptr;
+    void *ev_prod = nullptr;
+    unsigned *d_counter2 = nullptr;
     int *d_err = nullptr, *h_err = nullptr;
     int *h_async = nullptr;      // pinned copy of the kernel library's async error flag (mbarrier time-outs)
     unsigned *d_counter = nullptr;
@@ -128,6 +138,12 @@ struct GCN::Fused {
         if (h_err) gcnk_free_host(h_err);
         if (h_async) gcnk_free_host(h_async);
         if (rng_stream) { gcnk_stream_sync(rng_stream); gcnk_stream_destroy(rng_stream); }
+        if (comm_stream) { gcnk_stream_sync(comm_stream); gcnk_stream_destroy(comm_stream); }
+        if (ev_prod) gcnk_event_destroy(ev_prod);
+        for (gcnk_graph *v : {rows_own[1], rows_own[2], rows_own[3], rows_rem[1], rows_rem[2], rows_rem[3]}) if (v) gcnk_graph_destroy(v);   // row views first: they borrow
+        for (gcnk_graph *v : {g_own, g_rem, gt_own, gt_rem}) if (v) gcnk_graph_destroy(v);
+        if (partial) gcnk_free(partial);
+        if (d_counter2) gcnk_free(d_counter2);
         if (seq_stream) { gcnk_stream_sync(seq_stream); gcnk_stream_destroy(seq_stream); }
         if (stream) { gcnk_stream_sync(stream); gcnk_stream_destroy(stream); }
         if (ev_l2) gcnk_event_destroy(ev_l2);

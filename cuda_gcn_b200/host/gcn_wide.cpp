@@ -71,6 +71,7 @@ void GCN::build_wide() {
 }
 
 void GCN::wide_enqueue(int current_split, bool training, int slot) {
+    consume_pending_input();
     Fused &z = *fz;
     gcnk_stream_t st = z.stream;
     gpu_timer_set_stream(st);

@@ -80,7 +80,8 @@ int gcnk_graph_create(gcnk_graph **g, const int *d_indptr, const int *d_indices,
  *   d_col_keep (int[n_cols] flags, NULL = all): entries whose column flag is 0 are dropped (e.g. the rows of the
  *               gathered matrix that are known to be zero: the loss gradient of unlabelled nodes).
  * Degrees — hence d^-1/2 of rows and columns — remain those of the base graph.  gcnk_graph_stats on a view
- * reports the entries its launches touch. */
+ * reports the entries its launches touch.  `base` may itself be a column-filtered view when only d_row_keep is given (the
+ * new view shares that view's CSR, which must outlive it).  The filtering runs on the device. */
 int gcnk_graph_create_view(gcnk_graph **view, const gcnk_graph *base, const int *d_row_keep, const int *d_col_keep,
                            gcnk_stream_t stream);
 int gcnk_graph_destroy(gcnk_graph *g);
@@ -327,6 +328,12 @@ int gcnk_peer_push_barrier(const float *local_rows, float *const *peer_rows, int
 int gcnk_peer_push_signal(const float *local_rows, float *const *peer_rows, int n_peers, size_t n_floats, const int *const *d_row_lists,
                           const int *h_row_counts, int dim, int *const *peer_flag_slots, int value, unsigned *d_counter, gcnk_stream_t stream);
 int gcnk_gather_wait_next(const int *d_flags, int n_flags, int skip, int value, int *d_err);
+/* Split aggregation (the overlap of the exchange with the local part of a GraphSum): gcnk_gather_raw over a view that keeps
+ * only the columns this rank owns writes the UNSCALED partial row sums; gcnk_gather_init_next(partial) makes the next
+ * gcnk_gather_* launch — over the view of the remaining columns — start every row sum from partial[s, :] before it applies
+ * its usual epilogue.  Own columns first, remote columns second: a fixed order. */
+int gcnk_gather_raw(const gcnk_graph *g, const float *in_scaled, float *out_raw, int dim, gcnk_stream_t stream);
+int gcnk_gather_init_next(const float *d_partial);
 /* Deterministic sum all-reduce over peer memory for small vectors (weight gradients, scalars): every rank writes
  * its n_segs segments, packed, into slot[rank] of every rank's exchange area (slot_areas[r] = rank r's area of
  * world * slot_floats floats), passes the barrier, and sums the slots in rank order back into the segments —

@@ -581,7 +581,7 @@ def test_wide_rowlocal_kernels(abi, chk, D):
     abi.k.gcnk_drop_scale_rows(D(x), n, f, None, 2.0, D(dinv), out.ptr, None)
     close(out.numpy(), x * dinv[:, None], rtol=1e-6, what="scale_rows only")
     # ReLU + dropout forward and backward: same mask bits as applying the reference's two modules in turn
-    z = rng.standard_normal(n * h + 5).astype(np.float32)            # not a multiple of 32
+    z = rng.standard_normal(n * h + 12).astype(np.float32)           # a multiple of 4, not of 32
     keep1 = rng.random(len(z)) < 0.5
     zd = abi.dev(z)
     mask = abi.DeviceArray.zeros(((len(z) + 31) // 32,), np.uint32)
