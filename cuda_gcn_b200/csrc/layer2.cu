@@ -172,6 +172,9 @@ __global__ void __launch_bounds__(L2_THREADS) layer2_h16_kernel(const float *__r
         const int my_truth = (my_row < n && split[my_row] == current_split) ? label[my_row] : -1;   // set_truth (gcn.cpp:78-81)
         unsigned todo = __ballot_sync(FULL, logits_out ? my_row < n : my_truth >= 0);
         if (terms && !term_index && my_row < n && my_truth < 0) terms[my_row] = 0.f;
+        // where this lane's row stores its loss term: read coalesced here, not per row on the dependent chain below
+        const int my_slot = (terms && my_truth >= 0) ? (term_index ? term_index[my_row] : my_row) : 0;
+        float my_term = 0.f;
         if (training) {
             // rows without a label carry no gradient: zero their G rows, 32 consecutive floats per store
             const unsigned labelled = __ballot_sync(FULL, my_truth >= 0);
@@ -235,7 +238,7 @@ __global__ void __launch_bounds__(L2_THREADS) layer2_h16_kernel(const float *__r
         wrong += wr;
         const float term = logf(sum) - (tl - mx);
         loss += term;
-        if (terms && lane == 0) terms[term_index ? term_index[s] : s] = term;
+        if (lane == r_in) my_term = term;                                    // stored after the block, one coalesced-ish pass
         if (training) {
             // dlogits of this lane's classes; dW2 += P^T dlogits; partial of dlogits * W2^T over this lane's classes
             float pk[H];
@@ -272,6 +275,7 @@ __global__ void __launch_bounds__(L2_THREADS) layer2_h16_kernel(const float *__r
             }
         }
         }   // labelled rows of the block
+        if (terms && my_truth >= 0) terms[my_slot] = my_term;
     }
 
     __shared__ float s_loss[L2_WARPS];

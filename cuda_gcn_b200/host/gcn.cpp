@@ -280,8 +280,11 @@ void GCN::build(GCNPlan plan) {
         GCNK_CHECK(gcnk_graph_create_view(&fz->cols_train, g, nullptr, fz->keep[0], nullptr));
     }
     {
+        // Opt-in (GCN_OVERLAP=1).  Measured on 2 B200 at Reddit shape (profiles/r02h_*): the exchange leaves the critical path
+        // (comm 0.19 -> 0.04 ms per step) but the two extra cross-stream event hops per exchange and the split row sums
+        // (every row's chunks are ragged twice) cost more than the hidden push: 570 vs 585 epochs/s.
         const char *ov = getenv("GCN_OVERLAP");
-        const bool want = !(ov && *ov && !strcmp(ov, "0"));
+        const bool want = ov && *ov && strcmp(ov, "0");
         if (dist.world > 1 && fz->p2p && fz->signal_exchange && fz->use_views && want) {
             // column blocks of this rank's CSR slice: the columns it owns itself / the columns the peers own, each also
             // restricted to training columns (the backward GraphSum); row-subset views of both per split on top

@@ -118,3 +118,27 @@ def test_reddit_preprocess(host, tmp_path, by_position):
         assert tm[0] == tt[0] and [t.split(":")[0] for t in tm[1:]] == [t.split(":")[0] for t in tt[1:]]
         vm = np.array([float(t.split(":")[1]) for t in tm[1:]]); vt = np.array([float(t.split(":")[1]) for t in tt[1:]])
         assert np.allclose(vm, vt, rtol=1e-13, atol=0)
+
+
+def test_reddit_preprocess_matches_reference_script(tmp_path):
+    """tools/reddit_preprocess.py against the output of the UNMODIFIED reference script on the same GraphSAGE-format input
+    (tests/golden/reddit_preprocess/, made by tools/make_reddit_preprocess_golden.py, which executes
+    /root/reference/reddit_preprocess.py under three import shims): the .graph and .split files are identical text,
+    the .svmlight file has the same labels, the same keys and values equal to 1e-12 relative (StandardScaler vs numpy)."""
+    gold = ROOT / "tests" / "golden" / "reddit_preprocess"
+    out = tmp_path / "reddit"
+    r = subprocess.run([sys.executable, str(ROOT / "tools" / "reddit_preprocess.py"), "--prefix", str(gold / "reddit"), "--out", str(out)],
+                       capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    assert (tmp_path / "reddit.graph").read_text() == (gold / "reddit.graph").read_text()
+    assert (tmp_path / "reddit.split").read_text() == (gold / "reddit.split").read_text()
+    ours = (tmp_path / "reddit.svmlight").read_text().splitlines()
+    ref = (gold / "reddit.svmlight").read_text().splitlines()
+    assert len(ours) == len(ref) == 56
+    for a, b in zip(ours, ref):
+        fa, fb = a.split(), b.split()
+        assert int(float(fa[0])) == int(float(fb[0]))                       # sklearn writes the label as given
+        ka, kb = [t.split(":") for t in fa[1:]], [t.split(":") for t in fb[1:]]
+        assert [k for k, _ in ka] == [k for k, _ in kb]
+        for (_, va), (_, vb) in zip(ka, kb):
+            assert abs(float(va) - float(vb)) <= 1e-12 * max(1.0, abs(float(vb)))
