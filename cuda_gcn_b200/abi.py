@@ -106,6 +106,9 @@ SIGNATURES = {
     "gcnk_sum_squares": (i32, [vp, i64, vp, vp]),
     "gcnk_layer2_fused": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, sz, vp]),
     "gcnk_layer2_fused_terms": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, sz, vp, vp, vp]),
+    "gcnk_dense_transform_tc": (i32, [vp, i32, i32, i32, vp, vp, i32, vp, f32, vp, i32, vp]),
+    "gcnk_dense_transform_bw_tc_workspace": (sz, [i32, i32, i32]),
+    "gcnk_dense_transform_bw_tc": (i32, [vp, i32, i32, i32, vp, vp, i32, vp, f32, vp, sz, vp]),
     "gcnk_matmul_nn": (i32, [vp, i32, vp, i32, vp, i32, i32, i32, i32, vp, vp]),
     "gcnk_matmul_nt": (i32, [vp, i32, vp, i32, vp, i32, i32, i32, i32, vp]),
     "gcnk_matmul_tn_workspace": (sz, [i32, i32, i32]),
@@ -145,7 +148,7 @@ SIGNATURES = {
 # functions whose return value is not an error code
 _NOT_RC = {"gcnk_dense_transform_bw_workspace", "gcnk_mirror_pending", "gcnk_version", "gcnk_last_error", "gcnk_launch_count", "gcnk_matmul_bw_b_workspace",
            "gcnk_softmax_ce_workspace", "gcnk_layer2_workspace", "gcnk_mask_row_stride_bits", "gcnk_gather_variant", "gcnk_matmul_tn_workspace",
-           "gcnk_ce_rows_workspace", "gcnk_async_error"}
+           "gcnk_ce_rows_workspace", "gcnk_async_error", "gcnk_dense_transform_bw_tc_workspace"}
 
 _lib = None
 

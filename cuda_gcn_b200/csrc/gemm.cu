@@ -18,10 +18,11 @@ using namespace gcnk;
 namespace gcnk {   // matmul_tc.cu
 bool matmul_tc_nn_supported(int m, int k, int n, int lda, int ldc, bool b_is_nk);
 int matmul_tc_nn(const float *a, int lda, const float *b, int ldb, bool b_is_nk, float *c, int ldc, int m, int k, int n, const float *row_scale,
-                 cudaStream_t st);
+                 cudaStream_t st, const uint32_t *keep = nullptr, float out_scale = 1.0f, int relu = 0);
 bool matmul_tc_tn_supported(int m, int ka, int n, int lda, int ldb);
 size_t matmul_tc_tn_workspace(int m, int ka, int n);
-int matmul_tc_tn(const float *a, int lda, const float *b, int ldb, float *c, int ldc, int m, int ka, int n, float *ws, size_t ws_bytes, cudaStream_t st);
+int matmul_tc_tn(const float *a, int lda, const float *b, int ldb, float *c, int ldc, int m, int ka, int n, float *ws, size_t ws_bytes, cudaStream_t st,
+                 const uint32_t *keep = nullptr, float out_scale = 1.0f);
 }
 
 namespace {
@@ -134,6 +135,31 @@ int gcnk_matmul_nt(const float *a, int lda, const float *b, int ldb, float *c, i
     gemm_ld_kernel<false, true><<<grid, 256, 0, S(stream)>>>(a, lda, b, ldb, c, ldc, m, n, k, k, nullptr);
     GCNK_LAUNCHED();
     return GCNK_OK;
+}
+
+// Dropout-on-read forms for the dense feature transform (SparseMatmul with a dense X, module.cpp:47-77, with the Dropout of
+// module.cpp:207-224 applied while the tile is split in shared memory): tensor-core path only.
+int gcnk_dense_transform_tc(const float *xp, int ld, int m, int n, const float *w, float *c, int p, const uint32_t *drop_bits, float drop_scale,
+                            const float *row_scale, int relu, gcnk_stream_t stream) {
+    GCNK_REQUIRE(xp && w && c && m >= 0 && n > 0 && p > 0 && ld >= n, "bad arguments");
+    if (m == 0) return GCNK_OK;
+    if (tc_off() || !matmul_tc_nn_supported(m, n, p, ld, p, false) || reinterpret_cast<uintptr_t>(xp) % 16) {
+        set_error("gcnk_dense_transform_tc: shape not supported by the tcgen05 kernel");
+        return GCNK_EUNSUPPORTED;
+    }
+    return matmul_tc_nn(xp, ld, w, p, false, c, p, m, n, p, row_scale, S(stream), drop_bits, drop_bits ? drop_scale : 1.0f, relu);
+}
+
+size_t gcnk_dense_transform_bw_tc_workspace(int m, int n, int p) { return matmul_tc_tn_workspace(m, n, p); }
+
+int gcnk_dense_transform_bw_tc(const float *xp, int ld, int m, int n, const float *g, float *w_grad, int p, const uint32_t *drop_bits, float drop_scale,
+                               float *workspace, size_t workspace_bytes, gcnk_stream_t stream) {
+    GCNK_REQUIRE(xp && g && w_grad && m >= 0 && n > 0 && p > 0 && ld >= n, "bad arguments");
+    if (tc_off() || !matmul_tc_tn_supported(m, n, p, ld, p) || reinterpret_cast<uintptr_t>(xp) % 16 || reinterpret_cast<uintptr_t>(g) % 16) {
+        set_error("gcnk_dense_transform_bw_tc: shape not supported by the tcgen05 kernel");
+        return GCNK_EUNSUPPORTED;
+    }
+    return matmul_tc_tn(xp, ld, g, p, w_grad, p, m, n, p, workspace, workspace_bytes, S(stream), drop_bits, drop_bits ? drop_scale : 1.0f);
 }
 
 size_t gcnk_matmul_tn_workspace(int m, int ka, int n) {

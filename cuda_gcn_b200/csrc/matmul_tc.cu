@@ -84,7 +84,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) matmul_tc_kernel(const __grid_c
                                                                    const __grid_constant__ CUtensorMap map_bb,
                                                                    const __grid_constant__ CUtensorMap map_bs, float *__restrict__ c,
                                                                    int ldc, const float *__restrict__ row_scale, int M, int N, int Npad,
-                                                                   int ntn, int kblocks, int *err) {
+                                                                   int ntn, int kblocks, const uint32_t *__restrict__ keep, int K,
+                                                                   float out_scale, int relu, int *err) {
+    // keep (optional): Dropout on read — bit (row*K + col) of the reference's flat draw order decides whether A[row, col]
+    // takes part (module.cpp:207-224); the 1/(1-p) factor is out_scale, applied with the row scale in the epilogue.
     // Npad = columns of one n tile (a multiple of 16, <= 64); this CTA owns n tile `nt` and walks row tiles
     // tile0, tile0 + tstep, ...
     extern __shared__ uint8_t smem_raw[];
@@ -166,7 +169,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) matmul_tc_kernel(const __grid_c
                 float4 *big = reinterpret_cast<float4 *>(a_big + s * A_TILE_BYTES), *sm = reinterpret_cast<float4 *>(a_small + s * A_TILE_BYTES);
 #pragma unroll
                 for (int i = 0; i < A_TILE_BYTES / 16 / 128; i++) {
-                    const float4 v = big[tid + 128 * i];
+                    float4 v = big[tid + 128 * i];
+                    if (keep) {
+                        // float4 `idx` of the swizzled [128 x 32] tile: row idx/8, 16-byte chunk (idx%8) ^ (row%8)
+                        const int idx = tid + 128 * i, row = idx >> 3, col = (((idx & 7) ^ (row & 7)) << 2) + kb * BK;
+                        const int grow = tile * BM + row;
+                        uint32_t nib = 0;
+                        if (grow < M && col < K) {
+                            const size_t bit = (size_t)grow * K + col;
+                            const uint32_t lo32 = keep[bit >> 5], hi32 = (bit & 31) > 28 ? keep[(bit >> 5) + 1] : 0u;
+                            nib = __funnelshift_r(lo32, hi32, (uint32_t)(bit & 31)) & 0xfu;
+                        }
+                        v.x = (nib & 1u) ? v.x : 0.f; v.y = (nib & 2u) ? v.y : 0.f; v.z = (nib & 4u) ? v.z : 0.f; v.w = (nib & 8u) ? v.w : 0.f;
+                    }
                     float4 hi, lo;
                     hi.x = __uint_as_float(__float_as_uint(v.x) & TF32_MASK); lo.x = __uint_as_float(__float_as_uint(v.x - hi.x) & TF32_MASK);
                     hi.y = __uint_as_float(__float_as_uint(v.y) & TF32_MASK); lo.y = __uint_as_float(__float_as_uint(v.y - hi.y) & TF32_MASK);
@@ -220,7 +235,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) matmul_tc_kernel(const __grid_c
                             const int rr = 2 * it + (lane >> 4);
                             if (c4 < cpr && rr < rows) {
                                 float4 v = *reinterpret_cast<const float4 *>(stage + rr * EPI_STRIDE + 4 * c4);
-                                if (row_scale) { const float rs = row_scale[row0 + rr]; v.x *= rs; v.y *= rs; v.z *= rs; v.w *= rs; }
+                                if (relu) { v.x = v.x > 0.f ? v.x : 0.f; v.y = v.y > 0.f ? v.y : 0.f; v.z = v.z > 0.f ? v.z : 0.f; v.w = v.w > 0.f ? v.w : 0.f; }
+                                const float rs = (row_scale ? row_scale[row0 + rr] : 1.0f) * out_scale;
+                                v.x *= rs; v.y *= rs; v.z *= rs; v.w *= rs;
                                 *reinterpret_cast<float4 *>(out + (size_t)rr * ldc + 4 * c4) = v;
                             }
                         }
@@ -228,8 +245,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) matmul_tc_kernel(const __grid_c
                         const int total = rows * cols;
                         for (int f = lane; f < total; f += 32) {
                             const int rr = f / cols, cc = f - rr * cols;
-                            const float v = stage[rr * EPI_STRIDE + cc];
-                            out[(size_t)rr * ldc + cc] = row_scale ? row_scale[row0 + rr] * v : v;
+                            float v = stage[rr * EPI_STRIDE + cc];
+                            if (relu) v = v > 0.f ? v : 0.f;
+                            out[(size_t)rr * ldc + cc] = (row_scale ? row_scale[row0 + rr] : 1.0f) * out_scale * v;
                         }
                     }
                 }
@@ -269,7 +287,8 @@ __device__ __forceinline__ uint64_t make_desc_mn(uint32_t smem_addr) {
 
 __global__ void __launch_bounds__(TC_THREADS, 1) matmul_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                                                                    float *__restrict__ ws, int ld_ws, int rows_ws, int M, int rows_per_part, int mt,
-                                                                   int ntn, int nt_cols, int *err) {
+                                                                   int ntn, int nt_cols, const uint32_t *__restrict__ keep, int KA, int *err) {
+    // keep (optional): Dropout on read for the A operand — bit (row*KA + col) of the flat draw order (module.cpp:207-224)
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     TnBars *bars = reinterpret_cast<TnBars *>(smem + (size_t)TN_STAGES * TN_STAGE_BYTES);
@@ -344,6 +363,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1) matmul_tn_kernel(const __grid_c
                     sm[i] = lo;
                 }
             };
+            if (keep) {
+                // A: four [32 rows x 128 bytes] boxes, 32-byte chunks of a row XORed with row%4 (SWIZZLE_128B_ATOM_32B)
+                float4 *a4 = reinterpret_cast<float4 *>(st);
+                for (int i = tid; i < TN_OPERAND_BYTES / 16; i += 128) {
+                    const int fg = i >> 8, in_box = i & 255, row = in_box >> 3, sub = in_box & 7;
+                    const int col = m_tile * 128 + fg * 32 + ((((sub >> 1) ^ (row & 3)) << 3) | ((sub & 1) << 2));
+                    const int grow = r_lo + it * TN_ROWS + row;
+                    uint32_t nib = 0;
+                    if (grow < M && col < KA) {
+                        const size_t bit = (size_t)grow * KA + col;
+                        const uint32_t lo32 = keep[bit >> 5], hi32 = (bit & 31) > 28 ? keep[(bit >> 5) + 1] : 0u;
+                        nib = __funnelshift_r(lo32, hi32, (uint32_t)(bit & 31)) & 0xfu;
+                    }
+                    float4 v = a4[i];
+                    v.x = (nib & 1u) ? v.x : 0.f; v.y = (nib & 2u) ? v.y : 0.f; v.z = (nib & 4u) ? v.z : 0.f; v.w = (nib & 8u) ? v.w : 0.f;
+                    a4[i] = v;
+                }
+                __syncwarp();
+            }
             split(reinterpret_cast<float4 *>(st), reinterpret_cast<float4 *>(st + TN_OPERAND_BYTES), TN_OPERAND_BYTES / 16);
             split(reinterpret_cast<float4 *>(st + 2 * TN_OPERAND_BYTES), reinterpret_cast<float4 *>(st + 3 * TN_OPERAND_BYTES), b_vec);
             fence_proxy_async();
@@ -377,7 +415,8 @@ teardown:
 }
 
 // C[r, c] (pitch ldc) = sum over parts of ws[part][r][c], in part order
-__global__ void reduce_tn_kernel(const float *__restrict__ ws, float *__restrict__ c, int ka, int n, int ld_ws, int rows_ws, int ldc, int parts) {
+__global__ void reduce_tn_kernel(const float *__restrict__ ws, float *__restrict__ c, int ka, int n, int ld_ws, int rows_ws, int ldc, int parts,
+                                 float out_scale) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= ka * n) return;
     const int r = i / n, cc = i % n;
@@ -388,7 +427,7 @@ __global__ void reduce_tn_kernel(const float *__restrict__ ws, float *__restrict
         s1 += ws[((size_t)(b + 1) * rows_ws + r) * ld_ws + cc];
     }
     if (b < parts) s0 += ws[((size_t)b * rows_ws + r) * ld_ws + cc];
-    c[(size_t)r * ldc + cc] = s0 + s1;
+    c[(size_t)r * ldc + cc] = out_scale * (s0 + s1);
 }
 
 }  // namespace
@@ -447,7 +486,7 @@ bool matmul_tc_nn_supported(int m, int k, int n, int lda, int ldc, bool b_is_nk)
 bool matmul_tc_supported(int m, int k, int n) { return k >= 64 && k % 4 == 0 && n <= 64 && matmul_tc_nn_supported(m, k, n, k, n, false); }
 
 int matmul_tc_nn(const float *a, int lda, const float *b, int ldb, bool b_is_nk, float *c, int ldc, int m, int k, int n, const float *row_scale,
-                 cudaStream_t st) {
+                 cudaStream_t st, const uint32_t *keep, float out_scale, int relu) {
     const int nt_cols = nn_tile(n), ntn = (n + nt_cols - 1) / nt_cols, npad_all = ntn * nt_cols;
     const int kpad = (k + BK - 1) / BK * BK, kblocks = kpad / BK;
     int dev = 0;
@@ -479,13 +518,14 @@ int matmul_tc_nn(const float *a, int lda, const float *b, int ldb, bool b_is_nk,
     }
     const int n_tiles = (m + BM - 1) / BM;
     const int grid = std::max(1, std::min(n_tiles, sm_count() / ntn)) * ntn;      // a multiple of ntn: every CTA owns one n tile
-    matmul_tc_kernel<<<grid, TC_THREADS, smem, st>>>(map_a, map_bb, map_bs, c, ldc, row_scale, m, n, nt_cols, ntn, kblocks, async_err_flag());
+    matmul_tc_kernel<<<grid, TC_THREADS, smem, st>>>(map_a, map_bb, map_bs, c, ldc, row_scale, m, n, nt_cols, ntn, kblocks, keep, k, out_scale, relu,
+                                                     async_err_flag());
     GCNK_LAUNCHED();
     return GCNK_OK;
 }
 
 int matmul_tc_fw(const float *a, const float *b, float *c, int m, int k, int n, cudaStream_t st) {
-    return matmul_tc_nn(a, k, b, n, false, c, n, m, k, n, nullptr, st);
+    return matmul_tc_nn(a, k, b, n, false, c, n, m, k, n, nullptr, st, nullptr, 1.0f, 0);
 }
 
 // ----------------------------------------------------------------------------------------- tn ----
@@ -501,7 +541,8 @@ size_t matmul_tc_tn_workspace(int m, int ka, int n) {
     return sizeof(float) * (size_t)tn_parts(m, mt * ntn) * (mt * 128) * (ntn * nt_cols);
 }
 
-int matmul_tc_tn(const float *a, int lda, const float *b, int ldb, float *c, int ldc, int m, int ka, int n, float *ws, size_t ws_bytes, cudaStream_t st) {
+int matmul_tc_tn(const float *a, int lda, const float *b, int ldb, float *c, int ldc, int m, int ka, int n, float *ws, size_t ws_bytes, cudaStream_t st,
+                 const uint32_t *keep, float out_scale) {
     const int nt_cols = tn_tile_n(n), mt = (ka + 127) / 128, ntn = (n + nt_cols - 1) / nt_cols, tiles = mt * ntn;
     const int parts = tn_parts(m, tiles);
     if (!ws || ws_bytes < matmul_tc_tn_workspace(m, ka, n)) { set_error("matmul_tc_tn: workspace too small"); return GCNK_EINVAL; }
@@ -523,9 +564,10 @@ int matmul_tc_tn(const float *a, int lda, const float *b, int ldb, float *c, int
     int rows_per_part = ((m + parts - 1) / parts + TN_ROWS - 1) / TN_ROWS * TN_ROWS;
     const int parts_used = (m + rows_per_part - 1) / rows_per_part;
     const size_t smem = (size_t)TN_STAGES * TN_STAGE_BYTES + sizeof(TnBars) + 1024;
-    matmul_tn_kernel<<<tiles * parts_used, TC_THREADS, smem, st>>>(map_a, map_b, ws, ld_ws, rows_ws, m, rows_per_part, mt, ntn, nt_cols, async_err_flag());
+    matmul_tn_kernel<<<tiles * parts_used, TC_THREADS, smem, st>>>(map_a, map_b, ws, ld_ws, rows_ws, m, rows_per_part, mt, ntn, nt_cols, keep, ka,
+                                                                   async_err_flag());
     GCNK_LAUNCHED();
-    reduce_tn_kernel<<<(ka * n + 255) / 256, 256, 0, st>>>(ws, c, ka, n, ld_ws, rows_ws, ldc, parts_used);
+    reduce_tn_kernel<<<(ka * n + 255) / 256, 256, 0, st>>>(ws, c, ka, n, ld_ws, rows_ws, ldc, parts_used, out_scale);
     GCNK_LAUNCHED();
     return GCNK_OK;
 }

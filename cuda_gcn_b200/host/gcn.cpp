@@ -156,8 +156,9 @@ void GCN::build(GCNPlan plan) {
         // all-reduce area: world slots | loss terms]; export it, import every peer's
         fz->slot_floats = ((size_t)F * H + (size_t)H * C + 4 + 3) / 4 * 4;
         const int max_terms = std::max(split_count[1], std::max(split_count[2], split_count[3]));
+        fz->term_region = ((size_t)max_terms + 4 * (size_t)dist.world + 3) / 4 * 4;       // one region per split
         const size_t terms_off = nbuf * buf + 128 + fz->slot_floats * dist.world;         // in floats, a multiple of 4
-        const size_t slab_bytes = sizeof(float) * (terms_off + (size_t)max_terms + 4);
+        const size_t slab_bytes = sizeof(float) * (terms_off + 3 * fz->term_region);
         GCNK_CHECK(gcnk_malloc((void **)&fz->slab, slab_bytes));
         GCNK_CHECK(gcnk_memset(fz->slab, 0, slab_bytes, nullptr));
         GCNK_CHECK(gcnk_malloc((void **)&fz->d_counter, sizeof(unsigned)));
@@ -233,7 +234,9 @@ void GCN::build(GCNPlan plan) {
         if (fz->seq_loss) {
             if (!fz->terms) {
                 const int max_terms = std::max(split_count[1], std::max(split_count[2], split_count[3]));
-                GCNK_CHECK(gcnk_malloc((void **)&fz->terms, sizeof(float) * ((size_t)max_terms + 4)));
+                fz->term_region = ((size_t)max_terms + 4 * (size_t)dist.world + 3) / 4 * 4;
+                GCNK_CHECK(gcnk_malloc((void **)&fz->terms, sizeof(float) * 3 * fz->term_region));
+                GCNK_CHECK(gcnk_memset(fz->terms, 0, sizeof(float) * 3 * fz->term_region, nullptr));
                 fz->terms_owned = true;
             }
             GCNK_CHECK(gcnk_malloc((void **)&fz->d_seq, 2 * sizeof(float)));
@@ -242,16 +245,25 @@ void GCN::build(GCNPlan plan) {
             GCNK_CHECK(gcnk_event_create(&fz->ev_l2));
             GCNK_CHECK(gcnk_event_create(&fz->ev_seq));
             for (int sp = 1; sp <= 3; sp++) {
-                // rank of every local labelled row among the labelled rows of its split, in global row order
+                // Where every local labelled row of split sp stores its loss term: rank r's terms are contiguous (row order)
+                // and start at a multiple of 4 floats (so that its push is 16-byte aligned); the gaps hold +0.0f, which a
+                // sequential fp32 sum passes over unchanged.  One region per split, so the gaps stay zero.
                 std::vector<int> index((size_t)n_loc, 0);
-                int c = 0;
-                for (int i = 0; i < r0; i++) c += full_data->split[i] == sp && full_data->label[i] >= 0;
-                fz->term_c0[sp] = c;
+                int off = 0, mine = 0;
+                for (int r = 0; r < dist.world; r++) {
+                    const int lo = dist.world > 1 ? row_begin[r] : 0, hi = dist.world > 1 ? row_begin[r + 1] : N;
+                    int cnt = 0;
+                    for (int i = lo; i < hi; i++) cnt += full_data->split[i] == sp && full_data->label[i] >= 0;
+                    if (r == dist.rank) { mine = off; fz->term_cnt[sp] = cnt; }
+                    off += (cnt + 3) / 4 * 4;
+                }
+                fz->term_c0[sp] = mine;
+                fz->term_len[sp] = off;
+                int c = mine;
                 for (int i = 0; i < n_loc; i++) {
                     index[i] = c;
                     c += data->split[i] == sp && data->label[i] >= 0;
                 }
-                fz->term_cnt[sp] = c - fz->term_c0[sp];
                 fz->term_index[sp] = upload(index);
             }
         }
@@ -338,7 +350,11 @@ void GCN::build(GCNPlan plan) {
             GCNK_CHECK(gcnk_free(fz->AX));
             fz->AX = nullptr;
         }
-        fz->bw_ws_bytes = gcnk_dense_transform_bw_workspace(n_loc, F);
+        // GCN_TC_TRANSFORM=1: the tcgen05 forms of the two feature-transform products (csrc/matmul_tc.cu) instead of the
+        // mma.sync ones (csrc/feature_tma.cu)
+        const char *tc = getenv("GCN_TC_TRANSFORM");
+        fz->tc_transform = tc && *tc && strcmp(tc, "0") && n_loc >= 2048;
+        fz->bw_ws_bytes = std::max(gcnk_dense_transform_bw_workspace(n_loc, F), fz->tc_transform ? gcnk_dense_transform_bw_tc_workspace(n_loc, F, H) : 0);
         GCNK_CHECK(gcnk_malloc((void **)&fz->bw_ws, fz->bw_ws_bytes));
         GCNK_CHECK(gcnk_stream_sync(nullptr));
     }
@@ -608,42 +624,35 @@ void GCN::await(float *d_all, int dim) {
     GCNK_CHECK(gcnk_gather_wait_next(z.flag_arrays[dist.rank] + 64 + 8 * b, dist.world, dist.rank, z.seq[b], z.d_err));
 }
 
-// The reference's own summation order for the printed loss (module.cpp:125-143), off the critical path: the per-row loss
-// terms of split `sidx` (written by the layer-2 / CE kernel just enqueued) are pushed to the peers and added up by
-// gcnk_sequential_sum.
+// The reference's own summation order for the printed loss (module.cpp:125-143): the per-row loss terms of split `sidx`
+// (written by the layer-2 / CE kernel just enqueued, into the split's region of the terms buffer) are added up by
+// gcnk_sequential_sum, and the result replaces the parallel sum in ws[0] — the value the pass reports.
+// Row-partitioned: only rank 0 adds (the other ranks push their range of terms to rank 0 — one 16-byte-aligned copy to
+// ONE peer — and contribute 0 to the sum of ws[0] over ranks that ends every pass, so every rank still reports the same
+// number, bit-identical to a single-GPU run).  Training: on a side stream, under the backward pass.
 void GCN::enqueue_loss_sum(int sidx_l, bool training, int slot) {
     Fused &z = *fz;
     gcnk_stream_t st = z.stream;
-    {
-        // the reference's own summation order for the printed loss (module.cpp:125-143), off the critical path
-        const int *flags = nullptr;
-        if (dist.world > 1) {
-            float *peers[8];
-            int *slots[8], n = 0;
-            const size_t off = (size_t)(z.terms - z.slab) + (size_t)z.term_c0[sidx_l];
-            for (int r = 0; r < dist.world; r++) {
-                if (r == dist.rank) continue;
-                peers[n] = static_cast<float *>(z.peer_slab[r]) + off;
-                slots[n] = z.flag_arrays[r] + 64 + 8 * 4 + dist.rank;
-                n++;
-            }
-            ++z.seq[4];
-            GCNK_CHECK(gcnk_peer_push_signal(z.terms + z.term_c0[sidx_l], peers, n, (size_t)z.term_cnt[sidx_l], nullptr, nullptr, 1, slots,
-                                             z.seq[4], z.d_counter, st));
-            flags = z.flag_arrays[dist.rank] + 64 + 8 * 4;
-        }
-        // training: on the side stream, under the backward pass; eval: nothing follows that could hide it, and the stream
-        // hop would cost more than the ~10 us the sum takes for a validation split
-        gcnk_stream_t ss = training ? z.seq_stream : st;
-        if (training) {
-            GCNK_CHECK(gcnk_event_record(z.ev_l2, st));
-            GCNK_CHECK(gcnk_stream_wait_event(z.seq_stream, z.ev_l2));
-        }
-        GCNK_CHECK(gcnk_sequential_sum(z.terms, split_count[sidx_l], z.d_seq + slot, 0.f, flags, flags ? dist.world : 0, dist.rank, z.seq[4],
-                                       z.d_err, ss));
-        GCNK_CHECK(gcnk_memcpy_d2h(z.h_seq + slot, z.d_seq + slot, sizeof(float), ss));
-        if (training) GCNK_CHECK(gcnk_event_record(z.ev_seq, z.seq_stream));
+    (void)slot;
+    float *region = z.terms + (size_t)(sidx_l - 1) * z.term_region;
+    if (dist.world > 1 && dist.rank != 0) {
+        float *peer[1] = {static_cast<float *>(z.peer_slab[0]) + (size_t)(region - z.slab) + z.term_c0[sidx_l]};
+        int *slot_flag[1] = {z.flag_arrays[0] + 64 + 8 * 4 + dist.rank};
+        ++z.seq[4];
+        GCNK_CHECK(gcnk_peer_push_signal(region + z.term_c0[sidx_l], peer, 1, (size_t)(z.term_cnt[sidx_l] + 3) / 4 * 4, nullptr, nullptr, 1,
+                                         slot_flag, z.seq[4], z.d_counter, st));
+        GCNK_CHECK(gcnk_memset(z.ws, 0, sizeof(float), st));           // this rank's share of the summed loss: rank 0 supplies it
+        return;
     }
+    const int *flags = nullptr;
+    if (dist.world > 1) { ++z.seq[4]; flags = z.flag_arrays[0] + 64 + 8 * 4; }
+    gcnk_stream_t ss = training ? z.seq_stream : st;                    // eval: nothing follows that could hide it
+    if (training) {
+        GCNK_CHECK(gcnk_event_record(z.ev_l2, st));
+        GCNK_CHECK(gcnk_stream_wait_event(z.seq_stream, z.ev_l2));
+    }
+    GCNK_CHECK(gcnk_sequential_sum(region, z.term_len[sidx_l], z.ws, 0.f, flags, flags ? dist.world : 0, 0, z.seq[4], z.d_err, ss));
+    if (training) GCNK_CHECK(gcnk_event_record(z.ev_seq, z.seq_stream));
 }
 
 // The end of every fused pass: cross-rank sums, the scalars to the host, the optimiser step.
@@ -653,7 +662,7 @@ void GCN::finish_pass(bool training, bool seq, int slot) {
     Variable &W1 = variables[2], &W2 = variables[5];
     // the pass is complete only with its loss; and (row-partitioned) no peer may overwrite the loss terms in this rank's
     // slab — which it can do as soon as it has passed the barrier below — before they have been added up
-    if (seq && training) GCNK_CHECK(gcnk_stream_wait_event(st, z.ev_seq));
+    if (seq && training && (dist.world == 1 || dist.rank == 0)) GCNK_CHECK(gcnk_stream_wait_event(st, z.ev_seq));
     if (dist.world > 1) {
         // sums over nodes: dW1, dW2 and {sum of loss terms, count, wrong}; every rank then applies the same update.
         // This is also the one true barrier of the pass: nobody starts the next pass (and overwrites a gather source
@@ -743,7 +752,8 @@ void GCN::fused_enqueue(int current_split, bool training, int slot) {
         // eval: A_hat*(X*W1) = (A_hat*X)*W1, ReLU and the pre-scale for the next gather in the epilogue
         gpu_timer_begin(TMR_SPMATMUL_FW);
         mirror(z.h1_s, H);
-        if (z.AXp) GCNK_CHECK(gcnk_dense_transform_ld(z.AXp, z.ld, n_loc, F, W1.data, z.h1_s + own, H, nullptr, 1.0f, dinv, 1, st));
+        if (z.AXp && z.tc_transform) GCNK_CHECK(gcnk_dense_transform_tc(z.AXp, z.ld, n_loc, F, W1.data, z.h1_s + own, H, nullptr, 1.0f, dinv, 1, st));
+        else if (z.AXp) GCNK_CHECK(gcnk_dense_transform_ld(z.AXp, z.ld, n_loc, F, W1.data, z.h1_s + own, H, nullptr, 1.0f, dinv, 1, st));
         else GCNK_CHECK(gcnk_dense_transform(z.AX, n_loc, F, W1.data, z.h1_s + own, H, nullptr, 1.0f, dinv, 1, st));
         gpu_timer_end(TMR_SPMATMUL_FW);
     } else {
@@ -752,7 +762,8 @@ void GCN::fused_enqueue(int current_split, bool training, int slot) {
         gpu_timer_begin(TMR_SPMATMUL_FW);
         if (z.xp_dirty) { GCNK_CHECK(gcnk_dense_pack(d_feature_value, n_loc, F, z.Xp, z.ld, st)); z.xp_dirty = false; }
         mirror(z.xw_s, H);
-        if (z.Xp) GCNK_CHECK(gcnk_dense_transform_ld(z.Xp, z.ld, n_loc, F, W1.data, z.xw_s + own, H, drop ? z.keep0 : nullptr, scale, dinv, 0, st));
+        if (z.Xp && z.tc_transform) GCNK_CHECK(gcnk_dense_transform_tc(z.Xp, z.ld, n_loc, F, W1.data, z.xw_s + own, H, drop ? z.keep0 : nullptr, scale, dinv, 0, st));
+        else if (z.Xp) GCNK_CHECK(gcnk_dense_transform_ld(z.Xp, z.ld, n_loc, F, W1.data, z.xw_s + own, H, drop ? z.keep0 : nullptr, scale, dinv, 0, st));
         else GCNK_CHECK(gcnk_spmm_fw(sp, d_feature_value, W1.data, z.xw_s + own, H, drop ? z.keep0 : nullptr, scale, dinv, st));
         gpu_timer_end(TMR_SPMATMUL_FW);
         if (drop && z.rng_stream) {
@@ -803,7 +814,7 @@ void GCN::fused_enqueue(int current_split, bool training, int slot) {
     GCNK_CHECK(gcnk_layer2_fused_terms(z.P, W2.data, d_split, d_label, current_split, n_loc, H, C, training,
                                        split_count[current_split & 3], dinv, training ? z.G + own : nullptr,
                                        training ? W2.grad : nullptr, nullptr, z.d_result, z.ws, z.ws_bytes,
-                                       seq ? z.terms : nullptr, seq ? z.term_index[sidx_l] : nullptr, st));
+                                       seq ? z.terms + (size_t)(sidx_l - 1) * z.term_region : nullptr, seq ? z.term_index[sidx_l] : nullptr, st));
     gpu_timer_end(TMR_LOSS_FW);
     if (seq) enqueue_loss_sum(sidx_l, training, slot);
     z.seq_used[slot] = seq;
@@ -824,7 +835,8 @@ void GCN::fused_enqueue(int current_split, bool training, int slot) {
         GCNK_CHECK(gcnk_gather_plain(v, z.Gm, z.dxw, H, st));
         gpu_timer_end(TMR_GATHER_FULL);
         gpu_timer_begin(TMR_SPMATMUL_BW);
-        if (z.Xp) GCNK_CHECK(gcnk_dense_transform_bw_ld(z.Xp, z.ld, n_loc, F, z.dxw, W1.grad, H, drop ? z.keep0 : nullptr, scale, z.bw_ws, z.bw_ws_bytes, st));
+        if (z.Xp && z.tc_transform) GCNK_CHECK(gcnk_dense_transform_bw_tc(z.Xp, z.ld, n_loc, F, z.dxw, W1.grad, H, drop ? z.keep0 : nullptr, scale, z.bw_ws, z.bw_ws_bytes, st));
+        else if (z.Xp) GCNK_CHECK(gcnk_dense_transform_bw_ld(z.Xp, z.ld, n_loc, F, z.dxw, W1.grad, H, drop ? z.keep0 : nullptr, scale, z.bw_ws, z.bw_ws_bytes, st));
         else GCNK_CHECK(gcnk_spmm_bw(sp, d_feature_value, z.dxw, W1.grad, H, drop ? z.keep0 : nullptr, scale, st));
         gpu_timer_end(TMR_SPMATMUL_BW);
     }
@@ -848,8 +860,7 @@ std::pair<float, float> GCN::fused_collect(int slot, bool sync) {
     const float *red = z.h_red + 4 * slot;
     last_count = (int)red[1];
     last_wrong = (int)red[2];
-    const float loss_sum = z.seq_used[slot] ? z.h_seq[slot] : red[0];
-    const float mean_loss = loss_sum / (float)last_count;                // count == 0 -> NaN, as the reference
+    const float mean_loss = red[0] / (float)last_count;                  // count == 0 -> NaN, as the reference
     const float sumsq = z.sumsq_used[slot] >= 0.f ? z.sumsq_used[slot] : z.sumsq;
     const float l2 = params.weight_decay * sumsq / 2;
     return {mean_loss + l2, float(last_count - last_wrong) / last_count};

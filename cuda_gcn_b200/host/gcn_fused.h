@@ -81,7 +81,7 @@ struct GCN::Fused {
     float *Xp = nullptr, *AXp = nullptr, *bw_ws = nullptr;
     size_t bw_ws_bytes = 0;
     int ld = 0;
-    bool xp_dirty = false;
+    bool xp_dirty = false, tc_transform = false;
     // Row-partitioned runs: the four gather sources live in ONE slab that every peer maps over NVLink (CUDA IPC);
     // producers mirror their rows into the peers' slabs and a flag barrier replaces the all-gather collective.
     bool p2p = false;
@@ -101,7 +101,8 @@ struct GCN::Fused {
     float *terms = nullptr, *d_seq = nullptr, *h_seq = nullptr;
     bool terms_owned = false;
     int *term_index[4] = {nullptr, nullptr, nullptr, nullptr};
-    int term_c0[4] = {0, 0, 0, 0}, term_cnt[4] = {0, 0, 0, 0};
+    int term_c0[4] = {0, 0, 0, 0}, term_cnt[4] = {0, 0, 0, 0}, term_len[4] = {0, 0, 0, 0};
+    size_t term_region = 0;     // floats per split region of `terms`
     gcnk_stream_t seq_stream = nullptr;
     void *ev_l2 = nullptr, *ev_seq = nullptr;
     int *halo_rows[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};

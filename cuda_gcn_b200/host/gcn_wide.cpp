@@ -145,7 +145,7 @@ void GCN::wide_enqueue(int current_split, bool training, int slot) {
     gpu_timer_begin(TMR_LOSS_FW);
     const bool seq = z.seq_loss && sidx != 0;
     GCNK_CHECK(gcnk_ce_rows(z.logits, Cp, d_split, d_label, current_split, n_loc, C, training, split_count[current_split & 3], dinv,
-                            training ? z.D_s + own : nullptr, z.d_result, z.ws, z.ws_bytes, seq ? z.terms : nullptr,
+                            training ? z.D_s + own : nullptr, z.d_result, z.ws, z.ws_bytes, seq ? z.terms + (size_t)(sidx - 1) * z.term_region : nullptr,
                             seq ? z.term_index[sidx] : nullptr, st));
     gpu_timer_end(TMR_LOSS_FW);
     if (seq) enqueue_loss_sum(sidx, training, slot);

@@ -164,6 +164,16 @@ size_t gcnk_dense_transform_bw_workspace(int m, int n);
 int gcnk_dense_transform_bw_ld(const float *xp, int ld, int m, int n, const float *g, float *w_grad, int p, const uint32_t *drop_bits,
                                float drop_scale, float *workspace, size_t workspace_bytes, gcnk_stream_t stream);
 
+/* The same transform and weight gradient on the 5th-generation tensor cores (csrc/matmul_tc.cu: tcgen05.mma kind::tf32 with
+ * 3xTF32 split products, accumulators in TMEM, X tiles staged by TMA; Dropout applied while a tile is split in shared
+ * memory).  xp: packed as for gcnk_dense_transform_ld; any p that is a multiple of 4 up to 256.  GCNK_EUNSUPPORTED when
+ * the shape does not qualify (fewer than ~2,000 rows, GCNK_NO_TCGEN05=1): callers fall back to the _ld forms. */
+int gcnk_dense_transform_tc(const float *xp, int ld, int m, int n, const float *w, float *c, int p, const uint32_t *drop_bits,
+                            float drop_scale, const float *row_scale, int relu, gcnk_stream_t stream);
+size_t gcnk_dense_transform_bw_tc_workspace(int m, int n, int p);
+int gcnk_dense_transform_bw_tc(const float *xp, int ld, int m, int n, const float *g, float *w_grad, int p, const uint32_t *drop_bits,
+                               float drop_scale, float *workspace, size_t workspace_bytes, gcnk_stream_t stream);
+
 /* ---- Matmul: K1/K2/K3, cuda_kernel.cu:6-96 (CPU: module.cpp:11-42) -------------------------------- */
 int gcnk_matmul_fw(const float *a, const float *b, float *c, int m, int n, int p, gcnk_stream_t stream);   /* c = a*b       */
 int gcnk_matmul_bw_a(const float *c_grad, const float *b, float *a_grad, int m, int n, int p, gcnk_stream_t stream); /* a_grad = c_grad * b^T */

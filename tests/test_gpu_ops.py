@@ -319,6 +319,18 @@ def test_dense_transform_tma(abi, chk, m, f, drop):
     abi.k.gcnk_dense_transform_bw_ld(dxp.ptr, ld, m, f, dg.ptr, dwg.ptr, h, bits.ptr if drop else None, 2.0, ws.ptr, wsb, None)
     close(dwg.numpy(), want_bw, rtol=5e-5, what="tma bw")
     abi.k.gcnk_async_error(None)                                   # no mbarrier wait timed out
+    if m >= 2048:
+        # the tcgen05 forms of the same two products (dropout applied while the tile is split in shared memory)
+        abi.k.gcnk_dense_transform_tc(dxp.ptr, ld, m, f, dw.ptr, dc.ptr, h, bits.ptr if drop else None, 2.0, None, 0, None)
+        close(dc.numpy(), want_fw, what="tcgen05 fw")
+        abi.k.gcnk_dense_transform_tc(dxp.ptr, ld, m, f, dw.ptr, dc.ptr, h, bits.ptr if drop else None, 2.0, drs.ptr, 1, None)
+        close(dc.numpy(), np.maximum(want_fw, 0) * rs[:, None], what="tcgen05 fw + relu + row scale")
+        wsb2 = abi.k.gcnk_dense_transform_bw_tc_workspace(m, f, h)
+        ws2 = abi.DeviceArray((max(wsb2, 16) // 4 + 4,), np.float32)
+        dwg2 = abi.DeviceArray.zeros((f, h), np.float32)
+        abi.k.gcnk_dense_transform_bw_tc(dxp.ptr, ld, m, f, dg.ptr, dwg2.ptr, h, bits.ptr if drop else None, 2.0, ws2.ptr, wsb2, None)
+        close(dwg2.numpy(), want_bw, rtol=5e-5, what="tcgen05 bw")
+        assert abi.k.gcnk_async_error(None) == 0
 
 
 @pytest.mark.parametrize("m,n,p", [(1, 1, 1), (300, 16, 7), (1000, 16, 41), (777, 256, 47), (5000, 100, 256), (64, 64, 64)])
