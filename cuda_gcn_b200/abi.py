@@ -139,6 +139,8 @@ SIGNATURES = {
     "gcnk_peer_push_barrier": (i32, [vp, vp, i32, sz, vp, i32, i32, i32, vp, vp, vp]),
     "gcnk_peer_push_signal": (i32, [vp, vp, i32, sz, vp, vp, i32, vp, i32, vp, vp]),
     "gcnk_gather_wait_next": (i32, [vp, i32, i32, i32, vp]),
+    "gcnk_graph_rotate": (i32, [vp, i32, i32, vp]),
+    "gcnk_gather_exchange_next": (i32, [vp, sz, vp, i32, vp, vp, i32, i32, i32, vp, vp]),
     "gcnk_gather_raw": (i32, [vp, vp, vp, i32, vp]),
     "gcnk_gather_init_next": (i32, [vp]),
     "gcnk_peer_allreduce": (i32, [vp, vp, i32, vp, sz, vp, i32, i32, i32, vp, vp, vp]),

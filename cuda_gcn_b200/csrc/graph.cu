@@ -46,6 +46,11 @@ struct gcnk_graph {
     const gcnk_graph *base = nullptr;
     int *own_indptr = nullptr, *own_indices = nullptr;
     int n_rows_scheduled = 0;
+    // rotated order (gcnk_graph_rotate, row-partitioned runs): every row lists the columns this rank owns first, then the
+    // columns of higher ranks, then those of lower ranks; seg1[s] / seg2[s] are the two boundaries (absolute offsets)
+    int rot_lo = -1, rot_hi = -1;
+    int *seg1 = nullptr, *seg2 = nullptr;
+    bool seg_owned = false;
 };
 
 namespace {
@@ -75,12 +80,23 @@ struct GatherArgs {
     long long wait_limit;
     // accumulate: the row sum starts from init[s, :] (the raw partial sum an earlier launch over other columns left there)
     const float *init;
+    // fused exchange (xgather_kernel): the first x_ctas CTAs copy this rank's rows of the source to the peers and publish
+    // x_value in their flag slots; the others aggregate in rotated order, waiting for a peer's rows only when they get there
+    const float4 *x_src;
+    float4 *x_dst[7];
+    int *x_flag[7];
+    size_t x_vec;
+    unsigned *x_counter;
+    int x_peers, x_ctas, x_value, x_rank, x_world;
+    const int *seg1, *seg2;
 };
 
 // Registered by gcnk_gather_wait_next for the next gather launched by this thread.
 struct GatherWait { const int *flags; int n, skip, value; int *err; };
 thread_local GatherWait t_wait = {nullptr, 0, -1, 0, nullptr};
 thread_local const float *t_init = nullptr;     // gcnk_gather_init_next
+struct GatherXchg { const float *src; float *dst[7]; int *flag[7]; size_t n_floats; unsigned *counter; int peers, value, rank, world; const int *wait_flags; int *err; bool armed; };
+thread_local GatherXchg t_xchg = {};            // gcnk_gather_exchange_next
 
 // All rows of the source that other ranks produce must be in place before any of them is read: thread r of every CTA
 // polls rank r's flag (an acquire load at system scope: the peer wrote the rows, fenced, then the flag), the CTA
@@ -457,6 +473,116 @@ __global__ void __launch_bounds__(THREADS, NACC != 1 ? 1 : IDX4 == 3 ? 4 : IDX4 
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// GraphSum with the exchange of its source fused in (row-partitioned runs, width 12 / 16): ONE launch pushes this rank's
+// rows of the gather source to the peers over NVLink and aggregates, overlapping the two.
+//   CTAs [0, x_ctas)   copy the rank's finished rows (x_vec float4) into every peer's buffer with coalesced 16-byte stores;
+//                      the last of them to finish publishes x_value in the peers' flag slots.
+//   the other CTAs     aggregate as gather_kernel does, on the ROTATED row order (own columns, higher ranks, lower ranks):
+//                      the first row of every warp is taken in three pieces — own columns need nothing from anybody, the
+//                      flags of the higher ranks are awaited before the second piece, those of the lower ranks before the
+//                      third — by which time the pushes, which started together with this kernel on every rank, have
+//                      landed.  Later rows run in one piece (same entry order).  Which rows are split is a property of the
+//                      static schedule, not of timing: results stay reproducible.
+// Nothing of a peer's block is read before its flag has been seen (acquire at system scope); partition cuts are even, so
+// no 128-byte line of a 64-byte-row source holds rows of two ranks.
+__device__ __forceinline__ void x_wait(const GatherArgs &a, int lo, int hi, int lane) {
+    const int r = lo + lane;
+    if (r < hi) {
+        const int *f = a.wait_flags + r;
+        const long long t0 = clock64();
+        for (;;) {
+            int v;
+            asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+            if (v >= a.wait_value) break;
+            if (clock64() - t0 > a.wait_limit) { *a.wait_err = 1; break; }
+            __nanosleep(32);
+        }
+    }
+    __syncwarp();
+}
+
+template <bool EXACT>
+__global__ void __launch_bounds__(THREADS, 6) xgather_kernel(const GatherArgs a) {
+    extern __shared__ float smem[];   // heavy rows only: [WARPS][dim]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if ((int)blockIdx.x < a.x_ctas) {
+        // ---------------- pushers
+        const size_t stride = (size_t)a.x_ctas * THREADS;
+        for (size_t i = blockIdx.x * (size_t)THREADS + threadIdx.x; i < a.x_vec; i += stride) {
+            const float4 v = a.x_src[i];
+#pragma unroll 1
+            for (int p = 0; p < a.x_peers; p++) a.x_dst[p][i] = v;
+        }
+        __shared__ bool s_last;
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const unsigned prev = atomicAdd(a.x_counter, 1u);
+            s_last = prev == (unsigned)a.x_ctas - 1;
+            if (s_last) *a.x_counter = 0;
+        }
+        __syncthreads();
+        if (s_last && (int)threadIdx.x < a.x_peers) {
+            __threadfence_system();
+            *reinterpret_cast<volatile int *>(a.x_flag[threadIdx.x]) = a.x_value;
+        }
+        return;
+    }
+    const int bid = (int)blockIdx.x - a.x_ctas;
+    Acc<4> acc[1];
+    if (bid < a.n_heavy) {
+        const int s = a.heavy_rows[bid];
+        const int beg = a.indptr[s], end = a.indptr[s + 1], m1 = a.seg1[s], m2 = a.seg2[s];
+        acc[0].zero();
+        accumulate_idx4<EXACT, WARPS, 4>(acc[0], a, beg, m1, warp, lane);
+        x_wait(a, a.x_rank + 1, a.x_world, lane);
+        accumulate_idx4<EXACT, WARPS, 4>(acc[0], a, m1, m2, warp, lane);
+        x_wait(a, 0, a.x_rank, lane);
+        accumulate_idx4<EXACT, WARPS, 4>(acc[0], a, m2, end, warp, lane);
+        reduce_groups<4, 4, 1>(acc);
+        const int q = lane % 4;
+        if (lane < 4) {
+#pragma unroll
+            for (int v = 0; v < 4; v++)
+                if (q * 4 + v < a.dim) smem[warp * a.dim + q * 4 + v] = acc[0].get(v);
+        }
+        __syncthreads();
+        if (warp == 0) {
+#pragma unroll
+            for (int v = 0; v < 4; v++) {
+                float sum = 0.f;
+                if (lane < 4 && q * 4 + v < a.dim)
+                    for (int w = 0; w < WARPS; w++) sum += smem[w * a.dim + q * 4 + v];
+                acc[0].set(v, sum);
+            }
+            epilogue<4, 4, 1>(acc, a, s, lane);
+        }
+        return;
+    }
+    const int bin = (bid - a.n_heavy) * WARPS + warp;
+    const int r_end = a.bin_ptr[bin + 1];
+    bool waited = false;
+    for (int r = a.bin_ptr[bin]; r < r_end; r++) {
+        const int s = a.bin_rows[r];
+        const int beg = a.indptr[s], end = a.indptr[s + 1];
+        acc[0].zero();
+        if (!waited) {
+            const int m1 = a.seg1[s], m2 = a.seg2[s];
+            accumulate_idx4<EXACT, 1, 4>(acc[0], a, beg, m1, 0, lane);
+            x_wait(a, a.x_rank + 1, a.x_world, lane);
+            accumulate_idx4<EXACT, 1, 4>(acc[0], a, m1, m2, 0, lane);
+            x_wait(a, 0, a.x_rank, lane);
+            accumulate_idx4<EXACT, 1, 4>(acc[0], a, m2, end, 0, lane);
+            waited = true;
+        } else {
+            accumulate_idx4<EXACT, 1, 4>(acc[0], a, beg, end, 0, lane);
+        }
+        reduce_groups<4, 4, 1>(acc);
+        epilogue<4, 4, 1>(acc, a, s, lane);
+    }
+}
+
 // Which index-fetch variant the dim 12 / 16 gather uses (see gather_kernel): GCNK_GATHER_IDX4 in the environment, or
 // gcnk_gather_variant() at run time.
 int g_gather_variant = -1;
@@ -522,6 +648,26 @@ int launch_gather(const gcnk_graph *g, GatherArgs a, cudaStream_t st) {
     a.mask_stride = mask_stride_bits(dim);
     a.init = t_init;
     t_init = nullptr;
+    if (t_xchg.armed) {
+        t_xchg.armed = false;
+        if (!(g->seg1 && g->seg2 && g->idx4_ok && (dim == 16 || dim == 12) && reinterpret_cast<uintptr_t>(a.in) % 16 == 0 &&
+              reinterpret_cast<uintptr_t>(a.out) % 16 == 0 && t_xchg.n_floats % 4 == 0 && !a.init)) {
+            set_error("gather: the fused exchange needs a rotated graph (gcnk_graph_rotate), width 12 or 16 and 16-byte-aligned buffers");
+            return GCNK_EUNSUPPORTED;
+        }
+        a.x_src = reinterpret_cast<const float4 *>(t_xchg.src); a.x_vec = t_xchg.n_floats / 4; a.x_peers = t_xchg.peers;
+        for (int i = 0; i < t_xchg.peers; i++) { a.x_dst[i] = reinterpret_cast<float4 *>(t_xchg.dst[i]); a.x_flag[i] = t_xchg.flag[i]; }
+        a.x_counter = t_xchg.counter; a.x_value = t_xchg.value; a.x_rank = t_xchg.rank; a.x_world = t_xchg.world;
+        a.x_ctas = (int)std::max<size_t>(1, std::min<size_t>((a.x_vec + 2 * THREADS - 1) / (2 * THREADS), (size_t)sm_count()));   // short-lived: they leave their slots to the gather CTAs
+        a.wait_flags = t_xchg.wait_flags; a.wait_value = t_xchg.value; a.wait_err = t_xchg.err; a.wait_limit = peer_spin_cycles();
+        a.seg1 = g->seg1; a.seg2 = g->seg2;
+        const int grid = a.x_ctas + g->n_heavy + g->n_bins / WARPS;
+        const size_t smem = g->n_heavy ? sizeof(float) * WARPS * (size_t)dim : 0;
+        if (dim == 16) xgather_kernel<true><<<grid, THREADS, smem, st>>>(a);
+        else xgather_kernel<false><<<grid, THREADS, smem, st>>>(a);
+        GCNK_LAUNCHED();
+        return GCNK_OK;
+    }
     if (t_wait.flags) {
         a.wait_flags = t_wait.flags; a.wait_n = t_wait.n; a.wait_skip = t_wait.skip; a.wait_value = t_wait.value;
         a.wait_err = t_wait.err; a.wait_limit = peer_spin_cycles();
@@ -601,6 +747,41 @@ __global__ void scale_rows_kernel(const float *__restrict__ dinv, const float *_
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (; i < total; i += stride) out[i] = dinv[i / dim] * in[i];
+}
+
+// Rotated order of a row-partition's CSR slice (gcnk_graph_rotate): a warp per row rewrites its entries as
+// [columns in [lo, hi) | columns >= hi | columns < lo], each class in its original order, and records the two boundaries.
+__global__ void rotate_rows_kernel(const int *__restrict__ indptr, const int *__restrict__ indices, int n, int lo, int hi, int *__restrict__ out,
+                                   int *__restrict__ seg1, int *__restrict__ seg2) {
+    const int s = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32, lane = threadIdx.x & 31;
+    if (s >= n) return;
+    const int beg = indptr[s], end = indptr[s + 1];
+    int w = beg;
+    for (int cls = 0; cls < 3; cls++) {
+        for (int e0 = beg; e0 < end; e0 += 32) {
+            const int e = e0 + lane;
+            const int d = e < end ? indices[e] : -1;
+            const int c = d < 0 ? -1 : (d >= lo && d < hi) ? 0 : d >= hi ? 1 : 2;
+            const unsigned m = __ballot_sync(FULL, c == cls);
+            if (c == cls) out[w + __popc(m & ((1u << lane) - 1u))] = d;
+            w += __popc(m);
+        }
+        if (lane == 0) { if (cls == 0) seg1[s] = w; else if (cls == 1) seg2[s] = w; }
+    }
+}
+// boundaries of an already rotated row (a column-filtered view of a rotated graph keeps the order)
+__global__ void segment_rows_kernel(const int *__restrict__ indptr, const int *__restrict__ indices, int n, int lo, int hi, int *__restrict__ seg1,
+                                    int *__restrict__ seg2) {
+    const int s = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32, lane = threadIdx.x & 31;
+    if (s >= n) return;
+    int own = 0, up = 0;
+    for (int e = indptr[s] + lane; e < indptr[s + 1]; e += 32) {
+        const int d = indices[e];
+        own += d >= lo && d < hi;
+        up += d >= hi;
+    }
+    own = warp_sum_int(own); up = warp_sum_int(up);
+    if (lane == 0) { seg1[s] = indptr[s] + own; seg2[s] = indptr[s] + own + up; }
 }
 
 // Column-filtered views (gcnk_graph_create_view): a warp per row counts / compacts the entries whose column flag is set,
@@ -742,6 +923,7 @@ int gcnk_graph_create_view(gcnk_graph **out, const gcnk_graph *base, const int *
     g->base = base->base ? base->base : base;        // d^-1/2 always comes from the root graph
     g->heavy_rows = nullptr; g->bin_ptr = nullptr; g->bin_rows = nullptr; g->scratch = nullptr; g->scratch_elems = 0;
     g->own_indptr = nullptr; g->own_indices = nullptr;   // (a row view of a column view borrows that view's CSR: it must outlive this one)
+    g->seg_owned = false;                                 // ... and the parent's rotation boundaries
 
     std::vector<int> indptr((size_t)n + 1, 0), row_keep;
     if (d_row_keep) {
@@ -771,6 +953,14 @@ int gcnk_graph_create_view(gcnk_graph **out, const gcnk_graph *base, const int *
         g->indptr = g->own_indptr; g->indices = g->own_indices; g->nnz = w;
         g->idx4_ok = w > 0 && idx4_readable(g->own_indices, w);
         g->symmetric = 0;
+        if (base->seg1) {                     // a view of a rotated graph: its own boundaries (the filter keeps the order)
+            g->seg1 = nullptr; g->seg2 = nullptr;
+            GCNK_CUDA(cudaMalloc(&g->seg1, sizeof(int) * std::max(n, 1)));
+            GCNK_CUDA(cudaMalloc(&g->seg2, sizeof(int) * std::max(n, 1)));
+            g->seg_owned = true;
+            if (n) { segment_rows_kernel<<<(n + 7) / 8, 256, 0, st>>>(g->own_indptr, g->own_indices, n, base->rot_lo, base->rot_hi, g->seg1, g->seg2); GCNK_LAUNCHED(); }
+            GCNK_CUDA(cudaStreamSynchronize(st));
+        }
     } else {
         GCNK_CUDA(cudaMemcpyAsync(indptr.data(), base->indptr, sizeof(int) * ((size_t)n + 1), cudaMemcpyDeviceToHost, st));
         GCNK_CUDA(cudaStreamSynchronize(st));
@@ -795,6 +985,7 @@ int gcnk_graph_destroy(gcnk_graph *g) {
     if (!g->base) cudaFree(g->dinv);                  // views borrow d^-1/2 from the root graph
     cudaFree(g->heavy_rows); cudaFree(g->bin_ptr); cudaFree(g->bin_rows); cudaFree(g->scratch);
     cudaFree(g->own_indptr); cudaFree(g->own_indices);
+    if (g->seg_owned) { cudaFree(g->seg1); cudaFree(g->seg2); }
     delete g;
     return GCNK_OK;
 }
@@ -846,6 +1037,37 @@ int gcnk_gather_mask(const gcnk_graph *g, const float *in_scaled, float *out_sca
 }
 
 int gcnk_mask_row_stride_bits(int dim) { return mask_stride_bits(dim); }
+
+int gcnk_graph_rotate(gcnk_graph *g, int col_lo, int col_hi, gcnk_stream_t stream) {
+    GCNK_REQUIRE(g && !g->base && !g->seg1 && col_lo >= 0 && col_hi >= col_lo && col_hi <= g->n_cols, "needs a base graph that is not rotated yet and a column range");
+    cudaStream_t st = S(stream);
+    int *rot = nullptr;
+    GCNK_CUDA(cudaMalloc(&rot, sizeof(int) * ((size_t)g->nnz + 4)));
+    GCNK_CUDA(cudaMemsetAsync(rot + g->nnz, 0, sizeof(int) * 4, st));
+    GCNK_CUDA(cudaMalloc(&g->seg1, sizeof(int) * std::max(g->n, 1)));
+    GCNK_CUDA(cudaMalloc(&g->seg2, sizeof(int) * std::max(g->n, 1)));
+    g->seg_owned = true;
+    if (g->n) { rotate_rows_kernel<<<(g->n + 7) / 8, 256, 0, st>>>(g->indptr, g->indices, g->n, col_lo, col_hi, rot, g->seg1, g->seg2); GCNK_LAUNCHED(); }
+    GCNK_CUDA(cudaStreamSynchronize(st));
+    g->own_indices = rot;                 // freed with the handle; the caller's array is no longer referenced
+    g->indices = rot;
+    g->idx4_ok = g->nnz > 0 && idx4_readable(rot, g->nnz);
+    g->rot_lo = col_lo; g->rot_hi = col_hi;
+    g->symmetric = 0;                     // (a slice is never square anyway)
+    return GCNK_OK;
+}
+
+int gcnk_gather_exchange_next(const float *own_rows, size_t n_floats, float *const *peer_rows, int n_peers, int *const *peer_flag_slots,
+                              const int *d_wait_flags, int rank, int world, int value, unsigned *d_counter, int *d_err) {
+    GCNK_REQUIRE(own_rows && peer_rows && peer_flag_slots && d_wait_flags && d_counter && d_err && n_peers >= 1 && n_peers <= 7 && world >= 2 &&
+                     world <= 8 && rank >= 0 && rank < world && n_floats % 4 == 0,
+                 "bad arguments");
+    t_xchg.src = own_rows; t_xchg.n_floats = n_floats; t_xchg.peers = n_peers;
+    for (int i = 0; i < n_peers; i++) { t_xchg.dst[i] = peer_rows[i]; t_xchg.flag[i] = peer_flag_slots[i]; }
+    t_xchg.counter = d_counter; t_xchg.value = value; t_xchg.rank = rank; t_xchg.world = world; t_xchg.wait_flags = d_wait_flags; t_xchg.err = d_err;
+    t_xchg.armed = true;
+    return GCNK_OK;
+}
 
 int gcnk_gather_init_next(const float *d_partial) {
     t_init = d_partial;
@@ -903,7 +1125,8 @@ int gcnk_partition_rows(const int *h_indptr, int n, int parts, int *h_row_begin)
         // first row whose prefix nnz reaches k/parts of the total (keeps every cut monotone)
         const int64_t target = (nnz * k + parts - 1) / parts;
         const int *p = std::lower_bound(h_indptr + h_row_begin[k - 1], h_indptr + n, (int)std::min<int64_t>(target, INT32_MAX));
-        h_row_begin[k] = (int)(p - h_indptr);
+        // even cuts: with 64-byte rows (width 16) no 128-byte line of a gather source then holds rows of two ranks
+        h_row_begin[k] = std::min(n, ((int)(p - h_indptr) + 1) & ~1);
     }
     h_row_begin[parts] = n;
     return GCNK_OK;

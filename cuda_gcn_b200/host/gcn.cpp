@@ -276,6 +276,17 @@ void GCN::build(GCNPlan plan) {
     if (wide) { build_wide(); finish_build(); return; }
     gcnk_spmat *sp = data->feature_index.spmat(n_loc, F);     // build the handle (dense detection) up front
     gcnk_graph *g = graph_handle();
+    {
+        // Exchange fused into the consuming GraphSum (csrc/graph.cu: xgather_kernel): one launch pushes this rank's rows of
+        // the source to the peers and aggregates, own columns first.  Needs the rotated row order, set up here before any
+        // view of the slice graph exists.  GCN_FUSED_EXCHANGE=0: separate push kernel + wait at the start of the gather.
+        const char *fx = getenv("GCN_FUSED_EXCHANGE");
+        const bool want = !(fx && *fx && !strcmp(fx, "0"));
+        if (dist.world > 1 && fz->p2p && fz->signal_exchange && !fz->use_halo && (H == 16 || H == 12) && want) {
+            GCNK_CHECK(gcnk_graph_rotate(g, r0, r0 + n_loc, nullptr));
+            fz->fused_xchg = true;
+        }
+    }
 
     const char *nv = getenv("GCN_NO_VIEWS"), *na = getenv("GCN_NO_AX");
     fz->use_views = !(nv && *nv && strcmp(nv, "0"));
@@ -615,6 +626,27 @@ bool GCN::exchange_overlapped(float *buf, int dim, gcnk_graph *v_own, gcnk_graph
     return true;
 }
 
+// Fused form of publish + await: arms the next gather launch to push this rank's rows of `d_all` itself and to wait for the
+// peers' rows as it reaches their columns (gcnk_gather_exchange_next).  false: not in use, take the two-step path.
+bool GCN::arm_exchange(float *d_all, int dim) {
+    Fused &z = *fz;
+    if (dist.world <= 1 || !z.fused_xchg) return false;
+    const int b = (int)((size_t)(d_all - z.slab) / z.buf_floats);
+    float *peers[8];
+    int *slots[8], n = 0;
+    const size_t off = (size_t)(d_all - z.slab) + (size_t)r0 * dim;
+    for (int r = 0; r < dist.world; r++) {
+        if (r == dist.rank) continue;
+        peers[n] = static_cast<float *>(z.peer_slab[r]) + off;
+        slots[n] = z.flag_arrays[r] + 64 + 8 * b + dist.rank;
+        n++;
+    }
+    ++z.seq[b];
+    GCNK_CHECK(gcnk_gather_exchange_next(d_all + (size_t)r0 * dim, (size_t)n_loc * dim, peers, n, slots, z.flag_arrays[dist.rank] + 64 + 8 * b,
+                                         dist.rank, dist.world, z.seq[b], z.d_counter, z.d_err));
+    return true;
+}
+
 // Arms the next gather launch: it reads buffer `d_all`, so it must see every rank's rows of production seq[b].
 void GCN::await(float *d_all, int dim) {
     Fused &z = *fz;
@@ -782,7 +814,8 @@ void GCN::fused_enqueue(int current_split, bool training, int slot) {
         // M2 GraphSum + M3 ReLU + M4 Dropout in the gather's epilogue
         gpu_timer_begin(TMR_GATHER_FULL);
         gcnk_graph *v = g;
-        if (exchange_overlapped(z.xw_s, H, z.g_own, z.g_rem)) v = z.g_rem;
+        if (arm_exchange(z.xw_s, H)) {}
+        else if (exchange_overlapped(z.xw_s, H, z.g_own, z.g_rem)) v = z.g_rem;
         else { publish(z.xw_s, H); await(z.xw_s, H); }
         mirror(z.h1_s, H);
         GCNK_CHECK(gcnk_gather_relu_drop(v, z.xw_s, z.h1_s + own, drop ? z.keep1 : nullptr, training ? z.mask : nullptr,
@@ -799,7 +832,8 @@ void GCN::fused_enqueue(int current_split, bool training, int slot) {
             GCNK_CHECK(gcnk_graph_create_view(&z.rows_rem[sv], z.g_rem, z.keep[sv], nullptr, nullptr));
             GCNK_CHECK(gcnk_stream_sync(nullptr));
         }
-        if (exchange_overlapped(z.h1_s, H, sv ? z.rows_own[sv] : z.g_own, sv ? z.rows_rem[sv] : z.g_rem)) v = sv ? z.rows_rem[sv] : z.g_rem;
+        if (arm_exchange(z.h1_s, H)) {}
+        else if (exchange_overlapped(z.h1_s, H, sv ? z.rows_own[sv] : z.g_own, sv ? z.rows_rem[sv] : z.g_rem)) v = sv ? z.rows_rem[sv] : z.g_rem;
         else { publish(z.h1_s, H); await(z.h1_s, H); }
         GCNK_CHECK(gcnk_gather_plain(v, z.h1_s, z.P, H, st));
     }
@@ -823,14 +857,16 @@ void GCN::fused_enqueue(int current_split, bool training, int slot) {
         // backward of M6/M5 is inside layer2; M4/M3/M2 backward = one masked gather + one plain gather
         gpu_timer_begin(gather_timer(g_cols));
         gcnk_graph *v = g_cols;
-        if (exchange_overlapped(z.G, H, z.gt_own, z.gt_rem)) v = z.gt_rem;
+        if (arm_exchange(z.G, H)) {}
+        else if (exchange_overlapped(z.G, H, z.gt_own, z.gt_rem)) v = z.gt_rem;
         else { publish(z.G, H); await(z.G, H); }
         mirror(z.Gm, H);
         GCNK_CHECK(gcnk_gather_mask(v, z.G, z.Gm + own, z.mask, scale, H, st));
         gpu_timer_end(gather_timer(g_cols));
         gpu_timer_begin(TMR_GATHER_FULL);
         v = g;
-        if (exchange_overlapped(z.Gm, H, z.g_own, z.g_rem)) v = z.g_rem;
+        if (arm_exchange(z.Gm, H)) {}
+        else if (exchange_overlapped(z.Gm, H, z.g_own, z.g_rem)) v = z.g_rem;
         else { publish(z.Gm, H); await(z.Gm, H); }
         GCNK_CHECK(gcnk_gather_plain(v, z.Gm, z.dxw, H, st));
         gpu_timer_end(TMR_GATHER_FULL);

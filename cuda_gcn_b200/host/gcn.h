@@ -99,6 +99,7 @@ private:
     void mirror(float *d_all, int dim);
     void publish(float *d_all, int dim, bool on_comm_stream = false);
     bool exchange_overlapped(float *buf, int dim, gcnk_graph *v_own, gcnk_graph *v_rem);
+    bool arm_exchange(float *d_all, int dim);
     void await(float *d_all, int dim);
     GCNData *data;                           // what this rank computes on: the caller's data, or `local` (its row slice)
     GCNData *full_data = nullptr;            // the caller's full data

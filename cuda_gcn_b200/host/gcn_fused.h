@@ -112,7 +112,7 @@ struct GCN::Fused {
     // Overlap of the exchange with the local part of the consuming GraphSum (GCN::exchange_overlapped; GCN_OVERLAP=0 turns
     // it off): own-columns / remote-columns views of the CSR slice (gt_*: training columns only; rows_*: per split), the
     // raw partial sums, and the communication stream the pushes run on.
-    bool overlap = false;
+    bool overlap = false, fused_xchg = false;
     gcnk_graph *g_own = nullptr, *g_rem = nullptr, *gt_own = nullptr, *gt_rem = nullptr;
     gcnk_graph *rows_own[4] = {nullptr, nullptr, nullptr, nullptr}, *rows_rem[4] = {nullptr, nullptr, nullptr, nullptr};
     float *partial = nullptr;

@@ -342,6 +342,16 @@ int gcnk_gather_wait_next(const int *d_flags, int n_flags, int skip, int value, 
  * only the columns this rank owns writes the UNSCALED partial row sums; gcnk_gather_init_next(partial) makes the next
  * gcnk_gather_* launch — over the view of the remaining columns — start every row sum from partial[s, :] before it applies
  * its usual epilogue.  Own columns first, remote columns second: a fixed order. */
+/* The exchange fused INTO the consuming GraphSum (width 12 / 16): gcnk_graph_rotate(g, lo, hi) re-orders every row of a
+ * row-partition's slice graph (before any view of it is created) as [columns this rank owns: lo <= c < hi | higher ranks |
+ * lower ranks]; gcnk_gather_exchange_next then makes the NEXT gcnk_gather_* launch on g (or a view of it) one kernel that
+ * (a) copies own_rows (this rank's finished rows of the gather source, n_floats) into peer_rows[i] and publishes `value`
+ * in peer_flag_slots[i], with a few CTAs, and (b) aggregates with the others, starting with the own columns and waiting
+ * for d_wait_flags[r] >= value only when it reaches rank r's columns — the transfer overlaps the aggregation inside
+ * one launch.  Replaces gcnk_peer_push_signal + gcnk_gather_wait_next for that launch. */
+int gcnk_graph_rotate(gcnk_graph *g, int col_lo, int col_hi, gcnk_stream_t stream);
+int gcnk_gather_exchange_next(const float *own_rows, size_t n_floats, float *const *peer_rows, int n_peers, int *const *peer_flag_slots,
+                              const int *d_wait_flags, int rank, int world, int value, unsigned *d_counter, int *d_err);
 int gcnk_gather_raw(const gcnk_graph *g, const float *in_scaled, float *out_raw, int dim, gcnk_stream_t stream);
 int gcnk_gather_init_next(const float *d_partial);
 /* Deterministic sum all-reduce over peer memory for small vectors (weight gradients, scalars): every rank writes
