@@ -486,17 +486,21 @@ __global__ void __launch_bounds__(THREADS, NACC != 1 ? 1 : IDX4 == 3 ? 4 : IDX4 
 //                      static schedule, not of timing: results stay reproducible.
 // Nothing of a peer's block is read before its flag has been seen (acquire at system scope); partition cuts are even, so
 // no 128-byte line of a 64-byte-row source holds rows of two ranks.
+// Polls with plain volatile loads (served by L2, where the peer's flag store lands): tens of thousands of warps pass through
+// here, and an acquire at system scope per warp — a full fence each — was measured to cost more than the exchange it
+// guards.  Ordering still holds: the writer fences (system scope) between its rows and its flag; this side reads a peer's
+// rows only after the loop has seen the flag (a control dependence the hardware does not speculate past), and has never
+// touched those lines before, so they cannot be stale in L1.
 __device__ __forceinline__ void x_wait(const GatherArgs &a, int lo, int hi, int lane) {
     const int r = lo + lane;
     if (r < hi) {
-        const int *f = a.wait_flags + r;
-        const long long t0 = clock64();
-        for (;;) {
-            int v;
-            asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
-            if (v >= a.wait_value) break;
-            if (clock64() - t0 > a.wait_limit) { *a.wait_err = 1; break; }
-            __nanosleep(32);
+        const volatile int *f = a.wait_flags + r;
+        if (*f < a.wait_value) {
+            const long long t0 = clock64();
+            while (*f < a.wait_value) {
+                if (clock64() - t0 > a.wait_limit) { *a.wait_err = 1; break; }
+                __nanosleep(32);
+            }
         }
     }
     __syncwarp();

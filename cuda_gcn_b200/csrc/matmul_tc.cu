@@ -41,8 +41,9 @@ namespace {
 
 constexpr int TC_THREADS = 384;                        // warps 0-3: TMA / MMA / TMEM alloc / idle, 4-7: splitters, 8-11: epilogue
 constexpr int BM = 128, BK = 32, STAGES = 3, ACC_STAGES = 2, TMEM_COLS = 128;   // two 64-column accumulators
-constexpr int EPI_STRIDE = 68;                         // floats per staged row (Npad <= 64): 16-byte aligned rows, and 68 = 4 mod 32 keeps the
-                                                       // quarter-warp float4 accesses of eight different rows on distinct banks
+// floats per staged epilogue row: Npad + 4 (20, 36, 52, 68) — 16-byte aligned rows, and (Npad + 4) / 4 is odd, which keeps the
+// quarter-warp float4 accesses of eight different rows on distinct banks
+__host__ __device__ constexpr int epi_stride(int npad) { return npad + 4; }
 constexpr int A_TILE_BYTES = BM * BK * 4;              // 16 KB
 constexpr uint32_t TF32_MASK = 0xffffe000u;
 
@@ -96,6 +97,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) matmul_tc_kernel(const __grid_c
     uint8_t *a_big = smem, *a_small = smem + STAGES * A_TILE_BYTES;
     const uint32_t b_block_bytes = (uint32_t)Npad * BK * 4;
     uint8_t *b_big = a_small + STAGES * A_TILE_BYTES, *b_small = b_big + (size_t)kblocks * b_block_bytes;
+    const int EPI_STRIDE = epi_stride(Npad);
     float *epi = reinterpret_cast<float *>(b_small + (size_t)kblocks * b_block_bytes);        // [4 warps][32 rows][EPI_STRIDE]
     Bars *bars = reinterpret_cast<Bars *>(epi + 4 * 32 * EPI_STRIDE);
 
@@ -474,7 +476,7 @@ static bool tc_disabled() {
 static int nn_tile(int n) { const int npad = (n + 15) / 16 * 16; return npad <= 64 ? npad : 64; }
 static size_t nn_smem(int k, int nt_cols) {
     const int kpad = (k + BK - 1) / BK * BK;
-    return 2 * (size_t)STAGES * A_TILE_BYTES + 2 * (size_t)nt_cols * kpad * 4 + 4 * 32 * EPI_STRIDE * sizeof(float) + sizeof(Bars) + 1024;
+    return 2 * (size_t)STAGES * A_TILE_BYTES + 2 * (size_t)nt_cols * kpad * 4 + 4 * 32 * (size_t)epi_stride(nt_cols) * sizeof(float) + sizeof(Bars) + 1024;
 }
 
 // shapes the kernel takes: enough rows to matter, A's row pitch a multiple of 16 bytes, both split copies of the CTA's B tile resident

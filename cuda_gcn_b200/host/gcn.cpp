@@ -588,12 +588,15 @@ void GCN::publish(float *d_all, int dim, bool on_comm_stream) {
             if (r == dist.rank) continue;
             peers[n] = static_cast<float *>(z.peer_slab[r]) + off;
             slots[n] = z.flag_arrays[r] + 64 + 8 * b + dist.rank;
-            lists[n] = z.halo_rows[r]; counts[n] = z.halo_count[r];
+            lists[n] = z.halo_now ? z.halo_now->rows[r] : z.halo_rows[r];
+            counts[n] = z.halo_now ? z.halo_now->count[r] : z.halo_count[r];
             n++;
         }
+        const bool listed = !mirrored && (z.halo_now ? z.halo_now->valid : z.use_halo);
+        z.halo_now = nullptr;
         if (z.signal_exchange) {
             ++z.seq[b];
-            GCNK_CHECK(gcnk_peer_push_signal(own, peers, n, mirrored ? 0 : (size_t)n_loc * dim, z.use_halo && !mirrored ? lists : nullptr, counts, dim,
+            GCNK_CHECK(gcnk_peer_push_signal(own, peers, n, mirrored ? 0 : (size_t)n_loc * dim, listed ? lists : nullptr, counts, dim,
                                              slots, z.seq[b], counter, ps));
         } else if (!mirrored) {
             GCNK_CHECK(gcnk_peer_push_barrier(own, peers, n, (size_t)n_loc * dim, z.flag_arrays, dist.rank, dist.world, ++z.barrier_value,

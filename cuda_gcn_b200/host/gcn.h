@@ -91,6 +91,7 @@ private:
     gcnk_graph *graph_handle();
     void build_halo();
     void build_wide();
+    void build_wide_halo();
     void finish_build();
     void wide_enqueue(int current_split, bool training, int slot);
     void enqueue_loss_sum(int split_index, bool training, int slot);

@@ -108,6 +108,12 @@ struct GCN::Fused {
     int *halo_rows[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     int halo_count[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     bool use_halo = false, signal_exchange = true;
+    // Wide plan: what a peer reads of an exchanged class-width source is much less than all rows — the forward GraphSum only
+    // aggregates the labelled rows of the split (their neighbours), the backward one only reads training columns.  Per
+    // consumer a row list per peer (gcn_wide.cpp: build_wide_halo); `halo_now` selects the set the next publish() uses.
+    struct HaloSet { int *rows[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}; int count[8] = {0, 0, 0, 0, 0, 0, 0, 0}; bool valid = false; };
+    HaloSet halo_T[4], halo_D;
+    const HaloSet *halo_now = nullptr;
     gcnk_stream_t stream = nullptr;   // everything the fused plan enqueues runs on this (non-blocking) stream
     // Overlap of the exchange with the local part of the consuming GraphSum (GCN::exchange_overlapped; GCN_OVERLAP=0 turns
     // it off): own-columns / remote-columns views of the CSR slice (gt_*: training columns only; rows_*: per split), the
@@ -159,6 +165,7 @@ struct GCN::Fused {
                         (void *)dW2p, (void *)wkeep0, (void *)wkeep1, (void *)wmask, (void *)mm_ws})
             if (q) gcnk_free(q);
         for (int *h : halo_rows) if (h) gcnk_free(h);
+        for (HaloSet *hs : {&halo_T[1], &halo_T[2], &halo_T[3], &halo_D}) for (int *h : hs->rows) if (h) gcnk_free(h);
         if (ev_ready) gcnk_event_destroy(ev_ready);
         if (ev_go) gcnk_event_destroy(ev_go);
         for (uint32_t *b : {keep0_buf[1], keep1_buf[1]}) if (b) gcnk_free(b);

@@ -45,8 +45,21 @@ void GCN::build_wide() {
     for (float **p : {&z.Tl, &z.logits, &z.dT}) GCNK_CHECK(gcnk_malloc((void **)p, nc_loc));
     GCNK_CHECK(gcnk_memset(z.logits, 0, nc_loc, nullptr));
     for (float **p : {&z.W2p, &z.dW2p}) GCNK_CHECK(gcnk_malloc((void **)p, sizeof(float) * (size_t)H * Cp));
-    GCNK_CHECK(gcnk_malloc((void **)&z.wkeep0, sizeof(uint32_t) * ((size_t)N * F / 32 + 4)));
-    GCNK_CHECK(gcnk_malloc((void **)&z.wkeep1, sizeof(uint32_t) * ((size_t)n_loc * H / 32 + 4)));
+    // keep bits, double-buffered: the NEXT training pass's draws run on a low-priority side stream under this pass's GEMMs
+    // (the generator is ALU-bound, the tcgen05 kernels leave the ALUs idle) — same scheme as the hidden-16 plan
+    for (int b = 0; b < 2; b++) {
+        GCNK_CHECK(gcnk_malloc((void **)&z.keep0_buf[b], sizeof(uint32_t) * ((size_t)N * F / 32 + 4)));
+        GCNK_CHECK(gcnk_malloc((void **)&z.keep1_buf[b], sizeof(uint32_t) * ((size_t)n_loc * H / 32 + 4)));
+    }
+    z.keep0 = z.keep0_buf[0]; z.keep1 = z.keep1_buf[0];
+    {
+        const char *ns = getenv("GCN_NO_RNG_OVERLAP");
+        if (!(ns && *ns && strcmp(ns, "0"))) {
+            GCNK_CHECK(gcnk_stream_create_low_priority(&z.rng_stream));
+            GCNK_CHECK(gcnk_event_create(&z.ev_ready));
+            GCNK_CHECK(gcnk_event_create(&z.ev_go));
+        }
+    }
     GCNK_CHECK(gcnk_malloc((void **)&z.wmask, sizeof(uint32_t) * ((size_t)n_loc * H / 32 + 4)));
     z.mm_ws_bytes = std::max(gcnk_matmul_tn_workspace(n_loc, F, H), gcnk_matmul_tn_workspace(n_loc, H, Cp));
     GCNK_CHECK(gcnk_malloc((void **)&z.mm_ws, std::max<size_t>(z.mm_ws_bytes, 16)));
@@ -63,11 +76,55 @@ void GCN::build_wide() {
     z.keep[0] = upload(train_cols);
     GCNK_CHECK(gcnk_graph_create_view(&z.cols_train, g, nullptr, z.keep[0], nullptr));
 
+    if (dist.world > 1 && z.p2p && z.signal_exchange) build_wide_halo();
+
     // A_hat * X for this rank's rows, once (eval passes)
     GCNK_CHECK(gcnk_drop_scale_rows(z.X_all, N, F, nullptr, 1.0f, z.dinv_all, z.Xd_s, nullptr));
     GCNK_CHECK(gcnk_gather_plain(g, z.Xd_s, z.AXw, F, nullptr));
     GCNK_CHECK(gcnk_stream_sync(nullptr));
     z.ax_valid = true;
+}
+
+// Halo lists of the wide plan.  Rank p reads, of the forward source T_s, only the columns its labelled rows of
+// the current split are adjacent to (at products shape: 8 % training rows x ~50 neighbours = about 40 % of all nodes, 10 %
+// for the validation split), and of the backward source D_s only training columns it is adjacent to (8 % of all nodes).
+// Every rank marks those columns in bit maps (one per split + one for "any row"), the maps are all-gathered once, and
+// each rank keeps, per consumer and peer, the list of its own rows to send.  GCN_HALO=0 turns the lists off.
+void GCN::build_wide_halo() {
+    Fused &z = *fz;
+    const char *hv = getenv("GCN_HALO");
+    if (hv && *hv && !strcmp(hv, "0")) return;
+    const int N = params.num_nodes;
+    const size_t bytes = ((size_t)N + 7) / 8;
+    std::vector<unsigned char> mine(4 * bytes, 0), all(4 * bytes * (size_t)dist.world, 0);
+    const std::vector<int> &ip = data->graph.indptr, &ix = data->graph.indices;
+    for (int i = 0; i < n_loc; i++) {
+        const int sp = data->label[i] >= 0 && data->split[i] >= 1 && data->split[i] <= 3 ? data->split[i] : 0;
+        for (int e = ip[i]; e < ip[i + 1]; e++) {
+            const int c = ix[e];
+            mine[(size_t)c >> 3] |= (unsigned char)(1u << (c & 7));                              // map 0: any row
+            if (sp) mine[(size_t)sp * bytes + ((size_t)c >> 3)] |= (unsigned char)(1u << (c & 7));
+        }
+    }
+    GCNK_CHECK(gcnk_comm_allgather_bytes(dist.comm, mine.data(), all.data(), (int)(4 * bytes)));
+    for (int p = 0; p < dist.world; p++) {
+        if (p == dist.rank) continue;
+        const unsigned char *maps = all.data() + 4 * bytes * (size_t)p;
+        auto bit = [&](int map, int i) { return (maps[(size_t)map * bytes + ((size_t)i >> 3)] >> (i & 7)) & 1u; };
+        for (int sp = 1; sp <= 3; sp++) {
+            std::vector<int> rows;
+            for (int i = r0; i < r0 + n_loc; i++) if (bit(sp, i)) rows.push_back(i - r0);
+            z.halo_T[sp].count[p] = (int)rows.size();
+            if (!rows.empty()) z.halo_T[sp].rows[p] = upload(rows);
+            z.halo_T[sp].valid = true;
+        }
+        std::vector<int> rows;
+        for (int i = r0; i < r0 + n_loc; i++)
+            if (bit(0, i) && data->split[i - r0] == 1 && data->label[i - r0] >= 0) rows.push_back(i - r0);
+        z.halo_D.count[p] = (int)rows.size();
+        if (!rows.empty()) z.halo_D.rows[p] = upload(rows);
+        z.halo_D.valid = true;
+    }
 }
 
 void GCN::wide_enqueue(int current_split, bool training, int slot) {
@@ -107,33 +164,52 @@ void GCN::wide_enqueue(int current_split, bool training, int slot) {
         gpu_timer_begin(TMR_DROPOUT_FW);
         uint64_t state[2];
         GCNK_CHECK(gcnk_rng_get_state(global_rng(), state));
-        if (drop) {
-            GCNK_CHECK(gcnk_rng_set_state(z.slice_rng, state[0], state[1]));
-            GCNK_CHECK(gcnk_dropout_mask(z.slice_rng, z.wkeep0, (int64_t)N * F, p, st));
-            GCNK_CHECK(gcnk_rng_set_state(z.slice_rng, state[0], state[1]));
+        auto draw_masks = [&](const uint64_t *from, uint32_t *k0, uint32_t *k1, gcnk_stream_t stream) {
+            GCNK_CHECK(gcnk_rng_set_state(z.slice_rng, from[0], from[1]));
+            GCNK_CHECK(gcnk_dropout_mask(z.slice_rng, k0, (int64_t)N * F, p, stream));
+            GCNK_CHECK(gcnk_rng_set_state(z.slice_rng, from[0], from[1]));
             GCNK_CHECK(gcnk_rng_skip(z.slice_rng, (uint64_t)N * F + (uint64_t)r0 * H));
-            GCNK_CHECK(gcnk_dropout_mask(z.slice_rng, z.wkeep1, (int64_t)n_loc * H, p, st));
+            GCNK_CHECK(gcnk_dropout_mask(z.slice_rng, k1, (int64_t)n_loc * H, p, stream));
+        };
+        if (drop) {
+            z.keep0 = z.keep0_buf[z.cur]; z.keep1 = z.keep1_buf[z.cur];
+            const bool ahead = z.pre_valid && z.pre_state[0] == state[0] && z.pre_state[1] == state[1];
+            if (z.pre_valid) GCNK_CHECK(gcnk_stream_wait_event(st, z.ev_ready));      // the side stream's last draw targets this buffer pair
+            if (!ahead) draw_masks(state, z.keep0, z.keep1, st);
+            z.pre_valid = false;
         }
         GCNK_CHECK(gcnk_rng_skip(global_rng(), (uint64_t)N * F + (uint64_t)N * H));   // consumed even when p == 0
         gpu_timer_end(TMR_DROPOUT_FW);
 
         // M0 Dropout + M2 GraphSum, re-ordered in front of M1: AXd = A_hat * drop(X) for the local rows
         gpu_timer_begin(TMR_GRAPHSUM_FW);
-        GCNK_CHECK(gcnk_drop_scale_rows(z.X_all, N, F, drop ? z.wkeep0 : nullptr, scale, z.dinv_all, z.Xd_s, st));
+        GCNK_CHECK(gcnk_drop_scale_rows(z.X_all, N, F, drop ? z.keep0 : nullptr, scale, z.dinv_all, z.Xd_s, st));
         GCNK_CHECK(gcnk_gather_plain(g, z.Xd_s, z.AXd, F, st));
+        if (drop && z.rng_stream) {
+            // the next training pass's bits, into the other buffer pair, released now: the rest of this pass is GEMMs and
+            // narrow gathers (the other buffers' last readers finished with the previous training pass: host sync)
+            GCNK_CHECK(gcnk_event_record(z.ev_go, st));
+            GCNK_CHECK(gcnk_stream_wait_event(z.rng_stream, z.ev_go));
+            GCNK_CHECK(gcnk_rng_get_state(global_rng(), z.pre_state));
+            draw_masks(z.pre_state, z.keep0_buf[z.cur ^ 1], z.keep1_buf[z.cur ^ 1], z.rng_stream);
+            GCNK_CHECK(gcnk_event_record(z.ev_ready, z.rng_stream));
+            z.pre_valid = true;
+            z.cur ^= 1;
+        }
         gpu_timer_end(TMR_GRAPHSUM_FW);
         ax = z.AXd;
     }
     // M1 (Sparse)Matmul: Z1 = AX * W1; M3 ReLU + M4 Dropout in place
     gpu_timer_begin(TMR_SPMATMUL_FW);
     GCNK_CHECK(gcnk_matmul_nn(ax, F, W1.data, H, z.H1, H, n_loc, F, H, nullptr, st));
-    GCNK_CHECK(gcnk_relu_dropout_fw(z.H1, (int64_t)n_loc * H, drop ? z.wkeep1 : nullptr, training ? scale : 1.0f, training ? z.wmask : nullptr, st));
+    GCNK_CHECK(gcnk_relu_dropout_fw(z.H1, (int64_t)n_loc * H, drop ? z.keep1 : nullptr, training ? scale : 1.0f, training ? z.wmask : nullptr, st));
     gpu_timer_end(TMR_SPMATMUL_FW);
     // M5 Matmul: T = H1 * W2 (padded to Cp columns), pre-scaled by d^-1/2 straight into the exchanged gather source
     gpu_timer_begin(TMR_MATMUL_FW);
     GCNK_CHECK(gcnk_pad_cols(W2.data, z.W2p, H, C, Cp, st));
     GCNK_CHECK(gcnk_matmul_nn(z.H1, H, z.W2p, Cp, z.T_s + own, Cp, n_loc, H, Cp, dinv, st));
     gpu_timer_end(TMR_MATMUL_FW);
+    if (sidx && z.halo_T[sidx].valid) z.halo_now = &z.halo_T[sidx];
     publish(z.T_s, Cp);
     // M6 GraphSum at the class width, only for the rows whose logits the loss looks at
     gpu_timer_begin(TMR_GATHER_PART);
@@ -153,6 +229,7 @@ void GCN::wide_enqueue(int current_split, bool training, int slot) {
 
     if (training) {
         // M6 backward: dT = A_hat * dlogits (all rows; only training columns carry a gradient)
+        if (z.halo_D.valid) z.halo_now = &z.halo_D;
         publish(z.D_s, Cp);
         gpu_timer_begin(TMR_GRAPHSUM_BW);
         await(z.D_s, Cp);
