@@ -478,12 +478,11 @@ __global__ void __launch_bounds__(THREADS, NACC != 1 ? 1 : IDX4 == 3 ? 4 : IDX4 
 // rows of the gather source to the peers over NVLink and aggregates, overlapping the two.
 //   CTAs [0, x_ctas)   copy the rank's finished rows (x_vec float4) into every peer's buffer with coalesced 16-byte stores;
 //                      the last of them to finish publishes x_value in the peers' flag slots.
-//   the other CTAs     aggregate as gather_kernel does, on the ROTATED row order (own columns, higher ranks, lower ranks):
-//                      the first row of every warp is taken in three pieces — own columns need nothing from anybody, the
-//                      flags of the higher ranks are awaited before the second piece, those of the lower ranks before the
-//                      third — by which time the pushes, which started together with this kernel on every rank, have
-//                      landed.  Later rows run in one piece (same entry order).  Which rows are split is a property of the
-//                      static schedule, not of timing: results stay reproducible.
+//   the other CTAs     aggregate as gather_kernel does, on the ROTATED row order (own columns, higher ranks, lower ranks),
+//                      in one pass per row: own columns need nothing from anybody; before the first 32-entry chunk that
+//                      reaches the higher ranks' columns the warp waits for their flags, likewise for the lower ranks —
+//                      by which time the pushes, which started together with this kernel on every rank, have landed.
+//                      The chunking does not depend on when the peers arrive: results stay reproducible.
 // Nothing of a peer's block is read before its flag has been seen (acquire at system scope); partition cuts are even, so
 // no 128-byte line of a 64-byte-row source holds rows of two ranks.
 // Polls with plain volatile loads (served by L2, where the peer's flag store lands): tens of thousands of warps pass through
@@ -504,6 +503,48 @@ __device__ __forceinline__ void x_wait(const GatherArgs &a, int lo, int hi, int 
         }
     }
     __syncwarp();
+}
+
+// The BATCH == 4 loop of accumulate_idx4 over the ROTATED row [beg, end) = [own columns | m1: higher ranks | m2: lower
+// ranks], in ONE pass: before a 32-entry chunk that reaches into a part whose owners have not been seen yet, the warp
+// waits for their flags (`state`: 0 nothing seen, 1 higher ranks seen, 2 all seen — kept across rows).  The chunking, hence
+// the order of the additions, does not depend on `state`: results are the same whenever the peers arrive.
+template <bool EXACT, int STEP>
+__device__ __forceinline__ void accumulate_x(Acc<4> &acc, const GatherArgs &a, int beg, int end, int m1, int m2, int first, int lane, int &state) {
+    constexpr int STRIDE = 32 * STEP;
+    const int g4 = (lane >> 2) * 4, q = lane & 3;
+    const int dim = EXACT ? 16 : a.dim;
+    const int base = (beg & ~3) + 32 * first;
+    int left = end - base;
+    if (left <= 0) return;
+    const int *ip = a.indices + base + g4;
+    const float *in_q = a.in + q * 4;
+    const bool active = EXACT || q * 4 < dim;              // (lanes beyond the row width still take part in the waits)
+    int4 idx = make_int4(0, 0, 0, 0);
+    if (left > g4) idx = load_idx4(ip);
+    int4 idx_next = idx;
+    if (left - STRIDE > g4) idx_next = load_idx4(ip + STRIDE);
+    auto need = [&](int chunk_end) {
+        if (state < 1 && chunk_end > m1) { x_wait(a, a.x_rank + 1, a.x_world, lane); state = 1; }
+        if (state < 2 && chunk_end > m2) { x_wait(a, 0, a.x_rank, lane); state = 2; }
+    };
+    if (state < 2) need(min(end, base + 32));
+    if (active) {
+        if (base >= beg && left >= 32) gather4_full<true>(acc, in_q, dim, idx);
+        else gather4_edge(acc, in_q, dim, idx, beg - base - g4, left - g4);
+    }
+#pragma unroll 1
+    while (left > STRIDE) {
+        ip += STRIDE;
+        left -= STRIDE;
+        idx = idx_next;
+        if (left - STRIDE > g4) idx_next = load_idx4(ip + STRIDE);
+        if (state < 2) need(min(end, end - left + 32));
+        if (active) {
+            if (left >= 32) gather4_full<true>(acc, in_q, dim, idx);
+            else gather4_edge(acc, in_q, dim, idx, 0, left - g4);
+        }
+    }
 }
 
 template <bool EXACT>
@@ -537,13 +578,10 @@ __global__ void __launch_bounds__(THREADS, 6) xgather_kernel(const GatherArgs a)
     Acc<4> acc[1];
     if (bid < a.n_heavy) {
         const int s = a.heavy_rows[bid];
-        const int beg = a.indptr[s], end = a.indptr[s + 1], m1 = a.seg1[s], m2 = a.seg2[s];
+        const int beg = a.indptr[s], end = a.indptr[s + 1];
+        int state = 0;
         acc[0].zero();
-        accumulate_idx4<EXACT, WARPS, 4>(acc[0], a, beg, m1, warp, lane);
-        x_wait(a, a.x_rank + 1, a.x_world, lane);
-        accumulate_idx4<EXACT, WARPS, 4>(acc[0], a, m1, m2, warp, lane);
-        x_wait(a, 0, a.x_rank, lane);
-        accumulate_idx4<EXACT, WARPS, 4>(acc[0], a, m2, end, warp, lane);
+        accumulate_x<EXACT, WARPS>(acc[0], a, beg, end, a.seg1[s], a.seg2[s], warp, lane, state);
         reduce_groups<4, 4, 1>(acc);
         const int q = lane % 4;
         if (lane < 4) {
@@ -566,22 +604,13 @@ __global__ void __launch_bounds__(THREADS, 6) xgather_kernel(const GatherArgs a)
     }
     const int bin = (bid - a.n_heavy) * WARPS + warp;
     const int r_end = a.bin_ptr[bin + 1];
-    bool waited = false;
+    int state = 0;
     for (int r = a.bin_ptr[bin]; r < r_end; r++) {
         const int s = a.bin_rows[r];
         const int beg = a.indptr[s], end = a.indptr[s + 1];
         acc[0].zero();
-        if (!waited) {
-            const int m1 = a.seg1[s], m2 = a.seg2[s];
-            accumulate_idx4<EXACT, 1, 4>(acc[0], a, beg, m1, 0, lane);
-            x_wait(a, a.x_rank + 1, a.x_world, lane);
-            accumulate_idx4<EXACT, 1, 4>(acc[0], a, m1, m2, 0, lane);
-            x_wait(a, 0, a.x_rank, lane);
-            accumulate_idx4<EXACT, 1, 4>(acc[0], a, m2, end, 0, lane);
-            waited = true;
-        } else {
-            accumulate_idx4<EXACT, 1, 4>(acc[0], a, beg, end, 0, lane);
-        }
+        if (state < 2) accumulate_x<EXACT, 1>(acc[0], a, beg, end, a.seg1[s], a.seg2[s], 0, lane, state);
+        else accumulate_idx4<EXACT, 1, 4>(acc[0], a, beg, end, 0, lane);       // everything has arrived: the plain loop (same order)
         reduce_groups<4, 4, 1>(acc);
         epilogue<4, 4, 1>(acc, a, s, lane);
     }

@@ -241,6 +241,45 @@ def test_graph_row_partition(abi, chk, D):
     assert (re == indptr).all()
 
 
+@pytest.mark.parametrize("dim", [16, 12, 48, 100])
+def test_split_aggregation_views(abi, chk, D, dim):
+    """Column-filtered views built on the device, a row view of a column view (shared CSR), gcnk_gather_raw and
+    gcnk_gather_init_next: aggregating the columns below a cut first (raw partial sums) and the remaining columns second
+    equals the one-launch GraphSum; so does the same over a row subset."""
+    indptr, indices = make_graph(n=4000, n_undirected=30000, seed=17, alpha=1.4, hub=(5, 900))
+    n = len(indptr) - 1
+    x = np.random.default_rng(dim).standard_normal((n, dim)).astype(np.float32)
+    want = chk.graphsum(indptr, indices, x, dim).reshape(n, dim)
+    g = abi.Graph(indptr, indices)
+    dinv = g.dinv()
+    xs = abi.dev((x * dinv[:, None]).astype(np.float32))
+    lo_cols = (np.arange(n) < 1500).astype(np.int32)
+    rows = (np.arange(n) % 3 == 0).astype(np.int32)
+    v = [C.c_void_p() for _ in range(4)]
+    abi.k.gcnk_graph_create_view(C.byref(v[0]), g.h, None, D(lo_cols), None)
+    abi.k.gcnk_graph_create_view(C.byref(v[1]), g.h, None, D((1 - lo_cols).astype(np.int32)), None)
+    abi.k.gcnk_graph_create_view(C.byref(v[2]), v[0], D(rows), None, None)          # views of views: rows only
+    abi.k.gcnk_graph_create_view(C.byref(v[3]), v[1], D(rows), None, None)
+    nnz = [C.c_int64() for _ in range(2)]
+    abi.k.gcnk_graph_stats(v[0], None, C.byref(nnz[0]), None, None, None)
+    abi.k.gcnk_graph_stats(v[1], None, C.byref(nnz[1]), None, None, None)
+    assert nnz[0].value + nnz[1].value == len(indices) and nnz[0].value == int((indices < 1500).sum())
+    part, out = abi.DeviceArray.zeros((n, dim), np.float32), abi.DeviceArray.zeros((n, dim), np.float32)
+    abi.k.gcnk_gather_raw(v[0], xs.ptr, part.ptr, dim, None)
+    abi.k.gcnk_gather_init_next(part.ptr)
+    abi.k.gcnk_gather_plain(v[1], xs.ptr, out.ptr, dim, None)
+    close(out.numpy(), want, what="columns below the cut first, the rest second")
+    part2, out2 = abi.DeviceArray.zeros((n, dim), np.float32), abi.DeviceArray.zeros((n, dim), np.float32)
+    abi.k.gcnk_gather_raw(v[2], xs.ptr, part2.ptr, dim, None)
+    abi.k.gcnk_gather_init_next(part2.ptr)
+    abi.k.gcnk_gather_plain(v[3], xs.ptr, out2.ptr, dim, None)
+    got = out2.numpy()
+    close(got[rows == 1], want[rows == 1], what="row subset of the split aggregation")
+    assert (got[rows == 0] == 0).all()                                  # rows outside the view are left untouched
+    for h in (v[2], v[3], v[0], v[1]):
+        abi.k.gcnk_graph_destroy(h)
+
+
 @pytest.mark.parametrize("p_out", [1, 5, 16, 33, 64])
 @pytest.mark.parametrize("dense", [False, True])
 def test_spmm(abi, chk, D, p_out, dense):
