@@ -396,6 +396,7 @@ def run_ours(args):
                 "all-reduce in rank order; NCCL only for setup (handle exchange) and as fallback (GCN_COMM=nccl)",
                 "generate_s": round(t_gen, 1)}, wl),
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "graphsum_dims": dims, "cpu_baseline": cpu,
+            "host_enqueue_ms_per_step": (live["host_enqueue"][0] * 1e3 / max(live["host_enqueue"][1], 1)) if "host_enqueue" in live else None,
             "parity": parity, "breakdown": breakdown, "final": {"val_loss": last[0], "val_acc": last[1]}}
     print(json.dumps(line))
 

@@ -279,9 +279,12 @@ void GCN::build(GCNPlan plan) {
     {
         // Exchange fused into the consuming GraphSum (csrc/graph.cu: xgather_kernel): one launch pushes this rank's rows of
         // the source to the peers and aggregates, own columns first.  Needs the rotated row order, set up here before any
-        // view of the slice graph exists.  GCN_FUSED_EXCHANGE=0: separate push kernel + wait at the start of the gather.
+        // view of the slice graph exists.  Default up to 4 ranks, where it was measured faster than the separate push kernel +
+        // wait at the start of the gather (Reddit shape: +1 % on 2 GPUs, +2 % on 4); on 8 GPUs the own-columns share of a
+        // row (1/8) is too small to hide anything and the pushers compete with the gather CTAs: 7 % slower
+        // (profiles/r02p_bench_n8*.json).  GCN_FUSED_EXCHANGE=1 / 0 forces it on / off.
         const char *fx = getenv("GCN_FUSED_EXCHANGE");
-        const bool want = !(fx && *fx && !strcmp(fx, "0"));
+        const bool want = fx && *fx ? strcmp(fx, "0") != 0 : dist.world <= 4;
         if (dist.world > 1 && fz->p2p && fz->signal_exchange && !fz->use_halo && (H == 16 || H == 12) && want) {
             GCNK_CHECK(gcnk_graph_rotate(g, r0, r0 + n_loc, nullptr));
             fz->fused_xchg = true;
@@ -661,7 +664,7 @@ void GCN::await(float *d_all, int dim) {
 
 // The reference's own summation order for the printed loss (module.cpp:125-143): the per-row loss terms of split `sidx`
 // (written by the layer-2 / CE kernel just enqueued, into the split's region of the terms buffer) are added up by
-// gcnk_sequential_sum, and the result replaces the parallel sum in ws[0] — the value the pass reports.
+// gcnk_sequential_sum into ws[3] — the value the pass reports (ws[0] keeps the parallel sum).
 // Row-partitioned: only rank 0 adds (the other ranks push their range of terms to rank 0 — one 16-byte-aligned copy to
 // ONE peer — and contribute 0 to the sum of ws[0] over ranks that ends every pass, so every rank still reports the same
 // number, bit-identical to a single-GPU run).  Training: on a side stream, under the backward pass.
@@ -676,8 +679,7 @@ void GCN::enqueue_loss_sum(int sidx_l, bool training, int slot) {
         ++z.seq[4];
         GCNK_CHECK(gcnk_peer_push_signal(region + z.term_c0[sidx_l], peer, 1, (size_t)(z.term_cnt[sidx_l] + 3) / 4 * 4, nullptr, nullptr, 1,
                                          slot_flag, z.seq[4], z.d_counter, st));
-        GCNK_CHECK(gcnk_memset(z.ws, 0, sizeof(float), st));           // this rank's share of the summed loss: rank 0 supplies it
-        return;
+        return;                                                          // ws[3] stays 0 here: rank 0 supplies the sum
     }
     const int *flags = nullptr;
     if (dist.world > 1) { ++z.seq[4]; flags = z.flag_arrays[0] + 64 + 8 * 4; }
@@ -686,7 +688,9 @@ void GCN::enqueue_loss_sum(int sidx_l, bool training, int slot) {
         GCNK_CHECK(gcnk_event_record(z.ev_l2, st));
         GCNK_CHECK(gcnk_stream_wait_event(z.seq_stream, z.ev_l2));
     }
-    GCNK_CHECK(gcnk_sequential_sum(region, z.term_len[sidx_l], z.ws, 0.f, flags, flags ? dist.world : 0, 0, z.seq[4], z.d_err, ss));
+    // into ws[3], the slot the parallel reduction leaves at 0 on every rank: the sum over ranks that ends the pass carries
+    // it to everybody unchanged (S + 0 + ... + 0)
+    GCNK_CHECK(gcnk_sequential_sum(region, z.term_len[sidx_l], z.ws + 3, 0.f, flags, flags ? dist.world : 0, 0, z.seq[4], z.d_err, ss));
     if (training) GCNK_CHECK(gcnk_event_record(z.ev_seq, z.seq_stream));
 }
 
@@ -847,7 +851,7 @@ void GCN::fused_enqueue(int current_split, bool training, int slot) {
     gpu_timer_begin(TMR_LOSS_FW);
     if (training) mirror(z.G, H);
     const int sidx_l = current_split >= 1 && current_split <= 3 ? current_split : 0;
-    const bool seq = z.seq_loss && sidx_l != 0;
+    const bool seq = z.seq_loss && sidx_l != 0 && split_count[sidx_l] >= SEQ_LOSS_MIN_ROWS;
     GCNK_CHECK(gcnk_layer2_fused_terms(z.P, W2.data, d_split, d_label, current_split, n_loc, H, C, training,
                                        split_count[current_split & 3], dinv, training ? z.G + own : nullptr,
                                        training ? W2.grad : nullptr, nullptr, z.d_result, z.ws, z.ws_bytes,
@@ -899,7 +903,7 @@ std::pair<float, float> GCN::fused_collect(int slot, bool sync) {
     const float *red = z.h_red + 4 * slot;
     last_count = (int)red[1];
     last_wrong = (int)red[2];
-    const float mean_loss = red[0] / (float)last_count;                  // count == 0 -> NaN, as the reference
+    const float mean_loss = (z.seq_used[slot] ? red[3] : red[0]) / (float)last_count;   // count == 0 -> NaN, as the reference
     const float sumsq = z.sumsq_used[slot] >= 0.f ? z.sumsq_used[slot] : z.sumsq;
     const float l2 = params.weight_decay * sumsq / 2;
     return {mean_loss + l2, float(last_count - last_wrong) / last_count};
@@ -918,8 +922,10 @@ void GCN::epoch(int eval_split, float *train_loss, float *train_acc, float *eval
         std::tie(*eval_loss, *eval_acc) = eval(eval_split);
         return;
     }
+    timer_start(TMR_HOST_ENQUEUE);
     fused_enqueue(1, true, 0);
     fused_enqueue(eval_split, false, 1);
+    timer_stop(TMR_HOST_ENQUEUE);
     std::tie(*train_loss, *train_acc) = fused_collect(0, true);
     train_count = last_count; train_wrong = last_wrong;
     std::tie(*eval_loss, *eval_acc) = fused_collect(1, false);

@@ -219,7 +219,7 @@ void GCN::wide_enqueue(int current_split, bool training, int slot) {
 
     // M7 CrossEntropyLoss + get_accuracy; count = labelled rows of the split over ALL ranks (module.cpp:154-158)
     gpu_timer_begin(TMR_LOSS_FW);
-    const bool seq = z.seq_loss && sidx != 0;
+    const bool seq = z.seq_loss && sidx != 0 && split_count[sidx] >= SEQ_LOSS_MIN_ROWS;
     GCNK_CHECK(gcnk_ce_rows(z.logits, Cp, d_split, d_label, current_split, n_loc, C, training, split_count[current_split & 3], dinv,
                             training ? z.D_s + own : nullptr, z.d_result, z.ws, z.ws_bytes, seq ? z.terms + (size_t)(sidx - 1) * z.term_region : nullptr,
                             seq ? z.term_index[sidx] : nullptr, st));

@@ -43,7 +43,7 @@ void timer_reset_all() { for (auto &s : g_slots) { s.sum = 0; s.calls = 0; } }
 const char *timer_name(timer_instance t) {
     static const char *names[__NUM_TMR] = {"train", "test", "matmul_fw", "matmul_bw", "spmatmul_fw", "spmatmul_bw",
                                            "graphsum_fw", "graphsum_bw", "loss_fw", "relu_fw", "relu_bw", "dropout_fw",
-                                           "dropout_bw", "adam", "comm", "gather_full", "gather_part"};
+                                           "dropout_bw", "adam", "comm", "gather_full", "gather_part", "host_enqueue"};
     return t < __NUM_TMR ? names[t] : "?";
 }
 

@@ -11,6 +11,7 @@ typedef enum {
     // additions of this engine (not in the reference enum)
     TMR_ADAM, TMR_COMM,
     TMR_GATHER_FULL, TMR_GATHER_PART,   // GraphSum gather launches over the whole graph / over a row- or column-subset view
+    TMR_HOST_ENQUEUE,                   // host wall-clock spent enqueueing a fused epoch (launch-bound when it nears the step time)
     __NUM_TMR
 } timer_instance;
 
