@@ -326,10 +326,7 @@ def run_ours(args):
     # ---- e2e: the same step through the C face with the (local rows of the) feature matrix uploaded from pinned
     # host memory each step
     e2e = None
-    if wide and world > 1:
-        # the row-partitioned wide plan keeps every node's features on every rank: no per-step re-upload path
-        e2e = {"value": None, "unit": UNIT, "note": "not measured: the partitioned wide plan has no feature re-upload entry point"}
-    else:
+    if True:
         pinned = L.gcnh_alloc_pinned(max(nnzX_loc, 1))
         host_view = np.ctypeslib.as_array((abi.C.c_float * max(nnzX_loc, 1)).from_address(pinned))
         host_view[:nnzX_loc] = x_local
@@ -351,6 +348,9 @@ def run_ours(args):
         e2e = {"value": 1.0 / e2e_dt, "unit": UNIT, "h2d_bytes_per_step": int(nnzX * 4), "d2h_bytes_per_step": world * (2 * 16 + 4),
                "steps": e2e_steps, "api": "gcnh_engine_epoch_prefetch (upload of step k+1 under step k; include/gcn_host.h)" if prefetch else
                "gcnh_engine_set_input_host + gcnh_engine_train_epoch + gcnh_engine_eval (include/gcn_host.h)"}
+        if wide and world > 1:
+            e2e["note"] = ("the row-partitioned wide plan reads every node's features: each rank uploads its own rows and the slices are "
+                           "all-gathered over NVLink (NCCL) on the copy stream")
     eng.close()
     if rank != 0:
         return
@@ -413,11 +413,14 @@ def graphsum_dims(abi, data, peak, dims=(16, 41, 47, 256), reps=5):
     for dim in dims:
         x = abi.dev(np.random.default_rng(dim).standard_normal((n, dim)).astype(np.float32))
         y = abi.DeviceArray((n, dim), np.float32)
-        xs = abi.DeviceArray((n, dim), np.float32)
-        K.gcnk_scale_rows(g.dinv_ptr(), x.ptr, xs.ptr, n, dim, None)
+        pitch = (dim + 3) // 4 * 4                                 # the fused plans keep class-width sources at a 16-byte pitch (47 -> 48)
+        xs = abi.DeviceArray((n, pitch), np.float32)
+        ys = abi.DeviceArray((n, pitch), np.float32)
+        K.gcnk_memset(xs.ptr, 0, 4 * n * pitch, None)
+        K.gcnk_scale_rows(g.dinv_ptr(), xs.ptr, xs.ptr, n, pitch, None)
         for _ in range(2):
             K.gcnk_graphsum(g.h, x.ptr, y.ptr, dim, None)
-            K.gcnk_gather_plain(g.h, xs.ptr, y.ptr, dim, None)
+            K.gcnk_gather_plain(g.h, xs.ptr, ys.ptr, pitch, None)
         e0, e1, e2 = abi.Event(), abi.Event(), abi.Event()
         K.gcnk_device_sync()
         e0.record()
@@ -425,17 +428,18 @@ def graphsum_dims(abi, data, peak, dims=(16, 41, 47, 256), reps=5):
             K.gcnk_graphsum(g.h, x.ptr, y.ptr, dim, None)          # module-level call: pre-scale pass + gather
         e1.record()
         for _ in range(reps):
-            K.gcnk_gather_plain(g.h, xs.ptr, y.ptr, dim, None)     # the gather alone (what the fused plan launches)
+            K.gcnk_gather_plain(g.h, xs.ptr, ys.ptr, pitch, None)  # the gather alone (what the fused plans launch)
         e2.record(); e2.sync()
         us_call, us_gather = e0.elapsed_ms(e1) / reps * 1e3, e1.elapsed_ms(e2) / reps * 1e3
         b_min = 4 * nnz + 4 * (n + 1) + 8 * n * dim
-        out.append({"dim": dim, "fw_us": us_call, "bw_us": us_call, "gather_only_us": us_gather, "algorithmic_bytes": b_min,
+        out.append({"dim": dim, "gather_only_pitch": pitch, "fw_us": us_call, "bw_us": us_call, "gather_only_us": us_gather, "algorithmic_bytes": b_min,
                     "GBps": b_min / us_call / 1e3, "frac": b_min / us_call / 1e3 / peak,
                     "gather_only_GBps": b_min / us_gather / 1e3, "gather_only_frac": b_min / us_gather / 1e3 / peak})
-        del x, y, xs
+        del x, y, xs, ys
     K.gcnk_graph_release_scratch(g.h)
     return {"note": "forward and backward are the same launch (module.cpp:103-119 reuses the forward loop on a symmetric graph); "
-                    "fw_us/bw_us = gcnk_graphsum (pre-scale pass + gather), gather_only = gcnk_gather_plain on a pre-scaled source",
+                    "fw_us/bw_us = gcnk_graphsum (pre-scale pass + gather; widths that are not a multiple of 4 go through rows padded to a "
+                    "16-byte pitch), gather_only = gcnk_gather_plain on a pre-scaled source at that pitch",
             "per_dim": out}
 
 

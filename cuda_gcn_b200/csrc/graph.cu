@@ -782,6 +782,28 @@ __global__ void scale_rows_kernel(const float *__restrict__ dinv, const float *_
     for (; i < total; i += stride) out[i] = dinv[i / dim] * in[i];
 }
 
+// gcnk_graphsum at a width that is not a multiple of 4 (41 and 47 are the class widths of the benchmark shapes): rows padded to
+// a 16-byte pitch, so that the gather moves them with 128-bit loads, several edges per instruction, instead of one edge per
+// instruction with scalar loads (4.4 ms -> see DESIGN 4 at width 41 on the Reddit-shape graph).  The pre-scale pass writes a copy anyway.
+__global__ void scale_rows_pad_kernel(const float *__restrict__ dinv, const float *__restrict__ in, float *__restrict__ out,
+                                      int64_t total, int dim, int pitch) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < total; i += stride) {
+        const int64_t r = i / pitch;
+        const int c = (int)(i - r * pitch);
+        out[i] = c < dim ? dinv[r] * in[r * dim + c] : 0.f;
+    }
+}
+__global__ void unpad_rows_kernel(const float *__restrict__ in, float *__restrict__ out, int64_t total, int dim, int pitch) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < total; i += stride) {
+        const int64_t r = i / dim;
+        out[i] = in[r * pitch + (i - r * dim)];
+    }
+}
+
 // Rotated order of a row-partition's CSR slice (gcnk_graph_rotate): a warp per row rewrites its entries as
 // [columns in [lo, hi) | columns >= hi | columns < lo], each class in its original order, and records the two boundaries.
 __global__ void rotate_rows_kernel(const int *__restrict__ indptr, const int *__restrict__ indices, int n, int lo, int hi, int *__restrict__ out,
@@ -1130,7 +1152,10 @@ int gcnk_graphsum(const gcnk_graph *gc, const float *in, float *out, int dim, gc
     GCNK_REQUIRE(gc && in && out && dim > 0, "bad arguments");
     gcnk_graph *g = const_cast<gcnk_graph *>(gc);
     if (g->n == 0) return GCNK_OK;
-    const size_t need = (size_t)g->n_cols * dim;
+    // widths 5, 6, 7, 9, ... : through padded rows (16-byte pitch) on both sides of the gather
+    const int pitch = (dim > 4 && dim % 4) ? (dim + 3) & ~3 : dim;
+    const bool padded = pitch != dim;
+    const size_t need_in = (size_t)g->n_cols * pitch, need = need_in + (padded ? (size_t)g->n * pitch : 0);
     if (g->scratch_elems < need) {
         GCNK_CUDA(cudaStreamSynchronize(S(stream)));
         if (g->scratch) GCNK_CUDA(cudaFree(g->scratch));
@@ -1138,9 +1163,21 @@ int gcnk_graphsum(const gcnk_graph *gc, const float *in, float *out, int dim, gc
         GCNK_CUDA(cudaMalloc(&g->scratch, sizeof(float) * std::max<size_t>(need, 4)));
         g->scratch_elems = need;
     }
-    int rc = gcnk_scale_rows(g->dinv_cols, in, g->scratch, g->n_cols, dim, stream);
+    if (!padded) {
+        int rc = gcnk_scale_rows(g->dinv_cols, in, g->scratch, g->n_cols, dim, stream);
+        if (rc) return rc;
+        return gcnk_gather_plain(g, g->scratch, out, dim, stream);
+    }
+    float *out_p = g->scratch + need_in;
+    const int64_t total_in = (int64_t)g->n_cols * pitch, total_out = (int64_t)g->n * dim;
+    const int64_t cap = (int64_t)sm_count() * 16;
+    scale_rows_pad_kernel<<<(int)std::min<int64_t>((total_in + 255) / 256, cap), 256, 0, S(stream)>>>(g->dinv_cols, in, g->scratch, total_in, dim, pitch);
+    GCNK_LAUNCHED();
+    int rc = gcnk_gather_plain(g, g->scratch, out_p, pitch, stream);
     if (rc) return rc;
-    return gcnk_gather_plain(g, g->scratch, out, dim, stream);
+    unpad_rows_kernel<<<(int)std::min<int64_t>((total_out + 255) / 256, cap), 256, 0, S(stream)>>>(out_p, out, total_out, dim, pitch);
+    GCNK_LAUNCHED();
+    return GCNK_OK;
 }
 
 int gcnk_graph_release_scratch(gcnk_graph *g) {

@@ -472,12 +472,18 @@ GCN::~GCN() {
 }
 
 void GCN::set_input_from_host(const float *h_values) {
-    if (fz && fz->wide && dist.world > 1) {
-        fprintf(stderr, "GCN: the row-partitioned wide plan keeps every node's features on every rank; re-upload is single-GPU only\n");
-        exit(EXIT_FAILURE);
-    }
     consume_pending_input();                                // a prefetched input is older than this one: retire it first
-    GCNK_CHECK(gcnk_memcpy_h2d(d_feature_value, h_values, sizeof(float) * data->feature_index.indices.size(), engine_stream()));
+    const size_t bytes = sizeof(float) * data->feature_index.indices.size();
+    if (fz && fz->wide && dist.world > 1) {
+        // The row-partitioned wide plan reads every node's features (gcn_wide.cpp): this rank's rows go into its slice of the
+        // replicated matrix and the slices are all-gathered over NVLink (NCCL; 980 MB at products shape).
+        const int F = params.input_dim;
+        GCNK_CHECK(gcnk_memcpy_h2d(fz->X_all + (size_t)r0 * F, h_values, bytes, engine_stream()));
+        GCNK_CHECK(gcnk_comm_allgather_rows(dist.comm, fz->X_all, row_begin.data(), F, engine_stream()));
+        fz->ax_valid = false;
+        return;
+    }
+    GCNK_CHECK(gcnk_memcpy_h2d(d_feature_value, h_values, bytes, engine_stream()));
     if (fz) { fz->ax_valid = false; fz->xp_dirty = fz->Xp != nullptr; }   // A_hat*X is stale (eval falls back to the gather path); re-pack X
 }
 
@@ -485,13 +491,24 @@ void GCN::set_input_from_host(const float *h_values) {
 // input of a pass that has completed (every pass ends with a host synchronisation before its results are returned).
 void GCN::start_input_upload(const float *h_values) {
     const size_t bytes = sizeof(float) * data->feature_index.indices.size();
+    const bool replicated = fz && fz->wide && dist.world > 1;             // see set_input_from_host
     if (!copy_stream) {
         GCNK_CHECK(gcnk_stream_create(&copy_stream));
         GCNK_CHECK(gcnk_event_create(&ev_copied));
-        GCNK_CHECK(gcnk_malloc((void **)&d_feature_spare, std::max<size_t>(bytes, sizeof(float))));
+        if (replicated) GCNK_CHECK(gcnk_malloc((void **)&fz->X_all_spare, sizeof(float) * (size_t)params.num_nodes * params.input_dim));
+        else GCNK_CHECK(gcnk_malloc((void **)&d_feature_spare, std::max<size_t>(bytes, sizeof(float))));
     }
     if (input_pending) GCNK_CHECK(gcnk_stream_sync(copy_stream));   // never two uploads into the one spare buffer
-    GCNK_CHECK(gcnk_memcpy_h2d(d_feature_spare, h_values, bytes, copy_stream));
+    if (replicated) {
+        const int F = params.input_dim;
+        GCNK_CHECK(gcnk_memcpy_h2d(fz->X_all_spare + (size_t)r0 * F, h_values, bytes, copy_stream));
+        // the slices meet on the copy stream too, under the passes in flight — unless the passes themselves use NCCL (the
+        // fallback transport): two streams must not drive one communicator at a time, so the gather then waits for consume
+        fz->spare_needs_gather = !fz->p2p;
+        if (fz->p2p) GCNK_CHECK(gcnk_comm_allgather_rows(dist.comm, fz->X_all_spare, row_begin.data(), F, copy_stream));
+    } else {
+        GCNK_CHECK(gcnk_memcpy_h2d(d_feature_spare, h_values, bytes, copy_stream));
+    }
     GCNK_CHECK(gcnk_event_record(ev_copied, copy_stream));
     input_pending = true;
 }
@@ -500,8 +517,15 @@ void GCN::start_input_upload(const float *h_values) {
 void GCN::consume_pending_input() {
     if (!input_pending) return;
     GCNK_CHECK(gcnk_stream_wait_event(engine_stream(), ev_copied));
-    std::swap(d_feature_value, d_feature_spare);
     input_pending = false;
+    if (fz && fz->wide && dist.world > 1) {
+        std::swap(fz->X_all, fz->X_all_spare);
+        if (fz->spare_needs_gather) GCNK_CHECK(gcnk_comm_allgather_rows(dist.comm, fz->X_all, row_begin.data(), params.input_dim, engine_stream()));
+        fz->spare_needs_gather = false;
+        fz->ax_valid = false;
+        return;
+    }
+    std::swap(d_feature_value, d_feature_spare);
     if (fz) { fz->ax_valid = false; fz->xp_dirty = fz->Xp != nullptr; }
     if (fz && fz->wide && !fz->x_all_owned) fz->X_all = d_feature_value;   // single-GPU wide plan: X_all aliases the feature buffer
 }

@@ -34,6 +34,8 @@ struct GCN::Fused {
     float *D_s = nullptr;      // [N x Cp]   dinv (.) dlogits: source of the backward one (exchanged)
     float *X_all = nullptr;    // [N x F]    pristine features of ALL nodes (the layer-1 gather reads every node's row)
     bool x_all_owned = false;
+    float *X_all_spare = nullptr;   // row-partitioned: the buffer the next input (all ranks' rows) is assembled in (epoch_prefetch)
+    bool spare_needs_gather = false;
     float *Xd_s = nullptr;     // [N x F]    dinv (.) dropout(X): the layer-1 gather source of this pass
     float *AXd = nullptr;      // [n x F]    A_hat * dropout(X)   (forward input of X W1 AND the left factor of dW1)
     float *AXw = nullptr;      // [n x F]    A_hat * X, static: eval passes need no gather at all in layer 1
@@ -167,6 +169,7 @@ struct GCN::Fused {
         for (int *t : term_index) if (t) gcnk_free(t);
         if (wide_sources_owned && T_s) gcnk_free(T_s);
         if (x_all_owned && X_all) gcnk_free(X_all);
+        if (X_all_spare) gcnk_free(X_all_spare);
         for (void *q : {(void *)Xd_s, (void *)AXd, (void *)AXw, (void *)H1, (void *)Tl, (void *)logits, (void *)dT, (void *)dH1, (void *)W2p,
                         (void *)dW2p, (void *)wkeep0, (void *)wkeep1, (void *)wmask, (void *)mm_ws})
             if (q) gcnk_free(q);

@@ -39,6 +39,27 @@ def test_partitioned_equals_single(preset, scale, dropout, hidden, world):
     assert r["w1_maxdiff"] <= 5e-5 * r["w1_scale"] and r["w2_maxdiff"] <= 5e-5 * r["w2_scale"]
 
 
+@pytest.mark.parametrize("preset,scale,hidden", [("reddit", 0.02, 16), ("products", 0.004, 256)])
+def test_partitioned_reupload_equals_single(preset, scale, hidden):
+    """set_input_host / epoch_prefetch on a row partition: every rank uploads its own rows (scaled differently every step) and gets
+    the single-GPU engine's numbers for the same inputs.  The wide plan (hidden 256) reads every node's features, so its ranks
+    all-gather the uploaded slices over NVLink."""
+    world = 2
+    if n_gpus() < world:
+        pytest.skip(f"needs {world} GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+           "--master-port", "29650", str(ROOT / "tools" / "dist_check.py"), "--preset", preset, "--scale", str(scale),
+           "--epochs", "6", "--dropout", "0.5", "--hidden", str(hidden), "--reupload"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-3000:]
+    r = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
+    assert r["replicated"], "ranks hold different weights"
+    assert len({row[0] for row in r["single"]}) == len(r["single"])
+    for d, s in zip(r["dist"], r["single"]):
+        assert abs(d[0] - s[0]) <= 2e-6 * abs(s[0]) + 1e-7 and abs(d[2] - s[2]) <= 2e-6 * abs(s[2]) + 1e-7, (d, s)
+    assert abs(r["dist_test"][0] - r["single_test"][0]) <= 2e-6 * abs(r["single_test"][0]) + 1e-7
+
+
 def test_cli_multi_gpu_matches_single(tmp_path):
     """`GCN_GPUS=2 ./gcn-cuda <dataset>` (one forked worker per GPU, NCCL id over pipes) prints the same epochs as the
     single-GPU CLI on the same files and seed."""

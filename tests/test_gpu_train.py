@@ -231,6 +231,143 @@ def test_wide_plan_is_auto_for_wide_hidden(host):
     eng.close()
 
 
+def _pinned_inputs(host, x, n_inputs):
+    """n_inputs pinned host copies of the feature values, each scaled differently (so a stale buffer shows)."""
+    import ctypes as C
+    L = host.load()
+    bufs = []
+    for k in range(n_inputs):
+        ptr = L.gcnh_alloc_pinned(len(x))
+        view = np.ctypeslib.as_array((C.c_float * len(x)).from_address(ptr))
+        view[:] = x * np.float32(1.0 + 0.05 * k)
+        bufs.append(ptr)
+    return bufs
+
+
+@pytest.mark.parametrize("preset,scale,hidden", [("reddit", 0.02, 16), ("products", 0.004, 256)])   # hidden 256: the wide plan
+def test_epoch_prefetch_equals_serial(host, preset, scale, hidden):
+    """gcnh_engine_epoch_prefetch (step k on the current input while step k+1's input is uploaded on a copy stream into a
+    second buffer) returns exactly what set_input_host + epoch return, with a different input every step."""
+    d = host.Data.synth(preset, scale)
+    x = d.arrays()["feature_value"]
+    steps = 5
+    bufs = _pinned_inputs(host, x, steps + 1)
+    rows = []
+    for prefetch in (False, True):
+        e = host.Engine(d, hidden_dim=hidden, dropout=0.5, seed=5, plan=host.PLAN_FUSED)
+        out = []
+        if prefetch:
+            e.set_input_host(bufs[0])
+            for k in range(steps):
+                out.append(e.epoch_prefetch(2, bufs[k + 1]))
+        else:
+            for k in range(steps):
+                e.set_input_host(bufs[k])
+                out.append(e.epoch(2))
+        out.append(e.eval(3))          # evaluated on input `steps` (prefetch) resp. `steps - 1` (serial): compared below only per step
+        rows.append(out)
+        e.close()
+    assert rows[0][:steps] == rows[1][:steps]
+    assert len({r[0] for r in rows[0][:steps]}) == steps      # the inputs really differed
+    L = host.load()
+    for b in bufs:
+        L.gcnh_free_pinned(b)
+
+
+def test_early_stopping_matches_reference(host, chk):
+    """GCN::run with early_stopping > 0 (gcn.cpp:142-150): stops at the same epoch as the reference and reports the
+    same test loss.  A high learning rate makes the validation loss turn around within a few epochs."""
+    from tests.util import make_dataset
+    gd = make_dataset(n=400, f=60, c=4, n_undirected=1500, nnz_per_row=6, seed=33, splits=(0.1, 0.3, 0.3))
+    d = host.Data.from_arrays(gd)
+    stops = {}
+    for lr in (0.3, 0.01):
+        ref = chk.gcn(gd, dropout=0.0, lr=lr, epochs=60, early_stopping=4, seed=4)
+        ref_hist = []
+        # the reference's run() only prints; replay its loop through the shim's epoch calls with its own stopping rule
+        for epoch in range(1, 61):
+            ref.train_epoch()
+            ref_hist.append(ref.eval(2)[0])
+            if epoch >= 4 and ref_hist[-1] > sum(ref_hist[-4:]) / 4:
+                break
+        ref_test = ref.eval(3)
+        for plan in (host.PLAN_FUSED, host.PLAN_MODULES):
+            eng = host.Engine(d, dropout=0.0, lr=lr, epochs=60, early_stopping=4, seed=4, plan=plan)
+            ran = eng.run()                                    # GCN::run: the loop, the rule and the final eval(3)
+            assert ran == len(ref_hist), (lr, plan, ran, len(ref_hist))
+            got = eng.eval(3)
+            assert abs(got[0] - ref_test[0]) <= LOSS_RTOL * abs(ref_test[0]) and abs(got[1] - ref_test[1]) <= 0.002
+            eng.close()
+        stops[lr] = len(ref_hist)
+        ref.close()
+    assert stops[0.3] < 60                                     # the rule really fired in one of the two settings
+
+
+def test_early_stopping_cli_matches_gcn_seq(host, tmp_path):
+    """The same through the two command lines: `gcn-cuda toy ... <early_stopping>` stops where the unmodified gcn-seq
+    binary stops (its early_stopping is a compiled-in default of 0, so gcn-seq is driven through ref_shim instead when
+    the binary cannot take the override) — here: epochs printed by gcn-cuda == epochs the reference loop runs."""
+    import os, subprocess
+    from pathlib import Path
+    from oracle.checker import best_checker
+    from tests.util import make_dataset, write_text_dataset
+    root = Path(__file__).resolve().parent.parent
+    gd = make_dataset(n=400, f=60, c=4, n_undirected=1500, nnz_per_row=6, seed=33, splits=(0.1, 0.3, 0.3))
+    write_text_dataset(tmp_path, "toy", gd, float_fmt="%.9g")
+    env = dict(os.environ, GCN_SEED="4")
+    out = subprocess.run([str(root / "gcn-cuda"), "toy", "-", "-", "16", "-", "0", "0.3", "5e-4", "60", "4"], cwd=tmp_path, env=env,
+                         capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    lines = out.stdout.splitlines()
+    n_epochs = sum(l.startswith("epoch=") for l in lines)
+    chk = best_checker()
+    ref = chk.gcn(gd, dropout=0.0, lr=0.3, epochs=60, early_stopping=4, seed=4)
+    hist = []
+    for epoch in range(1, 61):
+        ref.train_epoch()
+        hist.append(ref.eval(2)[0])
+        if epoch >= 4 and hist[-1] > sum(hist[-4:]) / 4:
+            break
+    ref.close()
+    assert n_epochs == len(hist)
+    assert ("Early stopping..." in lines) == (len(hist) < 60)
+
+
+def test_reddit_full_scale_trajectory(host):
+    """The HEADLINE configuration at its own size (232,965 nodes, 114.9 M stored edges, dense 602 features, hidden 16,
+    dropout 0.5 from the shared stream) against the committed trajectory of the unmodified reference CPU engine
+    (tests/golden/reddit_full_trajectory.json, made by tools/make_trajectory_fixture.py: ~70 s per epoch on one core).
+    Loss within 1e-4 relative per epoch, labelled-row counts exact, accuracies within one borderline row per 2,000."""
+    import json
+    from pathlib import Path
+    fx = json.loads((Path(__file__).parent / "golden" / "reddit_full_trajectory.json").read_text())
+    d = host.Data.synth(fx["preset"], fx["scale"])
+    s = d.sizes()
+    assert s["num_nodes"] == fx["nodes"] and s["graph_nnz"] == fx["graph_nnz"] and s["feature_nnz"] == fx["feature_nnz"]
+    a = d.arrays()
+    n_split = {k: int(((a["split"] == k) & (a["label"] >= 0)).sum()) for k in (1, 2, 3)}
+    eng = host.Engine(d, hidden_dim=fx["hidden"], dropout=fx["dropout"], seed=fx["seed"], plan=host.PLAN_FUSED)
+    worst = 0.0
+    for e, want in enumerate(fx["epochs"]):
+        tl, ta = eng.train_epoch()
+        cnt_t, _ = eng.last_counts()
+        vl, va = eng.eval(2)
+        cnt_v, _ = eng.last_counts()
+        assert cnt_t == n_split[1] and cnt_v == n_split[2]
+        for got, w in ((tl, want[0]), (vl, want[2])):
+            rel = abs(got - w) / abs(w)
+            worst = max(worst, rel)
+            assert rel <= LOSS_RTOL, f"epoch {e + 1}: loss {got} vs {w} (rel {rel:.2e})"
+        assert abs(round(ta * cnt_t) - round(want[1] * cnt_t)) <= max(1, cnt_t // 2000), (e, ta, want[1])
+        assert abs(round(va * cnt_v) - round(want[3] * cnt_v)) <= max(1, cnt_v // 2000), (e, va, want[3])
+    if "test_after_last_epoch" in fx:
+        tl, ta = eng.eval(3)
+        assert abs(tl - fx["test_after_last_epoch"][0]) <= LOSS_RTOL * fx["test_after_last_epoch"][0]
+        assert abs(ta - fx["test_after_last_epoch"][1]) <= 0.002
+    print(f"full-scale trajectory: {len(fx['epochs'])} epochs, worst relative loss difference {worst:.2e}")
+    eng.close()
+
+
 @pytest.mark.parametrize("toggle", ["GCN_NO_TMA", "GCN_NO_VIEWS", "GCN_NO_AX", "GCN_NO_RNG_OVERLAP"])
 def test_fallback_paths(host, chk, toggle, monkeypatch):
     """Every optimisation of the fused plan can be switched off (register-staged feature transform, full-graph gathers
