@@ -1,5 +1,6 @@
 // common.cuh — shared plumbing for libgcnk.so (error capture, launch accounting, small device helpers).
 #pragma once
+#include <cstdlib>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -35,6 +36,20 @@ inline cudaStream_t S(gcnk_stream_t s) { return reinterpret_cast<cudaStream_t>(s
     } while (0)
 
 int sm_count();          // of the current device (cached per device)
+
+// Shared-memory carve-out of the kernels that run CONCURRENTLY on different streams (the gathers, the keep-bit generator
+// on its low-priority stream, the sequential loss sum): an SM can only switch its L1 / shared-memory split when it is
+// empty, so kernels that ask for different splits cannot share an SM and the block scheduler drains SMs to make room.
+// GCN_CARVEOUT=<percent> gives all of them the same preference (-1 / unset: the driver's per-kernel choice).
+inline int carveout_pct() {
+    static const int v = [] { const char *e = getenv("GCN_CARVEOUT"); return e && *e ? atoi(e) : -1; }();
+    return v;
+}
+template <typename Kernel>
+inline void prefer_carveout(Kernel k) {
+    const int pct = carveout_pct();
+    if (pct >= 0) cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, pct > 100 ? 100 : pct);
+}
 long long peer_spin_cycles();   // clock64 ticks a kernel waits for a peer's flag before raising its error flag (GCN_PEER_TIMEOUT_S)
 int *async_err_flag();   // per-device int raised by pipeline kernels whose mbarrier wait timed out
 

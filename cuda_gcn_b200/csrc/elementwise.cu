@@ -236,7 +236,7 @@ constexpr int SEQ_CHUNK = 4096;
 __global__ void __launch_bounds__(256) seq_sum_kernel(const float *__restrict__ terms, int n, float *__restrict__ out, float divide_by,
                                                       const int *wait_flags, int wait_n, int wait_skip, int wait_value, int *wait_err,
                                                       long long wait_limit) {
-    __shared__ float buf[2][SEQ_CHUNK];
+    __shared__ __align__(16) float buf[2][SEQ_CHUNK];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (wait_flags) {                                           // row-partitioned runs: every rank's terms must have landed
         if (tid < wait_n && tid != wait_skip) {
@@ -252,9 +252,26 @@ __global__ void __launch_bounds__(256) seq_sum_kernel(const float *__restrict__ 
         __syncthreads();
     }
     const int n_chunks = (n + SEQ_CHUNK - 1) / SEQ_CHUNK;
+    const bool vec_ok = (reinterpret_cast<uintptr_t>(terms) & 15) == 0;
     auto load_chunk = [&](int c) {                              // warps 1-7; terms beyond n read as +0, which a sum passes over unchanged
         const int base = c * SEQ_CHUNK;
         float *dst = buf[c & 1];
+        if (vec_ok && base + SEQ_CHUNK <= n) {
+            // all of this thread's loads in flight before the first store: one memory round trip per chunk, not five
+            constexpr int PER = (SEQ_CHUNK / 4 + 223) / 224;
+            float4 v[PER];
+#pragma unroll
+            for (int k = 0; k < PER; k++) {
+                const int i = tid - 32 + k * 224;
+                if (i < SEQ_CHUNK / 4) v[k] = ld_stream_f4(reinterpret_cast<const float4 *>(terms + base) + i);
+            }
+#pragma unroll
+            for (int k = 0; k < PER; k++) {
+                const int i = tid - 32 + k * 224;
+                if (i < SEQ_CHUNK / 4) reinterpret_cast<float4 *>(dst)[i] = v[k];
+            }
+            return;
+        }
         for (int i = tid - 32; i < SEQ_CHUNK; i += 224) dst[i] = base + i < n ? ld_stream_f32(terms + base + i) : 0.f;
     };
     if (warp > 0 && n_chunks > 0) load_chunk(0);
@@ -370,6 +387,7 @@ int gcnk_accuracy(const float *logits, const int *truth, int n, int c, int *d_wr
 int gcnk_sequential_sum(const float *terms, int n, float *d_out, float divide_by, const int *d_wait_flags, int n_flags, int skip,
                         int wait_value, int *d_err, gcnk_stream_t stream) {
     GCNK_REQUIRE(terms && d_out && n >= 0 && (!d_wait_flags || (n_flags > 0 && n_flags <= 32 && d_err)), "bad arguments");
+    prefer_carveout(seq_sum_kernel);
     seq_sum_kernel<<<1, 256, 0, S(stream)>>>(terms, n, d_out, divide_by, d_wait_flags, n_flags, skip, wait_value, d_err, peer_spin_cycles());
     GCNK_LAUNCHED();
     return GCNK_OK;

@@ -657,19 +657,19 @@ int launch_variant(const gcnk_graph *g, const GatherArgs &a, cudaStream_t st) {
         const int variant = g->idx4_ok ? gather_variant() : 0;
         const bool exact = a.dim == VEC * LPR * NACC;
         if (variant == 1) {
-            if (exact) gather_kernel<VEC, LPR, NACC, true, 1><<<grid, THREADS, smem, st>>>(a);
-            else gather_kernel<VEC, LPR, NACC, false, 1><<<grid, THREADS, smem, st>>>(a);
+            if (exact) { prefer_carveout(gather_kernel<VEC, LPR, NACC, true, 1>); gather_kernel<VEC, LPR, NACC, true, 1><<<grid, THREADS, smem, st>>>(a); }
+            else { prefer_carveout(gather_kernel<VEC, LPR, NACC, false, 1>); gather_kernel<VEC, LPR, NACC, false, 1><<<grid, THREADS, smem, st>>>(a); }
         } else if (variant == 2) {
-            if (exact) gather_kernel<VEC, LPR, NACC, true, 2><<<grid, THREADS, smem, st>>>(a);
-            else gather_kernel<VEC, LPR, NACC, false, 2><<<grid, THREADS, smem, st>>>(a);
+            if (exact) { prefer_carveout(gather_kernel<VEC, LPR, NACC, true, 2>); gather_kernel<VEC, LPR, NACC, true, 2><<<grid, THREADS, smem, st>>>(a); }
+            else { prefer_carveout(gather_kernel<VEC, LPR, NACC, false, 2>); gather_kernel<VEC, LPR, NACC, false, 2><<<grid, THREADS, smem, st>>>(a); }
         } else if (variant == 3) {
-            if (exact) gather_kernel<VEC, LPR, NACC, true, 3><<<grid, THREADS, smem, st>>>(a);
-            else gather_kernel<VEC, LPR, NACC, false, 3><<<grid, THREADS, smem, st>>>(a);
+            if (exact) { prefer_carveout(gather_kernel<VEC, LPR, NACC, true, 3>); gather_kernel<VEC, LPR, NACC, true, 3><<<grid, THREADS, smem, st>>>(a); }
+            else { prefer_carveout(gather_kernel<VEC, LPR, NACC, false, 3>); gather_kernel<VEC, LPR, NACC, false, 3><<<grid, THREADS, smem, st>>>(a); }
         }
         if (variant) { GCNK_LAUNCHED(); return GCNK_OK; }
     }
-    if (a.dim == VEC * LPR * NACC) gather_kernel<VEC, LPR, NACC, true, 0><<<grid, THREADS, smem, st>>>(a);
-    else gather_kernel<VEC, LPR, NACC, false, 0><<<grid, THREADS, smem, st>>>(a);
+    if (a.dim == VEC * LPR * NACC) { prefer_carveout(gather_kernel<VEC, LPR, NACC, true, 0>); gather_kernel<VEC, LPR, NACC, true, 0><<<grid, THREADS, smem, st>>>(a); }
+    else { prefer_carveout(gather_kernel<VEC, LPR, NACC, false, 0>); gather_kernel<VEC, LPR, NACC, false, 0><<<grid, THREADS, smem, st>>>(a); }
     GCNK_LAUNCHED();
     return GCNK_OK;
 }

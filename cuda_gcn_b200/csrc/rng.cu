@@ -18,6 +18,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "rng_bitsliced.cuh"
 
 using namespace gcnk;
 
@@ -169,6 +170,66 @@ U128 *device_tables() {
     return d_tab[dev];
 }
 
+// The bit-sliced form (rng_bitsliced.cuh): a thread runs 32 streams of 2^LS draws (one keep word per step for all of them),
+// ~9 instructions per draw instead of ~24.  Start states: the same cooperative jump to the CTA's offset and doubling fan-out
+// to the threads as above (a thread owns 2^(LS+5) draws), then the in-thread chain of jumps by 2^LS.
+template <int LS, bool HALF>
+__global__ void __launch_bounds__(CTA_THREADS) dropout_mask_bs_kernel(const U128 *__restrict__ J, const gcnk_bs::Entry *__restrict__ nib, U128 start,
+                                                                       uint32_t *__restrict__ keep, int64_t n, int threshold) {
+    constexpr int THREAD_SHIFT = LS + 5, CTA_SHIFT = THREAD_SHIFT + 7;
+    __shared__ U128 s_state[CTA_THREADS];
+    __shared__ uint64_t s_red[2][CTA_THREADS / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    U128 st = start;
+    for (unsigned b = 0, blk = blockIdx.x; blk; b++, blk >>= 1) {
+        if (!(blk & 1)) continue;
+        const bool bit = tid < 64 ? (st.lo >> tid) & 1 : (st.hi >> (tid - 64)) & 1;
+        const U128 col = J[(CTA_SHIFT + b) * 128 + tid];
+        uint64_t lo = bit ? col.lo : 0, hi = bit ? col.hi : 0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { lo ^= __shfl_xor_sync(FULL, lo, o); hi ^= __shfl_xor_sync(FULL, hi, o); }
+        if (lane == 0) { s_red[0][warp] = lo; s_red[1][warp] = hi; }
+        __syncthreads();
+        st.lo = s_red[0][0] ^ s_red[0][1] ^ s_red[0][2] ^ s_red[0][3];
+        st.hi = s_red[1][0] ^ s_red[1][1] ^ s_red[1][2] ^ s_red[1][3];
+        __syncthreads();
+    }
+    if (tid == 0) s_state[0] = st;
+    __syncthreads();
+    for (int b = 0; (1 << b) < CTA_THREADS; b++) {
+        const int have = 1 << b;
+        if (tid < have && (((int64_t)blockIdx.x << CTA_SHIFT) + ((int64_t)(tid + have) << THREAD_SHIFT)) < n)
+            s_state[tid + have] = apply_dev(J + (THREAD_SHIFT + b) * 128, s_state[tid]);
+        __syncthreads();
+    }
+    const int64_t first = ((int64_t)blockIdx.x << CTA_SHIFT) + ((int64_t)tid << THREAD_SHIFT);
+    if (first >= n) return;
+    const U128 s = s_state[tid];
+    gcnk_bs::generate<LS, HALF>(gcnk_bs::State128{s.lo, s.hi}, nib, threshold, keep + (first >> 5), n - first);
+}
+
+// nibble tables of M^(2^7) and M^(2^10) (the in-thread jump chain of the bit-sliced kernels), 8 KB each
+gcnk_bs::Entry *device_nibble_tables() {
+    static gcnk_bs::Entry *d_tab[64] = {nullptr};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+    if (!d_tab[dev]) {
+        const JumpTables &T = host_tables();
+        static_assert(sizeof(gcnk_bs::State128) == sizeof(U128), "same layout");
+        std::vector<gcnk_bs::Entry> h(2 * gcnk_bs::NIB_ENTRIES);
+        gcnk_bs::build_nibble_tables(reinterpret_cast<const gcnk_bs::State128 *>(T.J[7]), h.data());
+        gcnk_bs::build_nibble_tables(reinterpret_cast<const gcnk_bs::State128 *>(T.J[10]), h.data() + gcnk_bs::NIB_ENTRIES);
+        if (cudaMalloc(&d_tab[dev], sizeof(gcnk_bs::Entry) * h.size()) != cudaSuccess) return nullptr;
+        if (cudaMemcpy(d_tab[dev], h.data(), sizeof(gcnk_bs::Entry) * h.size(), cudaMemcpyHostToDevice) != cudaSuccess) return nullptr;
+    }
+    return d_tab[dev];
+}
+
+int rng_variant() {      // GCN_RNG_SCALAR=1: the scalar kernels only
+    const char *e = getenv("GCN_RNG_SCALAR");
+    return e && *e && strcmp(e, "0") ? 0 : 1;
+}
+
 }  // namespace
 
 struct gcnk_rng { U128 s; };
@@ -214,12 +275,28 @@ int gcnk_dropout_mask(gcnk_rng *rng, uint32_t *keep_bits, int64_t n, float p, gc
     const int threshold = (int)(p * (float)0x7fffffff);                    // int(p * MY_RAND_MAX) (module.cpp:211)
     // short streams (the N x hidden mask: 3.7 M draws at Reddit shape) get 128 draws per thread so that they still
     // fill the machine; long ones 512 (the per-CTA jump is amortised over more draws)
-    if (n < (64ll << 20)) {
+    if (rng_variant() == 1 && n >= (1ll << 20)) {
+        // long streams: the bit-sliced generator; 2^10 draws per stream once that still leaves a CTA for every few SMs
+        gcnk_bs::Entry *nib = device_nibble_tables();
+        if (!nib) return cuda_fail(cudaGetLastError(), "xorshift nibble tables", __FILE__, __LINE__);
+        const bool half = threshold == 0x40000000;                          // dropout 0.5: the keep bit is bit 30 of the draw
+        if (n >= (1ll << 26)) {
+            const unsigned ctas = (unsigned)((n + (1ll << 22) - 1) >> 22);
+            if (half) dropout_mask_bs_kernel<10, true><<<ctas, CTA_THREADS, 0, S(stream)>>>(tab, nib + gcnk_bs::NIB_ENTRIES, rng->s, keep_bits, n, threshold);
+            else dropout_mask_bs_kernel<10, false><<<ctas, CTA_THREADS, 0, S(stream)>>>(tab, nib + gcnk_bs::NIB_ENTRIES, rng->s, keep_bits, n, threshold);
+        } else {
+            const unsigned ctas = (unsigned)((n + (1ll << 19) - 1) >> 19);
+            if (half) dropout_mask_bs_kernel<7, true><<<ctas, CTA_THREADS, 0, S(stream)>>>(tab, nib, rng->s, keep_bits, n, threshold);
+            else dropout_mask_bs_kernel<7, false><<<ctas, CTA_THREADS, 0, S(stream)>>>(tab, nib, rng->s, keep_bits, n, threshold);
+        }
+    } else if (n < (64ll << 20)) {
         const int64_t ctas = (n + (1ll << 14) - 1) >> 14;
+        prefer_carveout(dropout_mask_kernel<7>);
         dropout_mask_kernel<7><<<(unsigned)ctas, CTA_THREADS, 0, S(stream)>>>(tab, rng->s, keep_bits, n, threshold);
     } else {
         const int64_t ctas = (n + (1ll << 16) - 1) >> 16;
         GCNK_REQUIRE(ctas <= 0x7fffffff, "too many draws for one launch");
+        prefer_carveout(dropout_mask_kernel<9>);
         dropout_mask_kernel<9><<<(unsigned)ctas, CTA_THREADS, 0, S(stream)>>>(tab, rng->s, keep_bits, n, threshold);
     }
     GCNK_LAUNCHED();

@@ -231,6 +231,7 @@ void GCN::build(GCNPlan plan) {
     {
         const char *tl = getenv("GCN_TREE_LOSS");
         fz->seq_loss = !(tl && *tl && strcmp(tl, "0")) && (dist.world == 1 || fz->p2p);
+        if (const char *sw = getenv("GCN_SEQ_WHEN")) fz->seq_when = std::max(0, std::min(2, atoi(sw)));
         if (fz->seq_loss) {
             if (!fz->terms) {
                 const int max_terms = std::max(split_count[1], std::max(split_count[2], split_count[3]));
@@ -705,17 +706,36 @@ void GCN::enqueue_loss_sum(int sidx_l, bool training, int slot) {
                                          slot_flag, z.seq[4], z.d_counter, st));
         return;                                                          // ws[3] stays 0 here: rank 0 supplies the sum
     }
+    if (training && z.seq_when != 0) { z.seq_pending = sidx_l; return; }   // launched later in the pass: flush_loss_sum
+    launch_loss_sum(sidx_l, training);
+}
+
+void GCN::flush_loss_sum() {
+    Fused &z = *fz;
+    if (!z.seq_pending) return;
+    launch_loss_sum(z.seq_pending, true);
+    z.seq_pending = 0;
+}
+
+void GCN::launch_loss_sum(int sidx_l, bool training) {
+    Fused &z = *fz;
+    gcnk_stream_t st = z.stream;
+    float *region = z.terms + (size_t)(sidx_l - 1) * z.term_region;
     const int *flags = nullptr;
     if (dist.world > 1) { ++z.seq[4]; flags = z.flag_arrays[0] + 64 + 8 * 4; }
-    gcnk_stream_t ss = training ? z.seq_stream : st;                    // eval: nothing follows that could hide it
-    if (training) {
+    const bool side = training && z.seq_when != 2;
+    gcnk_stream_t ss = side ? z.seq_stream : st;                        // eval: nothing follows that could hide it
+    if (side) {
         GCNK_CHECK(gcnk_event_record(z.ev_l2, st));
         GCNK_CHECK(gcnk_stream_wait_event(z.seq_stream, z.ev_l2));
     }
     // into ws[3], the slot the parallel reduction leaves at 0 on every rank: the sum over ranks that ends the pass carries
     // it to everybody unchanged (S + 0 + ... + 0)
     GCNK_CHECK(gcnk_sequential_sum(region, z.term_len[sidx_l], z.ws + 3, 0.f, flags, flags ? dist.world : 0, 0, z.seq[4], z.d_err, ss));
-    if (training) GCNK_CHECK(gcnk_event_record(z.ev_seq, z.seq_stream));
+    if (side) {
+        GCNK_CHECK(gcnk_event_record(z.ev_seq, z.seq_stream));
+        z.seq_joined = false;
+    }
 }
 
 // The end of every fused pass: cross-rank sums, the scalars to the host, the optimiser step.
@@ -725,7 +745,8 @@ void GCN::finish_pass(bool training, bool seq, int slot) {
     Variable &W1 = variables[2], &W2 = variables[5];
     // the pass is complete only with its loss; and (row-partitioned) no peer may overwrite the loss terms in this rank's
     // slab — which it can do as soon as it has passed the barrier below — before they have been added up
-    if (seq && training && (dist.world == 1 || dist.rank == 0)) GCNK_CHECK(gcnk_stream_wait_event(st, z.ev_seq));
+    flush_loss_sum();
+    if (!z.seq_joined) { GCNK_CHECK(gcnk_stream_wait_event(st, z.ev_seq)); z.seq_joined = true; }
     if (dist.world > 1) {
         // sums over nodes: dW1, dW2 and {sum of loss terms, count, wrong}; every rank then applies the same update.
         // This is also the one true barrier of the pass: nobody starts the next pass (and overwrites a gather source
@@ -901,6 +922,7 @@ void GCN::fused_enqueue(int current_split, bool training, int slot) {
         else { publish(z.Gm, H); await(z.Gm, H); }
         GCNK_CHECK(gcnk_gather_plain(v, z.Gm, z.dxw, H, st));
         gpu_timer_end(TMR_GATHER_FULL);
+        if (z.seq_when == 1) flush_loss_sum();                           // under the weight-gradient kernel, not under the gathers
         gpu_timer_begin(TMR_SPMATMUL_BW);
         if (z.Xp && z.tc_transform) GCNK_CHECK(gcnk_dense_transform_bw_tc(z.Xp, z.ld, n_loc, F, z.dxw, W1.grad, H, drop ? z.keep0 : nullptr, scale, z.bw_ws, z.bw_ws_bytes, st));
         else if (z.Xp) GCNK_CHECK(gcnk_dense_transform_bw_ld(z.Xp, z.ld, n_loc, F, z.dxw, W1.grad, H, drop ? z.keep0 : nullptr, scale, z.bw_ws, z.bw_ws_bytes, st));

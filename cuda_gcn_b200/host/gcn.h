@@ -95,6 +95,8 @@ private:
     void finish_build();
     void wide_enqueue(int current_split, bool training, int slot);
     void enqueue_loss_sum(int split_index, bool training, int slot);
+    void launch_loss_sum(int sidx_l, bool training);
+    void flush_loss_sum();
     void finish_pass(bool training, bool seq, int slot);
     gcnk_stream_t engine_stream() const;
     void mirror(float *d_all, int dim);

@@ -106,6 +106,10 @@ struct GCN::Fused {
     // (gcnk_sequential_sum) on a side stream, under the backward pass.  Row-partitioned: every rank pushes its compact
     // range to the peers and every rank computes the same global sum.  GCN_TREE_LOSS=1: the plain parallel sum instead.
     bool seq_loss = true;
+    int seq_when = 1;          // training pass: 0 = right behind layer 2 (under the backward gathers), 1 = behind the last gather (under the
+                               // weight-gradient kernel), 2 = on the main stream at the end of the pass.  GCN_SEQ_WHEN
+    bool seq_joined = true;    // the main stream has waited for the side stream's last loss sum
+    int seq_pending = 0;       // split whose loss sum is still to be launched in this pass
     float *terms = nullptr, *d_seq = nullptr, *h_seq = nullptr;
     bool terms_owned = false;
     int *term_index[4] = {nullptr, nullptr, nullptr, nullptr};

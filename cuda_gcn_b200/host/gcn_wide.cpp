@@ -235,6 +235,7 @@ void GCN::wide_enqueue(int current_split, bool training, int slot) {
         await(z.D_s, Cp);
         GCNK_CHECK(gcnk_gather_plain(z.cols_train, z.D_s, z.dT, Cp, st));
         gpu_timer_end(TMR_GRAPHSUM_BW);
+        if (z.seq_when == 1) flush_loss_sum();                           // under the backward GEMMs
         // M5 backward: dW2 = H1^T dT, dH1 = dT W2^T;  M4/M3 backward: the mask;  M1 backward: dW1 = AXd^T dZ1
         gpu_timer_begin(TMR_MATMUL_BW);
         GCNK_CHECK(gcnk_matmul_tn(z.H1, H, z.dT, Cp, z.dW2p, Cp, n_loc, H, Cp, z.mm_ws, z.mm_ws_bytes, st));

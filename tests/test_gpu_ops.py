@@ -431,7 +431,7 @@ def test_relu(abi, chk, D):
     assert (dmask.numpy() == before).all()
 
 
-@pytest.mark.parametrize("n", [1, 31, 512, 65536, 65537, 300001, 70_000_001])   # the last one takes the 512-draws-per-thread path (>= 64 Mi draws)
+@pytest.mark.parametrize("n", [1, 31, 512, 65536, 65537, 300001, 1_048_576, 1_048_577, 5_000_003, 70_000_001])   # >= 1 Mi draws: the bit-sliced kernels (128 draws per stream; 1,024 from 64 Mi draws on)
 @pytest.mark.parametrize("p", [0.0, 0.5, 0.9])
 def test_dropout_stream_bit_exact(abi, chk, n, p):
     """The device keep bits are the reference's xorshift128+ stream, bit for bit (rand.cpp:17-28,

@@ -368,7 +368,7 @@ def test_reddit_full_scale_trajectory(host):
     eng.close()
 
 
-@pytest.mark.parametrize("toggle", ["GCN_NO_TMA", "GCN_NO_VIEWS", "GCN_NO_AX", "GCN_NO_RNG_OVERLAP"])
+@pytest.mark.parametrize("toggle", ["GCN_NO_TMA", "GCN_NO_VIEWS", "GCN_NO_AX", "GCN_NO_RNG_OVERLAP", "GCN_RNG_SCALAR"])
 def test_fallback_paths(host, chk, toggle, monkeypatch):
     """Every optimisation of the fused plan can be switched off (register-staged feature transform, full-graph gathers
     instead of split views, no A_hat*X precompute, masks drawn in line): the result must not depend on it."""

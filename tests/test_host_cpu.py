@@ -212,3 +212,16 @@ def test_parser_fuzz_against_reference(host, oracle, tmp_path):
         for k in ("graph_indptr", "graph_indices", "feature_indptr", "feature_indices", "label", "split"):
             assert got[k].shape == want[k].shape and (got[k] == want[k]).all(), (name, k)
         assert (got["feature_value"].view(np.uint32) == want["feature_value"].view(np.uint32)).all(), name
+
+
+def test_bitsliced_rng_matches_scalar_stream(tmp_path):
+    """cuda_gcn_b200/csrc/rng_bitsliced.cuh (the per-thread part of the bit-sliced keep-bit kernels) compiled for the host: 32
+    streams per call against the scalar xorshift128+ stream (rand.cpp:17-28) and keep rule (module.cpp:211-216), for
+    128 / 1,024 draws per stream, thresholds incl. the dropout-0.5 special case, and ragged ends."""
+    import subprocess
+    from pathlib import Path
+    root = Path(__file__).resolve().parent.parent
+    exe = tmp_path / "rng_bs_host"
+    subprocess.run(["g++", "-O2", "-std=c++17", "-o", str(exe), str(root / "tests" / "rng_bitsliced_host.cpp")], check=True, timeout=300)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and out.stdout.strip() == "ok", out.stdout[-2000:]
