@@ -222,21 +222,42 @@ __device__ __forceinline__ bool seq_fast_block(float &S, const float *t, int cnt
     }
     ok = __all_sync(FULL, ok);
     if (!ok) return false;
-    const int R = __reduce_add_sync(FULL, r_sum);               // < 2^20 * 256: exact
+    const int R = __reduce_add_sync(FULL, r_sum);               // < 2^20 * 1,024: exact
     const uint32_t m = (sb & 0x7fffffu) | 0x800000u;            // S = m * u
     if (m + (uint32_t)R >= 0x1000000u) return false;            // would cross into the next binade
     S = __uint_as_float((sb & 0x7f800000u) | ((m + (uint32_t)R) & 0x7fffffu));
     return true;
 }
 
-// One CTA: warp 0 runs the (inherently serial) block-by-block sum out of shared memory, warps 1-7 stream the next 4,096
-// terms in meanwhile — a lone warp reading global memory spends ~700 cycles of load latency per 256 terms (measured:
-// 360 us for 153,756 terms), the shared-memory ring brings that to the ~150 cycles the arithmetic takes.
-constexpr int SEQ_CHUNK = 4096;
+// Per-lane part of a fast block with the exponent given: the integer sum of the lane's rounded terms; ok = false if any of
+// them is a tie, negative, as large as S itself or not a number (then the sequential path decides).
+__device__ __forceinline__ int seq_round_terms(int e, const float *t, int cnt, bool &ok) {
+    const float inv_u = __uint_as_float((uint32_t)(127 + 150 - e) << 23);     // 2^(150 - e) = 1 / ulp(S)
+    int r_sum = 0;
+    for (int j = 0; j < cnt; j++) {
+        const float x = t[j] * inv_u;
+        const float r = rintf(x);
+        if (!(x >= 0.f) || !(x < 1048576.f) || fabsf(x - r) == 0.5f) ok = false;
+        r_sum += (int)r;
+    }
+    return r_sum;
+}
+
+// One CTA of eight warps.  Per chunk of 4,096 terms (shared-memory ring, filled with 16-byte loads one chunk ahead):
+//   all warps   round the chunk's four 1,024-term blocks in parallel, SPECULATING that the running sum stays in the binade it
+//               is in at the start of the chunk (the rounding unit only depends on that exponent) — two warps per block;
+//   warp 0      then walks the four blocks in order: a block whose speculation holds (same exponent, every term fine, no carry
+//               out of the mantissa) is one integer addition; any other block is replayed from shared memory with the
+//               row-wise fast path / the reference's own scalar loop.
+// The serial part is ~40 instructions per 1,024 terms; a lone warp doing the rounding as well was issue-bound at 131 us for
+// 153,756 terms (r02x).
+constexpr int SEQ_CHUNK = 4096, SEQ_BLOCK = 1024, SEQ_BLOCKS = SEQ_CHUNK / SEQ_BLOCK;
 __global__ void __launch_bounds__(256) seq_sum_kernel(const float *__restrict__ terms, int n, float *__restrict__ out, float divide_by,
                                                       const int *wait_flags, int wait_n, int wait_skip, int wait_value, int *wait_err,
                                                       long long wait_limit) {
     __shared__ __align__(16) float buf[2][SEQ_CHUNK];
+    __shared__ int s_part[8], s_ok[8];
+    __shared__ float s_S;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (wait_flags) {                                           // row-partitioned runs: every rank's terms must have landed
         if (tid < wait_n && tid != wait_skip) {
@@ -253,49 +274,72 @@ __global__ void __launch_bounds__(256) seq_sum_kernel(const float *__restrict__ 
     }
     const int n_chunks = (n + SEQ_CHUNK - 1) / SEQ_CHUNK;
     const bool vec_ok = (reinterpret_cast<uintptr_t>(terms) & 15) == 0;
-    auto load_chunk = [&](int c) {                              // warps 1-7; terms beyond n read as +0, which a sum passes over unchanged
+    // terms beyond n read as +0, which a sum passes over unchanged
+    auto fetch = [&](int c, float4 (&v)[4]) {                   // chunk c -> registers (all loads in flight together)
         const int base = c * SEQ_CHUNK;
-        float *dst = buf[c & 1];
-        if (vec_ok && base + SEQ_CHUNK <= n) {
-            // all of this thread's loads in flight before the first store: one memory round trip per chunk, not five
-            constexpr int PER = (SEQ_CHUNK / 4 + 223) / 224;
-            float4 v[PER];
 #pragma unroll
-            for (int k = 0; k < PER; k++) {
-                const int i = tid - 32 + k * 224;
-                if (i < SEQ_CHUNK / 4) v[k] = ld_stream_f4(reinterpret_cast<const float4 *>(terms + base) + i);
+        for (int k = 0; k < 4; k++) {
+            const int i = (tid + k * 256) * 4;
+            if (vec_ok && base + i + 4 <= n) v[k] = ld_stream_f4(reinterpret_cast<const float4 *>(terms + base + i));
+            else {
+                v[k].x = base + i < n ? ld_stream_f32(terms + base + i) : 0.f;
+                v[k].y = base + i + 1 < n ? ld_stream_f32(terms + base + i + 1) : 0.f;
+                v[k].z = base + i + 2 < n ? ld_stream_f32(terms + base + i + 2) : 0.f;
+                v[k].w = base + i + 3 < n ? ld_stream_f32(terms + base + i + 3) : 0.f;
             }
-#pragma unroll
-            for (int k = 0; k < PER; k++) {
-                const int i = tid - 32 + k * 224;
-                if (i < SEQ_CHUNK / 4) reinterpret_cast<float4 *>(dst)[i] = v[k];
-            }
-            return;
         }
-        for (int i = tid - 32; i < SEQ_CHUNK; i += 224) dst[i] = base + i < n ? ld_stream_f32(terms + base + i) : 0.f;
     };
-    if (warp > 0 && n_chunks > 0) load_chunk(0);
-    __syncthreads();
-    constexpr int ROWS = 8;                                     // 8 x 32 = 256 terms per step
-    float S = 0.f;
-    for (int c = 0; c < n_chunks; c++) {
-        if (warp > 0) {
-            if (c + 1 < n_chunks) load_chunk(c + 1);
-        } else {
-            const float *src = buf[c & 1];
-            for (int sb = 0; sb < SEQ_CHUNK; sb += ROWS * 32) {
-                if (c * SEQ_CHUNK + sb >= n) break;
-                float cur[ROWS];
+    auto stash = [&](int c, const float4 (&v)[4]) {
 #pragma unroll
-                for (int j = 0; j < ROWS; j++) cur[j] = src[sb + j * 32 + lane];
-                if (!seq_fast_block(S, cur, ROWS)) {
+        for (int k = 0; k < 4; k++) reinterpret_cast<float4 *>(buf[c & 1])[tid + k * 256] = v[k];
+    };
+    float4 v[4];
+    if (n_chunks > 0) { fetch(0, v); stash(0, v); }
+    if (tid == 0) s_S = 0.f;
+    __syncthreads();
+    float S = 0.f;                                              // warp 0's copy is the truth; s_S broadcasts it once per chunk
+    for (int c = 0; c < n_chunks; c++) {
+        const float *src = buf[c & 1];
+        if (c + 1 < n_chunks) fetch(c + 1, v);                  // in flight during the rounding below
+        // speculative rounding: warp w takes rows [16 (w & 1), +16) of block w / 2
+        const uint32_t sb0 = __float_as_uint(s_S);
+        const int e0 = (int)((sb0 >> 23) & 0xff);
+        const bool spec = !(sb0 >> 31) && e0 >= 30 && e0 <= 250;
+        {
+            bool ok = spec;
+            int r = 0;
+            if (spec) {
+                float t[16];
+                const float *blk = src + (warp >> 1) * SEQ_BLOCK + (warp & 1) * 512;
+#pragma unroll
+                for (int j = 0; j < 16; j++) t[j] = blk[j * 32 + lane];
+                r = seq_round_terms(e0, t, 16, ok);
+            }
+            ok = __all_sync(FULL, ok);
+            r = __reduce_add_sync(FULL, r);                     // < 2^20 * 512: exact
+            if (lane == 0) { s_part[warp] = r; s_ok[warp] = ok; }
+        }
+        if (c + 1 < n_chunks) stash(c + 1, v);
+        __syncthreads();
+        if (warp == 0) {
+            for (int b = 0; b < SEQ_BLOCKS; b++) {
+                const int first = c * SEQ_CHUNK + b * SEQ_BLOCK;
+                if (first >= n) break;
+                const uint32_t sb = __float_as_uint(S);
+                const uint32_t m = (sb & 0x7fffffu) | 0x800000u;
+                const uint32_t R = (uint32_t)(s_part[2 * b] + s_part[2 * b + 1]);
+                if (s_ok[2 * b] && s_ok[2 * b + 1] && !(sb >> 31) && (int)((sb >> 23) & 0xff) == e0 && m + R < 0x1000000u) {
+                    S = __uint_as_float((sb & 0x7f800000u) | ((m + R) & 0x7fffffu));
+                    continue;
+                }
 #pragma unroll 1
-                    for (int j = 0; j < ROWS; j++) {            // a row of 32 at a time: fast if possible, else the reference's own loop
-                        if (seq_fast_block(S, &cur[j], 1)) continue;
-                        for (int l = 0; l < 32; l++) S = S + src[sb + j * 32 + l];
-                    }
+                for (int j = 0; j < SEQ_BLOCK / 32; j++) {      // a row of 32 at a time: fast if possible, else the reference's own loop
+                    const float one = src[b * SEQ_BLOCK + j * 32 + lane];
+                    if (seq_fast_block(S, &one, 1)) continue;
+                    for (int l = 0; l < 32; l++) S = S + src[b * SEQ_BLOCK + j * 32 + l];
                 }
             }
+            if (lane == 0) s_S = S;
         }
         __syncthreads();
     }

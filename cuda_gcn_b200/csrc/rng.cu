@@ -208,7 +208,8 @@ __global__ void __launch_bounds__(CTA_THREADS) dropout_mask_bs_kernel(const U128
     gcnk_bs::generate<LS, HALF>(gcnk_bs::State128{s.lo, s.hi}, nib, threshold, keep + (first >> 5), n - first);
 }
 
-// nibble tables of M^(2^7) and M^(2^10) (the in-thread jump chain of the bit-sliced kernels), 8 KB each
+// nibble tables of M^(2^LS), LS = 7..10 (the in-thread jump chain of the bit-sliced kernels), 8 KB each
+constexpr int BS_LS_MIN = 7, BS_LS_MAX = 10;
 gcnk_bs::Entry *device_nibble_tables() {
     static gcnk_bs::Entry *d_tab[64] = {nullptr};
     int dev = 0;
@@ -216,13 +217,21 @@ gcnk_bs::Entry *device_nibble_tables() {
     if (!d_tab[dev]) {
         const JumpTables &T = host_tables();
         static_assert(sizeof(gcnk_bs::State128) == sizeof(U128), "same layout");
-        std::vector<gcnk_bs::Entry> h(2 * gcnk_bs::NIB_ENTRIES);
-        gcnk_bs::build_nibble_tables(reinterpret_cast<const gcnk_bs::State128 *>(T.J[7]), h.data());
-        gcnk_bs::build_nibble_tables(reinterpret_cast<const gcnk_bs::State128 *>(T.J[10]), h.data() + gcnk_bs::NIB_ENTRIES);
+        std::vector<gcnk_bs::Entry> h((BS_LS_MAX - BS_LS_MIN + 1) * gcnk_bs::NIB_ENTRIES);
+        for (int ls = BS_LS_MIN; ls <= BS_LS_MAX; ls++)
+            gcnk_bs::build_nibble_tables(reinterpret_cast<const gcnk_bs::State128 *>(T.J[ls]), h.data() + (ls - BS_LS_MIN) * gcnk_bs::NIB_ENTRIES);
         if (cudaMalloc(&d_tab[dev], sizeof(gcnk_bs::Entry) * h.size()) != cudaSuccess) return nullptr;
         if (cudaMemcpy(d_tab[dev], h.data(), sizeof(gcnk_bs::Entry) * h.size(), cudaMemcpyHostToDevice) != cudaSuccess) return nullptr;
     }
     return d_tab[dev];
+}
+
+template <int LS>
+void launch_bs(const U128 *tab, const gcnk_bs::Entry *nib, U128 start, uint32_t *keep, int64_t n, int threshold, cudaStream_t st) {
+    const unsigned ctas = (unsigned)((n + (1ll << (LS + 12)) - 1) >> (LS + 12));
+    const gcnk_bs::Entry *t = nib + (LS - BS_LS_MIN) * gcnk_bs::NIB_ENTRIES;
+    if (threshold == 0x40000000) dropout_mask_bs_kernel<LS, true><<<ctas, CTA_THREADS, 0, st>>>(tab, t, start, keep, n, threshold);   // dropout 0.5: the keep bit is bit 30 of the draw
+    else dropout_mask_bs_kernel<LS, false><<<ctas, CTA_THREADS, 0, st>>>(tab, t, start, keep, n, threshold);
 }
 
 int rng_variant() {      // GCN_RNG_SCALAR=1: the scalar kernels only
@@ -279,16 +288,16 @@ int gcnk_dropout_mask(gcnk_rng *rng, uint32_t *keep_bits, int64_t n, float p, gc
         // long streams: the bit-sliced generator; 2^10 draws per stream once that still leaves a CTA for every few SMs
         gcnk_bs::Entry *nib = device_nibble_tables();
         if (!nib) return cuda_fail(cudaGetLastError(), "xorshift nibble tables", __FILE__, __LINE__);
-        const bool half = threshold == 0x40000000;                          // dropout 0.5: the keep bit is bit 30 of the draw
-        if (n >= (1ll << 26)) {
-            const unsigned ctas = (unsigned)((n + (1ll << 22) - 1) >> 22);
-            if (half) dropout_mask_bs_kernel<10, true><<<ctas, CTA_THREADS, 0, S(stream)>>>(tab, nib + gcnk_bs::NIB_ENTRIES, rng->s, keep_bits, n, threshold);
-            else dropout_mask_bs_kernel<10, false><<<ctas, CTA_THREADS, 0, S(stream)>>>(tab, nib + gcnk_bs::NIB_ENTRIES, rng->s, keep_bits, n, threshold);
-        } else {
-            const unsigned ctas = (unsigned)((n + (1ll << 19) - 1) >> 19);
-            if (half) dropout_mask_bs_kernel<7, true><<<ctas, CTA_THREADS, 0, S(stream)>>>(tab, nib, rng->s, keep_bits, n, threshold);
-            else dropout_mask_bs_kernel<7, false><<<ctas, CTA_THREADS, 0, S(stream)>>>(tab, nib, rng->s, keep_bits, n, threshold);
-        }
+        // draws per stream: long streams amortise the jump chain (6.5 instructions per draw at 2^10, 8.4 at 2^7) but leave
+        // fewer, longer-running CTAs (a CTA owns 2^(LS+12) draws); GCN_RNG_LS overrides
+        // measured in the Reddit-shape step (r02w): 2^7 403, 2^8 405, 2^9 408, 2^10 396 epochs/s
+        int ls = n >= (1ll << 25) ? 9 : 7;
+        if (const char *e = getenv("GCN_RNG_LS")) { const int v = atoi(e); if (v >= BS_LS_MIN && v <= BS_LS_MAX) ls = v; }
+        GCNK_REQUIRE(((n + (1ll << (ls + 12)) - 1) >> (ls + 12)) <= 0x7fffffff, "too many draws for one launch");
+        if (ls == 7) launch_bs<7>(tab, nib, rng->s, keep_bits, n, threshold, S(stream));
+        else if (ls == 8) launch_bs<8>(tab, nib, rng->s, keep_bits, n, threshold, S(stream));
+        else if (ls == 9) launch_bs<9>(tab, nib, rng->s, keep_bits, n, threshold, S(stream));
+        else launch_bs<10>(tab, nib, rng->s, keep_bits, n, threshold, S(stream));
     } else if (n < (64ll << 20)) {
         const int64_t ctas = (n + (1ll << 14) - 1) >> 14;
         prefer_carveout(dropout_mask_kernel<7>);

@@ -231,6 +231,10 @@ void GCN::build(GCNPlan plan) {
     {
         const char *tl = getenv("GCN_TREE_LOSS");
         fz->seq_loss = !(tl && *tl && strcmp(tl, "0")) && (dist.world == 1 || fz->p2p);
+        // measured (r02s/r02t, 1 GPU): right behind layer 2 the one-CTA kernel makes the two backward gathers 40 us slower
+        // each; behind the last gather it hides under the weight-gradient kernel.  Row-partitioned, that kernel is too
+        // short to hide rank 0's sum of ALL ranks' terms, so there it starts early.
+        fz->seq_when = dist.world == 1 ? 1 : 0;
         if (const char *sw = getenv("GCN_SEQ_WHEN")) fz->seq_when = std::max(0, std::min(2, atoi(sw)));
         if (fz->seq_loss) {
             if (!fz->terms) {
