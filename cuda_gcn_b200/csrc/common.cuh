@@ -99,13 +99,17 @@ __device__ __forceinline__ void reduce_parts_block(const float *__restrict__ par
     __shared__ float s_part[8][33];
     const int e = threadIdx.x & 31, q = threadIdx.x >> 5;
     const int i = blockIdx.x * 32 + e;
-    float s0 = 0.f, s1 = 0.f;
+    // eight independent chains per thread: the loop is pure load latency (measured: 45 us for 911 partials with two)
+    float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     if (i < elems) {
         int b = q;
-        for (; b + 8 < parts; b += 16) { s0 += partials[(size_t)b * elems + i]; s1 += partials[(size_t)(b + 8) * elems + i]; }
-        if (b < parts) s0 += partials[(size_t)b * elems + i];
+        for (; b + 56 < parts; b += 64) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) s[k] += partials[(size_t)(b + 8 * k) * elems + i];
+        }
+        for (int k = 0; b < parts; b += 8, k++) s[k] += partials[(size_t)b * elems + i];
     }
-    s_part[q][e] = s0 + s1;
+    s_part[q][e] = ((s[0] + s[1]) + (s[2] + s[3])) + ((s[4] + s[5]) + (s[6] + s[7]));
     __syncthreads();
     if (q == 0 && i < elems) {
         float v = 0.f;

@@ -332,6 +332,12 @@ __global__ void __launch_bounds__(256) seq_sum_kernel(const float *__restrict__ 
                     S = __uint_as_float((sb & 0x7f800000u) | ((m + R) & 0x7fffffu));
                     continue;
                 }
+                {                                               // the whole block again, in the binade S is in NOW (the speculation
+                    float cur[SEQ_BLOCK / 32];                  // fails for every block behind a binade crossing in the same chunk)
+#pragma unroll
+                    for (int j = 0; j < SEQ_BLOCK / 32; j++) cur[j] = src[b * SEQ_BLOCK + j * 32 + lane];
+                    if (seq_fast_block(S, cur, SEQ_BLOCK / 32)) continue;
+                }
 #pragma unroll 1
                 for (int j = 0; j < SEQ_BLOCK / 32; j++) {      // a row of 32 at a time: fast if possible, else the reference's own loop
                     const float one = src[b * SEQ_BLOCK + j * 32 + lane];

@@ -1,0 +1,6 @@
+set -x
+timeout 900 python -m pytest tests -m gpu -q -x > gpurun_out/r03a_gputests.log 2>&1; echo "rc=$?" >> gpurun_out/r03a_gputests.log; tail -n 5 gpurun_out/r03a_gputests.log
+B="python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-dims"
+run() { n=$1; shift; env "$@" timeout 300 $B > gpurun_out/r03a_$n.json 2> gpurun_out/r03a_$n.err; echo "$n rc=$?"; tail -n 2 gpurun_out/r03a_$n.err; }
+run default X=1
+run when2 GCN_SEQ_WHEN=2
