@@ -41,12 +41,15 @@ __device__ __forceinline__ void mma(float (&d)[4], uint32_t a0, uint32_t a1, uin
                  : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
                  : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
-__device__ __forceinline__ uint32_t bit_window(const uint32_t *__restrict__ bits, int64_t words, int64_t pos) {
-    const int64_t w = pos >> 5;
-    const uint32_t lo = w < words ? __ldg(bits + w) : 0u;
-    const uint32_t hi = w + 1 < words ? __ldg(bits + w + 1) : 0u;
-    return __funnelshift_r(lo, hi, (uint32_t)(pos & 31));
+// Keep-bit words travel global -> shared memory with 4-byte cp.async, several ring slots ahead of their use: a register
+// prefetch one step ahead did not cover the L2 round trip (measured with the loads removed: 23 us of the forward and 25 us
+// of the backward kernel were exposed keep-bit latency).  One group per step; a slot is read after wait_group + __syncwarp.
+constexpr int KW_SLOTS = 4, KW_AHEAD = 3;
+__device__ __forceinline__ void cp_async_4(void *smem_dst, const void *gmem_src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
 }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
 
 // ================================================================================== forward ====
 // CTA = 16 consumer warps (16 rows each: a 256-row tile) + 1 producer warp.  Stage = one [256 x 32] box (32 KB).
@@ -66,6 +69,7 @@ __global__ void __launch_bounds__(FW_THREADS, 1) dense_fw16_tma_kernel(const __g
     uint8_t *ring = smem;                                                        // [FW_STAGES][16 KB]
     float4 *sfrag = reinterpret_cast<float4 *>(smem + FW_STAGES * FW_STAGE_BYTES);   // [KS][32] big, [KS][32] small
     FwBars *bars = reinterpret_cast<FwBars *>(sfrag + 2 * KS * 32);
+    uint32_t *kws_all = reinterpret_cast<uint32_t *>(bars + 1);                  // [FW_CONSUMERS][KW_SLOTS][16 rows][2 words]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, t = lane & 3, g = lane >> 2;
     for (int i = threadIdx.x; i < KS * 32; i += FW_THREADS) {
@@ -102,20 +106,42 @@ __global__ void __launch_bounds__(FW_THREADS, 1) dense_fw16_tma_kernel(const __g
     }
     // -------------------------------------------------- consumers --------------------------------------------------
     uint32_t it = 0;
+    // keep words: lane l fetches word (l & 1) of the window of tile-local row 16 * warp + (l >> 1) (rows g and g + 8 of the
+    // lanes' fragments), KW_AHEAD batches ahead of the batch being multiplied, across tile boundaries
+    uint32_t *kws = kws_all + warp * (KW_SLOTS * 32);
+    int p_tile = blockIdx.x, p_b = 0;
+    uint32_t p_it = 0;
+    auto prefetch_keep = [&]() {
+        if (bits && p_tile < n_tiles) {
+            const int row = min(p_tile * FW_BM + 16 * warp + (lane >> 1), m - 1);
+            const int64_t w = (((int64_t)row * n + 32 * p_b) >> 5) + (lane & 1);
+            cp_async_4(kws + (p_it % KW_SLOTS) * 32 + lane, bits + (w < bit_words ? w : bit_words - 1));
+            if (++p_b == n_batches) { p_b = 0; p_tile += gridDim.x; }
+        }
+        p_it++;
+        cp_async_commit();
+    };
+    if (bits)
+        for (int k = 0; k < KW_AHEAD; k++) prefetch_keep();
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int lr = 16 * warp + g;                                  // tile-local rows lr and lr + 8 (both have (row & 7) == g)
         const int ra = tile * FW_BM + lr, rb = ra + 8;
         const bool va = ra < m, vb = rb < m;
         float acc0[4] = {0.f, 0.f, 0.f, 0.f}, acc1[4] = {0.f, 0.f, 0.f, 0.f};
-        uint32_t wa = 0, wb = 0;
-        if (bits) { wa = va ? bit_window(bits, bit_words, (int64_t)ra * n) : 0u; wb = vb ? bit_window(bits, bit_words, (int64_t)rb * n) : 0u; }
+        // bit offset of the rows' windows inside their first word (the same for every batch: batches advance by 32 bits)
+        const uint32_t sha = (uint32_t)(((int64_t)min(ra, m - 1) * n) & 31), shb = (uint32_t)(((int64_t)min(rb, m - 1) * n) & 31);
 #pragma unroll 1
         for (int b = 0; b < n_batches; b++, it++) {
             const int s = it % FW_STAGES;
-            uint32_t wa_n = 0, wb_n = 0;                               // next batch's keep windows, in flight during this batch
-            if (bits && b + 1 < n_batches) {
-                wa_n = va ? bit_window(bits, bit_words, (int64_t)ra * n + 32 * (b + 1)) : 0u;
-                wb_n = vb ? bit_window(bits, bit_words, (int64_t)rb * n + 32 * (b + 1)) : 0u;
+            uint32_t wa = 0, wb = 0;
+            if (bits) {
+                prefetch_keep();
+                cp_async_wait<KW_AHEAD>();                             // this batch's group has landed (for the lane that issued it)
+                __syncwarp();
+                const uint32_t *slot = kws + (it % KW_SLOTS) * 32;
+                const uint2 qa = *reinterpret_cast<const uint2 *>(slot + 2 * g), qb = *reinterpret_cast<const uint2 *>(slot + 2 * (8 + g));
+                wa = va ? __funnelshift_r(qa.x, qa.y, sha) : 0u;
+                wb = vb ? __funnelshift_r(qb.x, qb.y, shb) : 0u;
             }
             if (!mbar_wait(&bars->full[s], (it / FW_STAGES) & 1, err)) return;
             const uint8_t *st = ring + s * FW_STAGE_BYTES;
@@ -150,7 +176,6 @@ __global__ void __launch_bounds__(FW_THREADS, 1) dense_fw16_tma_kernel(const __g
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&bars->empty[s]);               // this warp is done with the slot
-            wa = wa_n; wb = wb_n;
         }
         if (relu) {
 #pragma unroll
@@ -189,6 +214,7 @@ __global__ void __launch_bounds__(BW_THREADS, 1) dense_bw16_tma_kernel(const __g
     uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 1 KB aligned, still a shared-space pointer (LDS, not LD)
     const uint32_t stage_bytes = (uint32_t)n_boxes * BW_BOX_BYTES + 1024;          // X boxes, then G (padded to keep 1 KB alignment)
     BwBars *bars = reinterpret_cast<BwBars *>(smem + BW_STAGES * stage_bytes);
+    uint32_t *kws_all = reinterpret_cast<uint32_t *>(bars + 1);                    // [20 warps][KW_SLOTS][8 rows][4 words]
     const int n_consumers = (n_boxes + 1) / 2;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, t = lane & 3, g = lane >> 2;
     if (threadIdx.x == 0) {
@@ -225,18 +251,38 @@ __global__ void __launch_bounds__(BW_THREADS, 1) dense_bw16_tma_kernel(const __g
 #pragma unroll
             for (int e = 0; e < 4; e++) acc[p][h][e] = 0.f;
 
+    // keep words of the stage's 8 rows of this warp's group, 64 + 31 bits from the band's first feature on: lane l fetches word
+    // (l & 3) of row (l >> 2), KW_AHEAD stages ahead
+    uint32_t *kws = kws_all + warp * (KW_SLOTS * 32);
+    int p_it = 0;
+    auto prefetch_keep = [&]() {
+        if (bits && p_it < n_stages) {
+            const int row = min(r_lo + p_it * BW_ROWS + 8 * group + (lane >> 2), m - 1);
+            const int64_t w = (((int64_t)row * n + f_band) >> 5) + (lane & 3);
+            cp_async_4(kws + (p_it % KW_SLOTS) * 32 + lane, bits + (w < bit_words ? w : bit_words - 1));
+        }
+        p_it++;
+        cp_async_commit();
+    };
+    if (bits)
+        for (int k = 0; k < KW_AHEAD; k++) prefetch_keep();
 #pragma unroll 1
     for (int it = 0; it < n_stages; it++) {
         const int s = it % BW_STAGES;
-        // keep windows of this lane's rows for both k-steps of the stage: 64 + 31 bits -> three windows of 32
+        // keep windows of this lane's rows for both k-steps of the stage: 64 + 31 bits -> two windows of 32 out of three words
         uint32_t kw[2][2];
         if (bits) {
+            prefetch_keep();
+            cp_async_wait<KW_AHEAD>();
+            __syncwarp();
+            const uint32_t *slot = kws + (it % KW_SLOTS) * 32;
 #pragma unroll
             for (int rr = 0; rr < 2; rr++) {
                 const int row = r_lo + it * BW_ROWS + 8 * group + 2 * t + rr;
-                const int64_t pos = (int64_t)row * n + f_band;
-#pragma unroll
-                for (int q = 0; q < 2; q++) kw[rr][q] = row < r_hi ? bit_window(bits, bit_words, pos + 32 * q) : 0u;
+                const uint4 q = *reinterpret_cast<const uint4 *>(slot + 4 * (2 * t + rr));
+                const uint32_t sh = (uint32_t)(((int64_t)min(row, m - 1) * n + f_band) & 31);
+                kw[rr][0] = row < r_hi ? __funnelshift_r(q.x, q.y, sh) : 0u;
+                kw[rr][1] = row < r_hi ? __funnelshift_r(q.y, q.z, sh) : 0u;
             }
         }
         if (!mbar_wait(&bars->full[s], (it / BW_STAGES) & 1, err)) return;
@@ -334,7 +380,8 @@ int gcnk_dense_transform_ld(const float *xp, int ld, int m, int n, const float *
     GCNK_REQUIRE(xp && w && c && m >= 0 && n > 0 && ld >= n && p > 0, "bad arguments");
     if (m == 0) return GCNK_OK;
     const int KS = (n + 7) / 8;
-    const size_t smem = (size_t)FW_STAGES * FW_STAGE_BYTES + sizeof(float4) * 2 * (size_t)KS * 32 + sizeof(FwBars) + 1024;
+    const size_t smem = (size_t)FW_STAGES * FW_STAGE_BYTES + sizeof(float4) * 2 * (size_t)KS * 32 + sizeof(FwBars) + 1024 +
+                        sizeof(uint32_t) * FW_CONSUMERS * KW_SLOTS * 32;
     if (p != P || ld % 4 || reinterpret_cast<uintptr_t>(xp) % 16 || reinterpret_cast<uintptr_t>(c) % 8 || smem > 227 * 1024 ||
         !tensor_maps_available()) {
         set_error("gcnk_dense_transform_ld: needs p == 16, a 16-byte aligned pitch and base, n <= ~760 (got n=%d ld=%d p=%d)", n, ld, p);
@@ -368,7 +415,8 @@ int gcnk_dense_transform_bw_ld(const float *xp, int ld, int m, int n, const floa
                                float drop_scale, float *workspace, size_t workspace_bytes, gcnk_stream_t stream) {
     GCNK_REQUIRE(xp && g && w_grad && m > 0 && n > 0 && ld >= n && p > 0, "bad arguments");
     const int n_boxes = (n + 31) / 32;
-    const size_t smem = (size_t)BW_STAGES * ((size_t)n_boxes * BW_BOX_BYTES + 1024) + sizeof(BwBars) + 1024;
+    const size_t smem = (size_t)BW_STAGES * ((size_t)n_boxes * BW_BOX_BYTES + 1024) + sizeof(BwBars) + 1024 +
+                        sizeof(uint32_t) * 20 * KW_SLOTS * 32;
     if (p != P || ld % 4 || reinterpret_cast<uintptr_t>(xp) % 16 || reinterpret_cast<uintptr_t>(g) % 16 || n_boxes > BW_MAX_BOXES ||
         smem > 227 * 1024 || !tensor_maps_available()) {
         set_error("gcnk_dense_transform_bw_ld: needs p == 16, a 16-byte aligned pitch and bases, n <= 640 (got n=%d ld=%d p=%d)", n, ld, p);
