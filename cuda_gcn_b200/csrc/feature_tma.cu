@@ -55,18 +55,21 @@ template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile(
 // CTA = 16 consumer warps (16 rows each: a 256-row tile) + 1 producer warp.  Stage = one [256 x 32] box (32 KB).
 // (8 consumer warps per SM were measured slower than the register-staged kernel: too few warps to hide the
 // shared-memory and MMA latencies of the dependent k-step chains.)
-constexpr int FW_CONSUMERS = 16, FW_THREADS = (FW_CONSUMERS + 1) * 32, FW_BM = 256, FW_STAGES = 4, FW_STAGE_BYTES = FW_BM * 128;
+// The tile height is a template parameter (11 .. 16 consumer warps), chosen by fw_pick_consumers.
+constexpr int FW_MAX_CONSUMERS = 16, FW_MIN_CONSUMERS = 11, FW_STAGES = 4;
 
 struct FwBars { uint64_t full[FW_STAGES], empty[FW_STAGES]; };
 
-__global__ void __launch_bounds__(FW_THREADS, 1) dense_fw16_tma_kernel(const __grid_constant__ CUtensorMap map_x, const float *__restrict__ w,
+template <int FW_CONSUMERS>
+__global__ void __launch_bounds__((FW_CONSUMERS + 1) * 32, 1) dense_fw16_tma_kernel(const __grid_constant__ CUtensorMap map_x, const float *__restrict__ w,
                                                                         float *__restrict__ c, int m, int n,
                                                                         const uint32_t *__restrict__ bits, int64_t bit_words, float scale,
                                                                         const float *__restrict__ row_scale, int relu, int *err) {
+    constexpr int FW_THREADS = (FW_CONSUMERS + 1) * 32, FW_BM = 16 * FW_CONSUMERS, FW_STAGE_BYTES = FW_BM * 128;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 1 KB aligned, still a shared-space pointer (LDS, not LD)
     const int KS = (n + 7) / 8, n_batches = (n + 31) / 32;
-    uint8_t *ring = smem;                                                        // [FW_STAGES][16 KB]
+    uint8_t *ring = smem;                                                        // [FW_STAGES][FW_BM x 128 B]
     float4 *sfrag = reinterpret_cast<float4 *>(smem + FW_STAGES * FW_STAGE_BYTES);   // [KS][32] big, [KS][32] small
     FwBars *bars = reinterpret_cast<FwBars *>(sfrag + 2 * KS * 32);
     uint32_t *kws_all = reinterpret_cast<uint32_t *>(bars + 1);                  // [FW_CONSUMERS][KW_SLOTS][16 rows][2 words]
@@ -357,6 +360,34 @@ __global__ void pack_rows_kernel(const float *__restrict__ x, float *__restrict_
 
 }  // namespace
 
+// Consumer warps (tile height / 16) of the forward kernel for m rows.  Measured at 232,965 rows (r03e): 16 warps 0.282 ms per
+// step, 13 warps 0.309, 11 warps 0.300 although 11 turns 6.15 rounds-run-as-7 into 8.95-run-as-9 — the warps hide more
+// latency than the last round costs, so several rounds always run at 16.  A matrix that fits ONE round (a rank's slice of a
+// row partition) takes the smallest tile that still fits one round: same number of rounds, fewer rows per SM.
+// GCN_FW_WARPS=11..16 overrides.
+int fw_pick_consumers(int m) {
+    if (const char *e = getenv("GCN_FW_WARPS")) { const int v = atoi(e); if (v >= FW_MIN_CONSUMERS && v <= FW_MAX_CONSUMERS) return v; }
+    const int sms = sm_count();
+    if ((m + 16 * FW_MAX_CONSUMERS - 1) / (16 * FW_MAX_CONSUMERS) > sms) return FW_MAX_CONSUMERS;
+    for (int cw = FW_MIN_CONSUMERS; cw < FW_MAX_CONSUMERS; cw++)
+        if ((m + 16 * cw - 1) / (16 * cw) <= sms) return cw;
+    return FW_MAX_CONSUMERS;
+}
+
+template <int CW>
+int fw_launch(int grid, size_t smem, cudaStream_t st, const CUtensorMap &map_x, const float *w, float *c, int m, int n, const uint32_t *bits,
+              int64_t words, float scale, const float *row_scale, int relu) {
+    static bool attr[64] = {false};
+    int dev = 0;
+    GCNK_CUDA(cudaGetDevice(&dev));
+    if (!attr[dev]) {
+        GCNK_CUDA(cudaFuncSetAttribute(dense_fw16_tma_kernel<CW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr[dev] = true;
+    }
+    dense_fw16_tma_kernel<CW><<<grid, (CW + 1) * 32, smem, st>>>(map_x, w, c, m, n, bits, words, scale, row_scale, relu, async_err_flag());
+    return GCNK_OK;
+}
+
 // timing experiment only (wrong results): the keep bits are never loaded (every window reads as "beyond the array")
 static bool debug_no_bit_loads() {
     const char *e = getenv("GCN_DEBUG_NO_BITLOADS");
@@ -380,28 +411,33 @@ int gcnk_dense_transform_ld(const float *xp, int ld, int m, int n, const float *
     GCNK_REQUIRE(xp && w && c && m >= 0 && n > 0 && ld >= n && p > 0, "bad arguments");
     if (m == 0) return GCNK_OK;
     const int KS = (n + 7) / 8;
-    const size_t smem = (size_t)FW_STAGES * FW_STAGE_BYTES + sizeof(float4) * 2 * (size_t)KS * 32 + sizeof(FwBars) + 1024 +
-                        sizeof(uint32_t) * FW_CONSUMERS * KW_SLOTS * 32;
+    const int consumers = fw_pick_consumers(m);
+    const int bm = 16 * consumers;
+    const size_t smem = (size_t)FW_STAGES * bm * 128 + sizeof(float4) * 2 * (size_t)KS * 32 + sizeof(FwBars) + 1024 +
+                        sizeof(uint32_t) * consumers * KW_SLOTS * 32;
     if (p != P || ld % 4 || reinterpret_cast<uintptr_t>(xp) % 16 || reinterpret_cast<uintptr_t>(c) % 8 || smem > 227 * 1024 ||
         !tensor_maps_available()) {
         set_error("gcnk_dense_transform_ld: needs p == 16, a 16-byte aligned pitch and base, n <= ~760 (got n=%d ld=%d p=%d)", n, ld, p);
         return GCNK_EUNSUPPORTED;
     }
     CUtensorMap map_x;
-    if (!make_tensor_map_2d(&map_x, xp, (uint64_t)m, (uint64_t)n, (uint64_t)ld, FW_BM, 32, true)) {
+    if (!make_tensor_map_2d(&map_x, xp, (uint64_t)m, (uint64_t)n, (uint64_t)ld, bm, 32, true)) {
         set_error("gcnk_dense_transform_ld: cuTensorMapEncodeTiled failed");
         return GCNK_EUNSUPPORTED;
     }
-    static bool attr[64] = {false};
-    int dev = 0;
-    GCNK_CUDA(cudaGetDevice(&dev));
-    if (!attr[dev]) {
-        GCNK_CUDA(cudaFuncSetAttribute(dense_fw16_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr[dev] = true;
+    const int n_tiles = (m + bm - 1) / bm;
+    const int grid = std::min(n_tiles, sm_count());
+    const int64_t words = debug_no_bit_loads() ? 0 : ((int64_t)m * n + 31) / 32;
+    int rc = GCNK_OK;
+    switch (consumers) {
+        case 11: rc = fw_launch<11>(grid, smem, S(stream), map_x, w, c, m, n, drop_bits, words, drop_scale, row_scale, relu); break;
+        case 12: rc = fw_launch<12>(grid, smem, S(stream), map_x, w, c, m, n, drop_bits, words, drop_scale, row_scale, relu); break;
+        case 13: rc = fw_launch<13>(grid, smem, S(stream), map_x, w, c, m, n, drop_bits, words, drop_scale, row_scale, relu); break;
+        case 14: rc = fw_launch<14>(grid, smem, S(stream), map_x, w, c, m, n, drop_bits, words, drop_scale, row_scale, relu); break;
+        case 15: rc = fw_launch<15>(grid, smem, S(stream), map_x, w, c, m, n, drop_bits, words, drop_scale, row_scale, relu); break;
+        default: rc = fw_launch<16>(grid, smem, S(stream), map_x, w, c, m, n, drop_bits, words, drop_scale, row_scale, relu); break;
     }
-    const int n_tiles = (m + FW_BM - 1) / FW_BM;
-    dense_fw16_tma_kernel<<<std::min(n_tiles, sm_count()), FW_THREADS, smem, S(stream)>>>(map_x, w, c, m, n, drop_bits, debug_no_bit_loads() ? 0 : ((int64_t)m * n + 31) / 32,
-                                                                                     drop_scale, row_scale, relu, async_err_flag());
+    if (rc) return rc;
     GCNK_LAUNCHED();
     return GCNK_OK;
 }
