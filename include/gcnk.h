@@ -90,7 +90,9 @@ int gcnk_graph_stats(const gcnk_graph *g, int *n, int64_t *nnz, int *max_degree,
 
 /* ---- GraphSum: K6/K7, cuda_kernel.cu:126-162 (CPU: module.cpp:83-119) ---------------------------
  * out[s,:] = sum_{d in row s} in[d,:] / sqrt(deg(s)*deg(d)).  Forward and backward are the same
- * operation on (data) resp. (grad) buffers, exactly as in the reference.  `in` has n_cols rows. */
+ * operation on (data) resp. (grad) buffers, exactly as in the reference.  `in` has n_cols rows.
+ * Widths above 4 that are not a multiple of 4 (41, 47: the class widths) run through rows padded to a 16-byte pitch inside the
+ * handle's scratch buffer, so that the gather moves them with 128-bit loads. */
 int gcnk_graphsum(const gcnk_graph *g, const float *in, float *out, int dim, gcnk_stream_t stream);
 /* gcnk_graphsum keeps a [n_cols x dim] pre-scaled copy of its input inside the handle for the next call; this frees it
  * (synchronise first): worth it after a one-off wide call such as A_hat*X at dim 602 (561 MB at Reddit shape). */
@@ -214,7 +216,8 @@ int gcnk_rng_get_state(const gcnk_rng *rng, uint64_t *h_state2);
 int gcnk_rng_set_state(gcnk_rng *rng, uint64_t s0, uint64_t s1);
 int gcnk_rng_skip(gcnk_rng *rng, uint64_t n_draws);          /* advance the host state by n draws, O(log n) */
 int gcnk_rng_next_host(gcnk_rng *rng, uint32_t *h_out, int64_t n);   /* host-side draws (Glorot init), advances */
-/* keep bits for the next n draws (bit i set = keep), advances the stream by n.  p is the dropout rate. */
+/* keep bits for the next n draws (bit i set = keep), advances the stream by n.  p is the dropout rate.  From 2^20 draws on the
+ * bit-sliced kernels run (csrc/rng_bitsliced.cuh: 32 streams per thread); the bits are the reference's either way. */
 int gcnk_dropout_mask(gcnk_rng *rng, uint32_t *keep_bits, int64_t n, float p, gcnk_stream_t stream);
 int gcnk_dropout_apply(float *x, const uint32_t *keep_bits, int64_t n, float p, gcnk_stream_t stream);  /* fw and bw: x *= keep ? 1/(1-p) : 0 */
 
@@ -262,7 +265,8 @@ int gcnk_layer2_fused_terms(const float *P, const float *W2, const int *split, c
                             gcnk_stream_t stream);
 /* d_out[0] = ((((0 + terms[0]) + terms[1]) + ...) + terms[n-1]) [/ divide_by if non-zero] in fp32, bit for bit what a scalar
  * loop computes — the reference accumulates its loss that way (module.cpp:125-143), and at 10^5 labelled rows the rounding
- * of that loop is larger than the parity tolerance — but evaluated block-parallel by one warp (~0.4 cycles per term).
+ * of that loop is larger than the parity tolerance — but evaluated block-parallel: one CTA rounds 4,096 terms at a time in the
+ * running sum's binade, one warp commits the blocks in order (exact integer additions; anything unusual is replayed term by term).
  * Optional d_wait_flags as in gcnk_gather_wait_next (row-partitioned runs: the terms of the other ranks arrive by push). */
 int gcnk_sequential_sum(const float *terms, int n, float *d_out, float divide_by, const int *d_wait_flags, int n_flags, int skip,
                         int wait_value, int *d_err, gcnk_stream_t stream);
