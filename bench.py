@@ -325,32 +325,30 @@ def run_ours(args):
 
     # ---- e2e: the same step through the C face with the (local rows of the) feature matrix uploaded from pinned
     # host memory each step
-    e2e = None
-    if True:
-        pinned = L.gcnh_alloc_pinned(max(nnzX_loc, 1))
-        host_view = np.ctypeslib.as_array((abi.C.c_float * max(nnzX_loc, 1)).from_address(pinned))
-        host_view[:nnzX_loc] = x_local
-        e2e_steps = max(3, min(args.steps, 10))
-        prefetch = not args.e2e_serial
-        eng.set_input_host(pinned); step(False)                 # warm the copy path
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            if prefetch:
-                eng.epoch_prefetch(2, pinned)                   # the step on the current input; H2D of the next step's input under it
-            else:
-                eng.set_input_host(pinned)                      # H2D of this rank's nnz(X) floats on the engine's stream
-                step(False)                                     # train_epoch + eval(2); each reads its scalars back (D2H)
-        barrier()
-        e2e_dt = (time.perf_counter() - t0) / e2e_steps
-        e2e_dt = float(eng.allreduce_host([e2e_dt], op_max=True)[0])
-        L.gcnh_free_pinned(pinned)
-        e2e = {"value": 1.0 / e2e_dt, "unit": UNIT, "h2d_bytes_per_step": int(nnzX * 4), "d2h_bytes_per_step": world * (2 * 16 + 4),
-               "steps": e2e_steps, "api": "gcnh_engine_epoch_prefetch (upload of step k+1 under step k; include/gcn_host.h)" if prefetch else
-               "gcnh_engine_set_input_host + gcnh_engine_train_epoch + gcnh_engine_eval (include/gcn_host.h)"}
-        if wide and world > 1:
-            e2e["note"] = ("the row-partitioned wide plan reads every node's features: each rank uploads its own rows and the slices are "
-                           "all-gathered over NVLink (NCCL) on the copy stream")
+    pinned = L.gcnh_alloc_pinned(max(nnzX_loc, 1))
+    host_view = np.ctypeslib.as_array((abi.C.c_float * max(nnzX_loc, 1)).from_address(pinned))
+    host_view[:nnzX_loc] = x_local
+    e2e_steps = max(3, min(args.steps, 10))
+    prefetch = not args.e2e_serial
+    eng.set_input_host(pinned); step(False)                 # warm the copy path
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        if prefetch:
+            eng.epoch_prefetch(2, pinned)                   # the step on the current input; H2D of the next step's input under it
+        else:
+            eng.set_input_host(pinned)                      # H2D of this rank's nnz(X) floats on the engine's stream
+            step(False)                                     # train_epoch + eval(2); each reads its scalars back (D2H)
+    barrier()
+    e2e_dt = (time.perf_counter() - t0) / e2e_steps
+    e2e_dt = float(eng.allreduce_host([e2e_dt], op_max=True)[0])
+    L.gcnh_free_pinned(pinned)
+    e2e = {"value": 1.0 / e2e_dt, "unit": UNIT, "h2d_bytes_per_step": int(nnzX * 4), "d2h_bytes_per_step": world * (2 * 16 + 4),
+           "steps": e2e_steps, "api": "gcnh_engine_epoch_prefetch (upload of step k+1 under step k; include/gcn_host.h)" if prefetch else
+           "gcnh_engine_set_input_host + gcnh_engine_train_epoch + gcnh_engine_eval (include/gcn_host.h)"}
+    if wide and world > 1:
+        e2e["note"] = ("the row-partitioned wide plan reads every node's features: each rank uploads its own rows and the slices are "
+                       "all-gathered over NVLink (NCCL) on the copy stream")
     eng.close()
     if rank != 0:
         return

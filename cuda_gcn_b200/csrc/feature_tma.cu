@@ -388,12 +388,6 @@ int fw_launch(int grid, size_t smem, cudaStream_t st, const CUtensorMap &map_x, 
     return GCNK_OK;
 }
 
-// timing experiment only (wrong results): the keep bits are never loaded (every window reads as "beyond the array")
-static bool debug_no_bit_loads() {
-    const char *e = getenv("GCN_DEBUG_NO_BITLOADS");
-    return e && *e && *e != '0';
-}
-
 extern "C" {
 
 int gcnk_dense_pack(const float *x, int m, int n, float *xp, int ld, gcnk_stream_t stream) {
@@ -427,7 +421,7 @@ int gcnk_dense_transform_ld(const float *xp, int ld, int m, int n, const float *
     }
     const int n_tiles = (m + bm - 1) / bm;
     const int grid = std::min(n_tiles, sm_count());
-    const int64_t words = debug_no_bit_loads() ? 0 : ((int64_t)m * n + 31) / 32;
+    const int64_t words = ((int64_t)m * n + 31) / 32;
     int rc = GCNK_OK;
     switch (consumers) {
         case 11: rc = fw_launch<11>(grid, smem, S(stream), map_x, w, c, m, n, drop_bits, words, drop_scale, row_scale, relu); break;
@@ -476,7 +470,7 @@ int gcnk_dense_transform_bw_ld(const float *xp, int ld, int m, int n, const floa
     int rows_per_cta = ((m + ctas - 1) / ctas + BW_ROWS - 1) / BW_ROWS * BW_ROWS;
     ctas = (m + rows_per_cta - 1) / rows_per_cta;
     dense_bw16_tma_kernel<<<ctas, BW_THREADS, smem, S(stream)>>>(map_x, map_g, workspace, m, n, n_boxes, rows_per_cta, drop_bits,
-                                                          debug_no_bit_loads() ? 0 : ((int64_t)m * n + 31) / 32, drop_scale, async_err_flag());
+                                                          ((int64_t)m * n + 31) / 32, drop_scale, async_err_flag());
     GCNK_LAUNCHED();
     const int elems = n * P;
     reduce_parts_tma_kernel<<<(elems + 31) / 32, 256, 0, S(stream)>>>(workspace, w_grad, elems, 2 * ctas);
