@@ -205,7 +205,8 @@ int ew_grid(int64_t n) { return (int)std::max<int64_t>(1, std::min<int64_t>((n +
 //   rounded in parallel (t/u is an exact power-of-two scaling), summed exactly as integers (REDUX), and added to the
 //   mantissa of S in integer arithmetic.  A block that would leave the binade, contains a tie, a negative or huge
 //   term, or starts from S = 0 is replayed with plain sequential additions, 32 terms at a time.
-// One warp; ~100 cycles per 256 terms (the dependent chain is one step per 256 terms instead of per term).
+// seq_fast_block is that step for one warp (the fallback granularity: 1,024 terms, then rows of 32); seq_sum_kernel spreads
+// the rounding over eight warps.
 __device__ __forceinline__ bool seq_fast_block(float &S, const float *t, int cnt) {
     // cnt terms per lane (lane-major inside a row is irrelevant here: the fast path is order-independent)
     const uint32_t sb = __float_as_uint(S);

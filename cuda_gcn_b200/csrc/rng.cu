@@ -285,7 +285,7 @@ int gcnk_dropout_mask(gcnk_rng *rng, uint32_t *keep_bits, int64_t n, float p, gc
     // short streams (the N x hidden mask: 3.7 M draws at Reddit shape) get 128 draws per thread so that they still
     // fill the machine; long ones 512 (the per-CTA jump is amortised over more draws)
     if (rng_variant() == 1 && n >= (1ll << 20)) {
-        // long streams: the bit-sliced generator; 2^10 draws per stream once that still leaves a CTA for every few SMs
+        // from 2^20 draws on: the bit-sliced generator (rng_bitsliced.cuh)
         gcnk_bs::Entry *nib = device_nibble_tables();
         if (!nib) return cuda_fail(cudaGetLastError(), "xorshift nibble tables", __FILE__, __LINE__);
         // draws per stream: long streams amortise the jump chain (6.5 instructions per draw at 2^10, 8.4 at 2^7) but leave
